@@ -1,0 +1,96 @@
+// Pieces shared by the CUDA-core and the tcgen05 variants of the convolution-as-GEMM engine.
+#pragma once
+#include "common.cuh"
+
+namespace vrcoc {
+
+// Kernel-side copy of vrcoc_conv_desc plus derived quantities (passed by value, < 4 KB of parameter space).
+struct ConvArgs {
+  int B, H_in, W_in, H_out, W_out, C0, C1, Cin, O, kh, kw, stride, pad;
+  int K;        // Cin * kh * kw
+  int P_in, P_out;
+  const void* src0; int src0_dtype; int64_t src0_bstride;
+  const void* src1; int src1_dtype; int64_t src1_bstride;
+  const int32_t* chan_src;
+  const double* gn_sums; const float* gn_gamma; const float* gn_beta; float gn_eps;
+  const float* table; int has_gate;
+  const void* weight; int weight_dtype;
+  const float* e_scale; const float* e_shift; int act; const float* post_scale;
+  const void* res; int res_dtype;
+  const float* f_scale; const float* f_shift;
+  void* out; int out_dtype; void* out2; int out2_dtype; int O_split;
+  double* out_sample_sums; uint32_t* out_minmax;
+  int fast1x1;  // 1x1, stride 1, no pad, P % 8 == 0, 16-byte aligned sources: vectorised slab loads
+  int vec_out;  // P_out % 8 == 0 and aligned outputs: vectorised stores
+};
+
+// Per-CTA prologue table tab[c] = {scale, shift, gate_a, gate_c} for the CTA's sample b.
+__device__ __forceinline__ void build_prologue_table(const ConvArgs& a, int b, float4* tab) {
+  if (a.gn_sums) {
+    // GroupNorm(1, C): per-sample mean / rstd from the {sum, sum^2} pair (vr_coc.py:105-111), folded with the
+    // per-channel affine so the slab loader does one FMA per element.
+    const double cnt = (double)a.C0 * (double)a.P_in;
+    const double mean = a.gn_sums[2 * b] / cnt;
+    double var = a.gn_sums[2 * b + 1] / cnt - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)a.gn_eps));
+    const float mu = (float)mean;
+    for (int c = threadIdx.x; c < a.Cin; c += blockDim.x) {
+      float sc = rstd * a.gn_gamma[c];
+      tab[c] = make_float4(sc, fmaf(-mu, sc, a.gn_beta[c]), 0.f, 88.f);
+    }
+  } else if (a.table) {
+    const float4* t = reinterpret_cast<const float4*>(a.table) + (int64_t)b * a.Cin;
+    for (int c = threadIdx.x; c < a.Cin; c += blockDim.x) tab[c] = t[c];
+  } else {
+    for (int c = threadIdx.x; c < a.Cin; c += blockDim.x) tab[c] = make_float4(1.f, 0.f, 0.f, 88.f);
+  }
+}
+
+struct EpiCoef { float es, eh, ps, fs, fh; };
+
+__device__ __forceinline__ EpiCoef load_epi(const ConvArgs& a, int o) {
+  EpiCoef e;
+  e.es = a.e_scale ? a.e_scale[o] : 1.f;
+  e.eh = a.e_shift ? a.e_shift[o] : 0.f;
+  e.ps = a.post_scale ? a.post_scale[o] : 1.f;
+  e.fs = a.f_scale ? a.f_scale[o] : 1.f;
+  e.fh = a.f_shift ? a.f_shift[o] : 0.f;
+  return e;
+}
+
+// y = act(acc*es + eh) * ps + res;  y = y*fs + fh
+__device__ __forceinline__ float epilogue_value(float acc, const EpiCoef& e, int act, float res) {
+  float y = apply_act(fmaf(acc, e.es, e.eh), act);
+  y = fmaf(y, e.ps, res);
+  return fmaf(y, e.fs, e.fh);
+}
+
+// warp-reduce the per-thread side statistics, then one atomic per warp
+__device__ __forceinline__ void emit_side_stats(const ConvArgs& a, int b, float ssum, float ssq, float vmax, float vmin) {
+  if (a.out_sample_sums) {
+    ssum = warp_sum(ssum);
+    ssq = warp_sum(ssq);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(&a.out_sample_sums[2 * b], (double)ssum);
+      atomicAdd(&a.out_sample_sums[2 * b + 1], (double)ssq);
+    }
+  }
+  if (a.out_minmax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+      vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMax(&a.out_minmax[0], __float_as_uint(vmax));
+      atomicMax(&a.out_minmax[1], ~__float_as_uint(vmin));
+    }
+  }
+}
+
+int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
+int launch_conv_tc(const ConvArgs& a, cudaStream_t st);       // tcgen05 bf16 path (conv_tc.cu)
+bool conv_tc_supported(const ConvArgs& a);
+
+}  // namespace vrcoc

@@ -1,0 +1,195 @@
+// Convolution-as-GEMM engine, CUDA-core fp32 path (exact arithmetic for the fp32 parity gate: TF32 tensor-core
+// products flip assignments and miss the 1e-4 gate).  See include/vrcoc.h for the operator contract.
+//
+// Tiling: one CTA = 128 output points (M) x 64 output channels (N) of one sample, K swept in slabs of 16 through
+// double-buffered shared memory with register prefetch.  Points are the contiguous axis of NCHW, so A-slab rows
+// (one logical input channel x 128 points) are 128-bit coalesced loads and each thread's 8x4 micro-tile writes
+// 8 consecutive points per output channel.  The prologue (GroupNorm apply / attention gate / ECA scale) is applied
+// while the slab is loaded; bias, activation, layer-scale, residual, BatchNorm affine and the side statistics are
+// applied on the accumulators, so no intermediate ever reaches HBM.
+#include "conv_common.cuh"
+
+namespace vrcoc {
+
+constexpr int BM = 128, BN = 64, BK = 16, BNP = 68;
+constexpr int SIMT_THREADS = 256;
+
+__device__ __forceinline__ void load8_any(const void* base, int64_t idx, int dtype, float (&v)[8]) {
+  if (dtype == VRCOC_F32) ld8<float>(reinterpret_cast<const float*>(base) + idx, v);
+  else ld8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(base) + idx, v);
+}
+__device__ __forceinline__ void store8_any(void* base, int64_t idx, int dtype, const float (&v)[8]) {
+  if (dtype == VRCOC_F32) st8<float>(reinterpret_cast<float*>(base) + idx, v);
+  else st8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(base) + idx, v);
+}
+
+__global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(ConvArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* As = reinterpret_cast<float*>(smem);                 // [2][BK][BM]
+  float* Bs = As + 2 * BK * BM;                               // [2][BK][BNP]
+  float4* tab = reinterpret_cast<float4*>(Bs + 2 * BK * BNP); // [Cin]
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * BM;
+  const int o0 = blockIdx.y * BN;
+  const int P = a.P_out;
+  const int taps = a.kh * a.kw;
+
+  build_prologue_table(a, b, tab);
+  __syncthreads();
+
+  // ---- slab loaders -------------------------------------------------------------------------------------------
+  const int a_k = tid >> 4;          // slab row (0..15)
+  const int a_pg = tid & 15;         // point group: 8 consecutive points
+  const int b_o = tid >> 2;          // weight row inside the tile (0..63)
+  const int b_kq = (tid & 3) * 4;    // 4 consecutive k
+  float areg[8], breg[4];
+
+  auto load_a = [&](int k0) {
+    const int kk = k0 + a_k;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) areg[i] = 0.f;
+    if (kk >= a.K) return;
+    const int c = kk / taps;
+    const int tap = kk - c * taps;
+    const int s = a.chan_src ? a.chan_src[c] : c;
+    const void* src; int dt; int64_t base;
+    if (s < a.C0) { src = a.src0; dt = a.src0_dtype; base = (int64_t)b * a.src0_bstride + (int64_t)s * a.P_in; }
+    else          { src = a.src1; dt = a.src1_dtype; base = (int64_t)b * a.src1_bstride + (int64_t)(s - a.C0) * a.P_in; }
+    const float4 t = tab[c];
+    const int q0 = p0 + a_pg * 8;
+    if (a.fast1x1) {
+      if (q0 < P) {
+        load8_any(src, base + q0, dt, areg);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float x = areg[i];
+          float y = fmaf(x, t.x, t.y);
+          if (a.has_gate) y *= sigmoidf_exact(fmaf(t.z, x, t.w));
+          areg[i] = y;
+        }
+      }
+    } else {
+      const int ky = tap / a.kw, kx = tap - ky * a.kw;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int q = q0 + i;
+        if (q < P) {
+          int oy = q / a.W_out, ox = q - oy * a.W_out;
+          int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
+          if (iy >= 0 && iy < a.H_in && ix >= 0 && ix < a.W_in) {
+            float x = ld_any(src, base + (int64_t)iy * a.W_in + ix, dt);
+            float y = fmaf(x, t.x, t.y);
+            if (a.has_gate) y *= sigmoidf_exact(fmaf(t.z, x, t.w));
+            areg[i] = y;
+          }
+        }
+      }
+    }
+  };
+  auto load_b = [&](int k0) {
+    const int o = o0 + b_o;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int kk = k0 + b_kq + j;
+      breg[j] = (o < a.O && kk < a.K) ? ld_any(a.weight, (int64_t)o * a.K + kk, a.weight_dtype) : 0.f;
+    }
+  };
+  auto store_slab = [&](int buf) {
+    float* ad = As + (buf * BK + a_k) * BM + a_pg * 8;
+    *reinterpret_cast<float4*>(ad) = make_float4(areg[0], areg[1], areg[2], areg[3]);
+    *reinterpret_cast<float4*>(ad + 4) = make_float4(areg[4], areg[5], areg[6], areg[7]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Bs[(buf * BK + b_kq + j) * BNP + b_o] = breg[j];
+  };
+
+  // ---- main loop ------------------------------------------------------------------------------------------------
+  const int pg = tid & 15;   // micro-tile: points pg*8..+8, outs og*4..+4
+  const int og = tid >> 4;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nk = (a.K + BK - 1) / BK;
+  load_a(0); load_b(0); store_slab(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) { load_a((kt + 1) * BK); load_b((kt + 1) * BK); }
+    const float* ap = As + buf * BK * BM + pg * 8;
+    const float* bp = Bs + buf * BK * BNP + og * 4;
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(ap + k * BM);
+      float4 a1 = *reinterpret_cast<const float4*>(ap + k * BM + 4);
+      float4 bv = *reinterpret_cast<const float4*>(bp + k * BNP);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bw[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) store_slab(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ---- epilogue ---------------------------------------------------------------------------------------------------
+  const int q0 = p0 + pg * 8;
+  float ssum = 0.f, ssq = 0.f, vmax = 0.f, vmin = __int_as_float(0x7f800000);
+  if (q0 < P) {
+    const bool full8 = a.vec_out && (q0 + 8 <= P);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int o = o0 + og * 4 + j;
+      if (o >= a.O) continue;
+      const EpiCoef ec = load_epi(a, o);
+      void* dst; int ddt; int64_t dbase;
+      if (o < a.O_split) { dst = a.out; ddt = a.out_dtype; dbase = ((int64_t)b * a.O_split + o) * P; }
+      else { dst = a.out2; ddt = a.out2_dtype; dbase = ((int64_t)b * (a.O - a.O_split) + (o - a.O_split)) * P; }
+      const int64_t rbase = ((int64_t)b * a.O + o) * P;
+      float y[8];
+      if (full8) {
+        float r[8];
+        if (a.res) load8_any(a.res, rbase + q0, a.res_dtype, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          y[i] = epilogue_value(acc[i][j], ec, a.act, a.res ? r[i] : 0.f);
+          ssum += y[i]; ssq = fmaf(y[i], y[i], ssq);
+          vmax = fmaxf(vmax, y[i]); vmin = fminf(vmin, y[i]);
+        }
+        store8_any(dst, dbase + q0, ddt, y);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (q0 + i < P) {
+            float r = a.res ? ld_any(a.res, rbase + q0 + i, a.res_dtype) : 0.f;
+            float v = epilogue_value(acc[i][j], ec, a.act, r);
+            ssum += v; ssq = fmaf(v, v, ssq);
+            vmax = fmaxf(vmax, v); vmin = fminf(vmin, v);
+            st_any(dst, dbase + q0 + i, ddt, v);
+          }
+        }
+      }
+    }
+  }
+  emit_side_stats(a, b, ssum, ssq, vmax, vmin);
+}
+
+int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {
+  size_t smem = (size_t)(2 * BK * BM + 2 * BK * BNP) * sizeof(float) + (size_t)a.Cin * sizeof(float4);
+  VRCOC_REQUIRE(smem <= 200 * 1024, "conv: too many input channels (%d) for the prologue table", a.Cin);
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(conv_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  dim3 grid((unsigned)cdiv(a.P_out, BM), (unsigned)cdiv(a.O, BN), (unsigned)a.B);
+  conv_simt_kernel<<<grid, SIMT_THREADS, smem, st>>>(a);
+  return check_launch("conv_simt");
+}
+
+}  // namespace vrcoc

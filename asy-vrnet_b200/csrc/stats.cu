@@ -1,0 +1,387 @@
+// Statistics, table builders and the bandwidth-bound elementwise passes of the fusion modules.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace vrcoc {
+
+// ---- error plumbing ------------------------------------------------------------------------------------------
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(VRCOC_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+  return VRCOC_OK;
+}
+
+// ---- block reduction of two floats -----------------------------------------------------------------------------
+__device__ __forceinline__ void block_sum2(float& a, float& b, float* red /*>=64 floats*/) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { red[w] = a; red[32 + w] = b; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float x = (int)threadIdx.x < nw ? red[threadIdx.x] : 0.f;
+    float y = (int)threadIdx.x < nw ? red[32 + threadIdx.x] : 0.f;
+    x = warp_sum(x);
+    y = warp_sum(y);
+    if (threadIdx.x == 0) { red[0] = x; red[32] = y; }
+  }
+  __syncthreads();
+  a = red[0];
+  b = red[32];
+}
+
+// ---- per-(sample, channel) sums --------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) channel_sums_kernel(const T* __restrict__ x, int HW, float* __restrict__ cs,
+                                                           double* __restrict__ ss, int C) {
+  __shared__ float red[64];
+  const int plane = blockIdx.x;
+  const T* p = x + (int64_t)plane * HW;
+  float s = 0.f, s2 = 0.f;
+  const bool vec = (HW % 8 == 0) && ((reinterpret_cast<uintptr_t>(p) & 31) == 0 || (sizeof(T) == 2 && (reinterpret_cast<uintptr_t>(p) & 15) == 0));
+  if (vec) {
+    for (int i = threadIdx.x * 8; i < HW; i += blockDim.x * 8) {
+      float v[8];
+      ld8<T>(p + i, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s += v[j]; s2 = fmaf(v[j], v[j], s2); }
+    }
+  } else {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      float v = ldf<T>(p + i);
+      s += v; s2 = fmaf(v, v, s2);
+    }
+  }
+  block_sum2(s, s2, red);
+  if (threadIdx.x == 0) {
+    if (cs) { cs[2 * plane] = s; cs[2 * plane + 1] = s2; }
+    if (ss) {
+      int b = plane / C;
+      atomicAdd(&ss[2 * b], (double)s);
+      atomicAdd(&ss[2 * b + 1], (double)s2);
+    }
+  }
+}
+
+// ---- y = act(x*s1+t1) + res; y = y*s2+t2, with optional per-plane sums and global min/max ------------------------
+template <typename TX, typename TR, typename TO>
+__global__ void __launch_bounds__(256)
+chan_affine_kernel(const TX* __restrict__ x, const TR* __restrict__ res, TO* __restrict__ out, const float* __restrict__ s1,
+                   const float* __restrict__ t1, int act, const float* __restrict__ s2, const float* __restrict__ t2, int C,
+                   int HW, float* __restrict__ cs, uint32_t* __restrict__ minmax) {
+  __shared__ float red[64];
+  const int plane = blockIdx.x, c = plane % C;
+  const float a1 = s1 ? s1[c] : 1.f, b1 = t1 ? t1[c] : 0.f, a2 = s2 ? s2[c] : 1.f, b2 = t2 ? t2[c] : 0.f;
+  const int64_t base = (int64_t)plane * HW;
+  float s = 0.f, sq = 0.f, mx = 0.f, mn = __int_as_float(0x7f800000);
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    float y = apply_act(fmaf(ldf<TX>(x + base + i), a1, b1), act);
+    if (res) y += ldf<TR>(res + base + i);
+    y = fmaf(y, a2, b2);
+    stf<TO>(out + base + i, y);
+    s += y; sq = fmaf(y, y, sq);
+    mx = fmaxf(mx, y); mn = fminf(mn, y);
+  }
+  if (cs) {
+    block_sum2(s, sq, red);
+    if (threadIdx.x == 0) { cs[2 * plane] = s; cs[2 * plane + 1] = sq; }
+  }
+  if (minmax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMax(&minmax[0], __float_as_uint(mx));
+      atomicMax(&minmax[1], ~__float_as_uint(mn));
+    }
+  }
+}
+
+// ---- ImageEnhanceByRadar tail -------------------------------------------------------------------------------------
+template <typename TK, typename TI, typename TO>
+__global__ void __launch_bounds__(256)
+img_enh_finish_kernel(const TK* __restrict__ k, const TI* __restrict__ img, TO* __restrict__ out,
+                      const uint32_t* __restrict__ minmax, const float* __restrict__ sc, const float* __restrict__ sh, int C,
+                      int HW, float* __restrict__ cs) {
+  __shared__ float red[64];
+  const int plane = blockIdx.x, c = plane % C;
+  const float mx = __uint_as_float(minmax[0]), mn = __uint_as_float(~minmax[1]);
+  const float dst = mx - mn;               // 0/0 -> NaN, like the reference's true_divide (vr_coc.py:66)
+  const float a = sc ? sc[c] : 1.f, b = sh ? sh[c] : 0.f;
+  const int64_t base = (int64_t)plane * HW;
+  float s = 0.f, sq = 0.f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    float kk = ldf<TK>(k + base + i);
+    float y = (1.0f + (kk - mn) / dst) * ldf<TI>(img + base + i);
+    y = fmaf(y, a, b);
+    stf<TO>(out + base + i, y);
+    s += y; sq = fmaf(y, y, sq);
+  }
+  if (cs) {
+    block_sum2(s, sq, red);
+    if (threadIdx.x == 0) { cs[2 * plane] = s; cs[2 * plane + 1] = sq; }
+  }
+}
+
+// ---- ShuffleAttention parameters + attended-channel means (shuffle_attention.py:48-66) -------------------------------
+// image channel c = g*(2q) + half*q + j.  attn[b][c] = {scale, gate_a, gate_c, mean_hw(attended channel)}
+//   half 0: attended = x * sigmoid(cw_j*mean + cb_j)                -> scale = that sigmoid, gate off (a=0, c=+88)
+//   half 1: attended = x * sigmoid(sw_j*(gw_j*(x-mu)*rstd + gb_j) + sb_j) -> scale = 1, gate_a = sw*gw*rstd, gate_c = sw*(gb - gw*mu*rstd)+sb
+// G == 0: no attention (RadarEnhanceByImage initial=True): scale 1, gate off, mean = channel mean.
+template <typename T>
+__global__ void __launch_bounds__(256)
+sa_gate_sums_kernel(const T* __restrict__ img, int Ci, int HW, int G, const float* __restrict__ cs,
+                    const float* __restrict__ cw, const float* __restrict__ cb, const float* __restrict__ sw,
+                    const float* __restrict__ sb, const float* __restrict__ gw, const float* __restrict__ gb,
+                    float* __restrict__ attn) {
+  __shared__ float red[64];
+  const int plane = blockIdx.x, c = plane % Ci;
+  const float inv_hw = 1.0f / (float)HW;
+  const float mean = cs[2 * plane] * inv_hw;
+  float scale = 1.f, ga = 0.f, gc = 88.f, amean = mean;
+  if (G > 0) {
+    const int q = Ci / (2 * G);
+    const int half = (c / q) & 1, j = c % q;
+    if (half == 0) {
+      scale = sigmoidf_exact(fmaf(cw[j], mean, cb[j]));
+      amean = mean * scale;
+    } else {
+      float var = fmaxf(cs[2 * plane + 1] * inv_hw - mean * mean, 0.f);
+      float rstd = rsqrtf(var + 1e-5f);
+      ga = sw[j] * gw[j] * rstd;
+      gc = fmaf(sw[j], gb[j] - gw[j] * mean * rstd, sb[j]);
+      const T* p = img + (int64_t)plane * HW;
+      float s = 0.f, dummy = 0.f;
+      for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+        float x = ldf<T>(p + i);
+        s = fmaf(x, sigmoidf_exact(fmaf(ga, x, gc)), s);
+      }
+      block_sum2(s, dummy, red);
+      amean = s * inv_hw;
+    }
+  }
+  if (threadIdx.x == 0) {
+    float4 o = make_float4(scale, ga, gc, amean);
+    reinterpret_cast<float4*>(attn)[plane] = o;
+  }
+}
+
+// ---- ECA over the shuffled concat + final conv prologue table (vr_coc.py:346-350, eca.py:16-22) -----------------------
+// logical channel k of z = shuffle_channels(cat[image_attn, radar]) reads concat channel chan_src[k]
+// (< Ci: attended image channel, else radar channel).  table[b][k] = {scale*eca, 0, gate_a, gate_c}
+__global__ void radar_enh_table_kernel(const float* __restrict__ attn, const float* __restrict__ cs_radar,
+                                       const int32_t* __restrict__ chan_src, const float* __restrict__ eca_w, int eca_k, int Ci,
+                                       int Cr, int HW, float* __restrict__ table) {
+  extern __shared__ float means[];   // [Ci+Cr] logical-channel means
+  const int b = blockIdx.x, K = Ci + Cr;
+  const float inv_hw = 1.0f / (float)HW;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    int s = chan_src ? chan_src[k] : k;
+    means[k] = s < Ci ? attn[((int64_t)b * Ci + s) * 4 + 3] : cs_radar[((int64_t)b * Cr + (s - Ci)) * 2] * inv_hw;
+  }
+  __syncthreads();
+  const int half = (eca_k - 1) / 2;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float a = 0.f;
+    for (int j = 0; j < eca_k; ++j) {
+      int kk = k + j - half;
+      if (kk >= 0 && kk < K) a = fmaf(eca_w[j], means[kk], a);
+    }
+    float eca = sigmoidf_exact(a);
+    int s = chan_src ? chan_src[k] : k;
+    float4 o;
+    if (s < Ci) {
+      const float* at = attn + ((int64_t)b * Ci + s) * 4;
+      o = make_float4(at[0] * eca, 0.f, at[1], at[2]);
+    } else {
+      o = make_float4(eca, 0.f, 0.f, 88.f);
+    }
+    reinterpret_cast<float4*>(table)[(int64_t)b * K + k] = o;
+  }
+}
+
+
+// ---- backward elementwise passes of the projections ------------------------------------------------------------------
+// dU = dy * gelu'(u),  gelu'(u) = Phi(u) + u*phi(u)     (Mlp.act = nn.GELU(), vr_coc.py:206,219)
+template <typename TY, typename TU, typename TO>
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const TY* __restrict__ dy, const TU* __restrict__ u, TO* __restrict__ out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float x = ldf<TU>(u + i);
+    float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+    stf<TO>(out + i, ldf<TY>(dy + i) * fmaf(x, pdf, cdf));
+  }
+}
+
+// GroupNorm(1,C) backward statistics: per-(b,c) {sum_p dz, sum_p dz*x}
+template <typename TZ, typename TX>
+__global__ void __launch_bounds__(256)
+gn_bwd_sums_kernel(const TZ* __restrict__ dz, const TX* __restrict__ x, int HW, float* __restrict__ out) {
+  __shared__ float red[64];
+  const int plane = blockIdx.x;
+  const int64_t base = (int64_t)plane * HW;
+  float s = 0.f, sx = 0.f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    float d = ldf<TZ>(dz + base + i);
+    s += d; sx = fmaf(d, ldf<TX>(x + base + i), sx);
+  }
+  block_sum2(s, sx, red);
+  if (threadIdx.x == 0) { out[2 * plane] = s; out[2 * plane + 1] = sx; }
+}
+
+// dx = dz*a[b,c] + x*bb[b] + cc[b] (+ extra)
+template <typename TZ, typename TX, typename TO>
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_kernel(const TZ* __restrict__ dz, const TX* __restrict__ x, const TO* __restrict__ extra, TO* __restrict__ out,
+                    const float* __restrict__ a, const float* __restrict__ bb, const float* __restrict__ cc, int C, int HW) {
+  const int plane = blockIdx.x, b = plane / C;
+  const float ka = a[plane], kb = bb[b], kc = cc[b];
+  const int64_t base = (int64_t)plane * HW;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    float v = fmaf(ldf<TZ>(dz + base + i), ka, fmaf(ldf<TX>(x + base + i), kb, kc));
+    if (extra) v += ldf<TO>(extra + base + i);
+    stf<TO>(out + base + i, v);
+  }
+}
+
+template <typename F>
+static int by_dtype(int dt, F&& f) {
+  if (dt == VRCOC_F32) return f((float*)nullptr);
+  if (dt == VRCOC_BF16) return f((__nv_bfloat16*)nullptr);
+  return fail(VRCOC_EINVAL, "unknown dtype %d", dt);
+}
+
+}  // namespace vrcoc
+
+using namespace vrcoc;
+
+extern "C" const char* vrcoc_version(void) { return "vrcoc-b200 0.1 (sm_100a)"; }
+extern "C" const char* vrcoc_last_error(void) { return err_buf(); }
+extern "C" int vrcoc_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" int vrcoc_channel_sums(const void* x, int dtype, int B, int C, int HW, float* chan_sums, double* sample_sums,
+                                  void* stream) {
+  VRCOC_REQUIRE(x && (chan_sums || sample_sums), "channel_sums: null pointer");
+  VRCOC_REQUIRE(B > 0 && C > 0 && HW > 0, "channel_sums: non-positive dimension");
+  cudaStream_t st = (cudaStream_t)stream;
+  return by_dtype(dtype, [&](auto* t) {
+    using T = typename std::remove_pointer<decltype(t)>::type;
+    channel_sums_kernel<T><<<B * C, 256, 0, st>>>((const T*)x, HW, chan_sums, sample_sums, C);
+    return check_launch("channel_sums");
+  });
+}
+
+extern "C" int vrcoc_chan_affine(const void* x, int x_dtype, const void* res, int res_dtype, void* out, int out_dtype,
+                                 const float* s1, const float* t1, int act, const float* s2, const float* t2, int B, int C,
+                                 int HW, float* out_chan_sums, uint32_t* out_minmax, void* stream) {
+  VRCOC_REQUIRE(x && out, "chan_affine: null pointer");
+  VRCOC_REQUIRE(B > 0 && C > 0 && HW > 0, "chan_affine: non-positive dimension");
+  VRCOC_REQUIRE(x_dtype == out_dtype && (!res || res_dtype == x_dtype), "chan_affine: mixed dtypes unsupported");
+  cudaStream_t st = (cudaStream_t)stream;
+  return by_dtype(x_dtype, [&](auto* t) {
+    using T = typename std::remove_pointer<decltype(t)>::type;
+    chan_affine_kernel<T, T, T><<<B * C, 256, 0, st>>>((const T*)x, (const T*)res, (T*)out, s1, t1, act, s2, t2, C, HW,
+                                                      out_chan_sums, out_minmax);
+    return check_launch("chan_affine");
+  });
+}
+
+extern "C" int vrcoc_img_enh_finish(const void* k, int k_dtype, const void* image, int image_dtype, void* out, int out_dtype,
+                                    const uint32_t* minmax, const float* s, const float* t, int B, int C, int HW,
+                                    float* out_chan_sums, void* stream) {
+  VRCOC_REQUIRE(k && image && out && minmax, "img_enh_finish: null pointer");
+  VRCOC_REQUIRE(B > 0 && C > 0 && HW > 0, "img_enh_finish: non-positive dimension");
+  VRCOC_REQUIRE(k_dtype == image_dtype && k_dtype == out_dtype, "img_enh_finish: mixed dtypes unsupported");
+  cudaStream_t st = (cudaStream_t)stream;
+  return by_dtype(k_dtype, [&](auto* tt) {
+    using T = typename std::remove_pointer<decltype(tt)>::type;
+    img_enh_finish_kernel<T, T, T><<<B * C, 256, 0, st>>>((const T*)k, (const T*)image, (T*)out, minmax, s, t, C, HW,
+                                                         out_chan_sums);
+    return check_launch("img_enh_finish");
+  });
+}
+
+extern "C" int vrcoc_sa_gate_sums(const void* image, int dtype, int B, int Ci, int HW, int G, const float* chan_sums_img,
+                                  const float* cweight, const float* cbias, const float* sweight, const float* sbias,
+                                  const float* gn_weight, const float* gn_bias, float* attn, void* stream) {
+  VRCOC_REQUIRE(image && chan_sums_img && attn, "sa_gate_sums: null pointer");
+  VRCOC_REQUIRE(B > 0 && Ci > 0 && HW > 0, "sa_gate_sums: non-positive dimension");
+  if (G > 0) {
+    VRCOC_REQUIRE(Ci % (2 * G) == 0 && Ci >= 2 * G, "sa_gate_sums: channels %d not divisible by 2*G=%d", Ci, 2 * G);
+    VRCOC_REQUIRE(cweight && cbias && sweight && sbias && gn_weight && gn_bias, "sa_gate_sums: null attention parameter");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  return by_dtype(dtype, [&](auto* t) {
+    using T = typename std::remove_pointer<decltype(t)>::type;
+    sa_gate_sums_kernel<T><<<B * Ci, 256, 0, st>>>((const T*)image, Ci, HW, G, chan_sums_img, cweight, cbias, sweight, sbias,
+                                                   gn_weight, gn_bias, attn);
+    return check_launch("sa_gate_sums");
+  });
+}
+
+extern "C" int vrcoc_radar_enh_table(const float* attn, const float* chan_sums_radar, const int32_t* chan_src,
+                                     const float* eca_weight, int eca_k, int B, int Ci, int Cr, int HW, float* table,
+                                     void* stream) {
+  VRCOC_REQUIRE(attn && chan_sums_radar && eca_weight && table, "radar_enh_table: null pointer");
+  VRCOC_REQUIRE(B > 0 && Ci > 0 && Cr > 0 && HW > 0 && eca_k > 0 && (eca_k & 1), "radar_enh_table: bad dimension");
+  int K = Ci + Cr;
+  VRCOC_REQUIRE(K * 4 <= 48 * 1024, "radar_enh_table: too many channels (%d)", K);
+  radar_enh_table_kernel<<<B, 256, K * sizeof(float), (cudaStream_t)stream>>>(attn, chan_sums_radar, chan_src, eca_weight,
+                                                                              eca_k, Ci, Cr, HW, table);
+  return check_launch("radar_enh_table");
+}
+
+extern "C" int vrcoc_gelu_bwd(const void* dy, const void* u, void* out, int dtype, int64_t n, void* stream) {
+  VRCOC_REQUIRE(dy && u && out && n > 0, "gelu_bwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)(cdiv(n, 256) < 148 * 16 ? cdiv(n, 256) : 148 * 16);
+  return by_dtype(dtype, [&](auto* t) {
+    using T = typename std::remove_pointer<decltype(t)>::type;
+    gelu_bwd_kernel<T, T, T><<<blocks, 256, 0, st>>>((const T*)dy, (const T*)u, (T*)out, n);
+    return check_launch("gelu_bwd");
+  });
+}
+
+extern "C" int vrcoc_gn_bwd_sums(const void* dz, const void* x, int dtype, int B, int C, int HW, float* out, void* stream) {
+  VRCOC_REQUIRE(dz && x && out && B > 0 && C > 0 && HW > 0, "gn_bwd_sums: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  return by_dtype(dtype, [&](auto* t) {
+    using T = typename std::remove_pointer<decltype(t)>::type;
+    gn_bwd_sums_kernel<T, T><<<B * C, 256, 0, st>>>((const T*)dz, (const T*)x, HW, out);
+    return check_launch("gn_bwd_sums");
+  });
+}
+
+extern "C" int vrcoc_gn_bwd_apply(const void* dz, const void* x, const void* extra, void* out, int dtype, const float* a,
+                                  const float* bb, const float* cc, int B, int C, int HW, void* stream) {
+  VRCOC_REQUIRE(dz && x && out && a && bb && cc && B > 0 && C > 0 && HW > 0, "gn_bwd_apply: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  return by_dtype(dtype, [&](auto* t) {
+    using T = typename std::remove_pointer<decltype(t)>::type;
+    gn_bwd_apply_kernel<T, T, T><<<B * C, 256, 0, st>>>((const T*)dz, (const T*)x, (const T*)extra, (T*)out, a, bb, cc, C, HW);
+    return check_launch("gn_bwd_apply");
+  });
+}

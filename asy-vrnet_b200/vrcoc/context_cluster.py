@@ -1,0 +1,230 @@
+"""Context-cluster (CoC) modules with the reference's constructor / forward signatures and state-dict layout,
+running on the hand-written sm_100a kernels.
+
+Mirrors reference backbone/fusion/vr_coc.py:83-300 (identical to backbone/vision/context_cluster.py:55-273 and
+backbone/radar/context_cluster.py): PointRecuder, GroupNorm, pairwise_cos_sim, Cluster, Mlp, ClusterBlock,
+basic_blocks.  Children that hold weights stay real nn.Conv2d / nn.GroupNorm modules so that `weights_init`
+(reference nets/yolo_training.py:482-500), the optimizer grouping (reference train.py:460-473), `load_state_dict`,
+`deepcopy` (EMA) and nn.DataParallel behave exactly as with the reference; only `forward` is replaced.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import ACT_GELU, ACT_NONE, VrcocError
+
+
+def to_2tuple(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
+class DropPath(nn.Module):
+    """Stochastic depth (timm.models.layers.DropPath semantics; reference vr_coc.py:10,258)."""
+
+    def __init__(self, drop_prob=0.0):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        keep = 1 - self.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep)
+        return x * mask / keep
+
+
+def pairwise_cos_sim(x1: torch.Tensor, x2: torch.Tensor):
+    """reference vr_coc.py:114-125.  Stand-alone helper kept for API parity; inside Cluster the similarity is computed
+    on chip by vrcoc_cluster_core_fwd."""
+    x1 = x1 / x1.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    x2 = x2 / x2.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    return torch.matmul(x1, x2.transpose(-2, -1))
+
+
+class PointRecuder(nn.Module):
+    """reference vr_coc.py:83-102: the point reducer is a strided conv; here one implicit-GEMM launch."""
+
+    def __init__(self, patch_size=16, stride=16, padding=0, in_chans=3, embed_dim=768, norm_layer=None):
+        super().__init__()
+        patch_size, stride, padding = to_2tuple(patch_size), to_2tuple(stride), to_2tuple(padding)
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=stride, padding=padding)
+        self.norm = norm_layer(embed_dim) if norm_layer else nn.Identity()
+
+    def forward(self, x, extra=None, extra_bstride=None):
+        """`extra` (optional, [C1,H,W] or [B,C1,H,W]) is concatenated after x along the channels inside the kernel
+        (the cat([x, pos]) of reference vr_coc.py:582-586 without materialising it)."""
+        from .fusion import conv2d_native
+        y = conv2d_native(x, self.proj.weight, self.proj.bias, stride=self.proj.stride[0], pad=self.proj.padding[0],
+                          extra=extra, extra_bstride=extra_bstride)
+        return self.norm(y)
+
+
+class GroupNorm(nn.GroupNorm):
+    """reference vr_coc.py:105-111: GroupNorm with one group.  Inside ClusterBlock it is folded into the prologue of the
+    following projection; called on its own it runs the same kernel with an identity weight."""
+
+    def __init__(self, num_channels, **kwargs):
+        super().__init__(1, num_channels, **kwargs)
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise VrcocError("vrcoc GroupNorm needs a CUDA tensor (no CPU fallback exists)")
+        C = x.shape[1]
+        eye = torch.eye(C, device=x.device, dtype=x.dtype)
+        return ops.GNProjFn.apply(x, ops.sample_sums_of(x), self.weight, self.bias, self.eps, eye, None, ACT_NONE, 0)
+
+
+class Cluster(nn.Module):
+    """reference vr_coc.py:128-192."""
+
+    def __init__(self, dim, out_dim, proposal_w=2, proposal_h=2, fold_w=2, fold_h=2, heads=4, head_dim=24,
+                 return_center=False):
+        super().__init__()
+        self.heads = heads
+        self.head_dim = head_dim
+        self.fc1 = nn.Conv2d(dim, heads * head_dim, kernel_size=1)
+        self.fc2 = nn.Conv2d(heads * head_dim, out_dim, kernel_size=1)
+        self.fc_v = nn.Conv2d(dim, heads * head_dim, kernel_size=1)
+        self.sim_alpha = nn.Parameter(torch.ones(1))
+        self.sim_beta = nn.Parameter(torch.zeros(1))
+        self.centers_proposal = nn.AdaptiveAvgPool2d((proposal_w, proposal_h))
+        self.fold_w = fold_w
+        self.fold_h = fold_h
+        self.return_center = return_center
+        if return_center:
+            raise VrcocError("return_center=True is deprecated in the reference (vr_coc.py:140) and not supported")
+
+    # -- pieces shared by the stand-alone forward and the fused ClusterBlock path ---------------------------------
+    def _proposal(self):
+        pw, ph = self.centers_proposal.output_size
+        return int(pw), int(ph)
+
+    def _project_in(self, x, gn):
+        """feat, value = fc1(x'), fc_v(x') in ONE launch (concatenated weights); x' = GroupNorm(x) when gn is given."""
+        ED = self.heads * self.head_dim
+        w = torch.cat([self.fc1.weight, self.fc_v.weight], dim=0)
+        b = torch.cat([self.fc1.bias, self.fc_v.bias], dim=0)
+        if gn is None:
+            y = ops.ProjFn.apply(x, w, b, ACT_NONE)
+            return y[:, :ED], y[:, ED:]
+        sums, norm = gn
+        y = ops.GNProjFn.apply(x, sums, norm.weight, norm.bias, norm.eps, w, b, ACT_NONE, ED)
+        if isinstance(y, tuple):          # bf16 storage: similarity operand stays fp32
+            return y
+        return y[:, :ED], y[:, ED:]
+
+    def _core(self, feat, value):
+        pw, ph = self._proposal()
+        return ops.ClusterCoreFn.apply(feat, value, self.sim_alpha, self.sim_beta, self.heads, self.fold_w, self.fold_h, pw, ph)
+
+    def forward(self, x):  # [b,c,w,h]
+        if not x.is_cuda:
+            raise VrcocError("vrcoc Cluster needs a CUDA tensor (no CPU fallback exists)")
+        feat, value = self._project_in(x, None)
+        out = self._core(feat, value)
+        return ops.ProjFn.apply(out, self.fc2.weight, self.fc2.bias, ACT_NONE)
+
+
+class Mlp(nn.Module):
+    """reference vr_coc.py:195-223 (1x1-conv MLP, exact-erf GELU)."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Conv2d(in_features, hidden_features, 1)
+        self.act = act_layer()
+        self.fc2 = nn.Conv2d(hidden_features, out_features, 1)
+        self.drop = nn.Dropout(drop)
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):
+        if isinstance(m, nn.Conv2d):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+
+    def _fusable(self):
+        return isinstance(self.act, nn.GELU) and getattr(self.act, "approximate", "none") == "none" and \
+            (self.drop.p == 0.0 or not self.training)
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise VrcocError("vrcoc Mlp needs a CUDA tensor (no CPU fallback exists)")
+        if self._fusable():
+            h = ops.ProjFn.apply(x, self.fc1.weight, self.fc1.bias, ACT_GELU)
+            return ops.ProjFn.apply(h, self.fc2.weight, self.fc2.bias, ACT_NONE)
+        h = self.drop(self.act(ops.ProjFn.apply(x, self.fc1.weight, self.fc1.bias, ACT_NONE)))
+        return self.drop(ops.ProjFn.apply(h, self.fc2.weight, self.fc2.bias, ACT_NONE))
+
+
+class ClusterBlock(nn.Module):
+    """reference vr_coc.py:226-275.  forward =  x += ls1 * Cluster(GN(x));  x += ls2 * Mlp(GN(x))  in five launches:
+    [GN+fc1|fc_v] -> [cluster core] -> [fc2 + ls1 + residual + stats] -> [GN+mlp.fc1+GELU] -> [mlp.fc2 + ls2 + residual + stats]."""
+
+    def __init__(self, dim, mlp_ratio=4., act_layer=nn.GELU, norm_layer=GroupNorm, drop=0., drop_path=0.,
+                 use_layer_scale=True, layer_scale_init_value=1e-5,
+                 proposal_w=2, proposal_h=2, fold_w=2, fold_h=2, heads=4, head_dim=24, return_center=False):
+        super().__init__()
+        self.norm1 = norm_layer(dim)
+        self.token_mixer = Cluster(dim=dim, out_dim=dim, proposal_w=proposal_w, proposal_h=proposal_h,
+                                   fold_w=fold_w, fold_h=fold_h, heads=heads, head_dim=head_dim, return_center=False)
+        self.norm2 = norm_layer(dim)
+        mlp_hidden_dim = int(dim * mlp_ratio)
+        self.mlp = Mlp(in_features=dim, hidden_features=mlp_hidden_dim, act_layer=act_layer, drop=drop)
+        self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+        self.use_layer_scale = use_layer_scale
+        if use_layer_scale:
+            self.layer_scale_1 = nn.Parameter(layer_scale_init_value * torch.ones((dim)), requires_grad=True)
+            self.layer_scale_2 = nn.Parameter(layer_scale_init_value * torch.ones((dim)), requires_grad=True)
+
+    def _fused_ok(self):
+        gn1 = isinstance(self.norm1, nn.GroupNorm) and self.norm1.num_groups == 1 and self.norm1.affine
+        gn2 = isinstance(self.norm2, nn.GroupNorm) and self.norm2.num_groups == 1 and self.norm2.affine
+        dp = isinstance(self.drop_path, nn.Identity) or not self.training
+        return gn1 and gn2 and dp and self.mlp._fusable()
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise VrcocError("vrcoc ClusterBlock needs a CUDA tensor (no CPU fallback exists)")
+        if not self._fused_ok():
+            return self._forward_composed(x)
+        ls1 = self.layer_scale_1 if self.use_layer_scale else None
+        ls2 = self.layer_scale_2 if self.use_layer_scale else None
+        tm, mlp = self.token_mixer, self.mlp
+        # token-mixer half
+        feat, value = tm._project_in(x, (ops.sample_sums_of(x), self.norm1))
+        o = tm._core(feat, value)
+        x1, sums1 = ops.ProjResidualFn.apply(o, tm.fc2.weight, tm.fc2.bias, ls1, x)
+        # channel-MLP half
+        h = ops.GNProjFn.apply(x1, sums1, self.norm2.weight, self.norm2.bias, self.norm2.eps,
+                               mlp.fc1.weight, mlp.fc1.bias, ACT_GELU, 0)
+        x2, sums2 = ops.ProjResidualFn.apply(h, mlp.fc2.weight, mlp.fc2.bias, ls2, x1)
+        x2._vrcoc_sums = sums2        # rides along to the next block's norm1 (same python object through nn.Sequential)
+        return x2
+
+    def _forward_composed(self, x):
+        """Non-default configurations (BatchNorm norm_layer, active DropPath/Dropout, other activations): same
+        kernels, composed module by module as the reference does (vr_coc.py:264-275)."""
+        if self.use_layer_scale:
+            x = x + self.drop_path(self.layer_scale_1.unsqueeze(-1).unsqueeze(-1) * self.token_mixer(self.norm1(x)))
+            x = x + self.drop_path(self.layer_scale_2.unsqueeze(-1).unsqueeze(-1) * self.mlp(self.norm2(x)))
+        else:
+            x = x + self.drop_path(self.token_mixer(self.norm1(x)))
+            x = x + self.drop_path(self.mlp(self.norm2(x)))
+        return x
+
+
+def basic_blocks(dim, index, layers, mlp_ratio=4., act_layer=nn.GELU, norm_layer=GroupNorm, drop_rate=.0,
+                 drop_path_rate=0., use_layer_scale=True, layer_scale_init_value=1e-5,
+                 proposal_w=2, proposal_h=2, fold_w=2, fold_h=2, heads=4, head_dim=24, return_center=False):
+    """reference vr_coc.py:278-300."""
+    blocks = []
+    for block_idx in range(layers[index]):
+        block_dpr = drop_path_rate * (block_idx + sum(layers[:index])) / (sum(layers) - 1)
+        blocks.append(ClusterBlock(
+            dim, mlp_ratio=mlp_ratio, act_layer=act_layer, norm_layer=norm_layer, drop=drop_rate, drop_path=block_dpr,
+            use_layer_scale=use_layer_scale, layer_scale_init_value=layer_scale_init_value,
+            proposal_w=proposal_w, proposal_h=proposal_h, fold_w=fold_w, fold_h=fold_h,
+            heads=heads, head_dim=head_dim, return_center=False))
+    return nn.Sequential(*blocks)

@@ -1,0 +1,536 @@
+"""Asymmetric vision<->radar fusion modules and their leaf helpers, reference signatures, native kernels.
+
+Mirrors reference backbone/fusion/vr_coc.py:59-80,303-359 (data_normal, shuffle_channels, ImageEnhanceByRadar,
+RadarEnhanceByImage), backbone/attention_modules/shuffle_attention.py:8-72, backbone/attention_modules/eca.py:6-22 and
+backbone/conv_utils/normal_conv.py:5-52.
+
+Forward (eval AND train mode) runs on the hand-written kernels:
+  ImageEnhanceByRadar  = [3x3 implicit-GEMM + BN + ReLU + global min/max] -> [(1 + minmax-normalise) * image -> BN]
+  RadarEnhanceByImage  = [channel sums x2] -> [ShuffleAttention gate params + attended means] -> [ECA + prologue table]
+                         -> [1x1 GEMM whose prologue applies attention/ECA/shuffle and whose epilogue applies
+                             BN + ReLU + radar residual + BN]
+Backward of these modules (training) is obtained by re-running a differentiable restatement of the same maths with
+torch CUDA ops inside the autograd Function (`_autograd_ref`); a native backward is future work.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SILU, VrcocError, check, lib)
+from .ops import _dt, _f32, _ptr, _stream, conv_desc, conv_fwd
+
+
+# ------------------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------------------
+def data_normal(origin_data):
+    """reference vr_coc.py:59-67 (whole-tensor min/max).  Stand-alone helper kept for API parity; inside
+    ImageEnhanceByRadar the min/max are a side output of the projection kernel."""
+    d_min = origin_data.min()
+    if d_min < 0:
+        origin_data += torch.abs(d_min)
+        d_min = origin_data.min()
+    d_max = origin_data.max()
+    return (origin_data - d_min).true_divide(d_max - d_min)
+
+
+def shuffle_perm(channels, groups=2):
+    """out[k] = in[perm[k]] for the channel shuffle of reference vr_coc.py:70-80; identity when C % groups != 0."""
+    if channels % groups:
+        return list(range(channels))
+    cpg = channels // groups
+    return [(k % groups) * cpg + k // groups for k in range(channels)]
+
+
+def shuffle_channels(x, groups=2):
+    """reference vr_coc.py:70-80 / neck/coc_fpn_dual.py:120-130 (pure permutation; inside the fused modules it is
+    folded into the consumer's channel map instead of being materialised)."""
+    batch_size, channels, h, w = x.size()
+    if channels % groups:
+        return x
+    x = x.view(batch_size, groups, channels // groups, h, w)
+    return torch.transpose(x, 1, 2).contiguous().view(batch_size, -1, h, w)
+
+
+def _bn_affine(bn, chan_sums=None, count=None):
+    """(scale, shift) fp32 such that BN(x) = x*scale + shift.  eval: running statistics.  train: batch statistics from
+    the per-(b,c) sums (biased variance), with the running-stat update of nn.BatchNorm2d (unbiased variance)."""
+    w = bn.weight.detach().float() if bn.affine else None
+    b = bn.bias.detach().float() if bn.affine else None
+    use_batch = bn.training or not bn.track_running_stats
+    if use_batch:
+        s = chan_sums.double().sum(0)                       # [C,2]
+        n = float(count)
+        mean = s[:, 0] / n
+        var = (s[:, 1] / n - mean * mean).clamp_min(0)
+        if bn.training and bn.track_running_stats:
+            with torch.no_grad():
+                bn.num_batches_tracked += 1
+                mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                bn.running_mean.mul_(1 - mom).add_(mean.to(bn.running_mean.dtype), alpha=mom)
+                bn.running_var.mul_(1 - mom).add_((var * (n / max(n - 1, 1))).to(bn.running_var.dtype), alpha=mom)
+        mean, var = mean.float(), var.float()
+    else:
+        mean, var = bn.running_mean.detach().float(), bn.running_var.detach().float()
+    scale = torch.rsqrt(var + bn.eps)
+    if w is not None:
+        scale = scale * w
+    shift = -mean * scale
+    if b is not None:
+        shift = shift + b
+    return scale.contiguous(), shift.contiguous()
+
+
+def conv2d_native(x, weight, bias=None, stride=1, pad=0, extra=None, extra_bstride=None, act=ACT_NONE,
+                  e_scale=None, out_minmax=None, out_dtype=None):
+    """Dense (groups=1) k x k convolution on the implicit-GEMM engine.  Differentiable through `_ConvFn`."""
+    return _ConvFn.apply(x, weight, bias, stride, pad, extra, extra_bstride, act, e_scale, out_minmax, out_dtype)
+
+
+def _conv_launch(x, weight, bias32, stride, pad, extra, extra_bstride, act, e_scale, out_minmax, out_dtype):
+    ops._need_cuda(x)
+    x = x.contiguous()
+    B, C0, H, W = x.shape
+    O, Cin, kh, kw = weight.shape
+    C1 = Cin - C0
+    if (C1 != 0) != (extra is not None):
+        raise VrcocError(f"conv: weight expects {Cin} input channels, got {C0} (+ extra: {extra is not None})")
+    if extra is not None:
+        extra = extra.contiguous()
+        if extra.dim() == 3:
+            extra_bstride = 0
+        if extra.shape[-3] != C1:
+            raise VrcocError("conv: extra channel count mismatch")
+    Ho, Wo = ops.out_hw(H, W, kh, stride, pad)
+    out = torch.empty(B, O, Ho, Wo, device=x.device, dtype=out_dtype or x.dtype)
+    w2 = weight.detach().reshape(O, -1).contiguous()
+    d = conv_desc(x, w2, out, src1=extra, src1_bstride=extra_bstride, kh=kh, kw=kw, stride=stride, pad=pad,
+                  e_scale=e_scale, e_shift=bias32, act=act, out_minmax=out_minmax)
+    conv_fwd(d)
+    return out
+
+
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, extra, extra_bstride, act, e_scale, out_minmax, out_dtype):
+        out = _conv_launch(x, weight, _f32(bias), stride, pad, extra, extra_bstride, act, _f32(e_scale), out_minmax, out_dtype)
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(x, weight, bias, extra, e_scale)
+            ctx.meta = (stride, pad, act)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import _autograd_ref as R
+        x, weight, bias, extra, e_scale = ctx.saved_tensors
+        stride, pad, act = ctx.meta
+        return R.grads(lambda x_, w_, b_, e_: R.conv_act(x_, w_, b_, stride, pad, extra, act, e_),
+                       [x, weight, bias, e_scale], dy,
+                       tuple(ctx.needs_input_grad[i] for i in (0, 1, 2, 8)), slots=(0, 1, 2, 8), total=11)
+
+
+_ACT_CODE = {"relu": ACT_RELU, "silu": ACT_SILU, "lrelu": ACT_LRELU}
+
+
+class SiLU(nn.Module):
+    """reference normal_conv.py:5-8"""
+    @staticmethod
+    def forward(x):
+        return x * torch.sigmoid(x)
+
+
+def get_activation(name="silu", inplace=True):
+    """reference normal_conv.py:11-20"""
+    if name == "silu":
+        return SiLU()
+    if name == "relu":
+        return nn.ReLU(inplace=inplace)
+    if name == "lrelu":
+        return nn.LeakyReLU(0.1, inplace=inplace)
+    raise AttributeError("Unsupported act type: {}".format(name))
+
+
+class DWConv(nn.Module):
+    """reference normal_conv.py:23-33: depthwise k x k + pointwise 1x1.  Only used by the detection head (outside the
+    CoC/fusion hot path): the depthwise part is a cuDNN library call, the pointwise part is native."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, bias=True):
+        super().__init__()
+        self.dconv = nn.Conv2d(in_channels, in_channels, kernel_size=kernel_size, stride=stride, groups=in_channels,
+                               padding=padding, dilation=dilation, bias=bias)
+        self.pconv = nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=1, groups=1, bias=bias)
+
+    def forward(self, x):
+        return self.pconv(self.dconv(x))
+
+
+class BaseConv(nn.Module):
+    """reference normal_conv.py:36-52: conv(pad=(k-1)//2, no bias) -> BatchNorm2d(eps 1e-3, momentum 0.03) -> act,
+    one launch in eval mode (BN folded into the GEMM epilogue), conv + stats + affine pass in train mode."""
+
+    def __init__(self, in_channels, out_channels, ksize, stride, groups=1, bias=False, act="relu", ds_conv=False):
+        super().__init__()
+        pad = (ksize - 1) // 2
+        if ds_conv is False:
+            self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=ksize, stride=stride, padding=pad,
+                                  groups=groups, bias=bias)
+        else:
+            self.conv = DWConv(in_channels, out_channels, kernel_size=ksize, stride=stride, padding=pad, bias=bias)
+        self.bn = nn.BatchNorm2d(out_channels, eps=0.001, momentum=0.03)
+        self.act = get_activation(act, inplace=True)
+        self._act_name = act
+
+    def _native(self):
+        return isinstance(self.conv, nn.Conv2d) and self.conv.groups == 1
+
+    def forward(self, x, out_minmax=None):
+        if not self._native():
+            return self.act(self.bn(self.conv(x)))        # depthwise-separable head convs: library path (out of scope)
+        if not x.is_cuda:
+            raise VrcocError("vrcoc BaseConv needs a CUDA tensor (no CPU fallback exists)")
+        return _BaseConvFn.apply(x, self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias, self, out_minmax)
+
+    def fuseforward(self, x):
+        return self.act(self.conv(x))
+
+
+def _base_conv_forward(mod, x, out_minmax):
+    conv, bn = mod.conv, mod.bn
+    act = _ACT_CODE[mod._act_name]
+    stride, pad = conv.stride[0], conv.padding[0]
+    bias32 = _f32(conv.bias)
+    if bn.training or not bn.track_running_stats:
+        u = _conv_launch(x, conv.weight, bias32, stride, pad, None, None, ACT_NONE, None, None, None)
+        B, O, H, W = u.shape
+        cs, _ = ops.channel_sums(u)
+        sc, sh = _bn_affine(bn, cs, B * H * W)
+        check(lib.vrcoc_chan_affine(_ptr(u), _dt(u), None, 0, _ptr(u), _dt(u), _ptr(sc), _ptr(sh), act, None, None,
+                                    B, O, H * W, None, _ptr(out_minmax), _stream()), "chan_affine")
+        return u
+    sc, sh = _bn_affine(bn)
+    if bias32 is not None:
+        sh = sh + bias32 * sc
+    return _conv_launch(x, conv.weight, sh, stride, pad, None, None, act, sc, out_minmax, None)
+
+
+class _BaseConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, bn_w, bn_b, mod, out_minmax):
+        training = mod.bn.training or not mod.bn.track_running_stats
+        rm = None if training else mod.bn.running_mean.detach().clone()
+        rv = None if training else mod.bn.running_var.detach().clone()
+        out = _base_conv_forward(mod, x, out_minmax)
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(x, weight, bias, bn_w, bn_b, rm, rv)
+            ctx.meta = (mod.conv.stride[0], mod.conv.padding[0], mod._act_name, mod.bn.eps, training)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import _autograd_ref as R
+        x, weight, bias, bn_w, bn_b, rm, rv = ctx.saved_tensors
+        stride, pad, act, eps, training = ctx.meta
+        return R.grads(lambda x_, w_, b_, g_, h_: R.base_conv(x_, w_, b_, g_, h_, rm, rv, stride, pad, act, eps, training),
+                       [x, weight, bias, bn_w, bn_b], dy, ctx.needs_input_grad[:5], slots=(0, 1, 2, 3, 4), total=7)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# attention leaves
+# ------------------------------------------------------------------------------------------------------------
+class ShuffleAttention(nn.Module):
+    """reference shuffle_attention.py:8-72 (same parameters; `channel=3, G=4` yields zero-size parameters and a
+    GroupNorm(0,0) that is constructed but never called, as in reference vr_coc.py:325)."""
+
+    def __init__(self, channel=512, reduction=16, G=8):
+        super().__init__()
+        self.G = G
+        self.channel = channel
+        q = channel // (2 * G)
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.gn = _group_norm_maybe_empty(q)
+        self.cweight = nn.Parameter(torch.zeros(1, q, 1, 1))
+        self.cbias = nn.Parameter(torch.ones(1, q, 1, 1))
+        self.sweight = nn.Parameter(torch.zeros(1, q, 1, 1))
+        self.sbias = nn.Parameter(torch.ones(1, q, 1, 1))
+        self.sigmoid = nn.Sigmoid()
+
+    def init_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out')
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, std=0.001)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+
+    @staticmethod
+    def channel_shuffle(x, groups):
+        b, c, h, w = x.shape
+        return x.reshape(b, groups, -1, h, w).permute(0, 2, 1, 3, 4).reshape(b, -1, h, w)
+
+    def params32(self):
+        return tuple(_f32(p).reshape(-1) for p in (self.cweight, self.cbias, self.sweight, self.sbias,
+                                                    self.gn.weight, self.gn.bias))
+
+    def gate_table(self, x):
+        """attn [B,C,4] = {scale, gate_a, gate_c, mean of the attended channel} for every input channel"""
+        B, Cc, H, W = x.shape
+        cs, _ = ops.channel_sums(x)
+        attn = torch.empty(B, Cc, 4, device=x.device, dtype=torch.float32)
+        cw, cb, sw, sb, gw, gb = self.params32()
+        check(lib.vrcoc_sa_gate_sums(_ptr(x), _dt(x), B, Cc, H * W, self.G, _ptr(cs), _ptr(cw), _ptr(cb), _ptr(sw), _ptr(sb),
+                                     _ptr(gw), _ptr(gb), _ptr(attn), _stream()), "sa_gate_sums")
+        return attn
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise VrcocError("vrcoc ShuffleAttention needs a CUDA tensor (no CPU fallback exists)")
+        return _ShuffleAttentionFn.apply(x, self.cweight, self.cbias, self.sweight, self.sbias, self.gn.weight, self.gn.bias, self)
+
+
+def _group_norm_maybe_empty(q):
+    if q > 0:
+        return nn.GroupNorm(q, q)
+    gn = nn.GroupNorm(1, 1)
+    gn.num_groups, gn.num_channels = 0, 0
+    gn.weight = nn.Parameter(torch.empty(0))
+    gn.bias = nn.Parameter(torch.empty(0))
+    return gn
+
+
+class _ShuffleAttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cw, cb, sw, sb, gw, gb, mod):
+        x = x.contiguous()
+        B, Cc, H, W = x.shape
+        attn = mod.gate_table(x)
+        table = torch.stack([attn[..., 0], torch.zeros_like(attn[..., 0]), attn[..., 1], attn[..., 2]], dim=-1).contiguous()
+        perm = torch.tensor(shuffle_perm(Cc, 2), device=x.device, dtype=torch.int32)
+        table = table[:, perm.long()].contiguous()
+        out = torch.empty_like(x)
+        d = conv_desc(x, x, out, chan_src=perm, table=table, has_gate=True)
+        check(lib.vrcoc_table_apply(d, _stream()), "table_apply")
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(x, cw, cb, sw, sb, gw, gb)
+            ctx.G = mod.G
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import _autograd_ref as R
+        saved = list(ctx.saved_tensors)
+        G = ctx.G
+        return R.grads(lambda *a: R.shuffle_attention(*a, G=G), saved, dy, ctx.needs_input_grad[:7], slots=tuple(range(7)), total=8)
+
+
+class eca_block(nn.Module):
+    """reference eca.py:6-22."""
+
+    def __init__(self, channel, b=1, gamma=2):
+        super().__init__()
+        kernel_size = int(abs((math.log(channel, 2) + b) / gamma))
+        kernel_size = kernel_size if kernel_size % 2 else kernel_size + 1
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.conv = nn.Conv1d(1, 1, kernel_size=kernel_size, padding=(kernel_size - 1) // 2, bias=False)
+        self.sigmoid = nn.Sigmoid()
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise VrcocError("vrcoc eca_block needs a CUDA tensor (no CPU fallback exists)")
+        return _EcaFn.apply(x, self.conv.weight)
+
+
+class _EcaFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w):
+        x = x.contiguous()
+        B, Cc, H, W = x.shape
+        cs, _ = ops.channel_sums(x)
+        k = w.shape[-1]
+        # attn records with scale 1 / gate off / mean = channel mean, then the same ECA table kernel as the fused path
+        attn = torch.empty(B, Cc, 4, device=x.device, dtype=torch.float32)
+        check(lib.vrcoc_sa_gate_sums(_ptr(x), _dt(x), B, Cc, H * W, 0, _ptr(cs), None, None, None, None, None, None,
+                                     _ptr(attn), _stream()), "sa_gate_sums")
+        table = torch.empty(B, Cc + 1, 4, device=x.device, dtype=torch.float32)
+        zero_cs = torch.zeros(B, 1, 2, device=x.device, dtype=torch.float32)
+        # a dummy zero radar channel at the end does not influence the zero-padded conv1d of the real channels
+        check(lib.vrcoc_radar_enh_table(_ptr(attn), _ptr(zero_cs), None, _ptr(_f32(w).reshape(-1)), k, B, Cc, 1, H * W,
+                                        _ptr(table), _stream()), "radar_enh_table")
+        table = table[:, :Cc].contiguous()
+        out = torch.empty_like(x)
+        check(lib.vrcoc_table_apply(conv_desc(x, x, out, table=table, has_gate=False), _stream()), "table_apply")
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import _autograd_ref as R
+        return R.grads(R.eca, list(ctx.saved_tensors), dy, ctx.needs_input_grad[:2], slots=(0, 1), total=2)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fusion modules
+# ------------------------------------------------------------------------------------------------------------
+class ImageEnhanceByRadar(nn.Module):
+    """reference vr_coc.py:303-316: out = BN((1 + data_normal(ReLU(BN(conv3x3(radar))))) * image)."""
+
+    def __init__(self, radar_in_channels, image_in_channels):
+        super().__init__()
+        self.radar_in_channels = radar_in_channels
+        self.image_in_channels = image_in_channels
+        self.radar_projection = BaseConv(in_channels=radar_in_channels, out_channels=image_in_channels, ksize=3, stride=1)
+        self.norm = nn.BatchNorm2d(image_in_channels)
+
+    def forward(self, image_map, radar_map):
+        if not image_map.is_cuda:
+            raise VrcocError("vrcoc ImageEnhanceByRadar needs CUDA tensors (no CPU fallback exists)")
+        rp = self.radar_projection
+        return _ImageEnhanceFn.apply(image_map, radar_map, rp.conv.weight, rp.bn.weight, rp.bn.bias,
+                                     self.norm.weight, self.norm.bias, self)
+
+
+class _ImageEnhanceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, radar, w, g1, b1, g2, b2, mod):
+        image = image.contiguous()
+        radar = radar.contiguous()
+        rp, bn2 = mod.radar_projection, mod.norm
+        train1 = rp.bn.training or not rp.bn.track_running_stats
+        train2 = bn2.training or not bn2.track_running_stats
+        stats = None
+        if any(ctx.needs_input_grad):
+            stats = tuple(None if t else s.detach().clone() for t, s in
+                          ((train1, rp.bn.running_mean), (train1, rp.bn.running_var), (train2, bn2.running_mean), (train2, bn2.running_var)))
+        B, Ci, H, W = image.shape
+        minmax = torch.zeros(2, device=image.device, dtype=torch.int32)
+        k = _base_conv_forward(rp, radar if radar.dtype == image.dtype else radar.to(image.dtype), minmax)
+        out = torch.empty_like(image)
+        if train2:
+            cs = torch.empty(B, Ci, 2, device=image.device, dtype=torch.float32)
+            check(lib.vrcoc_img_enh_finish(_ptr(k), _dt(k), _ptr(image), _dt(image), _ptr(out), _dt(out), _ptr(minmax),
+                                           None, None, B, Ci, H * W, _ptr(cs), _stream()), "img_enh_finish")
+            sc, sh = _bn_affine(bn2, cs, B * H * W)
+            check(lib.vrcoc_chan_affine(_ptr(out), _dt(out), None, 0, _ptr(out), _dt(out), _ptr(sc), _ptr(sh), ACT_NONE,
+                                        None, None, B, Ci, H * W, None, None, _stream()), "chan_affine")
+        else:
+            sc, sh = _bn_affine(bn2)
+            check(lib.vrcoc_img_enh_finish(_ptr(k), _dt(k), _ptr(image), _dt(image), _ptr(out), _dt(out), _ptr(minmax),
+                                           _ptr(sc), _ptr(sh), B, Ci, H * W, None, _stream()), "img_enh_finish")
+        if stats is not None:
+            ctx.save_for_backward(image, radar, w, g1, b1, g2, b2, *stats)
+            ctx.meta = (rp.bn.eps, bn2.eps, train1, train2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import _autograd_ref as R
+        image, radar, w, g1, b1, g2, b2, rm1, rv1, rm2, rv2 = ctx.saved_tensors
+        eps1, eps2, t1, t2 = ctx.meta
+        return R.grads(lambda *a: R.image_enhance(*a, rm1, rv1, rm2, rv2, eps1, eps2, t1, t2),
+                       [image, radar, w, g1, b1, g2, b2], dy, ctx.needs_input_grad[:7], slots=tuple(range(7)), total=8)
+
+
+class RadarEnhanceByImage(nn.Module):
+    """reference vr_coc.py:319-359."""
+
+    def __init__(self, radar_in_channels, image_in_channels, initial=False):
+        super().__init__()
+        self.initial = initial
+        self.radar_in_channels = radar_in_channels
+        self.image_in_channels = image_in_channels
+        self.image_attn = ShuffleAttention(channel=image_in_channels, G=4)
+        self.channel_attn = eca_block(channel=radar_in_channels + image_in_channels)
+        self.inverse_projection = BaseConv(in_channels=radar_in_channels + image_in_channels,
+                                           out_channels=radar_in_channels, ksize=1, stride=1)
+        self.norm = nn.BatchNorm2d(radar_in_channels)
+        # logical channel k of shuffle_channels(cat[image_attn(image), radar], 2) -> channel of the virtual concat
+        # [image | radar] as stored in memory; ShuffleAttention's own channel_shuffle(.,2) is folded in.
+        Ci, Cr = image_in_channels, radar_in_channels
+        outer = shuffle_perm(Ci + Cr, 2)
+        inner = list(range(Ci)) if initial else shuffle_perm(Ci, 2)
+        cmap = [inner[j] if j < Ci else j for j in outer]
+        self.register_buffer("_chan_src", torch.tensor(cmap, dtype=torch.int32), persistent=False)
+
+    def forward(self, image_map, radar_map):
+        if not image_map.is_cuda:
+            raise VrcocError("vrcoc RadarEnhanceByImage needs CUDA tensors (no CPU fallback exists)")
+        ip, sa = self.inverse_projection, self.image_attn
+        return _RadarEnhanceFn.apply(image_map, radar_map, ip.conv.weight, ip.bn.weight, ip.bn.bias, self.norm.weight,
+                                     self.norm.bias, self.channel_attn.conv.weight, sa.cweight, sa.cbias, sa.sweight,
+                                     sa.sbias, sa.gn.weight, sa.gn.bias, self)
+
+
+class _RadarEnhanceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, radar, w, g1, b1, g2, b2, eca_w, cw, cb, sw, sb, gw, gb, mod):
+        image = image.contiguous()
+        radar = radar.contiguous()
+        if image.dtype != radar.dtype:
+            image = image.to(radar.dtype)
+        ip, bn2, sa = mod.inverse_projection, mod.norm, mod.image_attn
+        train1 = ip.bn.training or not ip.bn.track_running_stats
+        train2 = bn2.training or not bn2.track_running_stats
+        stats = None
+        if any(ctx.needs_input_grad):
+            stats = tuple(None if t else s.detach().clone() for t, s in
+                          ((train1, ip.bn.running_mean), (train1, ip.bn.running_var), (train2, bn2.running_mean), (train2, bn2.running_var)))
+        B, Ci, H, W = image.shape
+        Cr = radar.shape[1]
+        HW = H * W
+        dev = image.device
+        # statistics + attention parameters + ECA -> conv prologue table
+        cs_img, _ = ops.channel_sums(image)
+        cs_rad, _ = ops.channel_sums(radar)
+        attn = torch.empty(B, Ci, 4, device=dev, dtype=torch.float32)
+        if mod.initial:
+            check(lib.vrcoc_sa_gate_sums(_ptr(image), _dt(image), B, Ci, HW, 0, _ptr(cs_img), None, None, None, None, None, None,
+                                         _ptr(attn), _stream()), "sa_gate_sums")
+        else:
+            pc = sa.params32()
+            check(lib.vrcoc_sa_gate_sums(_ptr(image), _dt(image), B, Ci, HW, sa.G, _ptr(cs_img), *[_ptr(p) for p in pc],
+                                         _ptr(attn), _stream()), "sa_gate_sums")
+        table = torch.empty(B, Ci + Cr, 4, device=dev, dtype=torch.float32)
+        ew = _f32(eca_w).reshape(-1)
+        check(lib.vrcoc_radar_enh_table(_ptr(attn), _ptr(cs_rad), _ptr(mod._chan_src), _ptr(ew), ew.numel(), B, Ci, Cr, HW,
+                                        _ptr(table), _stream()), "radar_enh_table")
+        w2 = w.detach().reshape(Cr, -1).contiguous()
+        out = torch.empty_like(radar)
+        gate = not mod.initial
+        if train1 or train2:
+            u = torch.empty_like(radar)
+            conv_fwd(conv_desc(image, w2, u, src1=radar, chan_src=mod._chan_src, table=table, has_gate=gate))
+            cs_u, _ = ops.channel_sums(u)
+            s1, t1 = _bn_affine(ip.bn, cs_u, B * HW)
+            cs_t = torch.empty(B, Cr, 2, device=dev, dtype=torch.float32)
+            check(lib.vrcoc_chan_affine(_ptr(u), _dt(u), _ptr(radar), _dt(radar), _ptr(u), _dt(u), _ptr(s1), _ptr(t1), ACT_RELU,
+                                        None, None, B, Cr, HW, _ptr(cs_t), None, _stream()), "chan_affine")
+            s2, t2 = _bn_affine(bn2, cs_t, B * HW)
+            check(lib.vrcoc_chan_affine(_ptr(u), _dt(u), None, 0, _ptr(out), _dt(out), _ptr(s2), _ptr(t2), ACT_NONE, None, None,
+                                        B, Cr, HW, None, None, _stream()), "chan_affine")
+        else:
+            s1, t1 = _bn_affine(ip.bn)
+            s2, t2 = _bn_affine(bn2)
+            conv_fwd(conv_desc(image, w2, out, src1=radar, chan_src=mod._chan_src, table=table, has_gate=gate,
+                               e_scale=s1, e_shift=t1, act=ACT_RELU, res=radar, f_scale=s2, f_shift=t2))
+        if stats is not None:
+            ctx.save_for_backward(image, radar, w, g1, b1, g2, b2, eca_w, cw, cb, sw, sb, gw, gb, *stats)
+            ctx.meta = (ip.bn.eps, bn2.eps, train1, train2, mod.initial, sa.G)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import _autograd_ref as R
+        t = ctx.saved_tensors
+        diff, (rm1, rv1, rm2, rv2) = list(t[:14]), t[14:]
+        eps1, eps2, t1, t2, initial, G = ctx.meta
+        return R.grads(lambda *a: R.radar_enhance(*a, rm1, rv1, rm2, rv2, eps1, eps2, t1, t2, initial, G),
+                       diff, dy, ctx.needs_input_grad[:14], slots=tuple(range(14)), total=15)

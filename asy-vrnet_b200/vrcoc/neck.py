@@ -1,0 +1,120 @@
+"""Dual FPN neck: reference neck/coc_fpn_dual.py:15-224 (CoCUpsample, CoC_Conv, ASPP, SpatialPyramidPooling,
+shuffle_channels, CoCFpnDual), same constructor arguments, module tree and state-dict keys.
+
+Hot-path content here = the three CoC_Conv ClusterBlocks, the 1x1 BaseConvs and the
+ShuffleAttention gates, all on the native kernels.  ASPP's dilated 3x3 convs and the bilinear upsamples are the
+"next" rows of SURVEY §8f and are cuDNN / ATen library calls for now.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .context_cluster import ClusterBlock
+from .fusion import BaseConv, DWConv, ShuffleAttention, eca_block, shuffle_channels  # noqa: F401
+from .vr_coc import coc_medium, coc_small  # noqa: F401
+
+
+class CoCUpsample(nn.Module):
+    """reference coc_fpn_dual.py:15-26"""
+
+    def __init__(self, in_channels, out_channels, scale=2, ds_conv=False):
+        super().__init__()
+        self.upsample = nn.Sequential(
+            BaseConv(in_channels, out_channels, 1, 1, act='relu', ds_conv=ds_conv),
+            nn.Upsample(scale_factor=scale, mode='bilinear', align_corners=True))
+
+    def forward(self, x):
+        return self.upsample(x)
+
+
+class CoC_Conv(nn.Module):
+    """reference coc_fpn_dual.py:29-39: default-argument ClusterBlock followed by a 1x1 BaseConv"""
+
+    def __init__(self, in_channels, out_channels, ksize=1, stride=1, act="relu", ds_conv=False):
+        super().__init__()
+        self.coc = ClusterBlock(dim=in_channels)
+        self.conv_att = BaseConv(in_channels, out_channels, ksize=ksize, stride=stride, act=act, ds_conv=ds_conv)
+
+    def forward(self, x):
+        return self.conv_att(self.coc(x))
+
+
+class ASPP(nn.Module):
+    """reference coc_fpn_dual.py:46-104"""
+
+    def __init__(self, dim_in, dim_out, rate=1, bn_mom=0.1):
+        super().__init__()
+
+        def branch(k, dil):
+            return nn.Sequential(nn.Conv2d(dim_in, dim_out, k, 1, padding=0 if k == 1 else dil, dilation=dil, bias=True),
+                                 nn.BatchNorm2d(dim_out, momentum=bn_mom), nn.ReLU(inplace=True))
+        self.branch1 = branch(1, rate)
+        self.branch2 = branch(3, 6 * rate)
+        self.branch3 = branch(3, 12 * rate)
+        self.branch4 = branch(3, 18 * rate)
+        self.branch5_conv = nn.Conv2d(dim_in, dim_out, 1, 1, 0, bias=True)
+        self.branch5_bn = nn.BatchNorm2d(dim_out, momentum=bn_mom)
+        self.branch5_relu = nn.ReLU(inplace=True)
+        self.conv_cat = nn.Sequential(nn.Conv2d(dim_out * 5, dim_out, 1, 1, padding=0, bias=True),
+                                      nn.BatchNorm2d(dim_out, momentum=bn_mom), nn.ReLU(inplace=True))
+
+    def forward(self, x):
+        b, c, row, col = x.size()
+        feats = [self.branch1(x), self.branch2(x), self.branch3(x), self.branch4(x)]
+        g = torch.mean(torch.mean(x, 2, True), 3, True)
+        g = self.branch5_relu(self.branch5_bn(self.branch5_conv(g)))
+        g = F.interpolate(g, (row, col), None, 'bilinear', True)
+        return self.conv_cat(torch.cat(feats + [g], dim=1))
+
+
+class SpatialPyramidPooling(nn.Module):
+    """reference coc_fpn_dual.py:107-117 (unused by the live model)"""
+
+    def __init__(self, pool_sizes=[5, 9, 13]):
+        super().__init__()
+        self.maxpools = nn.ModuleList([nn.MaxPool2d(p, 1, p // 2) for p in pool_sizes])
+
+    def forward(self, x):
+        return torch.cat([m(x) for m in self.maxpools[::-1]] + [x], dim=1)
+
+
+class CoCFpnDual(nn.Module):
+    """reference coc_fpn_dual.py:133-224"""
+
+    def __init__(self, num_seg_class=9, depth=1.0, width=1.0, in_features=("dark2", "dark3", "dark4", "dark5"),
+                 in_channels=[64, 128, 320, 512], aspp_channel=1024):
+        super().__init__()
+        Conv = CoC_Conv
+        self.backbone = coc_small(pretrained=False, width=width)
+        self.in_features = in_features
+        self.num_seg_class = num_seg_class
+        in_channels = [int(item * width) for item in in_channels]
+        self.aspp = ASPP(dim_in=in_channels[-1], dim_out=in_channels[-1])
+        self.upsample5_4 = CoCUpsample(in_channels=in_channels[-1], out_channels=in_channels[-2])
+        self.sc_attn_seg4 = ShuffleAttention(channel=in_channels[-2] * 2)
+        self.upsample4_3 = CoCUpsample(in_channels=in_channels[-2] * 2, out_channels=in_channels[-3])
+        self.sc_attn_seg3 = ShuffleAttention(channel=in_channels[-3] * 2)
+        self.upsample3_2 = CoCUpsample(in_channels=in_channels[-3] * 2, out_channels=in_channels[0])
+        self.sc_attn_seg2 = ShuffleAttention(channel=in_channels[0] * 2)
+        self.upsample2_0 = CoCUpsample(in_channels=in_channels[0] * 2, out_channels=self.num_seg_class, scale=4)
+        self.p5_out_det = Conv(in_channels=in_channels[-1], out_channels=in_channels[-1])
+        self.p5_4_det = CoCUpsample(in_channels=in_channels[-1], out_channels=in_channels[-2])
+        self.p4_out_det = Conv(in_channels=in_channels[-2] * 2, out_channels=in_channels[-2])
+        self.p4_3_det = CoCUpsample(in_channels=in_channels[-2], out_channels=in_channels[-3])
+        self.p3_out_det = Conv(in_channels=in_channels[-3] * 2, out_channels=in_channels[-3])
+
+    def forward(self, x, x_radar):
+        x_out, x_radar_out = self.backbone(x, x_radar)
+        s2, s3, s4, s5 = x_out
+        r2, r3, r4, r5 = x_radar_out
+        s5 = self.aspp(s5)
+        # segmentation branch (image features)
+        t = self.sc_attn_seg4(shuffle_channels(torch.cat([s4, self.upsample5_4(s5)], dim=1)))
+        t = self.sc_attn_seg3(shuffle_channels(torch.cat([self.upsample4_3(t), s3], dim=1)))
+        t = self.sc_attn_seg2(shuffle_channels(torch.cat([self.upsample3_2(t), s2], dim=1)))
+        seg = self.upsample2_0(t)
+        # detection branch (radar features)
+        p5 = self.p5_out_det(r5)
+        p4 = self.p4_out_det(torch.cat([r4, self.p5_4_det(p5)], dim=1))
+        p3 = self.p3_out_det(torch.cat([r3, self.p4_3_det(p4)], dim=1))
+        return (p3, p4, p5), seg

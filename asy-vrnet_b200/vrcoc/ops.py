@@ -1,0 +1,388 @@
+"""Tensor-level wrappers and autograd Functions over the C-ABI kernels.
+
+PyTorch is plumbing here: it owns device memory and streams; every arithmetic pass over a feature map is one of the
+hand-written kernels in csrc/.  Only O(B*C)-sized bookkeeping (GroupNorm backward coefficients, BatchNorm running
+statistics) is done with torch ops on tiny tensors.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, BF16, ENGINE_AUTO, F32, ConvDesc, check, lib
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _dt(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise _lib.VrcocError(f"unsupported dtype {t.dtype}: the CoC path runs in float32 or bfloat16") from None
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.VrcocError("vrcoc kernels need CUDA tensors on an sm_100 device (no CPU fallback exists)")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t):
+    """small parameter vectors are always consumed as fp32"""
+    if t is None:
+        return None
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# statistics
+# ------------------------------------------------------------------------------------------------------------
+def channel_sums(x, want_chan=True, want_sample=False):
+    """-> (chan_sums float [B,C,2] or None, sample_sums double [B,2] or None)"""
+    _need_cuda(x)
+    x = x.contiguous()
+    B, Cc, H, W = x.shape
+    cs = torch.empty(B, Cc, 2, device=x.device, dtype=torch.float32) if want_chan else None
+    ss = torch.zeros(B, 2, device=x.device, dtype=torch.float64) if want_sample else None
+    check(lib.vrcoc_channel_sums(_ptr(x), _dt(x), B, Cc, H * W, _ptr(cs), _ptr(ss), _stream()), "channel_sums")
+    return cs, ss
+
+
+def sample_sums_of(x):
+    """GroupNorm(1,C) statistics of x: reuse the producer's side output when it rode along on the tensor."""
+    ss = getattr(x, "_vrcoc_sums", None)
+    if ss is not None and ss.shape[0] == x.shape[0]:
+        return ss
+    return channel_sums(x, want_chan=False, want_sample=True)[1]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# conv engine
+# ------------------------------------------------------------------------------------------------------------
+def conv_desc(src0, weight, out, *, src1=None, src0_bstride=None, src1_bstride=None, chan_src=None,
+              gn=None, table=None, has_gate=False, kh=1, kw=1, stride=1, pad=0,
+              e_scale=None, e_shift=None, act=ACT_NONE, post_scale=None, res=None, f_scale=None, f_shift=None,
+              out2=None, out_sample_sums=None, out_minmax=None, engine=ENGINE_AUTO, keep=None):
+    """Fill a ConvDesc from tensors.  `keep` collects temporaries that must outlive the launch call."""
+    d = ConvDesc()
+    B = out.shape[0]
+    C0 = src0.shape[-3]
+    H_in, W_in = src0.shape[-2], src0.shape[-1]
+    C1 = 0 if src1 is None else src1.shape[-3]
+    d.B, d.H_in, d.W_in, d.H_out, d.W_out = B, H_in, W_in, out.shape[2], out.shape[3]
+    d.C0, d.C1 = C0, C1
+    O_split = out.shape[1]
+    d.O = O_split + (0 if out2 is None else out2.shape[1])
+    d.kh, d.kw, d.stride, d.pad = kh, kw, stride, pad
+    d.src0, d.src0_dtype = _ptr(src0), _dt(src0)
+    d.src0_bstride = C0 * H_in * W_in if src0_bstride is None else src0_bstride
+    if src1 is not None:
+        d.src1, d.src1_dtype = _ptr(src1), _dt(src1)
+        d.src1_bstride = C1 * H_in * W_in if src1_bstride is None else src1_bstride
+    d.chan_src = _ptr(chan_src)
+    if gn is not None:
+        sums, gamma, beta, eps = gn
+        d.gn_sums, d.gn_gamma, d.gn_beta, d.gn_eps = _ptr(sums), _ptr(gamma), _ptr(beta), eps
+    d.table, d.has_gate = _ptr(table), int(has_gate)
+    d.weight, d.weight_dtype = _ptr(weight), _dt(weight)
+    d.e_scale, d.e_shift, d.act, d.post_scale = _ptr(e_scale), _ptr(e_shift), act, _ptr(post_scale)
+    if res is not None:
+        d.res, d.res_dtype = _ptr(res), _dt(res)
+    d.f_scale, d.f_shift = _ptr(f_scale), _ptr(f_shift)
+    d.out, d.out_dtype = _ptr(out), _dt(out)
+    if out2 is not None:
+        d.out2, d.out2_dtype = _ptr(out2), _dt(out2)
+    d.O_split = O_split
+    d.out_sample_sums, d.out_minmax = _ptr(out_sample_sums), _ptr(out_minmax)
+    d.engine = engine
+    return d
+
+
+def conv_fwd(desc):
+    check(lib.vrcoc_conv_fwd(C.byref(desc), _stream()), "conv_fwd")
+
+
+def conv1x1_wgrad(desc, dy, want_db=True):
+    """dW [O,Cin] fp32, db [O] fp32 for the forward call described by `desc`."""
+    O, Cin = desc.O, desc.C0 + desc.C1
+    n = lib.vrcoc_conv1x1_wgrad_workspace(C.byref(desc))
+    if n < 0:
+        check(-1, "conv1x1_wgrad_workspace")
+    ws = torch.empty(n, device=dy.device, dtype=torch.float32)
+    dW = torch.empty(O, Cin, device=dy.device, dtype=torch.float32)
+    db = torch.empty(O, device=dy.device, dtype=torch.float32) if want_db else None
+    check(lib.vrcoc_conv1x1_wgrad(C.byref(desc), _ptr(dy), _dt(dy), _ptr(dW), _ptr(db), _ptr(ws), n, _stream()), "conv1x1_wgrad")
+    return dW, db
+
+
+def out_hw(h, w, k, stride, pad):
+    return (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+
+
+# ------------------------------------------------------------------------------------------------------------
+# cluster core
+# ------------------------------------------------------------------------------------------------------------
+def _bstride(t):
+    """batch stride (elements) of a [B, C, H, W] tensor that is dense in its last three dims"""
+    B, Cc, H, W = t.shape
+    if t.stride(3) != 1 or t.stride(2) != W or t.stride(1) != H * W:
+        raise _lib.VrcocError("tensor must be dense in (C,H,W)")
+    return t.stride(0) if B > 1 else Cc * H * W
+
+
+def _chw_dense(t):
+    B, Cc, H, W = t.shape
+    return t.stride(3) == 1 and t.stride(2) == W and t.stride(1) == H * W
+
+
+def cluster_core_fwd(feat, value, alpha, beta, heads, fold_w, fold_h, proposal_w, proposal_h, out_dtype=None,
+                     save_aux=False):
+    _need_cuda(feat, value)
+    if not _chw_dense(feat):
+        feat = feat.contiguous()
+    if not _chw_dense(value):
+        value = value.contiguous()
+    B, ED, H, W = feat.shape
+    if ED % heads:
+        raise _lib.VrcocError(f"channels {ED} not divisible by heads {heads}")
+    D = ED // heads
+    out = torch.empty(B, ED, H, W, device=feat.device, dtype=out_dtype or value.dtype)
+    idx = torch.empty(B, heads, H, W, device=feat.device, dtype=torch.uint8) if save_aux else None
+    smax = torch.empty(B, heads, H, W, device=feat.device, dtype=torch.float32) if save_aux else None
+    check(lib.vrcoc_cluster_core_fwd(_ptr(feat), _dt(feat), _ptr(value), _dt(value), _ptr(out), _dt(out), _ptr(idx), _ptr(smax),
+                                     _ptr(alpha), _ptr(beta), B, heads, D, H, W, fold_w, fold_h, proposal_w, proposal_h,
+                                     _bstride(feat), _bstride(value), 0, _stream()), "cluster_core_fwd")
+    return out, idx, smax
+
+
+def cluster_core_bwd(feat, value, dout, idx, smax, alpha, beta, heads, fold_w, fold_h, proposal_w, proposal_h,
+                     dfeat=None, dvalue=None):
+    B, ED, H, W = feat.shape
+    D = ED // heads
+    if not _chw_dense(dout):
+        dout = dout.contiguous()
+    if dfeat is None:
+        dfeat = torch.empty(B, ED, H, W, device=feat.device, dtype=feat.dtype)
+    if dvalue is None:
+        dvalue = torch.empty(B, ED, H, W, device=feat.device, dtype=value.dtype)
+    f1, f2 = (fold_w, fold_h) if (fold_w > 1 and fold_h > 1) else (1, 1)
+    R = B * heads * f1 * f2
+    partials = torch.empty(2 * R, device=feat.device, dtype=torch.float32)
+    dab = torch.empty(2, device=feat.device, dtype=torch.float32)
+    check(lib.vrcoc_cluster_core_bwd(_ptr(feat), _dt(feat), _ptr(value), _dt(value), _ptr(dout), _dt(dout), _ptr(idx), _ptr(smax),
+                                     _ptr(alpha), _ptr(beta), _ptr(dfeat), _dt(dfeat), _ptr(dvalue), _dt(dvalue), _ptr(dab),
+                                     _ptr(partials), B, heads, D, H, W, fold_w, fold_h, proposal_w, proposal_h,
+                                     _bstride(feat), _bstride(value), _bstride(dout), _bstride(dfeat), _bstride(dvalue),
+                                     _stream()), "cluster_core_bwd")
+    return dfeat, dvalue, dab
+
+
+class ClusterCoreFn(torch.autograd.Function):
+    """out = cluster_core(feat, value; alpha, beta)   (reference vr_coc.py:158-190)"""
+
+    @staticmethod
+    def forward(ctx, feat, value, alpha, beta, heads, fold_w, fold_h, proposal_w, proposal_h):
+        a32, b32 = _f32(alpha), _f32(beta)
+        need_grad = any(ctx.needs_input_grad[:4])
+        out, idx, smax = cluster_core_fwd(feat, value, a32, b32, heads, fold_w, fold_h, proposal_w, proposal_h,
+                                          save_aux=need_grad)
+        if need_grad:
+            ctx.save_for_backward(feat, value, idx, smax, a32, b32)
+            ctx.cfg = (heads, fold_w, fold_h, proposal_w, proposal_h)
+            ctx.ab_dtype = alpha.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        feat, value, idx, smax, a32, b32 = ctx.saved_tensors
+        # feat|value may be two views of one projection output: write the gradients into one buffer of the same
+        # layout so the projection backward consumes a single dense dy without a concat pass
+        B, ED, H, W = feat.shape
+        joint = (feat.dtype == value.dtype and feat.stride(0) == 2 * ED * H * W and value.stride(0) == feat.stride(0)
+                 and value.data_ptr() == feat.data_ptr() + ED * H * W * feat.element_size())
+        if joint:
+            buf = torch.empty(B, 2 * ED, H, W, device=feat.device, dtype=feat.dtype)
+            dfeat, dvalue = buf[:, :ED], buf[:, ED:]
+        else:
+            dfeat = dvalue = None
+        dfeat, dvalue, dab = cluster_core_bwd(feat, value, dout, idx, smax, a32, b32, *ctx.cfg, dfeat=dfeat, dvalue=dvalue)
+        return dfeat, dvalue, dab[0:1].to(ctx.ab_dtype), dab[1:2].to(ctx.ab_dtype), None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------------------
+# projections (1x1 convs) with GroupNorm prologue / layer-scale + residual epilogue
+# ------------------------------------------------------------------------------------------------------------
+def _w2d(w):
+    return w.detach().reshape(w.shape[0], -1)
+
+
+class GNProjFn(torch.autograd.Function):
+    """y = act(W * GroupNorm1(x) + b), optionally split along the output channels into (y[:split] as fp32, rest).
+
+    Replaces norm -> 1x1 conv (-> GELU) of reference vr_coc.py:156-157 / :218-219 with one kernel; the normalised
+    activation never reaches HBM."""
+
+    @staticmethod
+    def forward(ctx, x, sums, gamma, beta, eps, weight, bias, act, split_fp32):
+        _need_cuda(x)
+        x = x.contiguous()
+        B, Cc, H, W = x.shape
+        w2 = _w2d(weight).contiguous()
+        O = w2.shape[0]
+        g32, b32, bias32 = _f32(gamma), _f32(beta), _f32(bias)
+        if split_fp32 and x.dtype != torch.float32:
+            out = torch.empty(B, split_fp32, H, W, device=x.device, dtype=torch.float32)
+            out2 = torch.empty(B, O - split_fp32, H, W, device=x.device, dtype=x.dtype)
+        else:
+            out = torch.empty(B, O, H, W, device=x.device, dtype=x.dtype)
+            out2 = None
+        d = conv_desc(x, w2, out, gn=(sums, g32, b32, eps), e_shift=bias32, act=act, out2=out2)
+        conv_fwd(d)
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(x, sums, g32, b32, w2, bias32)
+            ctx.meta = (eps, act, gamma.dtype, weight.shape, weight.dtype, None if bias is None else bias.dtype, out2 is not None)
+        if out2 is not None:
+            return out, out2
+        return out
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x, sums, g32, b32, w2, bias32 = ctx.saved_tensors
+        eps, act, gdt, wshape, wdt, bdt, was_split = ctx.meta
+        B, Cc, H, W = x.shape
+        P = H * W
+        O = w2.shape[0]
+        if was_split:
+            dy = torch.cat([grads[0].to(x.dtype), grads[1].to(x.dtype)], dim=1)
+        else:
+            dy = grads[0]
+        dy = dy.contiguous()
+        if act == ACT_GELU:
+            # recompute the pre-activation instead of having saved the (r*C x P) hidden map
+            u = torch.empty(B, O, H, W, device=x.device, dtype=x.dtype)
+            conv_fwd(conv_desc(x, w2, u, gn=(sums, g32, b32, eps), e_shift=bias32))
+            check(lib.vrcoc_gelu_bwd(_ptr(dy), _ptr(u), _ptr(u), _dt(u), u.numel(), _stream()), "gelu_bwd")
+            dy = u
+        elif act != ACT_NONE:
+            raise _lib.VrcocError("GNProjFn backward supports act none / gelu")
+        # weight / bias gradients:  dW = dy . GN(x)^T
+        fdesc = conv_desc(x, w2, dy, gn=(sums, g32, b32, eps))
+        dW, db = conv1x1_wgrad(fdesc, dy, want_db=bias32 is not None)
+        # input gradient through the projection: dz = W^T dy
+        wt = w2.t().contiguous()
+        dz = torch.empty(B, Cc, H, W, device=x.device, dtype=x.dtype)
+        conv_fwd(conv_desc(dy, wt, dz))
+        # GroupNorm(1,C) backward
+        s = torch.empty(B, Cc, 2, device=x.device, dtype=torch.float32)
+        check(lib.vrcoc_gn_bwd_sums(_ptr(dz), _ptr(x), _dt(x), B, Cc, P, _ptr(s), _stream()), "gn_bwd_sums")
+        cnt = float(Cc * P)
+        mean = (sums[:, 0] / cnt)
+        var = (sums[:, 1] / cnt - mean * mean).clamp_min(0)
+        rstd = torch.rsqrt(var + eps)
+        mean32, rstd32 = mean.float(), rstd.float()
+        s1, s2 = s[..., 0].double(), s[..., 1].double()                       # sum dz, sum dz*x   [B,C]
+        sxh = (s2 - mean[:, None] * s1) * rstd[:, None]                         # sum dz*xhat
+        dgamma = sxh.sum(0)
+        dbeta = s1.sum(0)
+        g64 = g32.double()
+        m1 = (s1 * g64).sum(1) / cnt                                            # mean(gamma*dz)
+        m2 = (sxh * g64).sum(1) / cnt                                           # mean(gamma*dz*xhat)
+        a = (rstd32[:, None] * g32[None, :]).contiguous()                       # [B,C]
+        bb = (-(rstd * rstd * m2)).float().contiguous()                         # [B]
+        cc = (rstd * (mean * rstd * m2 - m1)).float().contiguous()              # [B]
+        dx = torch.empty_like(x)
+        check(lib.vrcoc_gn_bwd_apply(_ptr(dz), _ptr(x), None, _ptr(dx), _dt(x), _ptr(a), _ptr(bb), _ptr(cc), B, Cc, P, _stream()),
+              "gn_bwd_apply")
+        return (dx, None, dgamma.to(gdt), dbeta.to(gdt), None, dW.reshape(wshape).to(wdt),
+                None if db is None else db.to(bdt), None, None)
+
+
+class ProjResidualFn(torch.autograd.Function):
+    """out = res + ls * (W h + b)  (+ per-sample {sum, sum^2} of out for the next GroupNorm as a side output).
+
+    Replaces 1x1 conv -> layer-scale -> residual add of reference vr_coc.py:191,222 and :266-271."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, ls, res):
+        _need_cuda(h, res)
+        h = h.contiguous()
+        res = res.contiguous()
+        B, K, H, W = h.shape
+        w2 = _w2d(weight).contiguous()
+        O = w2.shape[0]
+        bias32, ls32 = _f32(bias), _f32(ls)
+        out = torch.empty(B, O, H, W, device=h.device, dtype=res.dtype)
+        sums = torch.zeros(B, 2, device=h.device, dtype=torch.float64)
+        conv_fwd(conv_desc(h, w2, out, e_shift=bias32, post_scale=ls32, res=res, out_sample_sums=sums))
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(h, w2, bias32, ls32)
+            ctx.meta = (weight.shape, weight.dtype, None if bias is None else bias.dtype, None if ls is None else ls.dtype)
+        ctx.mark_non_differentiable(sums)
+        return out, sums
+
+    @staticmethod
+    def backward(ctx, dout, _dsums):
+        h, w2, bias32, ls32 = ctx.saved_tensors
+        wshape, wdt, bdt, lsdt = ctx.meta
+        dout = dout.contiguous()
+        B, K, H, W = h.shape
+        # G[o,k] = sum dout[o,p] h[k,p];  s[o] = sum dout[o,p]
+        G, s = conv1x1_wgrad(conv_desc(h, w2, dout), dout, want_db=True)
+        if ls32 is not None:
+            dW = ls32[:, None] * G
+            db = ls32 * s
+            dls = (w2.float() * G).sum(1)
+            if bias32 is not None:
+                dls = dls + bias32 * s
+            wt = (w2.float() * ls32[:, None]).t().contiguous().to(w2.dtype)
+        else:
+            dW, db, dls = G, s, None
+            wt = w2.t().contiguous()
+        dh = torch.empty_like(h)
+        conv_fwd(conv_desc(dout, wt, dh))
+        return (dh, dW.reshape(wshape).to(wdt), None if bias32 is None else db.to(bdt),
+                None if dls is None else dls.to(lsdt), dout)
+
+
+class ProjFn(torch.autograd.Function):
+    """y = act(W x + b) for a 1x1 projection (stand-alone Cluster / Mlp forward without the block fusion)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        _need_cuda(x)
+        x = x.contiguous()
+        B, K, H, W = x.shape
+        w2 = _w2d(weight).contiguous()
+        bias32 = _f32(bias)
+        out = torch.empty(B, w2.shape[0], H, W, device=x.device, dtype=x.dtype)
+        conv_fwd(conv_desc(x, w2, out, e_shift=bias32, act=act))
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(x, w2, bias32)
+            ctx.meta = (act, weight.shape, weight.dtype, None if bias is None else bias.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w2, bias32 = ctx.saved_tensors
+        act, wshape, wdt, bdt = ctx.meta
+        dy = dy.contiguous()
+        if act == ACT_GELU:
+            u = torch.empty_like(dy)
+            conv_fwd(conv_desc(x, w2, u, e_shift=bias32))
+            check(lib.vrcoc_gelu_bwd(_ptr(dy), _ptr(u), _ptr(u), _dt(u), u.numel(), _stream()), "gelu_bwd")
+            dy = u
+        elif act != ACT_NONE:
+            raise _lib.VrcocError("ProjFn backward supports act none / gelu")
+        dW, db = conv1x1_wgrad(conv_desc(x, w2, dy), dy, want_db=bias32 is not None)
+        dx = torch.empty_like(x)
+        conv_fwd(conv_desc(dy, w2.t().contiguous(), dx))
+        return dx, dW.reshape(wshape).to(wdt), None if db is None else db.to(bdt), None

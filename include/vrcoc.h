@@ -1,0 +1,194 @@
+/*
+ * vrcoc.h — C-ABI of libvrcoc.so: hand-written sm_100a CUDA kernels for the ASY-VRNet hot path
+ * (context-cluster block + asymmetric vision<->radar fusion).
+ *
+ * The reference (GuanRunwei/ASY-VRNet) is pure PyTorch and has no FFI layer; its boundary for this path is the
+ * nn.Module surface.  The Python host side (asy-vrnet_b200/vrcoc) mirrors those modules and binds
+ * these entry points with ctypes.  Each entry point below cites the reference lines whose eager-op sequence it
+ * replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (PyTorch caching allocator); the library never
+ *    allocates, frees or retains memory, keeps no mutable global state and is re-entrant (DataParallel calls it
+ *    from one host thread per GPU, autograd from its own thread);
+ *  - tensors are dense NCHW; "dim2"/"dim3" are the two spatial axes; the reference names dim2 "w" and dim3 "h"
+ *    (backbone/fusion/vr_coc.py:155), so fold_w/proposal_w act on dim2 and fold_h/proposal_h on dim3;
+ *  - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream); launches are
+ *    asynchronous, never synchronise, and are CUDA-graph capturable;
+ *  - return value: 0 on success, a negative VRCOC_E* code otherwise; vrcoc_last_error() gives the message of the
+ *    last failure on the calling thread.  There is no CPU fallback anywhere.
+ */
+#ifndef VRCOC_H_
+#define VRCOC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VRCOC_OK 0
+#define VRCOC_EINVAL (-1)  /* bad argument (null pointer, unsupported shape/dtype) */
+#define VRCOC_ECUDA (-2)   /* CUDA runtime error at launch */
+#define VRCOC_ENODEV (-3)  /* not an sm_100 device */
+
+/* storage dtypes (arithmetic is always fp32 on chip; bf16 projections use tcgen05 with fp32 accumulation) */
+#define VRCOC_F32 0
+#define VRCOC_BF16 1
+
+/* epilogue activations */
+#define VRCOC_ACT_NONE 0
+#define VRCOC_ACT_RELU 1
+#define VRCOC_ACT_GELU 2 /* exact erf GELU, nn.GELU() default */
+#define VRCOC_ACT_SILU 3
+#define VRCOC_ACT_LRELU 4 /* LeakyReLU(0.1), reference normal_conv.py:17 */
+
+const char* vrcoc_version(void);
+const char* vrcoc_last_error(void);
+/* 1 if the current device can run the kernels (compute capability 10.x), else 0 */
+int vrcoc_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Statistics currency.
+ *   channel sums: float [B][C][2] = {sum_hw x, sum_hw x^2}   (ShuffleAttention GN / avg-pool: shuffle_attention.py:57-64,
+ *                 eca.py:17, BatchNorm2d batch statistics: normal_conv.py:45)
+ *   sample sums : double [B][2]   = {sum_chw x, sum_chw x^2} (GroupNorm(1,C): vr_coc.py:105-111)
+ * ---------------------------------------------------------------------------------------------------------- */
+int vrcoc_channel_sums(const void* x, int dtype, int B, int C, int HW, float* chan_sums, double* sample_sums /*nullable, must be zeroed*/,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Convolution-as-GEMM engine with table-driven prologue and fused epilogue.  One launch computes
+ *
+ *   z[b,k,p]   = T(src[b, chan_src[k], p])                               (prologue, per logical input channel k)
+ *                T(x) = (x*scale + shift) * sigmoid(gate_a*x + gate_c)    [gate only if has_gate]
+ *   acc[b,o,q] = sum_{k,ky,kx} W[o,k,ky,kx] * z[b,k, q*stride - pad + (ky,kx)]      (zero outside the map)
+ *   y = act(acc*e_scale[o] + e_shift[o]) * post_scale[o] + res[b,o,q];  y = y*f_scale[o] + f_shift[o]
+ *   out[b,o,q] = y        (+ optional side outputs: per-sample sums of y, global min/max of y)
+ *
+ * It replaces, in the reference: Cluster.fc1/fc_v/fc2 and Mlp.fc1/fc2 with the GroupNorm, GELU, layer-scale and
+ * residual around them (vr_coc.py:156-157,191,217-223,264-271); PointRecuder convs (vr_coc.py:99-102, incl. the
+ * cat([x,pos]) of :582-586 through the two-source input); BaseConv conv+BN+act (normal_conv.py:48-49); the
+ * shuffle/attention/ECA/1x1/BN chain of RadarEnhanceByImage (vr_coc.py:331-357) and the radar projection of
+ * ImageEnhanceByRadar (vr_coc.py:313).
+ *
+ * Prologue sources (exactly one of, or none):
+ *   gn_sums != NULL  : GroupNorm(1,C) of src0: scale = rstd_b*gamma[k], shift = beta[k] - mean_b*rstd_b*gamma[k]
+ *   table   != NULL  : float [B][Cin][4] = {scale, shift, gate_a, gate_c}
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct vrcoc_conv_desc {
+  /* geometry */
+  int32_t B, H_in, W_in, H_out, W_out;
+  int32_t C0, C1;          /* channels of src0 / src1; logical input channels Cin = C0 + C1 */
+  int32_t O;               /* output channels */
+  int32_t kh, kw, stride, pad;
+  /* inputs */
+  const void* src0; int32_t src0_dtype; int64_t src0_bstride; /* batch stride in elements (0 broadcasts, e.g. fea_pos) */
+  const void* src1; int32_t src1_dtype; int64_t src1_bstride; /* may be NULL when C1 == 0 */
+  const int32_t* chan_src; /* nullable [Cin]: logical channel k reads channel chan_src[k] of the virtual concat [src0|src1] */
+  /* prologue */
+  const double* gn_sums; const float* gn_gamma; const float* gn_beta; float gn_eps; /* GroupNorm(1,C0) on src0 */
+  const float* table; int32_t has_gate;
+  /* weights: [O][Cin*kh*kw] row-major (== PyTorch conv weight), fp32 or bf16 */
+  const void* weight; int32_t weight_dtype;
+  /* epilogue (every pointer nullable = identity) */
+  const float* e_scale; const float* e_shift; int32_t act; const float* post_scale;
+  const void* res; int32_t res_dtype;
+  const float* f_scale; const float* f_shift;
+  /* outputs: channels [0,O_split) -> out, [O_split,O) -> out2 (out2 may be NULL when O_split == O) */
+  void* out; int32_t out_dtype;
+  void* out2; int32_t out2_dtype; int32_t O_split;
+  double* out_sample_sums; /* nullable [B][2], accumulated (caller zeroes) */
+  uint32_t* out_minmax;    /* nullable [2] = {max bits(y), max ~bits(y)}, y >= 0 required, caller zeroes */
+  /* 0 = pick automatically, 1 = force CUDA-core fp32 path, 2 = force tcgen05 bf16 path */
+  int32_t engine;
+} vrcoc_conv_desc;
+
+int vrcoc_conv_fwd(const vrcoc_conv_desc* d, void* stream);
+
+/* Backward helpers of the 1x1 projections (training path of vr_coc.py:156-157,191,217-223).
+ *   wgrad: dW[o][k] (+)= sum_{b,p} dy[b,o,p] * z[b,k,p],  db[o] (+)= sum dy      (z = prologue(src), as in fwd)
+ *   dgrad is vrcoc_conv_fwd itself with the transposed weight. */
+int vrcoc_conv1x1_wgrad(const vrcoc_conv_desc* fwd_desc /* src*, tables, geometry of the forward call */,
+                        const void* dy, int dy_dtype, float* dW /*[O][Cin] fp32*/, float* db /*nullable [O]*/,
+                        float* workspace, int64_t workspace_floats, void* stream);
+int64_t vrcoc_conv1x1_wgrad_workspace(const vrcoc_conv_desc* fwd_desc);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Cluster core: everything of Cluster.forward between the projections (vr_coc.py:158-190): head split, region
+ * fold, adaptive-pool centre proposal, cosine similarity, sigmoid(beta + alpha*sim), arg-max hard assignment
+ * (lowest index wins ties), similarity-weighted aggregation to the centres, dispatch back to the points, unfold.
+ * feat/value/out are [B, E*D, H, W].  idx (uint8 [B,E,H,W]) and sim_max (float [B,E,H,W]) are optional outputs
+ * (saved for backward / mask-parity checks).  alpha/beta are device scalars (Cluster.sim_alpha / sim_beta).
+ * ---------------------------------------------------------------------------------------------------------- */
+int vrcoc_cluster_core_fwd(const void* feat, int feat_dtype, const void* value, int value_dtype,
+                           void* out, int out_dtype, uint8_t* idx, float* sim_max,
+                           const float* alpha, const float* beta,
+                           int B, int E, int D, int H, int W,
+                           int fold_w, int fold_h, int proposal_w, int proposal_h,
+                           int64_t feat_bstride, int64_t value_bstride, int64_t out_bstride /* elements; 0 = dense E*D*H*W */,
+                           void* stream);
+
+/* Backward of the above.  dalpha_beta: float [2], accumulated deterministically from
+ * `partials` (float [2*n_region_heads] workspace, n_region_heads = B*E*fold_w*fold_h). */
+int vrcoc_cluster_core_bwd(const void* feat, int feat_dtype, const void* value, int value_dtype,
+                           const void* dout, int dout_dtype, const uint8_t* idx, const float* sim_max,
+                           const float* alpha, const float* beta,
+                           void* dfeat, int dfeat_dtype, void* dvalue, int dvalue_dtype,
+                           float* dalpha_beta, float* partials,
+                           int B, int E, int D, int H, int W,
+                           int fold_w, int fold_h, int proposal_w, int proposal_h,
+                           int64_t feat_bstride, int64_t value_bstride, int64_t dout_bstride, int64_t dfeat_bstride,
+                           int64_t dvalue_bstride /* elements; 0 = dense */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fusion helpers.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* ShuffleAttention(G) + shuffle_channels(cat) + eca_block prologue table of RadarEnhanceByImage
+ * (vr_coc.py:344-350, shuffle_attention.py:48-72, eca.py:16-22).  Step 1 computes the per-(b, image channel)
+ * attention parameters and the spatial sums of the attended image; step 2 runs the ECA conv1d over the
+ * interleaved channel means and emits the conv prologue table [B][Ci+Cr][4]. */
+int vrcoc_sa_gate_sums(const void* image, int dtype, int B, int Ci, int HW, int G /*0 = no ShuffleAttention*/,
+                       const float* chan_sums_img /*[B][Ci][2]*/,
+                       const float* cweight, const float* cbias, const float* sweight, const float* sbias,
+                       const float* gn_weight, const float* gn_bias,
+                       float* attn /*[B][Ci][4] = {scale, gate_a, gate_c, mean of attended channel}*/, void* stream);
+int vrcoc_radar_enh_table(const float* attn /*[B][Ci][4]*/, const float* chan_sums_radar /*[B][Cr][2]*/,
+                          const int32_t* chan_src /*[Ci+Cr] logical -> concat channel; image channels already
+                                                    include ShuffleAttention's own channel_shuffle*/,
+                          const float* eca_weight, int eca_k, int B, int Ci, int Cr, int HW,
+                          float* table /*[B][Ci+Cr][4]*/, void* stream);
+
+/* Stand-alone application of a conv prologue (no contraction): out[b,k,p] = T(src[b, chan_src[k], p]) with T taken
+ * from desc->gn_* or desc->table exactly as in vrcoc_conv_fwd (weight/epilogue fields are ignored, O must equal
+ * C0+C1).  Used for GroupNorm, ShuffleAttention and eca_block when they are called outside a fused chain. */
+int vrcoc_table_apply(const vrcoc_conv_desc* d, void* stream);
+
+/* Per-channel affine / activation / residual / affine pass with optional side statistics:
+ *   y = act(x*s1[c] + t1[c]) + res;  y = y*s2[c] + t2[c]
+ * (BatchNorm2d application in train mode, normal_conv.py:49, vr_coc.py:315,341,356). */
+int vrcoc_chan_affine(const void* x, int x_dtype, const void* res, int res_dtype, void* out, int out_dtype,
+                      const float* s1, const float* t1, int act, const float* s2, const float* t2,
+                      int B, int C, int HW, float* out_chan_sums /*nullable [B][C][2]*/,
+                      uint32_t* out_minmax /*nullable*/, void* stream);
+
+/* ImageEnhanceByRadar tail (vr_coc.py:314-315, data_normal :59-67 for a non-negative map):
+ *   y = (1 + (k - mn)/(mx - mn)) * image;  out = y*s[c] + t[c]     mn/mx decoded from `minmax` (see out_minmax). */
+int vrcoc_img_enh_finish(const void* k, int k_dtype, const void* image, int image_dtype, void* out, int out_dtype,
+                         const uint32_t* minmax, const float* s, const float* t, int B, int C, int HW,
+                         float* out_chan_sums /*nullable [B][C][2]*/, void* stream);
+
+
+/* Backward elementwise passes of the projections (training path of ClusterBlock, vr_coc.py:264-271).
+ *   gelu_bwd    : out = dy * gelu'(u)                                   (all three tensors share `dtype`)
+ *   gn_bwd_sums : out[b][c] = {sum_p dz, sum_p dz*x}                    GroupNorm(1,C) backward statistics
+ *   gn_bwd_apply: out = dz*a[b,c] + x*bb[b] + cc[b] (+ extra)           GroupNorm(1,C) input gradient (+ residual grad) */
+int vrcoc_gelu_bwd(const void* dy, const void* u, void* out, int dtype, int64_t n, void* stream);
+int vrcoc_gn_bwd_sums(const void* dz, const void* x, int dtype, int B, int C, int HW, float* out, void* stream);
+int vrcoc_gn_bwd_apply(const void* dz, const void* x, const void* extra /*nullable*/, void* out, int dtype, const float* a,
+                       const float* bb, const float* cc, int B, int C, int HW, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRCOC_H_ */
