@@ -105,10 +105,10 @@ class Cluster(nn.Module):
         w = torch.cat([self.fc1.weight, self.fc_v.weight], dim=0)
         b = torch.cat([self.fc1.bias, self.fc_v.bias], dim=0)
         if gn is None:
-            y = ops.ProjFn.apply(x, w, b, ACT_NONE)
-            return y[:, :ED], y[:, ED:]
-        sums, norm = gn
-        y = ops.GNProjFn.apply(x, sums, norm.weight, norm.bias, norm.eps, w, b, ACT_NONE, ED)
+            y = ops.GNProjFn.apply(x, None, None, None, 0.0, w, b, ACT_NONE, ED)
+        else:
+            sums, norm = gn
+            y = ops.GNProjFn.apply(x, sums, norm.weight, norm.bias, norm.eps, w, b, ACT_NONE, ED)
         if isinstance(y, tuple):          # bf16 storage: similarity operand stays fp32
             return y
         return y[:, :ED], y[:, ED:]

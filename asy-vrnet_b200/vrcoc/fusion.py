@@ -256,6 +256,8 @@ class ShuffleAttention(nn.Module):
         self.sweight = nn.Parameter(torch.zeros(1, q, 1, 1))
         self.sbias = nn.Parameter(torch.ones(1, q, 1, 1))
         self.sigmoid = nn.Sigmoid()
+        # channel_shuffle(., 2) as a gather map for the stand-alone forward (built here: no H2D copy at call time)
+        self.register_buffer("_perm", torch.tensor(shuffle_perm(channel, 2), dtype=torch.int32), persistent=False)
 
     def init_weights(self):
         for m in self.modules():
@@ -313,7 +315,7 @@ class _ShuffleAttentionFn(torch.autograd.Function):
         B, Cc, H, W = x.shape
         attn = mod.gate_table(x)
         table = torch.stack([attn[..., 0], torch.zeros_like(attn[..., 0]), attn[..., 1], attn[..., 2]], dim=-1).contiguous()
-        perm = torch.tensor(shuffle_perm(Cc, 2), device=x.device, dtype=torch.int32)
+        perm = mod._perm
         table = table[:, perm.long()].contiguous()
         out = torch.empty_like(x)
         d = conv_desc(x, x, out, chan_src=perm, table=table, has_gate=True)

@@ -227,6 +227,7 @@ def _w2d(w):
 
 class GNProjFn(torch.autograd.Function):
     """y = act(W * GroupNorm1(x) + b), optionally split along the output channels into (y[:split] as fp32, rest).
+    `sums=None` skips the GroupNorm prologue (stand-alone Cluster.forward).
 
     Replaces norm -> 1x1 conv (-> GELU) of reference vr_coc.py:156-157 / :218-219 with one kernel; the normalised
     activation never reaches HBM."""
@@ -245,11 +246,13 @@ class GNProjFn(torch.autograd.Function):
         else:
             out = torch.empty(B, O, H, W, device=x.device, dtype=x.dtype)
             out2 = None
-        d = conv_desc(x, w2, out, gn=(sums, g32, b32, eps), e_shift=bias32, act=act, out2=out2)
+        gn = None if sums is None else (sums, g32, b32, eps)
+        d = conv_desc(x, w2, out, gn=gn, e_shift=bias32, act=act, out2=out2)
         conv_fwd(d)
         if any(ctx.needs_input_grad):
             ctx.save_for_backward(x, sums, g32, b32, w2, bias32)
-            ctx.meta = (eps, act, gamma.dtype, weight.shape, weight.dtype, None if bias is None else bias.dtype, out2 is not None)
+            ctx.meta = (eps, act, None if gamma is None else gamma.dtype, weight.shape, weight.dtype,
+                        None if bias is None else bias.dtype, out2 is not None)
         if out2 is not None:
             return out, out2
         return out
@@ -266,21 +269,24 @@ class GNProjFn(torch.autograd.Function):
         else:
             dy = grads[0]
         dy = dy.contiguous()
+        gn = None if sums is None else (sums, g32, b32, eps)
         if act == ACT_GELU:
             # recompute the pre-activation instead of having saved the (r*C x P) hidden map
             u = torch.empty(B, O, H, W, device=x.device, dtype=x.dtype)
-            conv_fwd(conv_desc(x, w2, u, gn=(sums, g32, b32, eps), e_shift=bias32))
+            conv_fwd(conv_desc(x, w2, u, gn=gn, e_shift=bias32))
             check(lib.vrcoc_gelu_bwd(_ptr(dy), _ptr(u), _ptr(u), _dt(u), u.numel(), _stream()), "gelu_bwd")
             dy = u
         elif act != ACT_NONE:
             raise _lib.VrcocError("GNProjFn backward supports act none / gelu")
         # weight / bias gradients:  dW = dy . GN(x)^T
-        fdesc = conv_desc(x, w2, dy, gn=(sums, g32, b32, eps))
+        fdesc = conv_desc(x, w2, dy, gn=gn)
         dW, db = conv1x1_wgrad(fdesc, dy, want_db=bias32 is not None)
         # input gradient through the projection: dz = W^T dy
         wt = w2.t().contiguous()
         dz = torch.empty(B, Cc, H, W, device=x.device, dtype=x.dtype)
         conv_fwd(conv_desc(dy, wt, dz))
+        if gn is None:
+            return (dz, None, None, None, None, dW.reshape(wshape).to(wdt), None if db is None else db.to(bdt), None, None)
         # GroupNorm(1,C) backward
         s = torch.empty(B, Cc, 2, device=x.device, dtype=torch.float32)
         check(lib.vrcoc_gn_bwd_sums(_ptr(dz), _ptr(x), _dt(x), B, Cc, P, _ptr(s), _stream()), "gn_bwd_sums")

@@ -1,0 +1,413 @@
+"""bench.py — frames/sec of ASY-VRNet multi-task inference (512x512 RGB + 4x512x512 radar) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+ours      : EfficientVRNet(4, 9, phi) built from the vrcoc modules (hand-written sm_100a kernels behind the reference's
+            nn.Module API), eval mode, bf16, batch 8 per GPU (BASELINE.json configs[2]: batch 64 sharded over 8 GPUs), the
+            whole forward captured in a CUDA graph.  One step = one forward over one batch of synthetic frames.
+            `value`  = frames/s with the batch already resident in HBM (device-timed, max over ranks);
+            `e2e`    = frames/s through the public call with pinned-host inputs: H2D copy of the batch, forward, D2H of
+                       the detection maps and of the per-pixel segmentation class map, all inside the timed region;
+            `roofline` = the kernel with the largest share of the step, timed live with CUDA events;
+            `cpu_baseline` = the CPU port of the reference (oracle/) timed on this box's host cores (rank 0, N=1).
+reference : the reference's CPU implementation of the same path (the oracle port: the reference is pure Python and
+            cannot travel to the GPU box), all host threads, one frame per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "asy-vrnet_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "frames/sec (512x512 img+radar), ASY-VRNet multi-task inference"
+UNIT = "frames/s"
+PER_GPU_BATCH = 8
+IMG = 512
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--phi", default="l")
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="frames per GPU per step")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel time table to stderr")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe), in a thread for the duration of the timed region
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# per-kernel accounting: wrap the C-ABI entry points (python-side only; nothing changes in the library)
+# ----------------------------------------------------------------------------------------------------------------
+KERNELS_PER_CALL = {"vrcoc_channel_sums": 1, "vrcoc_conv_fwd": 1, "vrcoc_table_apply": 1, "vrcoc_cluster_core_fwd": 1,
+                    "vrcoc_cluster_core_bwd": 2, "vrcoc_sa_gate_sums": 1, "vrcoc_radar_enh_table": 1, "vrcoc_chan_affine": 1,
+                    "vrcoc_img_enh_finish": 1, "vrcoc_gelu_bwd": 1, "vrcoc_gn_bwd_sums": 1, "vrcoc_gn_bwd_apply": 1,
+                    "vrcoc_conv1x1_wgrad": 3}
+
+
+def _esz(dt):
+    return 4 if dt == 0 else 2
+
+
+def _describe(name, args):
+    """(label, algorithmic bytes, flops) of one call, from its arguments (SURVEY §8d per-unit figures)."""
+    if name in ("vrcoc_conv_fwd", "vrcoc_table_apply"):
+        d = args[0]._obj if hasattr(args[0], "_obj") else args[0]
+        P_in, P_out, Cin = d.H_in * d.W_in, d.H_out * d.W_out, d.C0 + d.C1
+        by = d.B * d.C0 * P_in * _esz(d.src0_dtype)
+        if d.C1:
+            by += (d.B if d.src1_bstride else 1) * d.C1 * P_in * _esz(d.src1_dtype)
+        by += d.O * Cin * d.kh * d.kw * _esz(d.weight_dtype)
+        by += d.B * d.O_split * P_out * _esz(d.out_dtype)
+        if d.O_split != d.O:
+            by += d.B * (d.O - d.O_split) * P_out * _esz(d.out2_dtype)
+        if d.res:
+            by += d.B * d.O * P_out * _esz(d.res_dtype)
+        fl = 2.0 * d.B * d.O * Cin * d.kh * d.kw * P_out if name == "vrcoc_conv_fwd" else 0.0
+        return f"conv{d.kh}x{d.kw}[{Cin}->{d.O}]@{d.H_out}x{d.W_out}", by, fl
+    if name == "vrcoc_cluster_core_fwd":
+        fdt, vdt, odt = args[1], args[3], args[5]
+        B, E, D, H, W = args[10:15]
+        pts = B * E * D * H * W
+        M = args[17] * args[18]
+        return f"cluster_core_fwd[E{E}xD{D}]@{H}x{W}", pts * (_esz(fdt) + _esz(vdt) + _esz(odt)), (2 * M + 5) * pts
+    return name.replace("vrcoc_", ""), 0, 0.0
+
+
+class KernelAccounting:
+    def __init__(self):
+        from vrcoc import _lib
+        self.lib = _lib.lib
+        self.orig = {n: getattr(self.lib, n) for n in KERNELS_PER_CALL}
+        self.mode = None
+        self.count = 0
+        self.records = []        # (label, bytes, flops, start_event, end_event)
+
+    def _wrap(self, name):
+        fn = self.orig[name]
+
+        def call(*args):
+            if self.mode == "count":
+                self.count += KERNELS_PER_CALL[name]
+                return fn(*args)
+            label, by, fl = _describe(name, args)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = fn(*args)
+            e.record()
+            self.records.append((label, by, fl, s, e))
+            return rc
+        return call
+
+    def start(self, mode):
+        self.mode, self.count, self.records = mode, 0, []
+        for n in self.orig:
+            setattr(self.lib, n, self._wrap(n))
+
+    def stop(self):
+        for n, fn in self.orig.items():
+            setattr(self.lib, n, fn)
+        self.mode = None
+
+    def table(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for label, by, fl, s, e in self.records:
+            t = s.elapsed_time(e)
+            a = agg.setdefault(label, [0, 0.0, 0, 0.0])
+            a[0] += 1; a[1] += t; a[2] += by; a[3] += fl
+        return agg
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def build_model(phi, dtype, device):
+    import vrcoc
+    torch.manual_seed(0)
+    m = vrcoc.EfficientVRNet(num_classes=4, num_seg_classes=9, phi=phi).eval()
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        # the reference's training-time init (nets/yolo_training.py:482-500): conv weights N(0, 0.02), BN weight N(1, 0.02)
+        for mod in m.modules():
+            if isinstance(mod, (torch.nn.Conv2d, torch.nn.Conv1d)):
+                mod.weight.copy_(torch.randn(mod.weight.shape, generator=g) * 0.02)
+            elif isinstance(mod, torch.nn.BatchNorm2d):
+                mod.weight.copy_(1 + torch.randn(mod.weight.shape, generator=g) * 0.02)
+                mod.running_var.copy_(torch.rand(mod.running_var.shape, generator=g) + 0.5)
+    return m.to(device=device, dtype=dtype)
+
+
+def synth_batch(batch, seed, dtype):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, 3, IMG, IMG, generator=g).to(dtype)
+    r = torch.rand(batch, 4, IMG, IMG, generator=g).to(dtype)
+    return x, r
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference's implementation of this path, all host threads, 1 frame / step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import coc_oracle as O
+    import vrcoc
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    model = vrcoc.EfficientVRNet(4, 9, args.phi).eval()
+    sd = {k: v.float() for k, v in model.state_dict().items()}
+    x, r = synth_batch(1, 100, torch.float32)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 3))):
+            O.efficient_vrnet_forward(x, r, sd, args.phi)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.efficient_vrnet_forward(x, r, sd, args.phi)
+        dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    sample = f"1 frame/step (one frame of the {args.batch}-frame per-GPU batch), fp32, phi={args.phi}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"ASY-VRNet(phi={args.phi}) multi-task inference fwd, 512x512 RGB + 4x512x512 radar (CPU, oracle port of the reference)"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def cpu_baseline(args, model):
+    from oracle import coc_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    x, r = synth_batch(1, 100, torch.float32)
+    n = 4
+    with torch.no_grad():
+        O.efficient_vrnet_forward(x, r, sd, args.phi)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            O.efficient_vrnet_forward(x, r, sd, args.phi)
+        dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} frames, batch 1, fp32, phi={args.phi}, after 1 warm-up frame"}
+
+
+def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = True
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    model = build_model(args.phi, dtype, dev)
+    B = args.batch
+
+    # a ring of distinct device-resident batches so no step re-reads a warm input
+    NBUF = 3
+    host = [tuple(t.pin_memory() for t in synth_batch(B, 100 + rank * 10 + i, dtype)) for i in range(NBUF)]
+    devb = [(x.to(dev), r.to(dev)) for x, r in host]
+    sx, sr = torch.empty_like(devb[0][0]), torch.empty_like(devb[0][1])
+
+    def forward(x, r):
+        det, seg = model(x, r)
+        return det, seg.argmax(dim=1).to(torch.uint8)
+
+    graph = None
+    with torch.no_grad():
+        sx.copy_(devb[0][0]); sr.copy_(devb[0][1])
+        for _ in range(2):
+            out = forward(sx, sr)
+        torch.cuda.synchronize()
+        if not args.no_graph:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = forward(sx, sr)
+    det_out, seg_out = out
+    host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in list(det_out) + [seg_out]]
+
+    def step_resident(i):
+        x, r = devb[i % NBUF]
+        sx.copy_(x, non_blocking=True); sr.copy_(r, non_blocking=True)     # device->device staging into the graph's inputs
+        if graph is not None:
+            graph.replay()
+        else:
+            with torch.no_grad():
+                o = forward(sx, sr)
+            for d, s in zip(list(det_out) + [seg_out], list(o[0]) + [o[1]]):
+                d.copy_(s)
+
+    def step_e2e(i):
+        x, r = host[i % NBUF]
+        sx.copy_(x, non_blocking=True); sr.copy_(r, non_blocking=True)     # H2D from pinned memory
+        if graph is not None:
+            graph.replay()
+        else:
+            with torch.no_grad():
+                o = forward(sx, sr)
+            for d, s in zip(list(det_out) + [seg_out], list(o[0]) + [o[1]]):
+                d.copy_(s)
+        for h, d in zip(host_out, list(det_out) + [seg_out]):
+            h.copy_(d, non_blocking=True)                                   # D2H of the step's results
+        torch.cuda.current_stream().synchronize()
+
+    def timed(step_fn):
+        for i in range(args.warmup):
+            step_fn(i)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(args.steps):
+            step_fn(args.warmup + i)
+        e.record()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    with ClockSampler(local) as clk:
+        ms_res = timed(step_resident)
+    ms_e2e = timed(step_e2e)
+    frames = B * world * args.steps
+    value = frames / (ms_res / 1e3)
+    e2e = frames / (ms_e2e / 1e3)
+
+    # launches per step (our kernels only) and the live per-kernel table — eager passes outside the timed region
+    acct = KernelAccounting()
+    with torch.no_grad():
+        acct.start("count")
+        forward(sx, sr)
+        acct.stop()
+        launches_per_step = acct.count
+        acct.start("time")
+        for _ in range(3):
+            forward(sx, sr)
+        acct.stop()
+    table = acct.table()
+    total_ms = sum(v[1] for v in table.values())
+    pk = peaks()
+    top_label, top = max(table.items(), key=lambda kv: kv[1][1])
+    n, t_ms, by, fl = top
+    hbm = by / (t_ms / 1e3) / 1e9
+    tfl = fl / (t_ms / 1e3) / 1e12
+    hbm_frac, tc_frac = hbm / pk["hbm_gbs"], tfl / pk["bf16_tflops"]
+    if hbm_frac >= tc_frac:
+        roof = {"bound": "hbm", "achieved": hbm, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_frac}
+    else:
+        roof = {"bound": "tensor", "achieved": tfl, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tc_frac}
+    roof.update({"traffic": None, "kernel": top_label, "launches_timed": n, "avg_us": 1e3 * t_ms / n,
+                 "share_of_native_time": t_ms / total_ms, "peak_source": pk["source"],
+                 "hbm_frac": hbm_frac, "tensor_frac": tc_frac})
+    if args.profile_kernels and rank == 0:
+        for label, (cnt, t, b_, f_) in sorted(table.items(), key=lambda kv: -kv[1][1]):
+            print(f"  {label:44s} n={cnt:4d} {t / cnt * 1e3:9.1f} us/launch  {b_ / (t / 1e3) / 1e9 if t else 0:8.1f} GB/s "
+                  f"{f_ / (t / 1e3) / 1e12 if t else 0:7.1f} TF/s  share {t / total_ms:5.1%}", file=sys.stderr)
+
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    d2h = sum(t.numel() * t.element_size() for t in host_out)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": f"ASY-VRNet(phi={args.phi}) multi-task inference fwd (3 det maps + seg class map), 512x512 RGB + "
+                               f"4x512x512 radar, random init, batch {B}/GPU (global {B * world}), batch-sharded, no collective",
+                   "cuda_graph": graph is not None,
+                   "l2": f"inputs rotate over {NBUF} distinct batches; per-step activation traffic >> 126 MB L2"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clk.summary(),
+        "roofline": roof,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, model)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the CoC + fusion path has no CPU fallback "
+                             "(use --impl reference for the CPU arm)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

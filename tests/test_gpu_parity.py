@@ -134,7 +134,7 @@ def test_block_stock_layer_scale(V):
     mod, xs, y = _run_module(V.ClusterBlock(**fx.cfg), fx, ["x"])
     assert rel_err(y, fx.out["y"]) < 1e-6
     inc, ref_inc = y.detach().double().cpu() - fx.inp["x"].double(), fx.out["y"] - fx.inp["x"].double()
-    assert rel_err(inc, ref_inc) < 1e-2      # fp32 cancellation: the increment is 1e-5 of the signal
+    assert rel_err(inc, ref_inc) < 1e-1      # fp32 resolution: the increment is ~1e-6 of an O(1) signal (eps/1e-6 ~ 6e-2)
     _check_grads(mod, fx, xs, ["x"], y, FP32_TOL)
 
 
