@@ -1,0 +1,112 @@
+"""GPU: the two variants of the convolution-as-GEMM engine against each other and against a plain fp32 reference of
+the same op (torch conv2d on the same, already bf16-rounded, operands; TF32 disabled).  The tcgen05 variant must agree
+with the CUDA-core variant to accumulation-order noise: both multiply the same bf16 values with fp32 accumulation."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from golden_util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # B, C, O, H, W, k, stride, pad
+    (2, 64, 128, 16, 16, 1, 1, 0),        # one k-slab, one 128-point tile pair
+    (1, 64, 256, 128, 128, 1, 1, 0),      # S1 fc1|fc_v: N tile 256
+    (2, 320, 1280, 32, 32, 1, 1, 0),      # S3 mlp.fc1: 5 k-slabs, 5 N tiles
+    (2, 1280, 320, 32, 32, 1, 1, 0),      # S3 mlp.fc2: 20 k-slabs, 2 N tiles of 160
+    (1, 96, 512, 16, 16, 1, 1, 0),        # neck fc2: K = 96 (1.5 slabs)
+    (2, 7, 4, 64, 64, 1, 1, 0),           # ingest inverse projection: K = 7, O = 4
+    (1, 24, 40, 8, 8, 1, 1, 0),           # 64 points: half-empty M tile
+    (2, 4, 3, 64, 64, 3, 1, 1),           # ingest radar projection 3x3: K = 36 (not a multiple of 8)
+    (1, 64, 128, 32, 32, 3, 2, 1),        # point reducer 3x3 / stride 2
+    (2, 5, 64, 64, 64, 4, 4, 0),          # patch embed 4x4 / stride 4
+    (1, 128, 128, 16, 16, 3, 1, 1),       # fusion radar projection 3x3
+]
+
+
+@pytest.fixture(scope="module")
+def env():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from vrcoc import ops
+    return ops
+
+
+def _run(ops, x, w, engine, stride, pad, out_dtype=torch.float32, **kw):
+    from vrcoc._lib import check, lib
+    B, C, H, W = x.shape
+    O, _, kh, kwid = w.shape
+    Ho, Wo = ops.out_hw(H, W, kh, stride, pad)
+    out = torch.empty(B, O, Ho, Wo, device=x.device, dtype=out_dtype)
+    d = ops.conv_desc(x, w.reshape(O, -1).contiguous(), out, kh=kh, kw=kwid, stride=stride, pad=pad, engine=engine, **kw)
+    ops.conv_fwd(d)
+    return out
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=[f"C{s[1]}_O{s[2]}_{s[3]}x{s[4]}_k{s[5]}s{s[6]}" for s in SHAPES])
+def test_tcgen05_matches_reference_and_simt(env, shape):
+    ops = env
+    B, C, O, H, W, k, stride, pad = shape
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, C, H, W, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(O, C, k, k, generator=g) / (C * k * k) ** 0.5).to(torch.bfloat16).cuda()
+    ref = F.conv2d(x.float(), w.float(), None, stride=stride, padding=pad)
+    simt = _run(ops, x, w, 1, stride, pad)
+    tc = _run(ops, x, w, 2, stride, pad)
+    assert rel_err(simt, ref) < 1e-5
+    assert rel_err(tc, ref) < 1e-5, "tcgen05 engine disagrees with the fp32 reference"
+    assert rel_err(tc, simt) < 1e-5
+
+
+def test_tcgen05_full_epilogue_and_prologue(env):
+    """GroupNorm prologue (transform-on-load rounds the normalised activation to bf16 once), bias + GELU, layer-scale,
+    residual, final affine, split outputs and the per-sample side statistics"""
+    ops = env
+    g = torch.Generator().manual_seed(11)
+    B, C, O, H, W = 2, 64, 192, 32, 32
+    x = (torch.randn(B, C, H, W, generator=g) * 1.5 + 0.3).to(torch.bfloat16).cuda()
+    w = (torch.randn(O, C, 1, 1, generator=g) / C ** 0.5).to(torch.bfloat16).cuda()
+    gamma = (torch.rand(C, generator=g) + 0.5).cuda()
+    beta = (torch.randn(C, generator=g) * 0.1).cuda()
+    bias = (torch.randn(O, generator=g) * 0.1).cuda()
+    ls = (torch.rand(O, generator=g) + 0.5).cuda()
+    fs, fh = (torch.rand(O, generator=g) + 0.5).cuda(), torch.randn(O, generator=g).cuda()
+    res = torch.randn(B, O, H, W, generator=g).to(torch.bfloat16).cuda()
+    _, sums = ops.channel_sums(x, want_chan=False, want_sample=True)
+    xn = F.group_norm(x.float(), 1, gamma, beta, 1e-5)
+    ref = F.gelu(F.conv2d(xn, w.float(), bias)) * ls.view(1, -1, 1, 1) + res.float()
+    ref = ref * fs.view(1, -1, 1, 1) + fh.view(1, -1, 1, 1)
+    outs = {}
+    for engine in (1, 2):
+        from vrcoc._lib import ACT_GELU
+        o1 = torch.empty(B, 64, H, W, device="cuda", dtype=torch.float32)
+        o2 = torch.empty(B, O - 64, H, W, device="cuda", dtype=torch.bfloat16)
+        ss = torch.zeros(B, 2, device="cuda", dtype=torch.float64)
+        d = ops.conv_desc(x, w.reshape(O, C).contiguous(), o1, gn=(sums, gamma, beta, 1e-5), e_shift=bias, act=ACT_GELU,
+                          post_scale=ls, res=res, f_scale=fs, f_shift=fh, out2=o2, out_sample_sums=ss, engine=engine)
+        ops.conv_fwd(d)
+        got = torch.cat([o1, o2.float()], 1)
+        outs[engine] = got
+        tol = 1e-5 if engine == 1 else 6e-3          # engine 2 rounds GN(x) to bf16 before the tensor core
+        assert rel_err(got[:, :64], ref[:, :64]) < tol, engine
+        assert rel_err(got, ref) < 5e-3, engine      # bf16 storage of the second output
+        full = ref.double()
+        assert abs(ss[:, 0].sum().item() - full.sum().item()) < 2e-2 * full.abs().sum().item() ** 0.5 + 1e-3 * abs(full.sum().item())
+        assert abs(ss[:, 1].sum().item() / (full ** 2).sum().item() - 1) < 1e-2
+
+
+def test_auto_engine_picks_tcgen05_for_bf16_weights(env):
+    """fp32 weights -> exact CUDA-core path; bf16 weights -> tensor cores.  Seen through the numerics: with fp32
+    activations and bf16 weights the tcgen05 path rounds the activation operand to bf16, the CUDA-core path does not."""
+    ops = env
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 64, 16, 16, generator=g).cuda()
+    w = (torch.randn(64, 64, 1, 1, generator=g) / 8).to(torch.bfloat16).cuda()
+    ref = F.conv2d(x, w.float())
+    auto = _run(ops, x, w, 0, 1, 0)
+    simt = _run(ops, x, w, 1, 1, 0)
+    assert rel_err(simt, ref) < 1e-6
+    e = rel_err(auto, ref)
+    assert 1e-4 < e < 6e-3, e
