@@ -7,16 +7,27 @@
 //   smem tile holds 64 consecutive points (128 B) of one logical input channel, two 64-point blocks per tile,
 //   128-byte swizzled — the canonical UMMA layout  Sw<3,4,3> o ((8,2),(8,k)) : ((1,LBO),(8,SBO))  in 16-byte units
 //   with LBO = 8192 B (next 64-point block) and SBO = 1024 B (next group of 8 k-rows).
-// * A is produced by the CTA's own threads ("transform on load"): 128-bit coalesced global loads, the prologue
-//   (GroupNorm apply / attention gate / ECA scale / channel shuffle / im2col gather) applied in registers in fp32, one
-//   rounding to bf16, one 16-byte swizzled st.shared.  The normalised / gated / gathered activation never exists in HBM,
-//   and no weight folding (with its cancellation problem) is needed.
-// * B = weights [O][K] row-major = K-major operand: 8-row x 128-byte swizzle atoms, SBO = 1024 B.
-// * One elected thread issues tcgen05.mma (M=128, N=N_tile, K=16) per 16 k; completion is tracked with tcgen05.commit on
-//   mbarriers: one per smem stage (frees the stage for the next slab) and one for the finished accumulator.
+// * B = weights [O][K] row-major = K-major operand, fetched by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B box of
+//   64 k x N rows, out-of-range rows/columns zero-filled by the hardware) straight into the UMMA layout.
+// * Two kernels share the epilogue:
+//   conv_tc_tma_kernel   — prologue-free 1x1 projections (Cluster.fc2, Mlp.fc2, BaseConv 1x1, dgrad): A also arrives
+//                          by TMA (3-D map [B][C][P], two 64-point x 64-channel boxes per slab land directly in the
+//                          MN-major layout).  Warp-specialised: one producer thread runs the TMA ring ahead, one thread
+//                          issues tcgen05.mma; no SM instruction touches the operands.
+//   conv_tc_xform_kernel — everything with a prologue or a gather (GroupNorm->fc1|fc_v, GroupNorm->mlp.fc1, the
+//                          attention/ECA/shuffle prologue of RadarEnhanceByImage, k x k convs): A is produced by the
+//                          CTA's threads ("transform on load"): 128-bit coalesced loads, prologue in fp32 registers, one
+//                          rounding to bf16, one swizzled 16-byte st.shared; the raw loads of slab k+1 are in flight while
+//                          the tensor core works on slab k.  The normalised/gated/gathered activation never exists in HBM.
+// * tcgen05.commit on per-stage mbarriers frees smem stages; a last commit publishes the accumulator.
 // * Epilogue: 8 warps read the accumulator with tcgen05.ld (32 lanes x 16 columns per instruction; warp w owns TMEM lanes
-//   32*(w%4).. and column half w/4), apply bias/BN/activation/layer-scale/residual/BN and the side statistics in
-//   registers and store NCHW directly: lane = point, so every output channel is a coalesced 64/128-byte store per warp.
+//   32*(w%4).. and column half w/4), apply bias/BN/activation/layer-scale/residual/BN (coefficients staged in smem) and the
+//   side statistics in registers and store NCHW directly: lane = point, so every output channel is one coalesced
+//   64/128-byte store per warp.  ncu (profiles/) showed the first version of this epilogue was issue-bound at ~160 SASS
+//   instructions per output column; pointers are therefore hoisted, coefficients read with ld.shared, the activation is
+//   a template parameter and GELU uses a branch-free erfc (|err| < 2e-7, bf16 outputs).
+#include <cuda.h>
+
 #include "conv_common.cuh"
 
 namespace vrcoc {
@@ -26,7 +37,7 @@ constexpr int TC_BM = 128;            // points per CTA
 constexpr int TC_BK = 64;             // k per smem slab (128 B of bf16 per B row)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;       // 16 KB
 constexpr int TC_A_LBO = 64 * TC_BK * 2;            // 8192 B: second 64-point block
-constexpr int TC_STAGES = 2;
+constexpr int TC_MAX_STAGES = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -47,6 +58,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
   } while (!done);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+      : "memory");
 }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -77,16 +103,23 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
       : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+// issue the K=16 MMAs of one slab
+__device__ __forceinline__ void issue_slab_mmas(uint32_t tmem_base, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, int ksteps,
+                                                bool first_slab) {
+  for (int j = 0; j < ksteps; ++j) {
+    const uint64_t ad = make_desc(a_addr + j * 2048, TC_A_LBO, 1024);   // 16 k-rows = two 8-row groups
+    const uint64_t bd = make_desc(b_addr + j * 32, 16, 1024);           // 16 k = 32 B inside the 128 B row
+    tc_mma(tmem_base, ad, bd, idesc, (!first_slab || j > 0) ? 1u : 0u);
+  }
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
@@ -97,47 +130,337 @@ __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
   return r;
 }
 
+// branch-free GELU: 0.5 x (1 + erf(x/sqrt2)) through erfc(|z|) ~ poly(t) exp(-z^2), t = 1/(1 + p|z|)  (A&S 7.1.26,
+// |erfc error| < 1.5e-7); the two tails are formed without cancellation.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float u = p * t * __expf(-z * z);          // erfc(|z|)
+  const float half_u = 0.5f * u;
+  return x * (x >= 0.f ? 1.0f - half_u : half_u);
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_tc(float y) {
+  if (ACT == VRCOC_ACT_RELU) return fmaxf(y, 0.f);
+  if (ACT == VRCOC_ACT_GELU) return gelu_fast(y);
+  if (ACT == VRCOC_ACT_SILU) return y * sigmoidf_exact(y);
+  if (ACT == VRCOC_ACT_LRELU) return y > 0.f ? y : 0.1f * y;
+  return y;
+}
+
 struct TcLayout {
   int n_tile;       // output channels per CTA (multiple of 32, <= 256)
   int tmem_cols;    // power of two >= 32
   int b_bytes;      // n_tile * 128
-  int off_b, off_tab, off_bar, total;
+  int stages;
+  int use_tma_b;    // weights via TMA
+  int plain_epi;    // epilogue is y = act(acc*es + eh) into `out` only (no residual / post / final affine / stats / split)
+  int off_b, off_tab, off_epi, off_bar, total;
 };
 
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(ConvArgs a, TcLayout L) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  // 1024-byte alignment is required by the 128-byte swizzle atoms
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* sA = smem;                                   // [STAGES][16 KB]
-  unsigned char* sB = smem + L.off_b;                         // [STAGES][b_bytes]
-  float4* tab = reinterpret_cast<float4*>(smem + L.off_tab);  // [Cin]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);   // [STAGES] stage-free + [1] accumulator-done
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TC_STAGES + 1);
+struct TcSmem {
+  unsigned char* base;
+  unsigned char* sA; unsigned char* sB; float4* tab; float* epi;
+  uint64_t* bar_free; uint64_t* bar_full; uint64_t* bar_acc; uint32_t* tmem_slot;
+};
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.z;
-  const int p0 = blockIdx.x * TC_BM;
-  const int n0 = blockIdx.y * L.n_tile;
-  const int P = a.P_out;
-  const int taps = a.kh * a.kw;
+__device__ __forceinline__ TcSmem carve(unsigned char* smem_raw, const TcLayout& L) {
+  // 1024-byte alignment is required by the 128-byte swizzle atoms; computed on the shared-space address so that the
+  // compiler keeps emitting ld/st.shared for everything derived from it
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  TcSmem s;
+  s.base = smem_raw + pad;
+  s.sA = s.base;
+  s.sB = s.base + L.off_b;
+  s.tab = reinterpret_cast<float4*>(s.base + L.off_tab);
+  s.epi = reinterpret_cast<float*>(s.base + L.off_epi);
+  s.bar_free = reinterpret_cast<uint64_t*>(s.base + L.off_bar);
+  s.bar_full = s.bar_free + TC_MAX_STAGES;
+  s.bar_acc = s.bar_full + TC_MAX_STAGES;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar_acc + 1);
+  return s;
+}
 
+// common prologue: TMEM allocation, barrier init, epilogue coefficient staging
+__device__ __forceinline__ uint32_t tc_setup(const ConvArgs& a, const TcLayout& L, const TcSmem& S, int n0) {
+  const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)L.tmem_cols));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(S.tmem_slot)), "r"((uint32_t)L.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 32) {
-    for (int i = 0; i < TC_STAGES + 1; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < L.stages; ++i) { mbar_init(&S.bar_free[i], 1); mbar_init(&S.bar_full[i], 1); }
+    mbar_init(S.bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  build_prologue_table(a, b, tab);
+  for (int n = tid; n < L.n_tile; n += TC_THREADS) {
+    const int o = n0 + n;
+    const bool in = o < a.O;
+    S.epi[n] = (in && a.e_scale) ? a.e_scale[o] : 1.f;
+    S.epi[L.n_tile + n] = (in && a.e_shift) ? a.e_shift[o] : 0.f;
+    S.epi[2 * L.n_tile + n] = (in && a.post_scale) ? a.post_scale[o] : 1.f;
+    S.epi[3 * L.n_tile + n] = (in && a.f_scale) ? a.f_scale[o] : 1.f;
+    S.epi[4 * L.n_tile + n] = (in && a.f_shift) ? a.f_shift[o] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  return *S.tmem_slot;
+}
+
+// ---- epilogue -------------------------------------------------------------------------------------------------------------
+// PLAIN: out[o] = act(acc*es + eh), single output tensor of type TO.
+template <int ACT, typename TO>
+__device__ __forceinline__ void epi_plain(const ConvArgs& a, const TcLayout& L, const float* epi, uint32_t tbase, int c_begin,
+                                          int c_end, int n0, int b, int q, bool valid) {
+  const int64_t P = a.P_out;
+  TO* optr = reinterpret_cast<TO*>(a.out) + ((int64_t)b * a.O + n0 + c_begin) * P + q;
+  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tbase + (uint32_t)c0, r);
+    const int lim = min(16, a.O - n0 - c0);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < lim) {
+        const float y = act_tc<ACT>(fmaf(__uint_as_float(r[j]), epi[c0 + j], epi[L.n_tile + c0 + j]));
+        if (valid) stf<TO>(optr, y);
+      }
+      optr += P;
+    }
+  }
+}
+
+// FULL: y = act(acc*es + eh)*ps + res; y = y*fs + fh; split outputs; side statistics.
+template <int ACT>
+__device__ __forceinline__ void epi_full(const ConvArgs& a, const TcLayout& L, const float* epi, uint32_t tbase, int c_begin,
+                                         int c_end, int n0, int b, int q, bool valid) {
+  const int64_t P = a.P_out;
+  const int nt = L.n_tile;
+  float ssum = 0.f, ssq = 0.f, vmax = 0.f, vmin = __int_as_float(0x7f800000);
+  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tbase + (uint32_t)c0, r);
+    const int o0 = n0 + c0;
+    const int lim = min(16, a.O - o0);
+    // a 16-column group never straddles O_split when O_split % 16 == 0 (checked on the host)
+    const bool second = o0 >= a.O_split;
+    const int odt = second ? a.out2_dtype : a.out_dtype;
+    unsigned char* obase = reinterpret_cast<unsigned char*>(second ? a.out2 : a.out);
+    const int64_t ochan = second ? ((int64_t)b * (a.O - a.O_split) + (o0 - a.O_split)) : ((int64_t)b * a.O_split + o0);
+    const int64_t oidx = ochan * P + q;
+    const int64_t ridx = ((int64_t)b * a.O + o0) * P + q;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < lim && valid) {
+        const int n = c0 + j;
+        float y = act_tc<ACT>(fmaf(__uint_as_float(r[j]), epi[n], epi[nt + n]));
+        float res = 0.f;
+        if (a.res) res = (a.res_dtype == VRCOC_BF16) ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.res)[ridx + j * P])
+                                                      : reinterpret_cast<const float*>(a.res)[ridx + j * P];
+        y = fmaf(y, epi[2 * nt + n], res);
+        y = fmaf(y, epi[3 * nt + n], epi[4 * nt + n]);
+        ssum += y; ssq = fmaf(y, y, ssq);
+        vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
+        if (odt == VRCOC_BF16) reinterpret_cast<__nv_bfloat16*>(obase)[oidx + j * P] = __float2bfloat16_rn(y);
+        else reinterpret_cast<float*>(obase)[oidx + j * P] = y;
+      }
+    }
+  }
+  emit_side_stats(a, b, ssum, ssq, vmax, vmin);
+}
+
+__device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcLayout& L, const TcSmem& S, uint32_t tmem_base, int p0,
+                                            int n0, int b) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lq = warp & 3, chalf = warp >> 2;
+  const int q = p0 + lq * 32 + lane;
+  const bool valid = q < a.P_out;
+  const int ncols = L.n_tile >> 1;
+  const uint32_t tbase = tmem_base + ((uint32_t)(lq * 32) << 16);
+  const int c_begin = chalf * ncols;
+  int c_end = (chalf + 1) * ncols;
+  if (c_end > a.O - n0) c_end = a.O - n0;        // warp-uniform: skip all-padding column groups
+  if (L.plain_epi) {
+    const bool bf = a.out_dtype == VRCOC_BF16;
+#define PLAIN(ACTV)                                                                                        \
+  if (bf) epi_plain<ACTV, __nv_bfloat16>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid);             \
+  else epi_plain<ACTV, float>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid)
+    switch (a.act) {
+      case VRCOC_ACT_NONE: PLAIN(VRCOC_ACT_NONE); break;
+      case VRCOC_ACT_RELU: PLAIN(VRCOC_ACT_RELU); break;
+      case VRCOC_ACT_GELU: PLAIN(VRCOC_ACT_GELU); break;
+      case VRCOC_ACT_SILU: PLAIN(VRCOC_ACT_SILU); break;
+      default: PLAIN(VRCOC_ACT_LRELU); break;
+    }
+#undef PLAIN
+  } else {
+    switch (a.act) {
+      case VRCOC_ACT_NONE: epi_full<VRCOC_ACT_NONE>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid); break;
+      case VRCOC_ACT_RELU: epi_full<VRCOC_ACT_RELU>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid); break;
+      case VRCOC_ACT_GELU: epi_full<VRCOC_ACT_GELU>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid); break;
+      case VRCOC_ACT_SILU: epi_full<VRCOC_ACT_SILU>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid); break;
+      default: epi_full<VRCOC_ACT_LRELU>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid); break;
+    }
+  }
+}
+
+__device__ __forceinline__ void tc_teardown(const TcLayout& L, uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L.tmem_cols));
+  }
+}
+
+// ---- kernel 1: both operands by TMA, warp-specialised -----------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 4) conv_tc_tma_kernel(ConvArgs a, TcLayout L, const __grid_constant__ CUtensorMap tmapA,
+                                                                 const __grid_constant__ CUtensorMap tmapB) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const TcSmem S = carve(smem_raw, L);
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z, p0 = blockIdx.x * TC_BM, n0 = blockIdx.y * L.n_tile;
+  if (tid == 64) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapB)) : "memory");
+  }
+  const uint32_t tmem_base = tc_setup(a, L, S, n0);
+  const int nk = (a.K + TC_BK - 1) / TC_BK;
+  const int NS = L.stages;
+  if (tid == 0) {
+    // producer: keeps the TMA ring full
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % NS;
+      if (kc >= NS) mbar_wait(&S.bar_free[s], (uint32_t)((kc / NS) - 1) & 1);
+      mbar_expect_tx(&S.bar_full[s], (uint32_t)(TC_A_BYTES + L.b_bytes));
+      unsigned char* As = S.sA + s * TC_A_BYTES;
+      tma_load_3d(As, &tmapA, p0, kc * TC_BK, b, &S.bar_full[s]);
+      tma_load_3d(As + TC_A_LBO, &tmapA, p0 + 64, kc * TC_BK, b, &S.bar_full[s]);
+      tma_load_2d(S.sB + s * L.b_bytes, &tmapB, kc * TC_BK, n0, &S.bar_full[s]);
+    }
+  } else if (tid == 32) {
+    // MMA issuer
+    const uint32_t idesc = make_idesc(L.n_tile);
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % NS;
+      mbar_wait(&S.bar_full[s], (uint32_t)(kc / NS) & 1);
+      tc_fence_after();
+      const int ksteps = (min(TC_BK, a.K - kc * TC_BK) + 15) >> 4;
+      issue_slab_mmas(tmem_base, smem_u32(S.sA + s * TC_A_BYTES), smem_u32(S.sB + s * L.b_bytes), idesc, ksteps, kc == 0);
+      tc_commit(&S.bar_free[s]);
+      if (kc == nk - 1) tc_commit(S.bar_acc);
+    }
+  }
+  __syncwarp();
+  mbar_wait(S.bar_acc, 0);
+  tc_fence_after();
+  tc_epilogue(a, L, S, tmem_base, p0, n0, b);
+  tc_teardown(L, tmem_base);
+}
+
+// ---- kernel 2: transform-on-load A ------------------------------------------------------------------------------------------
+// raw (untransformed) slab data of one thread: 4 k-rows x 8 points, kept in the source dtype so that no instruction
+// depends on the loads until the next iteration's transform (the loads stay in flight across the MMA issue)
+template <typename TS>
+struct __align__(16) RawSlab {
+  TS v[32];
+  uint32_t mask;   // bit (i*8+j) = element (row i, point j) is a real in-range input
+};
+
+template <typename TS, bool FAST>
+__device__ __forceinline__ void slab_gload(const ConvArgs& a, int b, int kc, int a_krow0, int q0, int P, int taps, RawSlab<TS>& raw) {
+  raw.mask = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int kk = kc * TC_BK + a_krow0 + 16 * i;
+    if (kk >= a.K || q0 >= P) continue;
+    const int c = FAST ? kk : kk / taps;
+    const int sc = a.chan_src ? __ldg(a.chan_src + c) : c;
+    const TS* src;
+    if (sc < a.C0) src = reinterpret_cast<const TS*>(a.src0) + (int64_t)b * a.src0_bstride + (int64_t)sc * a.P_in;
+    else src = reinterpret_cast<const TS*>(a.src1) + (int64_t)b * a.src1_bstride + (int64_t)(sc - a.C0) * a.P_in;
+    if (FAST) {
+      raw.mask |= 0xFFu << (8 * i);
+      if (sizeof(TS) == 2) {
+        reinterpret_cast<uint4*>(raw.v)[i] = __ldg(reinterpret_cast<const uint4*>(src + q0));
+      } else {
+        reinterpret_cast<float4*>(raw.v)[2 * i] = __ldg(reinterpret_cast<const float4*>(src + q0));
+        reinterpret_cast<float4*>(raw.v)[2 * i + 1] = __ldg(reinterpret_cast<const float4*>(src + q0) + 1);
+      }
+    } else {
+      const int tap = kk - c * taps;
+      const int ky = tap / a.kw, kx = tap - ky * a.kw;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int q = q0 + j;
+        if (q < P) {
+          const int oy = q / a.W_out, ox = q - oy * a.W_out;
+          const int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
+          if (iy >= 0 && iy < a.H_in && ix >= 0 && ix < a.W_in) {
+            raw.v[8 * i + j] = src[(int64_t)iy * a.W_in + ix];
+            raw.mask |= 1u << (8 * i + j);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename TS, bool FAST, bool GATE>
+__device__ __forceinline__ void slab_sstore(int kc, int ksteps, int a_krow0, int a_blk, int a_c, int taps, const float4* tab,
+                                            const RawSlab<TS>& raw, unsigned char* As) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = a_krow0 + 16 * i;
+    if (k >= ksteps * 16) continue;
+    const int kk = kc * TC_BK + k;
+    float v[8];
+    const uint32_t mk = (raw.mask >> (8 * i)) & 0xFFu;
+    if (mk == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    } else {
+      if (FAST && sizeof(TS) == 2) {
+        const uint4 r = reinterpret_cast<const uint4*>(raw.v)[i];
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = ((mk >> j) & 1u) ? (float)raw.v[8 * i + j] : 0.f;
+      }
+      const float4 t = tab[FAST ? kk : kk / taps];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x = v[j];
+        float y = fmaf(x, t.x, t.y);
+        if (GATE) y *= sigmoidf_exact(fmaf(t.z, x, t.w));
+        v[j] = (FAST || ((mk >> j) & 1u)) ? y : 0.f;
+      }
+    }
+    *reinterpret_cast<uint4*>(As + a_blk * TC_A_LBO + k * 128 + ((a_c ^ (k & 7)) << 4)) = pack8_bf16(v);
+  }
+}
+
+template <typename TS, bool FAST>
+__global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_xform_kernel(ConvArgs a, TcLayout L, const __grid_constant__ CUtensorMap tmapB) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const TcSmem S = carve(smem_raw, L);
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z, p0 = blockIdx.x * TC_BM, n0 = blockIdx.y * L.n_tile;
+  const int P = a.P_out;
+  const int taps = a.kh * a.kw;
+  const int NS = L.stages;
+  if (tid == 64 && L.use_tma_b) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapB)) : "memory");
+  build_prologue_table(a, b, S.tab);
+  const uint32_t tmem_base = tc_setup(a, L, S, n0);
 
   const int nk = (a.K + TC_BK - 1) / TC_BK;
   const uint32_t idesc = make_idesc(L.n_tile);
-
   // A loader geometry: thread -> (8-point chunk, k-rows krow0 + 16*i)
   const int a_chunk = tid & 15;            // points a_chunk*8 .. +8 of the tile
   const int a_krow0 = tid >> 4;            // 0..15
@@ -145,170 +468,186 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(ConvArgs a, TcLayou
   const int a_c = a_chunk & 7;             // 16-byte chunk inside the 128-byte row
   const int q0 = p0 + a_chunk * 8;
 
+  RawSlab<TS> raw;
+  slab_gload<TS, FAST>(a, b, 0, a_krow0, q0, P, taps, raw);
+
   for (int kc = 0; kc < nk; ++kc) {
-    const int s = kc % TC_STAGES;
-    if (kc >= TC_STAGES) mbar_wait(&bars[s], (uint32_t)(((kc / TC_STAGES) - 1) & 1));
-    const int kvalid = min(TC_BK, a.K - kc * TC_BK);
-    const int ksteps = (kvalid + 15) >> 4;            // MMAs (K=16) for this slab
-    unsigned char* As = sA + s * TC_A_BYTES;
-    unsigned char* Bs = sB + s * L.b_bytes;
+    const int s = kc % NS;
+    const uint32_t use = (uint32_t)(kc / NS);
+    if (kc >= NS) mbar_wait(&S.bar_free[s], (use - 1) & 1);     // MMAs that read this stage have completed
+    const int ksteps = (min(TC_BK, a.K - kc * TC_BK) + 15) >> 4;
+    unsigned char* As = S.sA + s * TC_A_BYTES;
+    unsigned char* Bs = S.sB + s * L.b_bytes;
 
-    // ---- A slab: transform on load ---------------------------------------------------------------------------
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = a_krow0 + 16 * i;
-      if (k >= ksteps * 16) break;
-      const int kk = kc * TC_BK + k;
-      float v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.f;
-      if (kk < a.K && q0 < P) {
-        const int c = kk / taps;
-        const int tap = kk - c * taps;
-        const int sc = a.chan_src ? a.chan_src[c] : c;
-        const void* src; int dt; int64_t base;
-        if (sc < a.C0) { src = a.src0; dt = a.src0_dtype; base = (int64_t)b * a.src0_bstride + (int64_t)sc * a.P_in; }
-        else           { src = a.src1; dt = a.src1_dtype; base = (int64_t)b * a.src1_bstride + (int64_t)(sc - a.C0) * a.P_in; }
-        const float4 t = tab[c];
-        if (a.fast1x1) {
-          if (dt == VRCOC_F32) ld8<float>(reinterpret_cast<const float*>(src) + base + q0, v);
-          else ld8<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(src) + base + q0, v);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float x = v[j];
-            float y = fmaf(x, t.x, t.y);
-            if (a.has_gate) y *= sigmoidf_exact(fmaf(t.z, x, t.w));
-            v[j] = y;
-          }
-        } else {
-          const int ky = tap / a.kw, kx = tap - ky * a.kw;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int q = q0 + j;
-            if (q < P) {
-              const int oy = q / a.W_out, ox = q - oy * a.W_out;
-              const int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
-              if (iy >= 0 && iy < a.H_in && ix >= 0 && ix < a.W_in) {
-                float x = ld_any(src, base + (int64_t)iy * a.W_in + ix, dt);
-                float y = fmaf(x, t.x, t.y);
-                if (a.has_gate) y *= sigmoidf_exact(fmaf(t.z, x, t.w));
-                v[j] = y;
-              }
-            }
-          }
-        }
+    if (L.use_tma_b) {
+      if (tid == 0) {
+        mbar_expect_tx(&S.bar_full[s], (uint32_t)L.b_bytes);
+        tma_load_2d(Bs, &tmapB, kc * TC_BK, n0, &S.bar_full[s]);
       }
-      *reinterpret_cast<uint4*>(As + a_blk * TC_A_LBO + k * 128 + ((a_c ^ (k & 7)) << 4)) = pack8_bf16(v);
-    }
-
-    // ---- B slab: weights, K-major ---------------------------------------------------------------------------------
-    {
-      const int units = L.n_tile * (ksteps * 2);      // 16-byte chunks: n_tile rows x (ksteps*16/8) chunks
-      const int cpr = ksteps * 2;
-      const bool wvec = (a.K % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.weight) & 15) == 0);
+    } else {
+      // tiny / unaligned K: the threads stage B themselves
+      const int cpr = ksteps * 2;                            // 16-byte chunks per row
+      const int units = L.n_tile * cpr;
       const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(a.weight);
       for (int u = tid; u < units; u += TC_THREADS) {
         const int n = u / cpr, c = u - n * cpr;
         const int o = n0 + n;
         const int kk = kc * TC_BK + c * 8;
-        uint4 w = make_uint4(0u, 0u, 0u, 0u);
-        if (o < a.O && kk < a.K) {
-          const __nv_bfloat16* wp = W + (int64_t)o * a.K + kk;
-          if (wvec) {
-            w = __ldg(reinterpret_cast<const uint4*>(wp));
-          } else {
-            __nv_bfloat16 tmp[8];
+        __align__(16) __nv_bfloat16 tmp[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) tmp[j] = (kk + j < a.K) ? wp[j] : __float2bfloat16_rn(0.f);
-            w = *reinterpret_cast<uint4*>(tmp);
-          }
-        }
-        *reinterpret_cast<uint4*>(Bs + (n >> 3) * 1024 + (n & 7) * 128 + ((c ^ (n & 7)) << 4)) = w;
+        for (int j = 0; j < 8; ++j) tmp[j] = (o < a.O && kk + j < a.K) ? W[(int64_t)o * a.K + kk + j] : __float2bfloat16_rn(0.f);
+        *reinterpret_cast<uint4*>(Bs + (n >> 3) * 1024 + (n & 7) * 128 + ((c ^ (n & 7)) << 4)) = *reinterpret_cast<uint4*>(tmp);
       }
     }
 
+    // A slab: transform the prefetched raw data and store it in the UMMA layout
+    if (a.has_gate) slab_sstore<TS, FAST, true>(kc, ksteps, a_krow0, a_blk, a_c, taps, S.tab, raw, As);
+    else slab_sstore<TS, FAST, false>(kc, ksteps, a_krow0, a_blk, a_c, taps, S.tab, raw, As);
     fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
 
     if (tid == 0) {
+      if (L.use_tma_b) mbar_wait(&S.bar_full[s], use & 1);
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(As), b_addr = smem_u32(Bs);
-      for (int j = 0; j < ksteps; ++j) {
-        const uint64_t ad = make_desc(a_addr + j * 2048, TC_A_LBO, 1024);   // 16 k-rows = two 8-row groups
-        const uint64_t bd = make_desc(b_addr + j * 32, 16, 1024);           // 16 k = 32 B inside the 128 B row
-        tc_mma(tmem_base, ad, bd, idesc, (kc > 0 || j > 0) ? 1u : 0u);
-      }
-      tc_commit(&bars[s]);                       // stage s reusable once these MMAs have read it
-      if (kc == nk - 1) tc_commit(&bars[TC_STAGES]);
+      issue_slab_mmas(tmem_base, smem_u32(As), smem_u32(Bs), idesc, ksteps, kc == 0);
+      tc_commit(&S.bar_free[s]);                     // stage s reusable once these MMAs have read it
+      if (kc == nk - 1) tc_commit(S.bar_acc);
     }
+    // prefetch the next slab's raw data: in flight while the tensor core works on this slab
+    if (kc + 1 < nk) slab_gload<TS, FAST>(a, b, kc + 1, a_krow0, q0, P, taps, raw);
   }
 
-  // ---- epilogue ---------------------------------------------------------------------------------------------------------
-  mbar_wait(&bars[TC_STAGES], 0);
+  mbar_wait(S.bar_acc, 0);
   tc_fence_after();
-  const int lq = warp & 3, chalf = warp >> 2;
-  const int m = lq * 32 + lane;
-  const int q = p0 + m;
-  const bool valid = q < P;
-  const int ncols = L.n_tile >> 1;
-  float ssum = 0.f, ssq = 0.f, vmax = 0.f, vmin = __int_as_float(0x7f800000);
-  for (int c0 = chalf * ncols; c0 < (chalf + 1) * ncols; c0 += 16) {
-    if (n0 + c0 >= a.O) break;                   // warp-uniform
-    float acc[16];
-    tmem_ld16(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0, acc);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int o = n0 + c0 + j;
-      if (o < a.O && valid) {
-        const EpiCoef ec = load_epi(a, o);
-        const float r = a.res ? ld_any(a.res, ((int64_t)b * a.O + o) * P + q, a.res_dtype) : 0.f;
-        const float y = epilogue_value(acc[j], ec, a.act, r);
-        ssum += y; ssq = fmaf(y, y, ssq);
-        vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
-        if (o < a.O_split) st_any(a.out, ((int64_t)b * a.O_split + o) * P + q, a.out_dtype, y);
-        else st_any(a.out2, ((int64_t)b * (a.O - a.O_split) + (o - a.O_split)) * P + q, a.out2_dtype, y);
-      }
-    }
-  }
-  emit_side_stats(a, b, ssum, ssq, vmax, vmin);
+  tc_epilogue(a, L, S, tmem_base, p0, n0, b);
+  tc_teardown(L, tmem_base);
+}
 
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L.tmem_cols));
+// ---- host side ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+static int sm_count() {
+  static thread_local int cached_dev = -1, cached = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
   }
+  return cached;
+}
+
+static bool tma_a_eligible(const ConvArgs& a) {
+  return a.fast1x1 && a.src0_dtype == VRCOC_BF16 && !a.gn_sums && !a.table && !a.chan_src && a.C1 == 0 && (a.K % 8 == 0) &&
+         ((reinterpret_cast<uintptr_t>(a.weight) & 15) == 0) && encode_fn() != nullptr;
 }
 
 static TcLayout tc_layout(const ConvArgs& a) {
   TcLayout L{};
-  int ntiles = (int)cdiv(a.O, 256);
-  int per = (int)cdiv(a.O, ntiles);
+  const int64_t m_tiles = cdiv(a.P_out, TC_BM) * a.B;
+  const int nk = (a.K + TC_BK - 1) / TC_BK;
+  // N tiling.  Wide tiles re-read A less often; narrow tiles give more resident CTAs (TMEM: 512 columns per SM) so the
+  // epilogue of one CTA overlaps the main loop of another, and fill the chip when there are few point tiles.
+  const int cap = nk <= 2 ? 128 : 256;
+  int64_t n_tiles = cdiv(a.O, cap);
+  const int64_t want = cdiv(2 * sm_count(), m_tiles);
+  if (n_tiles < want) n_tiles = want;
+  const int64_t max_tiles = cdiv(a.O, 32);
+  if (n_tiles > max_tiles) n_tiles = max_tiles;
+  int per = (int)cdiv(a.O, n_tiles);
   L.n_tile = (int)cdiv(per, 32) * 32;
   if (L.n_tile > 256) L.n_tile = 256;
   L.tmem_cols = 32;
   while (L.tmem_cols < L.n_tile) L.tmem_cols *= 2;
   L.b_bytes = L.n_tile * 128;
-  L.off_b = TC_STAGES * TC_A_BYTES;
-  L.off_tab = L.off_b + TC_STAGES * L.b_bytes;
-  L.off_bar = L.off_tab + a.Cin * 16;
-  L.off_bar = (L.off_bar + 15) & ~15;
-  L.total = L.off_bar + (TC_STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+  const int fixed = a.Cin * 16 + 5 * L.n_tile * 4 + 256 + 1024;
+  int stages = nk < TC_MAX_STAGES ? nk : TC_MAX_STAGES;
+  const int ctas_by_tmem = 512 / L.tmem_cols;
+  const int budget = (ctas_by_tmem >= 4 ? 56 : 110) * 1024;      // keep as many CTAs resident as TMEM allows
+  while (stages > 2 && stages * (TC_A_BYTES + L.b_bytes) + fixed > budget) --stages;
+  if (stages < 1) stages = 1;
+  L.stages = stages;
+  L.use_tma_b = (a.K % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.weight) & 15) == 0) && encode_fn() != nullptr;
+  L.plain_epi = !a.res && !a.post_scale && !a.f_scale && !a.f_shift && !a.out_sample_sums && !a.out_minmax && a.O_split == a.O;
+  L.off_b = stages * TC_A_BYTES;
+  L.off_tab = L.off_b + stages * L.b_bytes;
+  L.off_epi = L.off_tab + a.Cin * 16;
+  L.off_bar = (L.off_epi + 5 * L.n_tile * 4 + 15) & ~15;
+  L.total = L.off_bar + (2 * TC_MAX_STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
   return L;
 }
 
 bool conv_tc_supported(const ConvArgs& a) {
   if (a.weight_dtype != VRCOC_BF16) return false;
+  if (a.C1 > 0 && a.src1_dtype != a.src0_dtype) return false;
+  if (a.O_split != a.O && (a.O_split % 16) != 0) return false;
   TcLayout L = tc_layout(a);
   return L.total <= 220 * 1024;
 }
 
+static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box) {
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VRCOC_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return VRCOC_OK;
+}
+
+template <typename K>
+static void set_smem(K kern, int bytes) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
+
 int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   TcLayout L = tc_layout(a);
   VRCOC_REQUIRE(L.total <= 220 * 1024, "conv(tcgen05): shared memory budget exceeded (%d bytes)", L.total);
-  cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+  VRCOC_REQUIRE(a.C1 == 0 || a.src1_dtype == a.src0_dtype, "conv(tcgen05): both sources must share a dtype");
+  CUtensorMap tmB, tmA;
+  memset(&tmB, 0, sizeof(tmB));
+  memset(&tmA, 0, sizeof(tmA));
+  if (L.use_tma_b) {
+    // weights [O][K] bf16 row-major; box = 64 k (128 B) x n_tile rows, 128-byte swizzle, zero fill outside
+    cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.O};
+    cuuint64_t strides[1] = {(cuuint64_t)a.K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)L.n_tile};
+    int rc = encode(&tmB, a.weight, 2, dims, strides, box);
+    if (rc) return rc;
+  }
   dim3 grid((unsigned)cdiv(a.P_out, TC_BM), (unsigned)cdiv(a.O, L.n_tile), (unsigned)a.B);
-  conv_tc_kernel<<<grid, TC_THREADS, L.total, st>>>(a, L);
-  return check_launch("conv_tc");
+  if (tma_a_eligible(a)) {
+    // activations [B][C][P] bf16; box = 64 points (128 B) x 64 channels, lands as one MN-major SW128 block
+    cuuint64_t dims[3] = {(cuuint64_t)a.P_in, (cuuint64_t)a.C0, (cuuint64_t)a.B};
+    cuuint64_t strides[2] = {(cuuint64_t)a.P_in * 2, (cuuint64_t)a.src0_bstride * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)TC_BK, 1};
+    int rc = encode(&tmA, a.src0, 3, dims, strides, box);
+    if (rc) return rc;
+    set_smem(conv_tc_tma_kernel, L.total);
+    conv_tc_tma_kernel<<<grid, TC_THREADS, L.total, st>>>(a, L, tmA, tmB);
+    return check_launch("conv_tc_tma");
+  }
+  const bool f32 = a.src0_dtype == VRCOC_F32;
+#define LAUNCH(TS, FASTV)                                                        \
+  do {                                                                           \
+    set_smem(conv_tc_xform_kernel<TS, FASTV>, L.total);                          \
+    conv_tc_xform_kernel<TS, FASTV><<<grid, TC_THREADS, L.total, st>>>(a, L, tmB); \
+  } while (0)
+  if (a.fast1x1) { if (f32) LAUNCH(float, true); else LAUNCH(__nv_bfloat16, true); }
+  else           { if (f32) LAUNCH(float, false); else LAUNCH(__nv_bfloat16, false); }
+#undef LAUNCH
+  return check_launch("conv_tc_xform");
 }
 
 }  // namespace vrcoc
