@@ -57,6 +57,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+    if (!done) __nanosleep(40);
   } while (!done);
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -220,29 +221,60 @@ __device__ __forceinline__ void epi_plain(const ConvArgs& a, const TcLayout& L, 
                                           int c_end, int n0, int b, int q, bool valid) {
   const int64_t P = a.P_out;
   TO* optr = reinterpret_cast<TO*>(a.out) + ((int64_t)b * a.O + n0 + c_begin) * P + q;
+  const bool all_valid = __all_sync(0xffffffffu, valid);
   for (int c0 = c_begin; c0 < c_end; c0 += 16) {
     uint32_t r[16];
     tmem_ld16(tbase + (uint32_t)c0, r);
     const int lim = min(16, a.O - n0 - c0);
+    if (lim == 16 && all_valid) {          // warp-uniform fast path: no per-column predicates
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (j < lim) {
-        const float y = act_tc<ACT>(fmaf(__uint_as_float(r[j]), epi[c0 + j], epi[L.n_tile + c0 + j]));
-        if (valid) stf<TO>(optr, y);
+      for (int j = 0; j < 16; ++j) {
+        stf<TO>(optr, act_tc<ACT>(fmaf(__uint_as_float(r[j]), epi[c0 + j], epi[L.n_tile + c0 + j])));
+        optr += P;
       }
-      optr += P;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < lim && valid) stf<TO>(optr, act_tc<ACT>(fmaf(__uint_as_float(r[j]), epi[c0 + j], epi[L.n_tile + c0 + j])));
+        optr += P;
+      }
     }
   }
 }
 
 // FULL: y = act(acc*es + eh)*ps + res; y = y*fs + fh; split outputs; side statistics.
+// The residual values of a 16-column group are requested one group ahead (the first group before the accumulator is
+// waited for), so their DRAM latency overlaps the main loop / the previous group instead of stalling every column.
+__device__ __forceinline__ void load_res16(const ConvArgs& a, int64_t ridx, int64_t P, int lim, bool valid, float (&rv)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    rv[j] = 0.f;
+    if (j < lim && valid)
+      rv[j] = (a.res_dtype == VRCOC_BF16) ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.res)[ridx + j * P])
+                                           : reinterpret_cast<const float*>(a.res)[ridx + j * P];
+  }
+}
+
 template <int ACT>
 __device__ __forceinline__ void epi_full(const ConvArgs& a, const TcLayout& L, const float* epi, uint32_t tbase, int c_begin,
-                                         int c_end, int n0, int b, int q, bool valid) {
+                                         int c_end, int n0, int b, int q, bool valid, uint64_t* bar_acc) {
   const int64_t P = a.P_out;
   const int nt = L.n_tile;
   float ssum = 0.f, ssq = 0.f, vmax = 0.f, vmin = __int_as_float(0x7f800000);
+  float rnext[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) rnext[j] = 0.f;
+  const bool has_res = a.res != nullptr;
+  if (has_res && c_begin < c_end)
+    load_res16(a, ((int64_t)b * a.O + n0 + c_begin) * P + q, P, min(16, a.O - n0 - c_begin), valid, rnext);
+  mbar_wait(bar_acc, 0);
+  tc_fence_after();
   for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+    float rcur[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) rcur[j] = rnext[j];
+    if (has_res && c0 + 16 < c_end)
+      load_res16(a, ((int64_t)b * a.O + n0 + c0 + 16) * P + q, P, min(16, a.O - n0 - c0 - 16), valid, rnext);
     uint32_t r[16];
     tmem_ld16(tbase + (uint32_t)c0, r);
     const int o0 = n0 + c0;
@@ -253,16 +285,12 @@ __device__ __forceinline__ void epi_full(const ConvArgs& a, const TcLayout& L, c
     unsigned char* obase = reinterpret_cast<unsigned char*>(second ? a.out2 : a.out);
     const int64_t ochan = second ? ((int64_t)b * (a.O - a.O_split) + (o0 - a.O_split)) : ((int64_t)b * a.O_split + o0);
     const int64_t oidx = ochan * P + q;
-    const int64_t ridx = ((int64_t)b * a.O + o0) * P + q;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       if (j < lim && valid) {
         const int n = c0 + j;
         float y = act_tc<ACT>(fmaf(__uint_as_float(r[j]), epi[n], epi[nt + n]));
-        float res = 0.f;
-        if (a.res) res = (a.res_dtype == VRCOC_BF16) ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.res)[ridx + j * P])
-                                                      : reinterpret_cast<const float*>(a.res)[ridx + j * P];
-        y = fmaf(y, epi[2 * nt + n], res);
+        y = fmaf(y, epi[2 * nt + n], rcur[j]);
         y = fmaf(y, epi[3 * nt + n], epi[4 * nt + n]);
         ssum += y; ssq = fmaf(y, y, ssq);
         vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
@@ -274,6 +302,7 @@ __device__ __forceinline__ void epi_full(const ConvArgs& a, const TcLayout& L, c
   emit_side_stats(a, b, ssum, ssq, vmax, vmin);
 }
 
+// waits for the accumulator, then drains it
 __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcLayout& L, const TcSmem& S, uint32_t tmem_base, int p0,
                                             int n0, int b) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -286,6 +315,8 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcLayout& L
   int c_end = (chalf + 1) * ncols;
   if (c_end > a.O - n0) c_end = a.O - n0;        // warp-uniform: skip all-padding column groups
   if (L.plain_epi) {
+    mbar_wait(S.bar_acc, 0);
+    tc_fence_after();
     const bool bf = a.out_dtype == VRCOC_BF16;
 #define PLAIN(ACTV)                                                                                        \
   if (bf) epi_plain<ACTV, __nv_bfloat16>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid);             \
@@ -300,11 +331,11 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcLayout& L
 #undef PLAIN
   } else {
     switch (a.act) {
-      case VRCOC_ACT_NONE: epi_full<VRCOC_ACT_NONE>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid); break;
-      case VRCOC_ACT_RELU: epi_full<VRCOC_ACT_RELU>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid); break;
-      case VRCOC_ACT_GELU: epi_full<VRCOC_ACT_GELU>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid); break;
-      case VRCOC_ACT_SILU: epi_full<VRCOC_ACT_SILU>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid); break;
-      default: epi_full<VRCOC_ACT_LRELU>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid); break;
+      case VRCOC_ACT_NONE: epi_full<VRCOC_ACT_NONE>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid, S.bar_acc); break;
+      case VRCOC_ACT_RELU: epi_full<VRCOC_ACT_RELU>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid, S.bar_acc); break;
+      case VRCOC_ACT_GELU: epi_full<VRCOC_ACT_GELU>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid, S.bar_acc); break;
+      case VRCOC_ACT_SILU: epi_full<VRCOC_ACT_SILU>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid, S.bar_acc); break;
+      default: epi_full<VRCOC_ACT_LRELU>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid, S.bar_acc); break;
     }
   }
 }
@@ -318,7 +349,7 @@ __device__ __forceinline__ void tc_teardown(const TcLayout& L, uint32_t tmem_bas
 }
 
 // ---- kernel 1: both operands by TMA, warp-specialised -----------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 4) conv_tc_tma_kernel(ConvArgs a, TcLayout L, const __grid_constant__ CUtensorMap tmapA,
+__global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_tma_kernel(ConvArgs a, TcLayout L, const __grid_constant__ CUtensorMap tmapA,
                                                                  const __grid_constant__ CUtensorMap tmapB) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const TcSmem S = carve(smem_raw, L);
@@ -356,8 +387,6 @@ __global__ void __launch_bounds__(TC_THREADS, 4) conv_tc_tma_kernel(ConvArgs a, 
     }
   }
   __syncwarp();
-  mbar_wait(S.bar_acc, 0);
-  tc_fence_after();
   tc_epilogue(a, L, S, tmem_base, p0, n0, b);
   tc_teardown(L, tmem_base);
 }
@@ -394,17 +423,18 @@ __device__ __forceinline__ void slab_gload(const ConvArgs& a, int b, int kc, int
     } else {
       const int tap = kk - c * taps;
       const int ky = tap / a.kw, kx = tap - ky * a.kw;
+      // q0 is a multiple of 8: when W_out % 8 == 0 the 8 points share one output row
+      int oy = q0 / a.W_out, ox = q0 - oy * a.W_out;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int q = q0 + j;
-        if (q < P) {
-          const int oy = q / a.W_out, ox = q - oy * a.W_out;
+        if (q0 + j < P) {
           const int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
           if (iy >= 0 && iy < a.H_in && ix >= 0 && ix < a.W_in) {
             raw.v[8 * i + j] = src[(int64_t)iy * a.W_in + ix];
             raw.mask |= 1u << (8 * i + j);
           }
         }
+        if (++ox == a.W_out) { ox = 0; ++oy; }
       }
     }
   }
@@ -517,8 +547,6 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_xform_kernel(ConvArgs a
     if (kc + 1 < nk) slab_gload<TS, FAST>(a, b, kc + 1, a_krow0, q0, P, taps, raw);
   }
 
-  mbar_wait(S.bar_acc, 0);
-  tc_fence_after();
   tc_epilogue(a, L, S, tmem_base, p0, n0, b);
   tc_teardown(L, tmem_base);
 }

@@ -43,62 +43,96 @@ __device__ __forceinline__ void block_sum2(float& a, float& b, float* red /*>=64
   b = red[32];
 }
 
+// Plane kernels below use grid = (chunks, planes): planes with many points (the 512x512 ingest maps have only B*3..B*4
+// planes) are split into PLANE_CHUNK-element chunks so the grid fills the chip; per-plane sums then go through float
+// atomics into a zeroed buffer (single-chunk planes store directly and stay bit-reproducible).
+constexpr int PLANE_CHUNK = 16384;
+
+template <typename T, typename F>
+__device__ __forceinline__ void for_chunk8(const T* p, int lo, int hi, F&& f) {
+  // f(index, value[8], count): 8-wide when the chunk allows it
+  const bool vec = ((hi - lo) % 8 == 0) && (lo % 8 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+  if (vec) {
+    for (int i = lo + threadIdx.x * 8; i < hi; i += blockDim.x * 8) {
+      float v[8];
+      ld8<T>(p + i, v);
+      f(i, v, 8);
+    }
+  } else {
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      float v[8];
+      v[0] = ldf<T>(p + i);
+      f(i, v, 1);
+    }
+  }
+}
+
+__device__ __forceinline__ void publish_sums(float s, float s2, float* cs, double* ss, int plane, int C, float* red) {
+  block_sum2(s, s2, red);
+  if (threadIdx.x == 0) {
+    if (cs) {
+      if (gridDim.x == 1) { cs[2 * plane] = s; cs[2 * plane + 1] = s2; }
+      else { atomicAdd(&cs[2 * plane], s); atomicAdd(&cs[2 * plane + 1], s2); }
+    }
+    if (ss) {
+      atomicAdd(&ss[2 * (plane / C)], (double)s);
+      atomicAdd(&ss[2 * (plane / C) + 1], (double)s2);
+    }
+  }
+}
+
 // ---- per-(sample, channel) sums --------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) channel_sums_kernel(const T* __restrict__ x, int HW, float* __restrict__ cs,
                                                            double* __restrict__ ss, int C) {
   __shared__ float red[64];
-  const int plane = blockIdx.x;
+  const int plane = blockIdx.y;
+  const int lo = blockIdx.x * PLANE_CHUNK, hi = min(HW, lo + PLANE_CHUNK);
   const T* p = x + (int64_t)plane * HW;
   float s = 0.f, s2 = 0.f;
-  const bool vec = (HW % 8 == 0) && ((reinterpret_cast<uintptr_t>(p) & 31) == 0 || (sizeof(T) == 2 && (reinterpret_cast<uintptr_t>(p) & 15) == 0));
-  if (vec) {
-    for (int i = threadIdx.x * 8; i < HW; i += blockDim.x * 8) {
-      float v[8];
-      ld8<T>(p + i, v);
+  for_chunk8<T>(p, lo, hi, [&](int, const float (&v)[8], int n) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s += v[j]; s2 = fmaf(v[j], v[j], s2); }
-    }
-  } else {
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-      float v = ldf<T>(p + i);
-      s += v; s2 = fmaf(v, v, s2);
-    }
-  }
-  block_sum2(s, s2, red);
-  if (threadIdx.x == 0) {
-    if (cs) { cs[2 * plane] = s; cs[2 * plane + 1] = s2; }
-    if (ss) {
-      int b = plane / C;
-      atomicAdd(&ss[2 * b], (double)s);
-      atomicAdd(&ss[2 * b + 1], (double)s2);
-    }
-  }
+    for (int j = 0; j < 8; ++j)
+      if (j < n) { s += v[j]; s2 = fmaf(v[j], v[j], s2); }
+  });
+  publish_sums(s, s2, cs, ss, plane, C, red);
 }
 
 // ---- y = act(x*s1+t1) + res; y = y*s2+t2, with optional per-plane sums and global min/max ------------------------
-template <typename TX, typename TR, typename TO>
+template <typename T>
 __global__ void __launch_bounds__(256)
-chan_affine_kernel(const TX* __restrict__ x, const TR* __restrict__ res, TO* __restrict__ out, const float* __restrict__ s1,
+chan_affine_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ out, const float* __restrict__ s1,
                    const float* __restrict__ t1, int act, const float* __restrict__ s2, const float* __restrict__ t2, int C,
                    int HW, float* __restrict__ cs, uint32_t* __restrict__ minmax) {
   __shared__ float red[64];
-  const int plane = blockIdx.x, c = plane % C;
+  const int plane = blockIdx.y, c = plane % C;
+  const int lo = blockIdx.x * PLANE_CHUNK, hi = min(HW, lo + PLANE_CHUNK);
   const float a1 = s1 ? s1[c] : 1.f, b1 = t1 ? t1[c] : 0.f, a2 = s2 ? s2[c] : 1.f, b2 = t2 ? t2[c] : 0.f;
   const int64_t base = (int64_t)plane * HW;
   float s = 0.f, sq = 0.f, mx = 0.f, mn = __int_as_float(0x7f800000);
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    float y = apply_act(fmaf(ldf<TX>(x + base + i), a1, b1), act);
-    if (res) y += ldf<TR>(res + base + i);
-    y = fmaf(y, a2, b2);
-    stf<TO>(out + base + i, y);
-    s += y; sq = fmaf(y, y, sq);
-    mx = fmaxf(mx, y); mn = fminf(mn, y);
-  }
-  if (cs) {
-    block_sum2(s, sq, red);
-    if (threadIdx.x == 0) { cs[2 * plane] = s; cs[2 * plane + 1] = sq; }
-  }
+  const bool rvec = !res || ((reinterpret_cast<uintptr_t>(res + base) & 15) == 0);
+  const bool ovec = (reinterpret_cast<uintptr_t>(out + base) & 15) == 0;
+  for_chunk8<T>(x + base, lo, hi, [&](int i, const float (&v)[8], int n) {
+    float y[8], r[8];
+    if (res) {
+      if (n == 8 && rvec) ld8<T>(res + base + i, r);
+      else r[0] = ldf<T>(res + base + i);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < n) {
+        float t = apply_act(fmaf(v[j], a1, b1), act);
+        if (res) t += r[j];
+        t = fmaf(t, a2, b2);
+        y[j] = t;
+        s += t; sq = fmaf(t, t, sq);
+        mx = fmaxf(mx, t); mn = fminf(mn, t);
+      }
+    }
+    if (n == 8 && ovec) st8<T>(out + base + i, y);
+    else for (int j = 0; j < n; ++j) stf<T>(out + base + i + j, y[j]);
+  });
+  if (cs) publish_sums(s, sq, cs, nullptr, plane, C, red);
   if (minmax) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -113,29 +147,37 @@ chan_affine_kernel(const TX* __restrict__ x, const TR* __restrict__ res, TO* __r
 }
 
 // ---- ImageEnhanceByRadar tail -------------------------------------------------------------------------------------
-template <typename TK, typename TI, typename TO>
+template <typename T>
 __global__ void __launch_bounds__(256)
-img_enh_finish_kernel(const TK* __restrict__ k, const TI* __restrict__ img, TO* __restrict__ out,
+img_enh_finish_kernel(const T* __restrict__ k, const T* __restrict__ img, T* __restrict__ out,
                       const uint32_t* __restrict__ minmax, const float* __restrict__ sc, const float* __restrict__ sh, int C,
                       int HW, float* __restrict__ cs) {
   __shared__ float red[64];
-  const int plane = blockIdx.x, c = plane % C;
+  const int plane = blockIdx.y, c = plane % C;
+  const int lo = blockIdx.x * PLANE_CHUNK, hi = min(HW, lo + PLANE_CHUNK);
   const float mx = __uint_as_float(minmax[0]), mn = __uint_as_float(~minmax[1]);
   const float dst = mx - mn;               // 0/0 -> NaN, like the reference's true_divide (vr_coc.py:66)
   const float a = sc ? sc[c] : 1.f, b = sh ? sh[c] : 0.f;
   const int64_t base = (int64_t)plane * HW;
   float s = 0.f, sq = 0.f;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    float kk = ldf<TK>(k + base + i);
-    float y = (1.0f + (kk - mn) / dst) * ldf<TI>(img + base + i);
-    y = fmaf(y, a, b);
-    stf<TO>(out + base + i, y);
-    s += y; sq = fmaf(y, y, sq);
-  }
-  if (cs) {
-    block_sum2(s, sq, red);
-    if (threadIdx.x == 0) { cs[2 * plane] = s; cs[2 * plane + 1] = sq; }
-  }
+  const bool ivec = (reinterpret_cast<uintptr_t>(img + base) & 15) == 0 && (reinterpret_cast<uintptr_t>(out + base) & 15) == 0;
+  for_chunk8<T>(k + base, lo, hi, [&](int i, const float (&v)[8], int n) {
+    float y[8], im[8];
+    if (n == 8 && ivec) ld8<T>(img + base + i, im);
+    else im[0] = ldf<T>(img + base + i);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < n) {
+        float t = (1.0f + (v[j] - mn) / dst) * im[j];
+        t = fmaf(t, a, b);
+        y[j] = t;
+        s += t; sq = fmaf(t, t, sq);
+      }
+    }
+    if (n == 8 && ivec) st8<T>(out + base + i, y);
+    else for (int j = 0; j < n; ++j) stf<T>(out + base + i + j, y[j]);
+  });
+  if (cs) publish_sums(s, sq, cs, nullptr, plane, C, red);
 }
 
 // ---- ShuffleAttention parameters + attended-channel means (shuffle_attention.py:48-66) -------------------------------
@@ -289,7 +331,9 @@ extern "C" int vrcoc_channel_sums(const void* x, int dtype, int B, int C, int HW
   cudaStream_t st = (cudaStream_t)stream;
   return by_dtype(dtype, [&](auto* t) {
     using T = typename std::remove_pointer<decltype(t)>::type;
-    channel_sums_kernel<T><<<B * C, 256, 0, st>>>((const T*)x, HW, chan_sums, sample_sums, C);
+    const int chunks = (int)cdiv(HW, PLANE_CHUNK);
+    if (chunks > 1 && chan_sums) cudaMemsetAsync(chan_sums, 0, sizeof(float) * 2 * B * C, st);
+    channel_sums_kernel<T><<<dim3(chunks, B * C), 256, 0, st>>>((const T*)x, HW, chan_sums, sample_sums, C);
     return check_launch("channel_sums");
   });
 }
@@ -303,8 +347,10 @@ extern "C" int vrcoc_chan_affine(const void* x, int x_dtype, const void* res, in
   cudaStream_t st = (cudaStream_t)stream;
   return by_dtype(x_dtype, [&](auto* t) {
     using T = typename std::remove_pointer<decltype(t)>::type;
-    chan_affine_kernel<T, T, T><<<B * C, 256, 0, st>>>((const T*)x, (const T*)res, (T*)out, s1, t1, act, s2, t2, C, HW,
-                                                      out_chan_sums, out_minmax);
+    const int chunks = (int)cdiv(HW, PLANE_CHUNK);
+    if (chunks > 1 && out_chan_sums) cudaMemsetAsync(out_chan_sums, 0, sizeof(float) * 2 * B * C, st);
+    chan_affine_kernel<T><<<dim3(chunks, B * C), 256, 0, st>>>((const T*)x, (const T*)res, (T*)out, s1, t1, act, s2, t2, C, HW,
+                                                               out_chan_sums, out_minmax);
     return check_launch("chan_affine");
   });
 }
@@ -318,8 +364,10 @@ extern "C" int vrcoc_img_enh_finish(const void* k, int k_dtype, const void* imag
   cudaStream_t st = (cudaStream_t)stream;
   return by_dtype(k_dtype, [&](auto* tt) {
     using T = typename std::remove_pointer<decltype(tt)>::type;
-    img_enh_finish_kernel<T, T, T><<<B * C, 256, 0, st>>>((const T*)k, (const T*)image, (T*)out, minmax, s, t, C, HW,
-                                                         out_chan_sums);
+    const int chunks = (int)cdiv(HW, PLANE_CHUNK);
+    if (chunks > 1 && out_chan_sums) cudaMemsetAsync(out_chan_sums, 0, sizeof(float) * 2 * B * C, st);
+    img_enh_finish_kernel<T><<<dim3(chunks, B * C), 256, 0, st>>>((const T*)k, (const T*)image, (T*)out, minmax, s, t, C, HW,
+                                                                  out_chan_sums);
     return check_launch("img_enh_finish");
   });
 }
