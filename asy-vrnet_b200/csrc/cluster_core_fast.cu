@@ -70,7 +70,8 @@ core_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_const
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t pad = (128u - (smem_u32(smem_raw) & 127u)) & 127u;
   unsigned char* smem = smem_raw + pad;
-  float4* wq = reinterpret_cast<float4*>(smem + G.off_w);          // [N] one-hot * g
+  float* wq = reinterpret_cast<float*>(smem + G.off_w);            // [4][N] one-hot * g, centre-major: every LDS.128 of
+                                                                   // 4 consecutive points is bank-conflict-free across a warp
   float* chat = reinterpret_cast<float*>(smem + G.off_chat);       // [D][4] normalised centres
   float* cnorm = reinterpret_cast<float*>(smem + G.off_misc);      // [4]
   int* cnt = reinterpret_cast<int*>(smem + G.off_misc + 16);       // [4]
@@ -121,6 +122,7 @@ core_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_const
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
       if (d < G.D) {
         const TF* plane = ft + d * G.N;
+#pragma unroll 4
         for (int i = sub; i < G.items; i += G.TPD) {
           const float4 x = load4<TF>(plane, i);
           const int m = (((i >> G.lcpr) >= half_rows) ? 2 : 0) | (((i & cpr_mask) >= half_items) ? 1 : 0);
@@ -152,6 +154,7 @@ core_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_const
       int kbest = 0;
       if (in) {
         float ss = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll 8
         for (int d = 0; d < G.D; ++d) {
           const float x = (float)ft[d * G.N + n];
           const float4 c = *reinterpret_cast<const float4*>(chat + 4 * d);
@@ -164,7 +167,10 @@ core_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_const
         if (alpha * d2 > tb) { tb = alpha * d2; db = d2; kbest = 2; }
         if (alpha * d3 > tb) { tb = alpha * d3; db = d3; kbest = 3; }
         const float g = sigmoidf_exact(fmaf(alpha, db * inv, beta));
-        wq[n] = make_float4(kbest == 0 ? g : 0.f, kbest == 1 ? g : 0.f, kbest == 2 ? g : 0.f, kbest == 3 ? g : 0.f);
+        wq[n] = kbest == 0 ? g : 0.f;
+        wq[G.N + n] = kbest == 1 ? g : 0.f;
+        wq[2 * G.N + n] = kbest == 2 ? g : 0.f;
+        wq[3 * G.N + n] = kbest == 3 ? g : 0.f;
         if (idx_out || smax_out) {
           const int64_t io = (int64_t)be * HW + (int64_t)(f1 * G.rw + (n >> G.lrh)) * G.W + f2 * G.rh + (n & (G.rh - 1));
           if (idx_out) idx_out[io] = (uint8_t)kbest;
@@ -187,13 +193,15 @@ core_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_const
       float A[4] = {0.f, 0.f, 0.f, 0.f}, Q[4] = {0.f, 0.f, 0.f, 0.f};
       if (d < G.D) {
         const TV* plane = vt + d * G.N;
+#pragma unroll 4
         for (int i = sub; i < G.items; i += G.TPD) {
           const float4 v = load4<TV>(plane, i);
-          const float4 w0 = wq[4 * i], w1 = wq[4 * i + 1], w2 = wq[4 * i + 2], w3 = wq[4 * i + 3];
-          A[0] = fmaf(w0.x, v.x, fmaf(w1.x, v.y, fmaf(w2.x, v.z, fmaf(w3.x, v.w, A[0]))));
-          A[1] = fmaf(w0.y, v.x, fmaf(w1.y, v.y, fmaf(w2.y, v.z, fmaf(w3.y, v.w, A[1]))));
-          A[2] = fmaf(w0.z, v.x, fmaf(w1.z, v.y, fmaf(w2.z, v.z, fmaf(w3.z, v.w, A[2]))));
-          A[3] = fmaf(w0.w, v.x, fmaf(w1.w, v.y, fmaf(w2.w, v.z, fmaf(w3.w, v.w, A[3]))));
+          const float4 w0 = *reinterpret_cast<const float4*>(wq + 4 * i), w1 = *reinterpret_cast<const float4*>(wq + G.N + 4 * i);
+          const float4 w2 = *reinterpret_cast<const float4*>(wq + 2 * G.N + 4 * i), w3 = *reinterpret_cast<const float4*>(wq + 3 * G.N + 4 * i);
+          A[0] = fmaf(w0.x, v.x, fmaf(w0.y, v.y, fmaf(w0.z, v.z, fmaf(w0.w, v.w, A[0]))));
+          A[1] = fmaf(w1.x, v.x, fmaf(w1.y, v.y, fmaf(w1.z, v.z, fmaf(w1.w, v.w, A[1]))));
+          A[2] = fmaf(w2.x, v.x, fmaf(w2.y, v.y, fmaf(w2.z, v.z, fmaf(w2.w, v.w, A[2]))));
+          A[3] = fmaf(w3.x, v.x, fmaf(w3.y, v.y, fmaf(w3.z, v.z, fmaf(w3.w, v.w, A[3]))));
           const int m = (((i >> G.lcpr) >= half_rows) ? 2 : 0) | (((i & cpr_mask) >= half_items) ? 1 : 0);
           add_quadrant(Q, m, (v.x + v.y) + (v.z + v.w));
         }
@@ -208,13 +216,15 @@ core_fwd_fast_kernel(const __grid_constant__ CUtensorMap tmF, const __grid_const
         const float a0 = fmaf(Q[0], inv_quadrant, A[0]) * den0, a1 = fmaf(Q[1], inv_quadrant, A[1]) * den1;
         const float a2 = fmaf(Q[2], inv_quadrant, A[2]) * den2, a3 = fmaf(Q[3], inv_quadrant, A[3]) * den3;
         TO* oplane = otile + d * G.N;
+#pragma unroll 4
         for (int i = sub; i < G.items; i += G.TPD) {
-          const float4 w0 = wq[4 * i], w1 = wq[4 * i + 1], w2 = wq[4 * i + 2], w3 = wq[4 * i + 3];
+          const float4 w0 = *reinterpret_cast<const float4*>(wq + 4 * i), w1 = *reinterpret_cast<const float4*>(wq + G.N + 4 * i);
+          const float4 w2 = *reinterpret_cast<const float4*>(wq + 2 * G.N + 4 * i), w3 = *reinterpret_cast<const float4*>(wq + 3 * G.N + 4 * i);
           float4 o;
-          o.x = fmaf(w0.x, a0, fmaf(w0.y, a1, fmaf(w0.z, a2, w0.w * a3)));
-          o.y = fmaf(w1.x, a0, fmaf(w1.y, a1, fmaf(w1.z, a2, w1.w * a3)));
-          o.z = fmaf(w2.x, a0, fmaf(w2.y, a1, fmaf(w2.z, a2, w2.w * a3)));
-          o.w = fmaf(w3.x, a0, fmaf(w3.y, a1, fmaf(w3.z, a2, w3.w * a3)));
+          o.x = fmaf(w0.x, a0, fmaf(w1.x, a1, fmaf(w2.x, a2, w3.x * a3)));
+          o.y = fmaf(w0.y, a0, fmaf(w1.y, a1, fmaf(w2.y, a2, w3.y * a3)));
+          o.z = fmaf(w0.z, a0, fmaf(w1.z, a1, fmaf(w2.z, a2, w3.z * a3)));
+          o.w = fmaf(w0.w, a0, fmaf(w1.w, a1, fmaf(w2.w, a2, w3.w * a3)));
           store4<TO>(oplane, i, o);
         }
       }
@@ -278,7 +288,10 @@ int cluster_core_fwd_fast(const void* feat, int fdt, const void* value, int vdt,
   if (G.f_bytes != D * G.N * esz(fdt) || G.v_bytes != D * G.N * esz(vdt)) return 1;   // tiles must be whole 128-byte units
   if (G.o_bytes > G.f_bytes) return 1;                                                 // the output tile aliases the feat tile
   const int fixed = r128(G.N * 16) + r128(D * 16) + 128 + 128 + 256;
-  G.stages = (2 * (G.f_bytes + G.v_bytes) + fixed <= 200 * 1024) ? 2 : 1;
+  // small tiles: single stage and four resident CTAs per SM (the loads of one CTA overlap the passes of the others and
+  // 32 warps hide the shared-memory latency of the FMA streams); larger tiles: two stages inside one CTA
+  const int one = G.f_bytes + G.v_bytes + fixed;
+  G.stages = (one <= 56 * 1024) ? 1 : ((2 * (G.f_bytes + G.v_bytes) + fixed <= 200 * 1024) ? 2 : 1);
   if (G.stages * (G.f_bytes + G.v_bytes) + fixed > 220 * 1024) return 1;
   int p = 0;
   G.off_f = p; p += G.stages * G.f_bytes;
