@@ -26,9 +26,8 @@
 //   64/128-byte store per warp.  ncu (profiles/) showed the first version of this epilogue was issue-bound at ~160 SASS
 //   instructions per output column; pointers are therefore hoisted, coefficients read with ld.shared, the activation is
 //   a template parameter and GELU uses a branch-free erfc (|err| < 2e-7, bf16 outputs).
-#include <cuda.h>
-
 #include "conv_common.cuh"
+#include "tma.cuh"
 
 namespace vrcoc {
 
@@ -39,48 +38,11 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;       // 16 KB
 constexpr int TC_A_LBO = 64 * TC_BK * 2;            // 8192 B: second 64-point block
 constexpr int TC_MAX_STAGES = 4;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (!done) __nanosleep(40);
-  } while (!done);
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
-      : "memory");
-}
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
 // version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
@@ -552,66 +514,56 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_xform_kernel(ConvArgs a
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
-
-static int sm_count() {
-  static thread_local int cached_dev = -1, cached = 148;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev != cached_dev) {
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-    cached_dev = dev;
-  }
-  return cached;
-}
-
 static bool tma_a_eligible(const ConvArgs& a) {
   return a.fast1x1 && a.src0_dtype == VRCOC_BF16 && !a.gn_sums && !a.table && !a.chan_src && a.C1 == 0 && (a.K % 8 == 0) &&
-         ((reinterpret_cast<uintptr_t>(a.weight) & 15) == 0) && encode_fn() != nullptr;
+         ((reinterpret_cast<uintptr_t>(a.weight) & 15) == 0) && tma_encode_fn() != nullptr;
+}
+
+static int tc_smem_bytes(const ConvArgs& a, int n_tile, int stages) {
+  return stages * (TC_A_BYTES + n_tile * 128) + a.Cin * 16 + 5 * n_tile * 4 + (2 * TC_MAX_STAGES + 1) * 8 + 64 + 1024;
+}
+
+static int tc_resident(const ConvArgs& a, int n_tile, int stages) {
+  int tmem = 32;
+  while (tmem < n_tile) tmem *= 2;
+  int by_tmem = 512 / tmem, by_smem = (227 * 1024) / tc_smem_bytes(a, n_tile, stages), by_regs = 3;
+  int r = by_tmem < by_smem ? by_tmem : by_smem;
+  return r < by_regs ? (r < 1 ? 1 : r) : by_regs;
 }
 
 static TcLayout tc_layout(const ConvArgs& a) {
   TcLayout L{};
   const int64_t m_tiles = cdiv(a.P_out, TC_BM) * a.B;
   const int nk = (a.K + TC_BK - 1) / TC_BK;
-  // N tiling.  Wide tiles re-read A less often; narrow tiles give more resident CTAs (TMEM: 512 columns per SM) so the
-  // epilogue of one CTA overlaps the main loop of another, and fill the chip when there are few point tiles.
-  const int cap = nk <= 2 ? 128 : 256;
-  int64_t n_tiles = cdiv(a.O, cap);
-  const int64_t want = cdiv(2 * sm_count(), m_tiles);
-  if (n_tiles < want) n_tiles = want;
-  const int64_t max_tiles = cdiv(a.O, 32);
-  if (n_tiles > max_tiles) n_tiles = max_tiles;
-  int per = (int)cdiv(a.O, n_tiles);
-  L.n_tile = (int)cdiv(per, 32) * 32;
-  if (L.n_tile > 256) L.n_tile = 256;
+  const int sms = sm_count();
+  // N tiling by a small cost model (measured on B200, profiles/): a CTA costs a fixed part + one slab latency per 64 k
+  // + an epilogue part per output column; the launch costs that times the number of waves over the resident-CTA slots,
+  // which depend on the tile through TMEM columns and shared memory.  Narrow tiles re-do the A transform more often
+  // but keep more CTAs resident (their phases overlap) and quantise better; wide tiles win when there are many point tiles.
+  const bool heavy_act = a.act == VRCOC_ACT_GELU || a.act == VRCOC_ACT_SILU;
+  double best = 1e30;
+  int best_tile = 32, best_stages = 1;
+  for (int nt = 32; nt <= 256; nt += 32) {
+    const int64_t n_tiles = cdiv(a.O, nt);
+    if (nt > 32 && n_tiles * (nt - 32) >= a.O) continue;          // a narrower tile covers O with the same count
+    int stages = nk < TC_MAX_STAGES ? nk : TC_MAX_STAGES;
+    while (stages > 2 && tc_resident(a, nt, stages) < tc_resident(a, nt, 2)) --stages;
+    if (tc_smem_bytes(a, nt, stages) > 220 * 1024) continue;
+    const int64_t slots = (int64_t)sms * tc_resident(a, nt, stages);
+    const int64_t waves = cdiv(m_tiles * n_tiles, slots);
+    const double cta = 2.0 + 1.0 * nk + (heavy_act ? 0.040 : 0.022) * nt;
+    const double cost = (double)waves * cta;
+    if (cost < best - 1e-9) { best = cost; best_tile = nt; best_stages = stages; }
+  }
+  L.n_tile = best_tile;
+  L.stages = best_stages;
   L.tmem_cols = 32;
   while (L.tmem_cols < L.n_tile) L.tmem_cols *= 2;
   L.b_bytes = L.n_tile * 128;
-  const int fixed = a.Cin * 16 + 5 * L.n_tile * 4 + 256 + 1024;
-  int stages = nk < TC_MAX_STAGES ? nk : TC_MAX_STAGES;
-  const int ctas_by_tmem = 512 / L.tmem_cols;
-  const int budget = (ctas_by_tmem >= 4 ? 56 : 110) * 1024;      // keep as many CTAs resident as TMEM allows
-  while (stages > 2 && stages * (TC_A_BYTES + L.b_bytes) + fixed > budget) --stages;
-  if (stages < 1) stages = 1;
-  L.stages = stages;
-  L.use_tma_b = (a.K % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.weight) & 15) == 0) && encode_fn() != nullptr;
+  L.use_tma_b = (a.K % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.weight) & 15) == 0) && tma_encode_fn() != nullptr;
   L.plain_epi = !a.res && !a.post_scale && !a.f_scale && !a.f_shift && !a.out_sample_sums && !a.out_minmax && a.O_split == a.O;
-  L.off_b = stages * TC_A_BYTES;
-  L.off_tab = L.off_b + stages * L.b_bytes;
+  L.off_b = L.stages * TC_A_BYTES;
+  L.off_tab = L.off_b + L.stages * L.b_bytes;
   L.off_epi = L.off_tab + a.Cin * 16;
   L.off_bar = (L.off_epi + 5 * L.n_tile * 4 + 15) & ~15;
   L.total = L.off_bar + (2 * TC_MAX_STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
@@ -628,12 +580,7 @@ bool conv_tc_supported(const ConvArgs& a) {
 
 static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                   const cuuint32_t* box) {
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
-                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(VRCOC_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-  return VRCOC_OK;
+  return tma_encode(tm, VRCOC_BF16, base, rank, dims, strides_bytes, box, true);
 }
 
 template <typename K>

@@ -304,6 +304,46 @@ gn_bwd_apply_kernel(const TZ* __restrict__ dz, const TX* __restrict__ x, const T
   }
 }
 
+
+// ---- bilinear upsample, align_corners=True (nn.Upsample in CoCUpsample, reference neck/coc_fpn_dual.py:21) ---------------
+// out[y][x] = lerp over the 2x2 source neighbourhood at (y*(H-1)/(Ho-1), x*(W-1)/(Wo-1)); one thread = 8 consecutive
+// output columns of one (plane, row): 128-bit stores, source rows served from L1/L2.
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample_bilinear_kernel(const T* __restrict__ x, T* __restrict__ out, int planes, int H, int W, int Ho, int Wo, float sy, float sx) {
+  const int cols8 = (Wo + 7) >> 3;
+  const int64_t total = (int64_t)planes * Ho * cols8;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(t % cols8);
+    const int64_t rowid = t / cols8;
+    const int oy = (int)(rowid % Ho);
+    const int64_t plane = rowid / Ho;
+    const float fy = oy * sy;
+    int y0 = (int)fy;
+    if (y0 > H - 1) y0 = H - 1;
+    const int y1 = min(y0 + 1, H - 1);
+    const float wy = fy - (float)y0;
+    const T* r0 = x + (plane * H + y0) * W;
+    const T* r1 = x + (plane * H + y1) * W;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ox = c8 * 8 + j;
+      const float fx = ox * sx;
+      int x0 = (int)fx;
+      if (x0 > W - 1) x0 = W - 1;
+      const int x1 = min(x0 + 1, W - 1);
+      const float wx = fx - (float)x0;
+      const float a = ldf<T>(r0 + x0), b = ldf<T>(r0 + x1), c = ldf<T>(r1 + x0), d = ldf<T>(r1 + x1);
+      const float top = fmaf(wx, b - a, a), bot = fmaf(wx, d - c, c);
+      v[j] = fmaf(wy, bot - top, top);
+    }
+    T* o = out + (plane * Ho + oy) * (int64_t)Wo + c8 * 8;
+    if (c8 * 8 + 8 <= Wo && (reinterpret_cast<uintptr_t>(o) & 15) == 0) st8<T>(o, v);
+    else for (int j = 0; j < 8 && c8 * 8 + j < Wo; ++j) stf<T>(o + j, v[j]);
+  }
+}
+
 template <typename F>
 static int by_dtype(int dt, F&& f) {
   if (dt == VRCOC_F32) return f((float*)nullptr);
@@ -431,5 +471,19 @@ extern "C" int vrcoc_gn_bwd_apply(const void* dz, const void* x, const void* ext
     using T = typename std::remove_pointer<decltype(t)>::type;
     gn_bwd_apply_kernel<T, T, T><<<B * C, 256, 0, st>>>((const T*)dz, (const T*)x, (const T*)extra, (T*)out, a, bb, cc, C, HW);
     return check_launch("gn_bwd_apply");
+  });
+}
+
+extern "C" int vrcoc_upsample_bilinear(const void* x, void* out, int dtype, int planes, int H, int W, int Ho, int Wo, void* stream) {
+  VRCOC_REQUIRE(x && out && planes > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0, "upsample_bilinear: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+  const float sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const int64_t total = (int64_t)planes * Ho * ((Wo + 7) / 8);
+  int blocks = (int)(cdiv(total, 256) < 148 * 16 ? cdiv(total, 256) : 148 * 16);
+  return by_dtype(dtype, [&](auto* t) {
+    using T = typename std::remove_pointer<decltype(t)>::type;
+    upsample_bilinear_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, (T*)out, planes, H, W, Ho, Wo, sy, sx);
+    return check_launch("upsample_bilinear");
   });
 }

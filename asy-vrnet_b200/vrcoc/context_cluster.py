@@ -184,11 +184,53 @@ class ClusterBlock(nn.Module):
         dp = isinstance(self.drop_path, nn.Identity) or not self.training
         return gn1 and gn2 and dp and self.mlp._fusable()
 
+    def _forward_infer(self, x):
+        """Gradient-free path: the same five launches, fed from memoised parameter views (concatenated fc1|fc_v weight,
+        fp32 copies of the small vectors), no autograd bookkeeping."""
+        tm, mlp, n1, n2 = self.token_mixer, self.mlp, self.norm1, self.norm2
+        f32 = ops._f32
+        x = x.contiguous()
+        B, C, H, W = x.shape
+        ED = tm.heads * tm.head_dim
+        w_in = ops.cached(self, "w_in", [tm.fc1.weight, tm.fc_v.weight],
+                          lambda: torch.cat([tm.fc1.weight, tm.fc_v.weight], 0).reshape(2 * ED, C).contiguous())
+        b_in = ops.cached(self, "b_in", [tm.fc1.bias, tm.fc_v.bias], lambda: torch.cat([tm.fc1.bias, tm.fc_v.bias], 0).float().contiguous())
+        ls1 = f32(self.layer_scale_1) if self.use_layer_scale else None
+        ls2 = f32(self.layer_scale_2) if self.use_layer_scale else None
+        dev, dt = x.device, x.dtype
+        sums0 = ops.sample_sums_of(x)
+        if dt == torch.float32:
+            y = torch.empty(B, 2 * ED, H, W, device=dev, dtype=dt)
+            ops.conv_fwd(ops.conv_desc(x, w_in, y, gn=(sums0, f32(n1.weight), f32(n1.bias), n1.eps), e_shift=b_in))
+            feat, value = y[:, :ED], y[:, ED:]
+        else:
+            feat = torch.empty(B, ED, H, W, device=dev, dtype=torch.float32)
+            value = torch.empty(B, ED, H, W, device=dev, dtype=dt)
+            ops.conv_fwd(ops.conv_desc(x, w_in, feat, gn=(sums0, f32(n1.weight), f32(n1.bias), n1.eps), e_shift=b_in, out2=value))
+        pw, ph = tm._proposal()
+        o, _, _ = ops.cluster_core_fwd(feat, value, f32(tm.sim_alpha), f32(tm.sim_beta), tm.heads, tm.fold_w, tm.fold_h, pw, ph,
+                                       out_dtype=dt)
+        sums = torch.zeros(2, B, 2, device=dev, dtype=torch.float64)
+        x1 = torch.empty_like(x)
+        ops.conv_fwd(ops.conv_desc(o, tm.fc2.weight.detach().reshape(C, ED), x1, e_shift=f32(tm.fc2.bias), post_scale=ls1, res=x,
+                                   out_sample_sums=sums[0]))
+        hid = mlp.fc1.weight.shape[0]
+        h = torch.empty(B, hid, H, W, device=dev, dtype=dt)
+        ops.conv_fwd(ops.conv_desc(x1, mlp.fc1.weight.detach().reshape(hid, C), h, gn=(sums[0], f32(n2.weight), f32(n2.bias), n2.eps),
+                                   e_shift=f32(mlp.fc1.bias), act=ACT_GELU))
+        x2 = torch.empty_like(x)
+        ops.conv_fwd(ops.conv_desc(h, mlp.fc2.weight.detach().reshape(C, hid), x2, e_shift=f32(mlp.fc2.bias), post_scale=ls2, res=x1,
+                                   out_sample_sums=sums[1]))
+        x2._vrcoc_sums = sums[1]
+        return x2
+
     def forward(self, x):
         if not x.is_cuda:
             raise VrcocError("vrcoc ClusterBlock needs a CUDA tensor (no CPU fallback exists)")
         if not self._fused_ok():
             return self._forward_composed(x)
+        if not torch.is_grad_enabled():
+            return self._forward_infer(x)
         ls1 = self.layer_scale_1 if self.use_layer_scale else None
         ls2 = self.layer_scale_2 if self.use_layer_scale else None
         tm, mlp = self.token_mixer, self.mlp

@@ -58,8 +58,8 @@ def shuffle_channels(x, groups=2):
 def _bn_affine(bn, chan_sums=None, count=None):
     """(scale, shift) fp32 such that BN(x) = x*scale + shift.  eval: running statistics.  train: batch statistics from
     the per-(b,c) sums (biased variance), with the running-stat update of nn.BatchNorm2d (unbiased variance)."""
-    w = bn.weight.detach().float() if bn.affine else None
-    b = bn.bias.detach().float() if bn.affine else None
+    def wb():
+        return (bn.weight.detach().float() if bn.affine else None, bn.bias.detach().float() if bn.affine else None)
     use_batch = bn.training or not bn.track_running_stats
     if use_batch:
         s = chan_sums.double().sum(0)                       # [C,2]
@@ -74,8 +74,13 @@ def _bn_affine(bn, chan_sums=None, count=None):
                 bn.running_var.mul_(1 - mom).add_((var * (n / max(n - 1, 1))).to(bn.running_var.dtype), alpha=mom)
         mean, var = mean.float(), var.float()
     else:
-        mean, var = bn.running_mean.detach().float(), bn.running_var.detach().float()
-    scale = torch.rsqrt(var + bn.eps)
+        return ops.cached(bn, "eval_affine", [bn.weight, bn.bias, bn.running_mean, bn.running_var], lambda: _fold_bn(
+            bn.running_mean.detach().float(), bn.running_var.detach().float(), *wb(), bn.eps))
+    return _fold_bn(mean, var, *wb(), bn.eps)
+
+
+def _fold_bn(mean, var, w, b, eps):
+    scale = torch.rsqrt(var + eps)
     if w is not None:
         scale = scale * w
     shift = -mean * scale
@@ -212,7 +217,7 @@ def _base_conv_forward(mod, x, out_minmax):
         return u
     sc, sh = _bn_affine(bn)
     if bias32 is not None:
-        sh = sh + bias32 * sc
+        sh = ops.cached(mod, "bias_fold", [conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var], lambda: sh + bias32 * sc)
     return _conv_launch(x, conv.weight, sh, stride, pad, None, None, act, sc, out_minmax, None)
 
 
@@ -279,8 +284,8 @@ class ShuffleAttention(nn.Module):
         return x.reshape(b, groups, -1, h, w).permute(0, 2, 1, 3, 4).reshape(b, -1, h, w)
 
     def params32(self):
-        return tuple(_f32(p).reshape(-1) for p in (self.cweight, self.cbias, self.sweight, self.sbias,
-                                                    self.gn.weight, self.gn.bias))
+        src = (self.cweight, self.cbias, self.sweight, self.sbias, self.gn.weight, self.gn.bias)
+        return ops.cached(self, "params32", list(src), lambda: tuple(p.detach().float().reshape(-1).contiguous() for p in src))
 
     def gate_table(self, x):
         """attn [B,C,4] = {scale, gate_a, gate_c, mean of the attended channel} for every input channel"""

@@ -36,11 +36,38 @@ def _stream():
 
 
 def _f32(t):
-    """small parameter vectors are always consumed as fp32"""
+    """Small parameter vectors are always consumed as fp32.  The converted copy is memoised on the tensor object and
+    keyed on (storage pointer, version counter): optimizer steps / load_state_dict / .to() invalidate it, so inference
+    pays the conversion kernel once instead of once per call."""
     if t is None:
         return None
-    t = t.detach()
-    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t.detach()
+    sig = (t.data_ptr(), t._version)
+    memo = t.__dict__.get("_vrcoc_f32") if hasattr(t, "__dict__") else None
+    if memo is not None and memo[0] == sig:
+        return memo[1]
+    v = t.detach().float().contiguous()
+    try:
+        t._vrcoc_f32 = (sig, v)
+    except Exception:
+        pass
+    return v
+
+
+def cached(mod, key, sources, build):
+    """Derived parameter tensors (concatenated projection weights, folded BatchNorm affines, ...) memoised on the module
+    while their sources are unchanged.  Bypassed whenever autograd could need the sources."""
+    if torch.is_grad_enabled() and any(s is not None and s.requires_grad for s in sources):
+        return build()
+    store = mod.__dict__.setdefault("_vrcoc_cache", {})
+    sig = tuple(None if s is None else (s.data_ptr(), s._version, s.dtype) for s in sources)
+    ent = store.get(key)
+    if ent is None or ent[0] != sig:
+        with torch.no_grad():
+            ent = (sig, build())
+        store[key] = ent
+    return ent[1]
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -179,6 +179,10 @@ int vrcoc_img_enh_finish(const void* k, int k_dtype, const void* image, int imag
                          float* out_chan_sums /*nullable [B][C][2]*/, void* stream);
 
 
+/* Bilinear upsample with align_corners=True over `planes` = B*C maps (nn.Upsample inside CoCUpsample,
+ * reference neck/coc_fpn_dual.py:19-22). */
+int vrcoc_upsample_bilinear(const void* x, void* out, int dtype, int planes, int H, int W, int Ho, int Wo, void* stream);
+
 /* Backward elementwise passes of the projections (training path of ClusterBlock, vr_coc.py:264-271).
  *   gelu_bwd    : out = dy * gelu'(u)                                   (all three tensors share `dtype`)
  *   gn_bwd_sums : out[b][c] = {sum_p dz, sum_p dz*x}                    GroupNorm(1,C) backward statistics

@@ -307,3 +307,79 @@ def test_reference_assert_is_mirrored(V):
     m = V.Cluster(8, 8, fold_w=4, fold_h=4, heads=2, head_dim=4).cuda()
     with pytest.raises(RuntimeError, match="can be divided by fold"):
         m(torch.randn(1, 8, 10, 10, device="cuda"))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# whole model (backbone + neck + head) vs the CPU oracle, and the neck's native upsample
+# ---------------------------------------------------------------------------------------------------------------
+def test_upsample_matches_interpolate(V):
+    import torch.nn.functional as F
+    from vrcoc.neck import BilinearUpsample
+    g = torch.Generator().manual_seed(4)
+    for shape, scale in (((2, 9, 32, 32), 4), ((1, 5, 7, 12), 2), ((2, 3, 16, 8), 2)):
+        x = torch.randn(*shape, generator=g).cuda()
+        ref = F.interpolate(x, scale_factor=scale, mode="bilinear", align_corners=True)
+        got = BilinearUpsample(scale_factor=scale, mode="bilinear", align_corners=True)(x)
+        assert rel_err(got, ref) < 1e-6
+        gb = BilinearUpsample(scale_factor=scale, mode="bilinear", align_corners=True)(x.bfloat16())
+        assert rel_err(gb.float(), ref) < 5e-3
+    xr = torch.randn(1, 2, 8, 8, generator=g).cuda().requires_grad_(True)
+    BilinearUpsample(scale_factor=2, mode="bilinear", align_corners=True)(xr).square().sum().backward()
+    xr2 = xr.detach().clone().requires_grad_(True)
+    F.interpolate(xr2, scale_factor=2, mode="bilinear", align_corners=True).square().sum().backward()
+    assert rel_err(xr.grad, xr2.grad) < 1e-5
+
+
+def _randomised_model(V, phi):
+    torch.manual_seed(0)
+    m = V.EfficientVRNet(4, 9, phi).eval()
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.numel() == 0:
+                continue
+            leaf = n.split(".")[-1]
+            if leaf.startswith("layer_scale"):
+                p.copy_(torch.rand(p.shape, generator=g) * 0.5 + 0.25)
+            elif leaf == "sim_alpha":
+                p.copy_(torch.rand(1, generator=g) + 0.5)
+            elif leaf == "sim_beta":
+                p.copy_(torch.rand(1, generator=g) - 0.5)
+        for n, b in m.named_buffers():
+            if n.endswith("running_var"):
+                b.copy_(torch.rand(b.shape, generator=g) + 0.5)
+            elif n.endswith("running_mean"):
+                b.copy_(torch.randn(b.shape, generator=g) * 0.1)
+    return m
+
+
+def test_whole_model_vs_oracle_fp32(V):
+    """EfficientVRNet(phi='nano'), B=2, 512x512: the product (no-grad inference path, CUDA) against the CPU oracle on the
+    same state_dict; O(1) layer scales so that the CoC blocks actually contribute."""
+    from oracle import coc_oracle as O
+    m = _randomised_model(V, "nano")
+    g = torch.Generator().manual_seed(2)
+    x, r = torch.randn(2, 3, 512, 512, generator=g), torch.rand(2, 4, 512, 512, generator=g)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        det_ref, seg_ref = O.efficient_vrnet_forward(x, r, sd, "nano")
+        m = m.cuda()
+        det, seg = m(x.cuda(), r.cuda())
+        det2, seg2 = m(x.cuda(), r.cuda())       # second call exercises the memoised parameter views
+    assert rel_err(seg, seg_ref) < 2e-3
+    for a, b in zip(det, det_ref):
+        assert rel_err(a, b) < 2e-3
+    # run-to-run differences come only from the order of the fp64 atomics behind the GroupNorm statistics
+    assert rel_err(seg2, seg) < 1e-3 and all(rel_err(a, b) < 1e-3 for a, b in zip(det2, det))
+
+
+def test_whole_model_bf16_runs_and_tracks_fp32(V):
+    m = _randomised_model(V, "nano").cuda()
+    g = torch.Generator().manual_seed(2)
+    x, r = torch.randn(1, 3, 512, 512, generator=g).cuda(), torch.rand(1, 4, 512, 512, generator=g).cuda()
+    with torch.no_grad():
+        det32, seg32 = m(x, r)
+        mb = m.bfloat16()
+        det16, seg16 = mb(x.bfloat16(), r.bfloat16())
+    assert seg16.dtype == torch.bfloat16 and torch.isfinite(seg16.float()).all()
+    assert rel_err(seg16.float(), seg32) < 0.15      # end-to-end bf16 drift over 27 blocks (information, loose)
