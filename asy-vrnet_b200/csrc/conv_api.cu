@@ -160,13 +160,10 @@ __global__ void __launch_bounds__(256) table_apply_kernel(ConvArgs a) {
   const int P = a.P_in;
   float4 t;
   if (a.gn_sums) {
-    const double cnt = (double)a.C0 * (double)P;
-    const double mean = a.gn_sums[2 * b] / cnt;
-    double var = a.gn_sums[2 * b + 1] / cnt - mean * mean;
-    var = var > 0.0 ? var : 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)a.gn_eps));
+    float mu, rstd;
+    gn_mean_rstd(a.gn_sums, b, (double)a.C0 * (double)P, a.gn_eps, mu, rstd);
     float sc = rstd * a.gn_gamma[k];
-    t = make_float4(sc, fmaf(-(float)mean, sc, a.gn_beta[k]), 0.f, 88.f);
+    t = make_float4(sc, fmaf(-mu, sc, a.gn_beta[k]), 0.f, 88.f);
   } else if (a.table) {
     t = reinterpret_cast<const float4*>(a.table)[(int64_t)b * a.Cin + k];
   } else {

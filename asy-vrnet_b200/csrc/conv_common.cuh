@@ -24,17 +24,28 @@ struct ConvArgs {
   int vec_out;  // P_out % 8 == 0 and aligned outputs: vectorised stores
 };
 
+// GroupNorm(1, C) statistics of sample b from the slot-wise partial sums: every warp reduces the 32 slots with shuffles
+// (lane = slot), so all threads get the same (mean, rstd) without shared memory.
+__device__ __forceinline__ void gn_mean_rstd(const double* gn_sums, int b, double cnt, float eps, float& mu, float& rstd) {
+  const int lane = threadIdx.x & 31;
+  double s = gn_sums[((int64_t)b * VRCOC_STAT_SLOTS + lane) * 2];
+  double s2 = gn_sums[((int64_t)b * VRCOC_STAT_SLOTS + lane) * 2 + 1];
+  s = warp_sum(s);
+  s2 = warp_sum(s2);
+  const double mean = s / cnt;
+  double var = s2 / cnt - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+  mu = (float)mean;
+}
+
 // Per-CTA prologue table tab[c] = {scale, shift, gate_a, gate_c} for the CTA's sample b.
 __device__ __forceinline__ void build_prologue_table(const ConvArgs& a, int b, float4* tab) {
   if (a.gn_sums) {
-    // GroupNorm(1, C): per-sample mean / rstd from the {sum, sum^2} pair (vr_coc.py:105-111), folded with the
-    // per-channel affine so the slab loader does one FMA per element.
-    const double cnt = (double)a.C0 * (double)a.P_in;
-    const double mean = a.gn_sums[2 * b] / cnt;
-    double var = a.gn_sums[2 * b + 1] / cnt - mean * mean;
-    var = var > 0.0 ? var : 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)a.gn_eps));
-    const float mu = (float)mean;
+    // GroupNorm(1, C): per-sample mean / rstd (vr_coc.py:105-111), folded with the per-channel affine so the slab
+    // loader does one FMA per element.
+    float mu, rstd;
+    gn_mean_rstd(a.gn_sums, b, (double)a.C0 * (double)a.P_in, a.gn_eps, mu, rstd);
     for (int c = threadIdx.x; c < a.Cin; c += blockDim.x) {
       float sc = rstd * a.gn_gamma[c];
       tab[c] = make_float4(sc, fmaf(-mu, sc, a.gn_beta[c]), 0.f, 88.f);
@@ -66,14 +77,22 @@ __device__ __forceinline__ float epilogue_value(float acc, const EpiCoef& e, int
   return fmaf(y, e.fs, e.fh);
 }
 
-// warp-reduce the per-thread side statistics, then one atomic per warp
+// block-reduce the per-thread side statistics, then ONE fp64 atomic pair per CTA into the CTA's slot
 __device__ __forceinline__ void emit_side_stats(const ConvArgs& a, int b, float ssum, float ssq, float vmax, float vmin) {
   if (a.out_sample_sums) {
+    __shared__ float red_stats[64];
     ssum = warp_sum(ssum);
     ssq = warp_sum(ssq);
-    if ((threadIdx.x & 31) == 0) {
-      atomicAdd(&a.out_sample_sums[2 * b], (double)ssum);
-      atomicAdd(&a.out_sample_sums[2 * b + 1], (double)ssq);
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red_stats[w] = ssum; red_stats[32 + w] = ssq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0, s2 = 0.0;
+      for (int i = 0; i < nw; ++i) { s += (double)red_stats[i]; s2 += (double)red_stats[32 + i]; }
+      const int slot = (blockIdx.x + 7 * blockIdx.y) & (VRCOC_STAT_SLOTS - 1);
+      double* dst = a.out_sample_sums + ((int64_t)b * VRCOC_STAT_SLOTS + slot) * 2;
+      atomicAdd(dst, s);
+      atomicAdd(dst + 1, s2);
     }
   }
   if (a.out_minmax) {

@@ -123,13 +123,16 @@ struct TcLayout {
   int stages;
   int use_tma_b;    // weights via TMA
   int plain_epi;    // epilogue is y = act(acc*es + eh) into `out` only (no residual / post / final affine / stats / split)
-  int off_b, off_tab, off_epi, off_bar, total;
+  int res_tma;      // residual epilogue through a TMA-staged [n_tile][128] bf16 tile (fetched at kernel start, rewritten in
+                    // place, stored by TMA): no per-thread global access, full memory-level parallelism
+  int off_b, off_tab, off_epi, off_res, off_bar, total;
 };
 
 struct TcSmem {
   unsigned char* base;
   unsigned char* sA; unsigned char* sB; float4* tab; float* epi;
-  uint64_t* bar_free; uint64_t* bar_full; uint64_t* bar_acc; uint32_t* tmem_slot;
+  uint64_t* bar_free; uint64_t* bar_full; uint64_t* bar_acc; uint64_t* bar_res; uint32_t* tmem_slot;
+  __nv_bfloat16* res_tile;
 };
 
 __device__ __forceinline__ TcSmem carve(unsigned char* smem_raw, const TcLayout& L) {
@@ -145,7 +148,9 @@ __device__ __forceinline__ TcSmem carve(unsigned char* smem_raw, const TcLayout&
   s.bar_free = reinterpret_cast<uint64_t*>(s.base + L.off_bar);
   s.bar_full = s.bar_free + TC_MAX_STAGES;
   s.bar_acc = s.bar_full + TC_MAX_STAGES;
-  s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar_acc + 1);
+  s.bar_res = s.bar_acc + 1;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(s.bar_res + 1);
+  s.res_tile = reinterpret_cast<__nv_bfloat16*>(s.base + L.off_res);
   return s;
 }
 
@@ -159,6 +164,7 @@ __device__ __forceinline__ uint32_t tc_setup(const ConvArgs& a, const TcLayout& 
   if (tid == 32) {
     for (int i = 0; i < L.stages; ++i) { mbar_init(&S.bar_free[i], 1); mbar_init(&S.bar_full[i], 1); }
     mbar_init(S.bar_acc, 1);
+    mbar_init(S.bar_res, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int n = tid; n < L.n_tile; n += TC_THREADS) {
@@ -264,9 +270,43 @@ __device__ __forceinline__ void epi_full(const ConvArgs& a, const TcLayout& L, c
   emit_side_stats(a, b, ssum, ssq, vmax, vmin);
 }
 
+// FULL epilogue on the TMA-staged tile: res_tile[n][m] (bf16, n = output channel in the tile, m = point in the tile) holds
+// the residual on entry and the result on exit.
+template <int ACT>
+__device__ __forceinline__ void epi_full_tile(const ConvArgs& a, const TcLayout& L, const TcSmem& S, uint32_t tbase, int c_begin,
+                                              int c_end, int n0, int b, int m, bool valid) {
+  const int nt = L.n_tile;
+  const float* epi = S.epi;
+  float ssum = 0.f, ssq = 0.f, vmax = 0.f, vmin = __int_as_float(0x7f800000);
+  mbar_wait(S.bar_acc, 0);
+  tc_fence_after();
+  mbar_wait(S.bar_res, 0);
+  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(tbase + (uint32_t)c0, r);
+    const int lim = min(16, a.O - n0 - c0);
+    __nv_bfloat16* rt = S.res_tile + c0 * TC_BM + m;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < lim) {
+        const int n = c0 + j;
+        float y = act_tc<ACT>(fmaf(__uint_as_float(r[j]), epi[n], epi[nt + n]));
+        y = fmaf(y, epi[2 * nt + n], __bfloat162float(rt[j * TC_BM]));
+        y = fmaf(y, epi[3 * nt + n], epi[4 * nt + n]);
+        rt[j * TC_BM] = __float2bfloat16_rn(y);
+        if (valid) {
+          ssum += y; ssq = fmaf(y, y, ssq);
+          vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
+        }
+      }
+    }
+  }
+  emit_side_stats(a, b, ssum, ssq, vmax, vmin);
+}
+
 // waits for the accumulator, then drains it
 __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcLayout& L, const TcSmem& S, uint32_t tmem_base, int p0,
-                                            int n0, int b) {
+                                            int n0, int b, const CUtensorMap* tmapO) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lq = warp & 3, chalf = warp >> 2;
   const int q = p0 + lq * 32 + lane;
@@ -276,7 +316,21 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcLayout& L
   const int c_begin = chalf * ncols;
   int c_end = (chalf + 1) * ncols;
   if (c_end > a.O - n0) c_end = a.O - n0;        // warp-uniform: skip all-padding column groups
-  if (L.plain_epi) {
+  if (L.res_tma) {
+    const int m = lq * 32 + lane;
+    switch (a.act) {
+      case VRCOC_ACT_NONE: epi_full_tile<VRCOC_ACT_NONE>(a, L, S, tbase, c_begin, c_end, n0, b, m, valid); break;
+      case VRCOC_ACT_RELU: epi_full_tile<VRCOC_ACT_RELU>(a, L, S, tbase, c_begin, c_end, n0, b, m, valid); break;
+      default: epi_full_tile<VRCOC_ACT_GELU>(a, L, S, tbase, c_begin, c_end, n0, b, m, valid); break;
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tma_store_3d(tmapO, S.res_tile, p0, n0, b);     // clipped to the tensor: padding channels / points are not written
+      tma_store_commit();
+      tma_store_wait_read();
+    }
+  } else if (L.plain_epi) {
     mbar_wait(S.bar_acc, 0);
     tc_fence_after();
     const bool bf = a.out_dtype == VRCOC_BF16;
@@ -310,18 +364,38 @@ __device__ __forceinline__ void tc_teardown(const TcLayout& L, uint32_t tmem_bas
   }
 }
 
+// optional per-CTA phase trace (debug aid for tools/trace_cta.py): 8 x u64 nanosecond timestamps per CTA
+__device__ unsigned long long* g_tc_trace = nullptr;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace(int slot) {
+  unsigned long long* tr = g_tc_trace;
+  if (tr) tr[((blockIdx.z * gridDim.y + blockIdx.y) * (size_t)gridDim.x + blockIdx.x) * 8 + slot] = gtime();
+}
+
 // ---- kernel 1: both operands by TMA, warp-specialised -----------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_tma_kernel(ConvArgs a, TcLayout L, const __grid_constant__ CUtensorMap tmapA,
-                                                                 const __grid_constant__ CUtensorMap tmapB) {
+                                                                 const __grid_constant__ CUtensorMap tmapB,
+                                                                 const __grid_constant__ CUtensorMap tmapR,
+                                                                 const __grid_constant__ CUtensorMap tmapO) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const TcSmem S = carve(smem_raw, L);
   const int tid = threadIdx.x;
   const int b = blockIdx.z, p0 = blockIdx.x * TC_BM, n0 = blockIdx.y * L.n_tile;
   if (tid == 64) {
+    trace(0);
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapB)) : "memory");
   }
   const uint32_t tmem_base = tc_setup(a, L, S, n0);
+  if (tid == 64) trace(1);
+  if (tid == 96 && L.res_tma) {                       // residual tile: in flight during the whole main loop
+    mbar_expect_tx(S.bar_res, (uint32_t)(L.n_tile * TC_BM * 2));
+    tma_load_3d(S.res_tile, &tmapR, p0, n0, b, S.bar_res);
+  }
   const int nk = (a.K + TC_BK - 1) / TC_BK;
   const int NS = L.stages;
   if (tid == 0) {
@@ -341,16 +415,19 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_tma_kernel(ConvArgs a, 
     for (int kc = 0; kc < nk; ++kc) {
       const int s = kc % NS;
       mbar_wait(&S.bar_full[s], (uint32_t)(kc / NS) & 1);
+      if (kc == 0) trace(2);
       tc_fence_after();
       const int ksteps = (min(TC_BK, a.K - kc * TC_BK) + 15) >> 4;
       issue_slab_mmas(tmem_base, smem_u32(S.sA + s * TC_A_BYTES), smem_u32(S.sB + s * L.b_bytes), idesc, ksteps, kc == 0);
       tc_commit(&S.bar_free[s]);
-      if (kc == nk - 1) tc_commit(S.bar_acc);
+      if (kc == nk - 1) { tc_commit(S.bar_acc); trace(3); }
     }
   }
   __syncwarp();
-  tc_epilogue(a, L, S, tmem_base, p0, n0, b);
+  tc_epilogue(a, L, S, tmem_base, p0, n0, b, &tmapO);
+  if (tid == 64) trace(4);
   tc_teardown(L, tmem_base);
+  if (tid == 64) trace(5);
 }
 
 // ---- kernel 2: transform-on-load A ------------------------------------------------------------------------------------------
@@ -439,7 +516,9 @@ __device__ __forceinline__ void slab_sstore(int kc, int ksteps, int a_krow0, int
 }
 
 template <typename TS, bool FAST>
-__global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_xform_kernel(ConvArgs a, TcLayout L, const __grid_constant__ CUtensorMap tmapB) {
+__global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_xform_kernel(ConvArgs a, TcLayout L, const __grid_constant__ CUtensorMap tmapB,
+                                                                   const __grid_constant__ CUtensorMap tmapR,
+                                                                   const __grid_constant__ CUtensorMap tmapO) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const TcSmem S = carve(smem_raw, L);
   const int tid = threadIdx.x;
@@ -450,6 +529,10 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_xform_kernel(ConvArgs a
   if (tid == 64 && L.use_tma_b) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmapB)) : "memory");
   build_prologue_table(a, b, S.tab);
   const uint32_t tmem_base = tc_setup(a, L, S, n0);
+  if (tid == 96 && L.res_tma) {
+    mbar_expect_tx(S.bar_res, (uint32_t)(L.n_tile * TC_BM * 2));
+    tma_load_3d(S.res_tile, &tmapR, p0, n0, b, S.bar_res);
+  }
 
   const int nk = (a.K + TC_BK - 1) / TC_BK;
   const uint32_t idesc = make_idesc(L.n_tile);
@@ -509,7 +592,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_xform_kernel(ConvArgs a
     if (kc + 1 < nk) slab_gload<TS, FAST>(a, b, kc + 1, a_krow0, q0, P, taps, raw);
   }
 
-  tc_epilogue(a, L, S, tmem_base, p0, n0, b);
+  tc_epilogue(a, L, S, tmem_base, p0, n0, b, &tmapO);
   tc_teardown(L, tmem_base);
 }
 
@@ -519,8 +602,15 @@ static bool tma_a_eligible(const ConvArgs& a) {
          ((reinterpret_cast<uintptr_t>(a.weight) & 15) == 0) && tma_encode_fn() != nullptr;
 }
 
+static bool res_tma_eligible(const ConvArgs& a) {
+  return a.res && a.res_dtype == VRCOC_BF16 && a.out_dtype == VRCOC_BF16 && a.O_split == a.O && a.P_out % 8 == 0 &&
+         ((reinterpret_cast<uintptr_t>(a.res) | reinterpret_cast<uintptr_t>(a.out)) & 15) == 0 && tma_encode_fn() != nullptr &&
+         (a.act == VRCOC_ACT_NONE || a.act == VRCOC_ACT_RELU || a.act == VRCOC_ACT_GELU);
+}
+
 static int tc_smem_bytes(const ConvArgs& a, int n_tile, int stages) {
-  return stages * (TC_A_BYTES + n_tile * 128) + a.Cin * 16 + 5 * n_tile * 4 + (2 * TC_MAX_STAGES + 1) * 8 + 64 + 1024;
+  return stages * (TC_A_BYTES + n_tile * 128) + a.Cin * 16 + 5 * n_tile * 4 + (res_tma_eligible(a) ? n_tile * TC_BM * 2 : 0) +
+         (2 * TC_MAX_STAGES + 2) * 8 + 64 + 1024 + 128;
 }
 
 static int tc_resident(const ConvArgs& a, int n_tile, int stages) {
@@ -565,8 +655,10 @@ static TcLayout tc_layout(const ConvArgs& a) {
   L.off_b = L.stages * TC_A_BYTES;
   L.off_tab = L.off_b + L.stages * L.b_bytes;
   L.off_epi = L.off_tab + a.Cin * 16;
-  L.off_bar = (L.off_epi + 5 * L.n_tile * 4 + 15) & ~15;
-  L.total = L.off_bar + (2 * TC_MAX_STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+  L.res_tma = res_tma_eligible(a) ? 1 : 0;
+  L.off_res = (L.off_epi + 5 * L.n_tile * 4 + 127) & ~127;
+  L.off_bar = L.off_res + (L.res_tma ? L.n_tile * TC_BM * 2 : 0);
+  L.total = L.off_bar + (2 * TC_MAX_STAGES + 2) * 8 + 16 + 1024;   // + alignment slack
   return L;
 }
 
@@ -586,13 +678,31 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t*
 template <typename K>
 static void set_smem(K kern, int bytes) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
 
+}  // namespace vrcoc
+extern "C" int vrcoc_debug_set_trace(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(vrcoc::g_tc_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -2;
+}
+namespace vrcoc {
+
 int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   TcLayout L = tc_layout(a);
   VRCOC_REQUIRE(L.total <= 220 * 1024, "conv(tcgen05): shared memory budget exceeded (%d bytes)", L.total);
   VRCOC_REQUIRE(a.C1 == 0 || a.src1_dtype == a.src0_dtype, "conv(tcgen05): both sources must share a dtype");
-  CUtensorMap tmB, tmA;
+  CUtensorMap tmB, tmA, tmR, tmO;
   memset(&tmB, 0, sizeof(tmB));
   memset(&tmA, 0, sizeof(tmA));
+  memset(&tmR, 0, sizeof(tmR));
+  memset(&tmO, 0, sizeof(tmO));
+  if (L.res_tma) {
+    // residual / output [B][O][P] bf16; box = 128 points x n_tile channels, dense
+    cuuint64_t dims[3] = {(cuuint64_t)a.P_out, (cuuint64_t)a.O, (cuuint64_t)a.B};
+    cuuint64_t strides[2] = {(cuuint64_t)a.P_out * 2, (cuuint64_t)a.O * a.P_out * 2};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BM, (cuuint32_t)L.n_tile, 1};
+    int rc = tma_encode(&tmR, VRCOC_BF16, a.res, 3, dims, strides, box, false);
+    if (rc) return rc;
+    rc = tma_encode(&tmO, VRCOC_BF16, a.out, 3, dims, strides, box, false);
+    if (rc) return rc;
+  }
   if (L.use_tma_b) {
     // weights [O][K] bf16 row-major; box = 64 k (128 B) x n_tile rows, 128-byte swizzle, zero fill outside
     cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.O};
@@ -610,14 +720,14 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     int rc = encode(&tmA, a.src0, 3, dims, strides, box);
     if (rc) return rc;
     set_smem(conv_tc_tma_kernel, L.total);
-    conv_tc_tma_kernel<<<grid, TC_THREADS, L.total, st>>>(a, L, tmA, tmB);
+    conv_tc_tma_kernel<<<grid, TC_THREADS, L.total, st>>>(a, L, tmA, tmB, tmR, tmO);
     return check_launch("conv_tc_tma");
   }
   const bool f32 = a.src0_dtype == VRCOC_F32;
 #define LAUNCH(TS, FASTV)                                                        \
   do {                                                                           \
     set_smem(conv_tc_xform_kernel<TS, FASTV>, L.total);                          \
-    conv_tc_xform_kernel<TS, FASTV><<<grid, TC_THREADS, L.total, st>>>(a, L, tmB); \
+    conv_tc_xform_kernel<TS, FASTV><<<grid, TC_THREADS, L.total, st>>>(a, L, tmB, tmR, tmO); \
   } while (0)
   if (a.fast1x1) { if (f32) LAUNCH(float, true); else LAUNCH(__nv_bfloat16, true); }
   else           { if (f32) LAUNCH(float, false); else LAUNCH(__nv_bfloat16, false); }

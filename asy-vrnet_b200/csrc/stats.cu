@@ -75,8 +75,9 @@ __device__ __forceinline__ void publish_sums(float s, float s2, float* cs, doubl
       else { atomicAdd(&cs[2 * plane], s); atomicAdd(&cs[2 * plane + 1], s2); }
     }
     if (ss) {
-      atomicAdd(&ss[2 * (plane / C)], (double)s);
-      atomicAdd(&ss[2 * (plane / C) + 1], (double)s2);
+      double* dst = ss + ((int64_t)(plane / C) * VRCOC_STAT_SLOTS + ((plane + 5 * blockIdx.x) & (VRCOC_STAT_SLOTS - 1))) * 2;
+      atomicAdd(dst, (double)s);
+      atomicAdd(dst + 1, (double)s2);
     }
   }
 }

@@ -210,7 +210,7 @@ class ClusterBlock(nn.Module):
         pw, ph = tm._proposal()
         o, _, _ = ops.cluster_core_fwd(feat, value, f32(tm.sim_alpha), f32(tm.sim_beta), tm.heads, tm.fold_w, tm.fold_h, pw, ph,
                                        out_dtype=dt)
-        sums = torch.zeros(2, B, 2, device=dev, dtype=torch.float64)
+        sums = ops.new_sample_sums(B, dev, n=2)
         x1 = torch.empty_like(x)
         ops.conv_fwd(ops.conv_desc(o, tm.fc2.weight.detach().reshape(C, ED), x1, e_shift=f32(tm.fc2.bias), post_scale=ls1, res=x,
                                    out_sample_sums=sums[0]))

@@ -74,14 +74,23 @@ def cached(mod, key, sources, build):
 # statistics
 # ------------------------------------------------------------------------------------------------------------
 def channel_sums(x, want_chan=True, want_sample=False):
-    """-> (chan_sums float [B,C,2] or None, sample_sums double [B,2] or None)"""
+    """-> (chan_sums float [B,C,2] or None, sample_sums double [B,STAT_SLOTS,2] or None)"""
     _need_cuda(x)
     x = x.contiguous()
     B, Cc, H, W = x.shape
     cs = torch.empty(B, Cc, 2, device=x.device, dtype=torch.float32) if want_chan else None
-    ss = torch.zeros(B, 2, device=x.device, dtype=torch.float64) if want_sample else None
+    ss = new_sample_sums(B, x.device) if want_sample else None
     check(lib.vrcoc_channel_sums(_ptr(x), _dt(x), B, Cc, H * W, _ptr(cs), _ptr(ss), _stream()), "channel_sums")
     return cs, ss
+
+
+STAT_SLOTS = 32      # == VRCOC_STAT_SLOTS (include/vrcoc.h)
+
+
+def new_sample_sums(B, device, n=None):
+    """zeroed slot-wise GroupNorm statistics buffer(s): [B, STAT_SLOTS, 2] (or [n, B, STAT_SLOTS, 2]) float64"""
+    shape = (B, STAT_SLOTS, 2) if n is None else (n, B, STAT_SLOTS, 2)
+    return torch.zeros(shape, device=device, dtype=torch.float64)
 
 
 def sample_sums_of(x):
@@ -318,8 +327,9 @@ class GNProjFn(torch.autograd.Function):
         s = torch.empty(B, Cc, 2, device=x.device, dtype=torch.float32)
         check(lib.vrcoc_gn_bwd_sums(_ptr(dz), _ptr(x), _dt(x), B, Cc, P, _ptr(s), _stream()), "gn_bwd_sums")
         cnt = float(Cc * P)
-        mean = (sums[:, 0] / cnt)
-        var = (sums[:, 1] / cnt - mean * mean).clamp_min(0)
+        tot = sums.sum(dim=1)                                                   # reduce the slots -> [B,2]
+        mean = (tot[:, 0] / cnt)
+        var = (tot[:, 1] / cnt - mean * mean).clamp_min(0)
         rstd = torch.rsqrt(var + eps)
         mean32, rstd32 = mean.float(), rstd.float()
         s1, s2 = s[..., 0].double(), s[..., 1].double()                       # sum dz, sum dz*x   [B,C]
@@ -354,7 +364,7 @@ class ProjResidualFn(torch.autograd.Function):
         O = w2.shape[0]
         bias32, ls32 = _f32(bias), _f32(ls)
         out = torch.empty(B, O, H, W, device=h.device, dtype=res.dtype)
-        sums = torch.zeros(B, 2, device=h.device, dtype=torch.float64)
+        sums = new_sample_sums(B, h.device)
         conv_fwd(conv_desc(h, w2, out, e_shift=bias32, post_scale=ls32, res=res, out_sample_sums=sums))
         if any(ctx.needs_input_grad):
             ctx.save_for_backward(h, w2, bias32, ls32)

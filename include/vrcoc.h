@@ -36,6 +36,8 @@ extern "C" {
 #define VRCOC_F32 0
 #define VRCOC_BF16 1
 
+#define VRCOC_STAT_SLOTS 32
+
 /* epilogue activations */
 #define VRCOC_ACT_NONE 0
 #define VRCOC_ACT_RELU 1
@@ -52,7 +54,10 @@ int vrcoc_device_ok(void);
  * Statistics currency.
  *   channel sums: float [B][C][2] = {sum_hw x, sum_hw x^2}   (ShuffleAttention GN / avg-pool: shuffle_attention.py:57-64,
  *                 eca.py:17, BatchNorm2d batch statistics: normal_conv.py:45)
- *   sample sums : double [B][2]   = {sum_chw x, sum_chw x^2} (GroupNorm(1,C): vr_coc.py:105-111)
+ *   sample sums : double [B][VRCOC_STAT_SLOTS][2], slot-wise partial {sum_chw x, sum_chw x^2}; the statistic of sample b is
+ *                 the sum over its slots (GroupNorm(1,C): vr_coc.py:105-111).  Producers add one partial per CTA into
+ *                 slot (cta index mod VRCOC_STAT_SLOTS): a trace of the first version showed ~16 K fp64 atomics on 16
+ *                 addresses serialising in L2 (15 us per CTA); spreading them removes the contention.
  * ---------------------------------------------------------------------------------------------------------- */
 int vrcoc_channel_sums(const void* x, int dtype, int B, int C, int HW, float* chan_sums, double* sample_sums /*nullable, must be zeroed*/,
                        void* stream);
@@ -98,7 +103,7 @@ typedef struct vrcoc_conv_desc {
   /* outputs: channels [0,O_split) -> out, [O_split,O) -> out2 (out2 may be NULL when O_split == O) */
   void* out; int32_t out_dtype;
   void* out2; int32_t out2_dtype; int32_t O_split;
-  double* out_sample_sums; /* nullable [B][2], accumulated (caller zeroes) */
+  double* out_sample_sums; /* nullable [B][VRCOC_STAT_SLOTS][2], accumulated (caller zeroes) */
   uint32_t* out_minmax;    /* nullable [2] = {max bits(y), max ~bits(y)}, y >= 0 required, caller zeroes */
   /* 0 = pick automatically, 1 = force CUDA-core fp32 path, 2 = force tcgen05 bf16 path */
   int32_t engine;
@@ -178,6 +183,10 @@ int vrcoc_img_enh_finish(const void* k, int k_dtype, const void* image, int imag
                          const uint32_t* minmax, const float* s, const float* t, int B, int C, int HW,
                          float* out_chan_sums /*nullable [B][C][2]*/, void* stream);
 
+
+/* Debug aid: when `buf` is non-NULL the tcgen05 TMA kernel writes 8 u64 nanosecond phase timestamps per CTA into it
+ * (start, setup done, first operands landed, last MMA committed, epilogue done, TMEM released); NULL switches it off. */
+int vrcoc_debug_set_trace(unsigned long long* buf);
 
 /* Bilinear upsample with align_corners=True over `planes` = B*C maps (nn.Upsample inside CoCUpsample,
  * reference neck/coc_fpn_dual.py:19-22). */

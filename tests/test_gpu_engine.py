@@ -83,7 +83,7 @@ def test_tcgen05_full_epilogue_and_prologue(env):
         from vrcoc._lib import ACT_GELU
         o1 = torch.empty(B, 64, H, W, device="cuda", dtype=torch.float32)
         o2 = torch.empty(B, O - 64, H, W, device="cuda", dtype=torch.bfloat16)
-        ss = torch.zeros(B, 2, device="cuda", dtype=torch.float64)
+        ss = ops.new_sample_sums(B, "cuda")
         d = ops.conv_desc(x, w.reshape(O, C).contiguous(), o1, gn=(sums, gamma, beta, 1e-5), e_shift=bias, act=ACT_GELU,
                           post_scale=ls, res=res, f_scale=fs, f_shift=fh, out2=o2, out_sample_sums=ss, engine=engine)
         ops.conv_fwd(d)
@@ -93,8 +93,8 @@ def test_tcgen05_full_epilogue_and_prologue(env):
         assert rel_err(got[:, :64], ref[:, :64]) < tol, engine
         assert rel_err(got, ref) < 5e-3, engine      # bf16 storage of the second output
         full = ref.double()
-        assert abs(ss[:, 0].sum().item() - full.sum().item()) < 2e-2 * full.abs().sum().item() ** 0.5 + 1e-3 * abs(full.sum().item())
-        assert abs(ss[:, 1].sum().item() / (full ** 2).sum().item() - 1) < 1e-2
+        assert abs(ss[..., 0].sum().item() - full.sum().item()) < 2e-2 * full.abs().sum().item() ** 0.5 + 1e-3 * abs(full.sum().item())
+        assert abs(ss[..., 1].sum().item() / (full ** 2).sum().item() - 1) < 1e-2
 
 
 def test_auto_engine_picks_tcgen05_for_bf16_weights(env):

@@ -72,7 +72,7 @@ def main():
             bias, ls = torch.zeros(O, device=dev), torch.ones(O, device=dev)
             res = torch.randn(B, O, H, H, device=dev, generator=g).to(dt)
             out = torch.empty_like(res)
-            sums = torch.zeros(B, 2, device=dev, dtype=torch.float64)
+            sums = ops.new_sample_sums(B, dev)
             d = ops.conv_desc(x, w, out, e_shift=bias, post_scale=ls, res=res, out_sample_sums=sums)
             fn = lambda: ops.conv_fwd(d)
             by, fl = B * P * (C + 2 * O) * es, 2.0 * B * P * C * O
