@@ -12,7 +12,9 @@ static int fill_args(const vrcoc_conv_desc* d, ConvArgs& a) {
   VRCOC_REQUIRE(d->B > 0 && d->H_in > 0 && d->W_in > 0 && d->H_out > 0 && d->W_out > 0 && d->O > 0 && d->C0 > 0 && d->C1 >= 0,
                 "conv: non-positive dimension");
   VRCOC_REQUIRE(d->kh > 0 && d->kw > 0 && d->stride > 0 && d->pad >= 0, "conv: bad kernel geometry");
-  VRCOC_REQUIRE(d->H_out == (d->H_in + 2 * d->pad - d->kh) / d->stride + 1 && d->W_out == (d->W_in + 2 * d->pad - d->kw) / d->stride + 1,
+  const int dil = d->dil > 0 ? d->dil : 1;
+  VRCOC_REQUIRE(d->H_out == (d->H_in + 2 * d->pad - dil * (d->kh - 1) - 1) / d->stride + 1 &&
+                    d->W_out == (d->W_in + 2 * d->pad - dil * (d->kw - 1) - 1) / d->stride + 1,
                 "conv: output size %dx%d inconsistent with input %dx%d k=%dx%d s=%d p=%d", d->H_out, d->W_out, d->H_in, d->W_in,
                 d->kh, d->kw, d->stride, d->pad);
   VRCOC_REQUIRE(d->src0 && d->weight && d->out, "conv: null src0/weight/out");
@@ -26,7 +28,7 @@ static int fill_args(const vrcoc_conv_desc* d, ConvArgs& a) {
                 "conv: unknown dtype");
   a.B = d->B; a.H_in = d->H_in; a.W_in = d->W_in; a.H_out = d->H_out; a.W_out = d->W_out;
   a.C0 = d->C0; a.C1 = d->C1; a.Cin = d->C0 + d->C1; a.O = d->O;
-  a.kh = d->kh; a.kw = d->kw; a.stride = d->stride; a.pad = d->pad;
+  a.kh = d->kh; a.kw = d->kw; a.stride = d->stride; a.pad = d->pad; a.dil = dil; a.k_order = d->k_order ? 1 : 0;
   a.K = a.Cin * d->kh * d->kw;
   a.P_in = d->H_in * d->W_in; a.P_out = d->H_out * d->W_out;
   a.src0 = d->src0; a.src0_dtype = d->src0_dtype; a.src0_bstride = d->src0_bstride;
@@ -206,6 +208,7 @@ extern "C" int vrcoc_conv_fwd(const vrcoc_conv_desc* d, void* stream) {
     VRCOC_REQUIRE(conv_tc_supported(a), "conv: tcgen05 engine forced but the problem is not supported by it");
     return launch_conv_tc(a, st);
   }
+  if (d->engine == 0 && conv_small_supported(a)) return launch_conv_small(a, st);
   if (d->engine == 0 && conv_tc_supported(a)) return launch_conv_tc(a, st);
   return launch_conv_simt(a, st);
 }

@@ -6,7 +6,8 @@ namespace vrcoc {
 
 // Kernel-side copy of vrcoc_conv_desc plus derived quantities (passed by value, < 4 KB of parameter space).
 struct ConvArgs {
-  int B, H_in, W_in, H_out, W_out, C0, C1, Cin, O, kh, kw, stride, pad;
+  int B, H_in, W_in, H_out, W_out, C0, C1, Cin, O, kh, kw, stride, pad, dil;
+  int k_order;  // 0: k = c*kh*kw + tap (PyTorch conv weight layout); 1: k = tap*Cin + c (tap-major, weight permuted by caller)
   int K;        // Cin * kh * kw
   int P_in, P_out;
   const void* src0; int src0_dtype; int64_t src0_bstride;
@@ -109,6 +110,8 @@ __device__ __forceinline__ void emit_side_stats(const ConvArgs& a, int b, float 
 }
 
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
+int launch_conv_small(const ConvArgs& a, cudaStream_t st);    // few-channel streaming kernel (conv_simt.cu)
+bool conv_small_supported(const ConvArgs& a);
 int launch_conv_tc(const ConvArgs& a, cudaStream_t st);       // tcgen05 bf16 path (conv_tc.cu)
 bool conv_tc_supported(const ConvArgs& a);
 

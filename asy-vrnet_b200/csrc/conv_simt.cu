@@ -51,8 +51,9 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(ConvArgs a) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) areg[i] = 0.f;
     if (kk >= a.K) return;
-    const int c = kk / taps;
-    const int tap = kk - c * taps;
+    int c, tap;
+    if (a.k_order) { tap = kk / a.Cin; c = kk - tap * a.Cin; }        // tap-major: k = tap*Cin + c
+    else { c = kk / taps; tap = kk - c * taps; }                      // channel-major (PyTorch weight layout)
     const int s = a.chan_src ? a.chan_src[c] : c;
     const void* src; int dt; int64_t base;
     if (s < a.C0) { src = a.src0; dt = a.src0_dtype; base = (int64_t)b * a.src0_bstride + (int64_t)s * a.P_in; }
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(ConvArgs a) {
         int q = q0 + i;
         if (q < P) {
           int oy = q / a.W_out, ox = q - oy * a.W_out;
-          int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
+          int iy = oy * a.stride - a.pad + ky * a.dil, ix = ox * a.stride - a.pad + kx * a.dil;
           if (iy >= 0 && iy < a.H_in && ix >= 0 && ix < a.W_in) {
             float x = ld_any(src, base + (int64_t)iy * a.W_in + ix, dt);
             float y = fmaf(x, t.x, t.y);
@@ -177,6 +178,75 @@ __global__ void __launch_bounds__(SIMT_THREADS) conv_simt_kernel(ConvArgs a) {
     }
   }
   emit_side_stats(a, b, ssum, ssq, vmax, vmin);
+}
+
+// ---- few-channel convolutions (the 512x512 ingest: 1x1 3->3 / 4->4 / 7->4 and the 3x3 4->3 radar projection) ---------------
+// O <= 8 outputs and K <= 64 taps: bandwidth-bound streaming work, one thread = one output pixel x all output channels;
+// the weights and the prologue table live in shared memory, the K gathered inputs of neighbouring pixels share L1 lines.
+// (On the GEMM tiles these layers waste >90 % of every 128x32x64 MMA slab and 16 K CTAs of fixed setup cost.)
+constexpr int SMALL_MAX_O = 8, SMALL_MAX_K = 64, SMALL_THREADS = 256;
+
+__global__ void __launch_bounds__(SMALL_THREADS) conv_small_kernel(ConvArgs a) {
+  __shared__ float wsm[SMALL_MAX_O * SMALL_MAX_K];
+  __shared__ float4 tab[SMALL_MAX_K];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < a.O * a.K; i += blockDim.x) wsm[i] = ld_any(a.weight, i, a.weight_dtype);
+  build_prologue_table(a, b, tab);
+  __syncthreads();
+  const int taps = a.kh * a.kw;
+  const int P = a.P_out;
+  float ssum = 0.f, ssq = 0.f, vmax = 0.f, vmin = __int_as_float(0x7f800000);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < P; q += gridDim.x * blockDim.x) {
+    const int oy = q / a.W_out, ox = q - oy * a.W_out;
+    float acc[SMALL_MAX_O];
+#pragma unroll
+    for (int o = 0; o < SMALL_MAX_O; ++o) acc[o] = 0.f;
+    int kk = 0;
+    for (int c = 0; c < a.Cin; ++c) {
+      const int s = a.chan_src ? a.chan_src[c] : c;
+      const void* src; int dt; int64_t base;
+      if (s < a.C0) { src = a.src0; dt = a.src0_dtype; base = (int64_t)b * a.src0_bstride + (int64_t)s * a.P_in; }
+      else          { src = a.src1; dt = a.src1_dtype; base = (int64_t)b * a.src1_bstride + (int64_t)(s - a.C0) * a.P_in; }
+      const float4 t = tab[c];
+      for (int ky = 0; ky < a.kh; ++ky) {
+        const int iy = oy * a.stride - a.pad + ky * a.dil;
+        for (int kx = 0; kx < a.kw; ++kx, ++kk) {
+          const int ix = ox * a.stride - a.pad + kx * a.dil;
+          float z = 0.f;
+          if (iy >= 0 && iy < a.H_in && ix >= 0 && ix < a.W_in) {
+            const float x = ld_any(src, base + (int64_t)iy * a.W_in + ix, dt);
+            z = fmaf(x, t.x, t.y);
+            if (a.has_gate) z *= sigmoidf_exact(fmaf(t.z, x, t.w));
+          }
+#pragma unroll
+          for (int o = 0; o < SMALL_MAX_O; ++o)
+            if (o < a.O) acc[o] = fmaf(wsm[o * a.K + kk], z, acc[o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < SMALL_MAX_O; ++o) {
+      if (o < a.O) {
+        const EpiCoef ec = load_epi(a, o);
+        const float r = a.res ? ld_any(a.res, ((int64_t)b * a.O + o) * P + q, a.res_dtype) : 0.f;
+        const float y = epilogue_value(acc[o], ec, a.act, r);
+        ssum += y; ssq = fmaf(y, y, ssq);
+        vmax = fmaxf(vmax, y); vmin = fminf(vmin, y);
+        if (o < a.O_split) st_any(a.out, ((int64_t)b * a.O_split + o) * P + q, a.out_dtype, y);
+        else st_any(a.out2, ((int64_t)b * (a.O - a.O_split) + (o - a.O_split)) * P + q, a.out2_dtype, y);
+      }
+    }
+  }
+  emit_side_stats(a, b, ssum, ssq, vmax, vmin);
+}
+
+bool conv_small_supported(const ConvArgs& a) { return a.O <= SMALL_MAX_O && a.K <= SMALL_MAX_K && a.k_order == 0; }
+
+int launch_conv_small(const ConvArgs& a, cudaStream_t st) {
+  int bx = (int)cdiv(a.P_out, SMALL_THREADS);
+  if (bx > 1024) bx = 1024;
+  conv_small_kernel<<<dim3(bx, a.B), SMALL_THREADS, 0, st>>>(a);
+  return check_launch("conv_small");
 }
 
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st) {

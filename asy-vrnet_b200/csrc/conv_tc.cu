@@ -442,11 +442,17 @@ struct __align__(16) RawSlab {
 template <typename TS, bool FAST>
 __device__ __forceinline__ void slab_gload(const ConvArgs& a, int b, int kc, int a_krow0, int q0, int P, int taps, RawSlab<TS>& raw) {
   raw.mask = 0;
+  // q0 is a multiple of 8: when W_out % 8 == 0 (every live map) the thread's 8 points share one output row
+  const int oy0 = FAST ? 0 : q0 / a.W_out, ox0 = FAST ? 0 : q0 - oy0 * a.W_out;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int kk = kc * TC_BK + a_krow0 + 16 * i;
     if (kk >= a.K || q0 >= P) continue;
-    const int c = FAST ? kk : kk / taps;
+    int c = kk, tap = 0;
+    if (!FAST) {
+      if (a.k_order) { tap = kk / a.Cin; c = kk - tap * a.Cin; }    // tap-major: the slab's rows are consecutive channels
+      else { c = kk / taps; tap = kk - c * taps; }
+    }
     const int sc = a.chan_src ? __ldg(a.chan_src + c) : c;
     const TS* src;
     if (sc < a.C0) src = reinterpret_cast<const TS*>(a.src0) + (int64_t)b * a.src0_bstride + (int64_t)sc * a.P_in;
@@ -460,28 +466,32 @@ __device__ __forceinline__ void slab_gload(const ConvArgs& a, int b, int kc, int
         reinterpret_cast<float4*>(raw.v)[2 * i + 1] = __ldg(reinterpret_cast<const float4*>(src + q0) + 1);
       }
     } else {
-      const int tap = kk - c * taps;
       const int ky = tap / a.kw, kx = tap - ky * a.kw;
-      // q0 is a multiple of 8: when W_out % 8 == 0 the 8 points share one output row
-      int oy = q0 / a.W_out, ox = q0 - oy * a.W_out;
+      int oy = oy0, ox = ox0;
+      int iy = oy * a.stride - a.pad + ky * a.dil;
+      const TS* row = src + (int64_t)iy * a.W_in;
+      int ix = ox * a.stride - a.pad + kx * a.dil;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (q0 + j < P) {
-          const int iy = oy * a.stride - a.pad + ky, ix = ox * a.stride - a.pad + kx;
-          if (iy >= 0 && iy < a.H_in && ix >= 0 && ix < a.W_in) {
-            raw.v[8 * i + j] = src[(int64_t)iy * a.W_in + ix];
-            raw.mask |= 1u << (8 * i + j);
-          }
+        if (q0 + j < P && iy >= 0 && iy < a.H_in && ix >= 0 && ix < a.W_in) {
+          raw.v[8 * i + j] = row[ix];
+          raw.mask |= 1u << (8 * i + j);
         }
-        if (++ox == a.W_out) { ox = 0; ++oy; }
+        ix += a.stride;
+        if (++ox == a.W_out) {                       // only when W_out % 8 != 0
+          ox = 0; ++oy;
+          iy = oy * a.stride - a.pad + ky * a.dil;
+          row = src + (int64_t)iy * a.W_in;
+          ix = -a.pad + kx * a.dil;
+        }
       }
     }
   }
 }
 
 template <typename TS, bool FAST, bool GATE>
-__device__ __forceinline__ void slab_sstore(int kc, int ksteps, int a_krow0, int a_blk, int a_c, int taps, const float4* tab,
-                                            const RawSlab<TS>& raw, unsigned char* As) {
+__device__ __forceinline__ void slab_sstore(int kc, int ksteps, int a_krow0, int a_blk, int a_c, int taps, int k_order, int cin,
+                                            const float4* tab, const RawSlab<TS>& raw, unsigned char* As) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int k = a_krow0 + 16 * i;
@@ -502,7 +512,7 @@ __device__ __forceinline__ void slab_sstore(int kc, int ksteps, int a_krow0, int
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = ((mk >> j) & 1u) ? (float)raw.v[8 * i + j] : 0.f;
       }
-      const float4 t = tab[FAST ? kk : kk / taps];
+      const float4 t = tab[FAST ? kk : (k_order ? kk % cin : kk / taps)];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float x = v[j];
@@ -576,8 +586,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_xform_kernel(ConvArgs a
     }
 
     // A slab: transform the prefetched raw data and store it in the UMMA layout
-    if (a.has_gate) slab_sstore<TS, FAST, true>(kc, ksteps, a_krow0, a_blk, a_c, taps, S.tab, raw, As);
-    else slab_sstore<TS, FAST, false>(kc, ksteps, a_krow0, a_blk, a_c, taps, S.tab, raw, As);
+    if (a.has_gate) slab_sstore<TS, FAST, true>(kc, ksteps, a_krow0, a_blk, a_c, taps, a.k_order, a.Cin, S.tab, raw, As);
+    else slab_sstore<TS, FAST, false>(kc, ksteps, a_krow0, a_blk, a_c, taps, a.k_order, a.Cin, S.tab, raw, As);
     fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
 

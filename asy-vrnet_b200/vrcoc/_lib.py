@@ -37,7 +37,7 @@ class ConvDesc(C.Structure):
         ("out", C.c_void_p), ("out_dtype", C.c_int32),
         ("out2", C.c_void_p), ("out2_dtype", C.c_int32), ("O_split", C.c_int32),
         ("out_sample_sums", C.c_void_p), ("out_minmax", C.c_void_p),
-        ("engine", C.c_int32),
+        ("engine", C.c_int32), ("dil", C.c_int32), ("k_order", C.c_int32),
     ]
 
 

@@ -95,7 +95,7 @@ def conv2d_native(x, weight, bias=None, stride=1, pad=0, extra=None, extra_bstri
     return _ConvFn.apply(x, weight, bias, stride, pad, extra, extra_bstride, act, e_scale, out_minmax, out_dtype)
 
 
-def _conv_launch(x, weight, bias32, stride, pad, extra, extra_bstride, act, e_scale, out_minmax, out_dtype):
+def _conv_launch(x, weight, bias32, stride, pad, extra, extra_bstride, act, e_scale, out_minmax, out_dtype, dil=1):
     ops._need_cuda(x)
     x = x.contiguous()
     B, C0, H, W = x.shape
@@ -109,11 +109,15 @@ def _conv_launch(x, weight, bias32, stride, pad, extra, extra_bstride, act, e_sc
             extra_bstride = 0
         if extra.shape[-3] != C1:
             raise VrcocError("conv: extra channel count mismatch")
-    Ho, Wo = ops.out_hw(H, W, kh, stride, pad)
+    Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
     out = torch.empty(B, O, Ho, Wo, device=x.device, dtype=out_dtype or x.dtype)
-    w2 = weight.detach().reshape(O, -1).contiguous()
+    # k x k convs on the tensor-core path use the tap-major K order (cheap gathers); few-channel convs (the 512x512 ingest)
+    # run on the streaming kernel, which takes the PyTorch order
+    tapm = kh * kw > 1 and weight.dtype == torch.bfloat16 and not (O <= 8 and Cin * kh * kw <= 64)
+    w2 = ops.tap_major(weight) if tapm else weight.detach().reshape(O, -1).contiguous()
     d = conv_desc(x, w2, out, src1=extra, src1_bstride=extra_bstride, kh=kh, kw=kw, stride=stride, pad=pad,
-                  e_scale=e_scale, e_shift=bias32, act=act, out_minmax=out_minmax)
+                  e_scale=e_scale, e_shift=bias32, act=act, out_minmax=out_minmax, dil=dil, k_order=1 if tapm else 0)
     conv_fwd(d)
     return out
 
@@ -138,6 +142,17 @@ class _ConvFn(torch.autograd.Function):
 
 
 _ACT_CODE = {"relu": ACT_RELU, "silu": ACT_SILU, "lrelu": ACT_LRELU}
+
+
+def conv_bn_relu_infer(x, conv, bn):
+    """Gradient-free eval-mode nn.Sequential(Conv2d(bias, dilation), BatchNorm2d, ReLU) (ASPP branches, reference
+    neck/coc_fpn_dual.py:49-79) as one implicit-GEMM launch: BN and the conv bias folded into the epilogue."""
+    sc, sh = _bn_affine(bn)
+    if conv.bias is not None:
+        sh = ops.cached(bn, "bias_fold", [conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var],
+                        lambda: sh + _f32(conv.bias) * sc)
+    return _conv_launch(x, conv.weight, sh, conv.stride[0], conv.padding[0], None, None, ACT_RELU, sc, None, None,
+                        dil=conv.dilation[0])
 
 
 class SiLU(nn.Module):

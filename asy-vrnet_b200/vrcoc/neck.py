@@ -94,11 +94,20 @@ class ASPP(nn.Module):
 
     def forward(self, x):
         b, c, row, col = x.size()
-        feats = [self.branch1(x), self.branch2(x), self.branch3(x), self.branch4(x)]
+        native = x.is_cuda and not torch.is_grad_enabled() and not self.training and x.dtype in (torch.float32, torch.bfloat16)
+        if native:     # eval, no autograd: every conv+BN+ReLU is one implicit-GEMM launch (dilation in the im2col gather)
+            from .fusion import conv_bn_relu_infer
+            feats = [conv_bn_relu_infer(x, br[0], br[1]) for br in (self.branch1, self.branch2, self.branch3, self.branch4)]
+        else:
+            feats = [self.branch1(x), self.branch2(x), self.branch3(x), self.branch4(x)]
         g = torch.mean(torch.mean(x, 2, True), 3, True)
         g = self.branch5_relu(self.branch5_bn(self.branch5_conv(g)))
         g = F.interpolate(g, (row, col), None, 'bilinear', True)
-        return self.conv_cat(torch.cat(feats + [g], dim=1))
+        cat = torch.cat(feats + [g], dim=1)
+        if native:
+            from .fusion import conv_bn_relu_infer
+            return conv_bn_relu_infer(cat, self.conv_cat[0], self.conv_cat[1])
+        return self.conv_cat(cat)
 
 
 class SpatialPyramidPooling(nn.Module):

@@ -107,7 +107,7 @@ def sample_sums_of(x):
 def conv_desc(src0, weight, out, *, src1=None, src0_bstride=None, src1_bstride=None, chan_src=None,
               gn=None, table=None, has_gate=False, kh=1, kw=1, stride=1, pad=0,
               e_scale=None, e_shift=None, act=ACT_NONE, post_scale=None, res=None, f_scale=None, f_shift=None,
-              out2=None, out_sample_sums=None, out_minmax=None, engine=ENGINE_AUTO, keep=None):
+              out2=None, out_sample_sums=None, out_minmax=None, engine=ENGINE_AUTO, keep=None, dil=1, k_order=0):
     """Fill a ConvDesc from tensors.  `keep` collects temporaries that must outlive the launch call."""
     d = ConvDesc()
     B = out.shape[0]
@@ -140,7 +140,23 @@ def conv_desc(src0, weight, out, *, src1=None, src0_bstride=None, src1_bstride=N
     d.O_split = O_split
     d.out_sample_sums, d.out_minmax = _ptr(out_sample_sums), _ptr(out_minmax)
     d.engine = engine
+    d.dil, d.k_order = dil, k_order
     return d
+
+
+def tap_major(weight):
+    """[O, C, kh, kw] -> [O, kh*kw*C] (k = tap*C + c), memoised on the weight tensor like `_f32`.  With this K order the
+    im2col rows of one 64-wide k slab are consecutive channels of a single tap, which makes the tcgen05 gather cheap."""
+    sig = (weight.data_ptr(), weight._version)
+    memo = weight.__dict__.get("_vrcoc_tapmajor") if hasattr(weight, "__dict__") else None
+    if memo is not None and memo[0] == sig:
+        return memo[1]
+    v = weight.detach().permute(0, 2, 3, 1).reshape(weight.shape[0], -1).contiguous()
+    try:
+        weight._vrcoc_tapmajor = (sig, v)
+    except Exception:
+        pass
+    return v
 
 
 def conv_fwd(desc):

@@ -107,6 +107,9 @@ typedef struct vrcoc_conv_desc {
   uint32_t* out_minmax;    /* nullable [2] = {max bits(y), max ~bits(y)}, y >= 0 required, caller zeroes */
   /* 0 = pick automatically, 1 = force CUDA-core fp32 path, 2 = force tcgen05 bf16 path */
   int32_t engine;
+  int32_t dil;     /* dilation (0 or 1 = dense); ASPP branches use 6/12/18 (neck/coc_fpn_dual.py:55-67) */
+  int32_t k_order; /* 0: weight[o][c][ky][kx] (PyTorch); 1: weight[o][ky][kx][c] (tap-major: the im2col rows of one k slab
+                      are consecutive channels of one tap -> cheap gathers on the tcgen05 path) */
 } vrcoc_conv_desc;
 
 int vrcoc_conv_fwd(const vrcoc_conv_desc* d, void* stream);

@@ -97,6 +97,23 @@ def test_tcgen05_full_epilogue_and_prologue(env):
         assert abs(ss[..., 1].sum().item() / (full ** 2).sum().item() - 1) < 1e-2
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 96, 16, 16, 3, 1, 1, 1), (1, 128, 64, 32, 32, 3, 2, 1, 1), (2, 64, 64, 16, 16, 3, 1, 6, 6),
+                                   (1, 320, 128, 16, 16, 3, 1, 12, 12), (2, 4, 3, 64, 64, 3, 1, 1, 1), (2, 7, 4, 64, 64, 1, 1, 0, 1)])
+def test_tap_major_dilation_and_small_kernel(env, shape):
+    """fusion._conv_launch picks: tap-major K order on the tensor-core path for k x k convs, dilation (ASPP), and the
+    few-channel streaming kernel for the ingest convs; all against torch conv2d on the same bf16 operands"""
+    from vrcoc import fusion
+    B, C, O, H, W, k, stride, pad, dil = shape
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, C, H, W, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(O, C, k, k, generator=g) / (C * k * k) ** 0.5).to(torch.bfloat16).cuda()
+    bias = torch.randn(O, generator=g).cuda()
+    ref = F.conv2d(x.float(), w.float(), bias, stride=stride, padding=pad, dilation=dil)
+    got = fusion._conv_launch(x, w, bias, stride, pad, None, None, 0, None, None, torch.float32, dil=dil)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < 1e-5
+
+
 def test_auto_engine_picks_tcgen05_for_bf16_weights(env):
     """fp32 weights -> exact CUDA-core path; bf16 weights -> tensor cores.  Seen through the numerics: with fp32
     activations and bf16 weights the tcgen05 path rounds the activation operand to bf16, the CUDA-core path does not."""
