@@ -345,6 +345,45 @@ upsample_bilinear_kernel(const T* __restrict__ x, T* __restrict__ out, int plane
   }
 }
 
+// ---- explicit im2col, tap-major: col[b][tap*C + c][q] = x[b][c][oy*s - p + ky*d][ox*s - p + kx*d] (0 outside) ---------------
+// Used for the k x k convolutions with many input channels on small maps (fusion radar projections, point reducers, ASPP):
+// the gathered matrix is written once (9x the input, a few MB at 16x16 / 32x32) and the GEMM then runs on the TMA-fed
+// tcgen05 kernel with no loader instructions, instead of every N-tile CTA re-gathering the same im2col rows.
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const T* __restrict__ x, T* __restrict__ col, int B, int C, int H, int W, int Ho, int Wo, int kh, int kw, int stride,
+              int pad, int dil) {
+  const int cols8 = (Wo + 7) >> 3;
+  const int taps = kh * kw;
+  const int64_t total = (int64_t)B * taps * C * Ho * cols8;
+  const int64_t Po = (int64_t)Ho * Wo;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(t % cols8);
+    int64_t r = t / cols8;
+    const int oy = (int)(r % Ho); r /= Ho;
+    const int c = (int)(r % C); r /= C;
+    const int tap = (int)(r % taps);
+    const int b = (int)(r / taps);
+    const int ky = tap / kw, kx = tap - ky * kw;
+    const int iy = oy * stride - pad + ky * dil;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (iy >= 0 && iy < H) {
+      const T* row = x + (((int64_t)b * C + c) * H + iy) * W;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ox = c8 * 8 + j;
+        const int ix = ox * stride - pad + kx * dil;
+        if (ox < Wo && ix >= 0 && ix < W) v[j] = ldf<T>(row + ix);
+      }
+    }
+    T* o = col + (((int64_t)b * taps + tap) * C + c) * Po + (int64_t)oy * Wo + c8 * 8;
+    if (c8 * 8 + 8 <= Wo && (reinterpret_cast<uintptr_t>(o) & 15) == 0) st8<T>(o, v);
+    else for (int j = 0; j < 8 && c8 * 8 + j < Wo; ++j) stf<T>(o + j, v[j]);
+  }
+}
+
 template <typename F>
 static int by_dtype(int dt, F&& f) {
   if (dt == VRCOC_F32) return f((float*)nullptr);
@@ -486,5 +525,20 @@ extern "C" int vrcoc_upsample_bilinear(const void* x, void* out, int dtype, int 
     using T = typename std::remove_pointer<decltype(t)>::type;
     upsample_bilinear_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, (T*)out, planes, H, W, Ho, Wo, sy, sx);
     return check_launch("upsample_bilinear");
+  });
+}
+
+extern "C" int vrcoc_im2col(const void* x, void* col, int dtype, int B, int C, int H, int W, int kh, int kw, int stride, int pad,
+                            int dil, void* stream) {
+  VRCOC_REQUIRE(x && col && B > 0 && C > 0 && H > 0 && W > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0 && dil > 0, "im2col: bad argument");
+  const int Ho = (H + 2 * pad - dil * (kh - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dil * (kw - 1) - 1) / stride + 1;
+  VRCOC_REQUIRE(Ho > 0 && Wo > 0, "im2col: empty output");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = (int64_t)B * kh * kw * C * Ho * ((Wo + 7) / 8);
+  int blocks = (int)(cdiv(total, 256) < 148 * 32 ? cdiv(total, 256) : 148 * 32);
+  return by_dtype(dtype, [&](auto* t) {
+    using T = typename std::remove_pointer<decltype(t)>::type;
+    im2col_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, (T*)col, B, C, H, W, Ho, Wo, kh, kw, stride, pad, dil);
+    return check_launch("im2col");
   });
 }

@@ -116,6 +116,14 @@ def _conv_launch(x, weight, bias32, stride, pad, extra, extra_bstride, act, e_sc
     # run on the streaming kernel, which takes the PyTorch order
     tapm = kh * kw > 1 and weight.dtype == torch.bfloat16 and not (O <= 8 and Cin * kh * kw <= 64)
     w2 = ops.tap_major(weight) if tapm else weight.detach().reshape(O, -1).contiguous()
+    if tapm and extra is None and Cin >= 32 and x.dtype == torch.bfloat16 and (Ho * Wo) % 8 == 0:
+        # many channels: materialise the tap-major im2col matrix once and run the TMA-only 1x1 kernel on it, instead of
+        # re-gathering the same rows in every N-tile CTA (9x the input: a few MB on the 16x16..64x64 maps where this is used)
+        col = torch.empty(B, kh * kw * Cin, Ho, Wo, device=x.device, dtype=x.dtype)
+        check(lib.vrcoc_im2col(_ptr(x), _ptr(col), _dt(x), B, Cin, H, W, kh, kw, stride, pad, dil, _stream()), "im2col")
+        d = conv_desc(col, w2, out, e_scale=e_scale, e_shift=bias32, act=act, out_minmax=out_minmax)
+        conv_fwd(d)
+        return out
     d = conv_desc(x, w2, out, src1=extra, src1_bstride=extra_bstride, kh=kh, kw=kw, stride=stride, pad=pad,
                   e_scale=e_scale, e_shift=bias32, act=act, out_minmax=out_minmax, dil=dil, k_order=1 if tapm else 0)
     conv_fwd(d)
