@@ -95,23 +95,36 @@ __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
 
 // branch-free GELU: 0.5 x (1 + erf(x/sqrt2)) through erfc(|z|) ~ poly(t) exp(-z^2), t = 1/(1 + p|z|)  (A&S 7.1.26,
 // |erfc error| < 1.5e-7); the two tails are formed without cancellation.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// (the first version used __frcp_rn / __expf: ncu + SASS showed a guarded Newton reciprocal with a CALL slow path and a
+// denormal-range fix-up around every exponential, ~35 instructions per output; this form is 16, all single-issue)
 __device__ __forceinline__ float gelu_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float u = p * t * __expf(-z * z);          // erfc(|z|)
-  const float half_u = 0.5f * u;
-  return x * (x >= 0.f ? 1.0f - half_u : half_u);
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);   // 0.5 * erfc polynomial
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  const float half_u = p * t * ex2_approx(z * z * -1.4426950408889634f);   // 0.5 * erfc(|z|)
+  const float r = x * half_u;
+  return x >= 0.f ? x - r : r;
 }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f)); }
 
 template <int ACT>
 __device__ __forceinline__ float act_tc(float y) {
   if (ACT == VRCOC_ACT_RELU) return fmaxf(y, 0.f);
   if (ACT == VRCOC_ACT_GELU) return gelu_fast(y);
-  if (ACT == VRCOC_ACT_SILU) return y * sigmoidf_exact(y);
+  if (ACT == VRCOC_ACT_SILU) return y * sigmoid_fast(y);
   if (ACT == VRCOC_ACT_LRELU) return y > 0.f ? y : 0.1f * y;
   return y;
 }
@@ -185,28 +198,39 @@ __device__ __forceinline__ uint32_t tc_setup(const ConvArgs& a, const TcLayout& 
 // ---- epilogue -------------------------------------------------------------------------------------------------------------
 // PLAIN: out[o] = act(acc*es + eh), single output tensor of type TO.
 template <int ACT, typename TO>
+__device__ __forceinline__ void epi_plain_group(const uint32_t (&r)[16], const float* es, const float* eh, TO* optr, int64_t P, int lim,
+                                                bool valid, bool fast) {
+  if (fast) {                                // warp-uniform fast path: no per-column predicates
+#pragma unroll
+    for (int j = 0; j < 16; ++j) stf<TO>(optr + j * P, act_tc<ACT>(fmaf(__uint_as_float(r[j]), es[j], eh[j])));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < lim && valid) stf<TO>(optr + j * P, act_tc<ACT>(fmaf(__uint_as_float(r[j]), es[j], eh[j])));
+  }
+}
+
+// PLAIN: out[o] = act(acc*es + eh); channels [0,O_split) go to `out`, the rest to `out2` (a 16-column group never straddles
+// the split: O_split % 16 == 0, host-checked), each with its own storage type.
+template <int ACT>
 __device__ __forceinline__ void epi_plain(const ConvArgs& a, const TcLayout& L, const float* epi, uint32_t tbase, int c_begin,
                                           int c_end, int n0, int b, int q, bool valid) {
   const int64_t P = a.P_out;
-  TO* optr = reinterpret_cast<TO*>(a.out) + ((int64_t)b * a.O + n0 + c_begin) * P + q;
   const bool all_valid = __all_sync(0xffffffffu, valid);
   for (int c0 = c_begin; c0 < c_end; c0 += 16) {
     uint32_t r[16];
     tmem_ld16(tbase + (uint32_t)c0, r);
-    const int lim = min(16, a.O - n0 - c0);
-    if (lim == 16 && all_valid) {          // warp-uniform fast path: no per-column predicates
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        stf<TO>(optr, act_tc<ACT>(fmaf(__uint_as_float(r[j]), epi[c0 + j], epi[L.n_tile + c0 + j])));
-        optr += P;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (j < lim && valid) stf<TO>(optr, act_tc<ACT>(fmaf(__uint_as_float(r[j]), epi[c0 + j], epi[L.n_tile + c0 + j])));
-        optr += P;
-      }
-    }
+    const int o0 = n0 + c0;
+    const int lim = min(16, a.O - o0);
+    const bool fast = lim == 16 && all_valid;
+    const bool second = o0 >= a.O_split;
+    const int odt = second ? a.out2_dtype : a.out_dtype;
+    void* obase = second ? a.out2 : a.out;
+    const int64_t oidx = (second ? ((int64_t)b * (a.O - a.O_split) + (o0 - a.O_split)) : ((int64_t)b * a.O_split + o0)) * P + q;
+    const float* es = epi + c0;
+    const float* eh = epi + L.n_tile + c0;
+    if (odt == VRCOC_BF16) epi_plain_group<ACT, __nv_bfloat16>(r, es, eh, reinterpret_cast<__nv_bfloat16*>(obase) + oidx, P, lim, valid, fast);
+    else epi_plain_group<ACT, float>(r, es, eh, reinterpret_cast<float*>(obase) + oidx, P, lim, valid, fast);
   }
 }
 
@@ -333,10 +357,7 @@ __device__ __forceinline__ void tc_epilogue(const ConvArgs& a, const TcLayout& L
   } else if (L.plain_epi) {
     mbar_wait(S.bar_acc, 0);
     tc_fence_after();
-    const bool bf = a.out_dtype == VRCOC_BF16;
-#define PLAIN(ACTV)                                                                                        \
-  if (bf) epi_plain<ACTV, __nv_bfloat16>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid);             \
-  else epi_plain<ACTV, float>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid)
+#define PLAIN(ACTV) epi_plain<ACTV>(a, L, S.epi, tbase, c_begin, c_end, n0, b, q, valid)
     switch (a.act) {
       case VRCOC_ACT_NONE: PLAIN(VRCOC_ACT_NONE); break;
       case VRCOC_ACT_RELU: PLAIN(VRCOC_ACT_RELU); break;
@@ -517,7 +538,7 @@ __device__ __forceinline__ void slab_sstore(int kc, int ksteps, int a_krow0, int
       for (int j = 0; j < 8; ++j) {
         const float x = v[j];
         float y = fmaf(x, t.x, t.y);
-        if (GATE) y *= sigmoidf_exact(fmaf(t.z, x, t.w));
+        if (GATE) y *= sigmoid_fast(fmaf(t.z, x, t.w));
         v[j] = (FAST || ((mk >> j) & 1u)) ? y : 0.f;
       }
     }
@@ -661,7 +682,7 @@ static TcLayout tc_layout(const ConvArgs& a) {
   while (L.tmem_cols < L.n_tile) L.tmem_cols *= 2;
   L.b_bytes = L.n_tile * 128;
   L.use_tma_b = (a.K % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.weight) & 15) == 0) && tma_encode_fn() != nullptr;
-  L.plain_epi = !a.res && !a.post_scale && !a.f_scale && !a.f_shift && !a.out_sample_sums && !a.out_minmax && a.O_split == a.O;
+  L.plain_epi = !a.res && !a.post_scale && !a.f_scale && !a.f_shift && !a.out_sample_sums && !a.out_minmax;
   L.off_b = L.stages * TC_A_BYTES;
   L.off_tab = L.off_b + L.stages * L.b_bytes;
   L.off_epi = L.off_tab + a.Cin * 16;
