@@ -384,6 +384,48 @@ im2col_kernel(const T* __restrict__ x, T* __restrict__ col, int B, int C, int H,
   }
 }
 
+// ---- depthwise k x k convolution (DWConv.dconv of the decoupled head, reference normal_conv.py:26-27) -------------------
+// one thread = 8 consecutive output columns of one (plane, row); weights of the plane in registers; bandwidth-bound.
+template <typename T, int K>
+__global__ void __launch_bounds__(256)
+dwconv_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out, int planes, int C,
+              int H, int W, int Ho, int Wo, int stride, int pad) {
+  const int cols8 = (Wo + 7) >> 3;
+  const int64_t total = (int64_t)planes * Ho * cols8;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(t % cols8);
+    const int64_t rowid = t / cols8;
+    const int oy = (int)(rowid % Ho);
+    const int64_t plane = rowid / Ho;
+    const int c = (int)(plane % C);
+    float wk[K * K];
+#pragma unroll
+    for (int i = 0; i < K * K; ++i) wk[i] = ldf<T>(w + (int64_t)c * K * K + i);
+    const float b0 = bias ? bias[c] : 0.f;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = b0;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      const int iy = oy * stride - pad + ky;
+      if (iy < 0 || iy >= H) continue;
+      const T* row = x + (plane * H + iy) * W;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ox = c8 * 8 + j;
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const int ix = ox * stride - pad + kx;
+          if (ox < Wo && ix >= 0 && ix < W) v[j] = fmaf(wk[ky * K + kx], ldf<T>(row + ix), v[j]);
+        }
+      }
+    }
+    T* o = out + (plane * Ho + oy) * (int64_t)Wo + c8 * 8;
+    if (c8 * 8 + 8 <= Wo && (reinterpret_cast<uintptr_t>(o) & 15) == 0) st8<T>(o, v);
+    else for (int j = 0; j < 8 && c8 * 8 + j < Wo; ++j) stf<T>(o + j, v[j]);
+  }
+}
+
 template <typename F>
 static int by_dtype(int dt, F&& f) {
   if (dt == VRCOC_F32) return f((float*)nullptr);
@@ -540,5 +582,21 @@ extern "C" int vrcoc_im2col(const void* x, void* col, int dtype, int B, int C, i
     using T = typename std::remove_pointer<decltype(t)>::type;
     im2col_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, (T*)col, B, C, H, W, Ho, Wo, kh, kw, stride, pad, dil);
     return check_launch("im2col");
+  });
+}
+
+extern "C" int vrcoc_dwconv(const void* x, const void* weight, const float* bias, void* out, int dtype, int B, int C, int H, int W,
+                            int k, int stride, int pad, void* stream) {
+  VRCOC_REQUIRE(x && weight && out && B > 0 && C > 0 && H > 0 && W > 0 && stride > 0 && pad >= 0, "dwconv: bad argument");
+  VRCOC_REQUIRE(k == 3 || k == 5, "dwconv: kernel size %d unsupported (3 or 5)", k);
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = (int64_t)B * C * Ho * ((Wo + 7) / 8);
+  int blocks = (int)(cdiv(total, 256) < 148 * 32 ? cdiv(total, 256) : 148 * 32);
+  return by_dtype(dtype, [&](auto* t) {
+    using T = typename std::remove_pointer<decltype(t)>::type;
+    if (k == 3) dwconv_kernel<T, 3><<<blocks, 256, 0, st>>>((const T*)x, (const T*)weight, bias, (T*)out, B * C, C, H, W, Ho, Wo, stride, pad);
+    else dwconv_kernel<T, 5><<<blocks, 256, 0, st>>>((const T*)x, (const T*)weight, bias, (T*)out, B * C, C, H, W, Ho, Wo, stride, pad);
+    return check_launch("dwconv");
   });
 }

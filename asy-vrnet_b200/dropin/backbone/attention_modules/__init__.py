@@ -1,0 +1,1 @@
+"""see backbone/__init__.py"""

@@ -61,6 +61,7 @@ SIGNATURES = {
     "vrcoc_img_enh_finish": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P, _P]),
     "vrcoc_debug_set_trace": (_I, [_P]),
     "vrcoc_im2col": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "vrcoc_dwconv": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vrcoc_upsample_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "vrcoc_gelu_bwd": (_I, [_P, _P, _P, _I, _L, _P]),
     "vrcoc_gn_bwd_sums": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),

@@ -214,9 +214,30 @@ class BaseConv(nn.Module):
     def _native(self):
         return isinstance(self.conv, nn.Conv2d) and self.conv.groups == 1
 
+    def _ds_infer(self, x):
+        """eval / no-grad DWConv + BN + act: native depthwise kernel, then the pointwise conv with BN and both biases
+        folded into one GEMM epilogue (head/decouplehead.py:24-37)."""
+        dconv, pconv, bn = self.conv.dconv, self.conv.pconv, self.bn
+        x = x.contiguous()
+        B, C, H, W = x.shape
+        k, stride, pad = dconv.kernel_size[0], dconv.stride[0], dconv.padding[0]
+        Ho, Wo = ops.out_hw(H, W, k, stride, pad)
+        y = torch.empty(B, C, Ho, Wo, device=x.device, dtype=x.dtype)
+        wd = dconv.weight.detach().reshape(C, k * k)
+        check(lib.vrcoc_dwconv(_ptr(x), _ptr(wd), _ptr(_f32(dconv.bias)), _ptr(y), _dt(x), B, C, H, W, k, stride, pad, _stream()), "dwconv")
+        sc, sh = _bn_affine(bn)
+        if pconv.bias is not None:
+            sh = ops.cached(self, "ds_bias_fold", [pconv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var],
+                            lambda: sh + _f32(pconv.bias) * sc)
+        return _conv_launch(y, pconv.weight, sh, 1, 0, None, None, _ACT_CODE[self._act_name], sc, None, None)
+
     def forward(self, x, out_minmax=None):
         if not self._native():
-            return self.act(self.bn(self.conv(x)))        # depthwise-separable head convs: library path (out of scope)
+            ds = isinstance(self.conv, DWConv) and self.conv.dconv.kernel_size[0] in (3, 5) and self.conv.dconv.dilation[0] == 1
+            if ds and x.is_cuda and not torch.is_grad_enabled() and not self.bn.training and x.dtype in (torch.float32, torch.bfloat16) \
+                    and self.conv.dconv.weight.dtype == x.dtype:
+                return self._ds_infer(x)
+            return self.act(self.bn(self.conv(x)))        # training / other configurations: library path (out of scope §8f)
         if not x.is_cuda:
             raise VrcocError("vrcoc BaseConv needs a CUDA tensor (no CPU fallback exists)")
         return _BaseConvFn.apply(x, self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias, self, out_minmax)

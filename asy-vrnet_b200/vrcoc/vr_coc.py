@@ -119,7 +119,8 @@ class VRCoC(nn.Module):
         x_radar = self.radar_initial(x_radar)
         x = self.image_enhance_by_radar1(x, x_radar)
         x_radar = self.radar_enhance_by_image1(x, x_radar)
-        pos = self.fea_pos.permute(2, 0, 1).to(x.dtype)
+        from . import ops
+        pos = ops.cached(self, "pos_" + str(x.dtype), [self.fea_pos], lambda: self.fea_pos.permute(2, 0, 1).to(x.dtype).contiguous())
         if pos.shape[-2:] != x.shape[-2:]:
             raise RuntimeError(f"Sizes of tensors must match: fea_pos is {tuple(pos.shape[-2:])}, input is {tuple(x.shape[-2:])}")
         x = self.patch_embed(x, extra=pos)

@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel time table to stderr")
+    ap.add_argument("--ncu-pass", action="store_true",
+                    help="profiling aid: run warmup+steps eager forwards (no CUDA graph, no timing, no JSON) and exit; used "
+                         "under `ncu --metrics gpu__time_duration.sum` to produce profiles/*launches*.csv")
     return ap.parse_args()
 
 
@@ -106,7 +109,8 @@ class ClockSampler:
 KERNELS_PER_CALL = {"vrcoc_channel_sums": 1, "vrcoc_conv_fwd": 1, "vrcoc_table_apply": 1, "vrcoc_cluster_core_fwd": 1,
                     "vrcoc_cluster_core_bwd": 2, "vrcoc_sa_gate_sums": 1, "vrcoc_radar_enh_table": 1, "vrcoc_chan_affine": 1,
                     "vrcoc_img_enh_finish": 1, "vrcoc_gelu_bwd": 1, "vrcoc_gn_bwd_sums": 1, "vrcoc_gn_bwd_apply": 1,
-                    "vrcoc_conv1x1_wgrad": 3}
+                    "vrcoc_conv1x1_wgrad": 3, "vrcoc_im2col": 1, "vrcoc_upsample_bilinear": 1,
+                    "vrcoc_dwconv": 1}
 
 
 def _esz(dt):
@@ -135,6 +139,13 @@ def _describe(name, args):
         pts = B * E * D * H * W
         M = args[17] * args[18]
         return f"cluster_core_fwd[E{E}xD{D}]@{H}x{W}", pts * (_esz(fdt) + _esz(vdt) + _esz(odt)), (2 * M + 5) * pts
+    if name == "vrcoc_im2col":
+        dt, B, C, H, W, kh, kw, stride, pad, dil = args[2:12]
+        Ho, Wo = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1, (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+        return f"im2col{kh}x{kw}[{C}]@{Ho}x{Wo}", B * C * _esz(dt) * (H * W + kh * kw * Ho * Wo), 0.0
+    if name == "vrcoc_upsample_bilinear":
+        dt, planes, H, W, Ho, Wo = args[2:8]
+        return f"upsample[{H}x{W}->{Ho}x{Wo}]", planes * _esz(dt) * (H * W + Ho * Wo), 0.0
     return name.replace("vrcoc_", ""), 0, 0.0
 
 
@@ -279,6 +290,14 @@ def run_ours(args):
         det, seg = model(x, r)
         return det, seg.argmax(dim=1).to(torch.uint8)
 
+    if args.ncu_pass:
+        with torch.no_grad():
+            for i in range(args.warmup + args.steps):
+                sx.copy_(devb[i % NBUF][0]); sr.copy_(devb[i % NBUF][1])
+                forward(sx, sr)
+        torch.cuda.synchronize()
+        return
+
     graph = None
     with torch.no_grad():
         sx.copy_(devb[0][0]); sr.copy_(devb[0][1])
@@ -367,7 +386,12 @@ def run_ours(args):
         roof = {"bound": "hbm", "achieved": hbm, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_frac}
     else:
         roof = {"bound": "tensor", "achieved": tfl, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tc_frac}
-    roof.update({"traffic": None, "kernel": top_label, "launches_timed": n, "avg_us": 1e3 * t_ms / n,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram__bytes_read+write per launch from `ncu --set full`
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(f"{top_label}|B{B}|{args.dtype}")
+    roof.update({"traffic": traffic, "kernel": top_label, "launches_timed": n, "avg_us": 1e3 * t_ms / n,
                  "share_of_native_time": t_ms / total_ms, "peak_source": pk["source"],
                  "hbm_frac": hbm_frac, "tensor_frac": tc_frac})
     if args.profile_kernels and rank == 0:

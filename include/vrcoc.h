@@ -196,6 +196,11 @@ int vrcoc_debug_set_trace(unsigned long long* buf);
 int vrcoc_im2col(const void* x, void* col, int dtype, int B, int C, int H, int W, int kh, int kw, int stride, int pad, int dil,
                  void* stream);
 
+/* Depthwise k x k convolution (k = 3 or 5; weight [C][k][k] in the activation dtype, optional fp32 bias): DWConv.dconv of the
+ * decoupled head (backbone/conv_utils/normal_conv.py:26-27, head/decouplehead.py:24-37). */
+int vrcoc_dwconv(const void* x, const void* weight, const float* bias, void* out, int dtype, int B, int C, int H, int W, int k,
+                 int stride, int pad, void* stream);
+
 /* Bilinear upsample with align_corners=True over `planes` = B*C maps (nn.Upsample inside CoCUpsample,
  * reference neck/coc_fpn_dual.py:19-22). */
 int vrcoc_upsample_bilinear(const void* x, void* out, int dtype, int planes, int H, int W, int Ho, int Wo, void* stream);
