@@ -240,9 +240,108 @@ __global__ void __launch_bounds__(SMALL_THREADS) conv_small_kernel(ConvArgs a) {
   emit_side_stats(a, b, ssum, ssq, vmax, vmin);
 }
 
+// Vectorised variant (stride 1, W_out % 8 == 0, one source dtype): one thread = 8 consecutive output pixels of a row x all
+// output channels; per (channel, ky) it loads the 8 + kw - 1 input window once (one 128-bit load + edge scalars) and reuses it
+// for the kw taps; outputs leave as 128-bit stores.
+template <typename TS, int MAXO>
+__global__ void __launch_bounds__(SMALL_THREADS) conv_small_vec_kernel(ConvArgs a) {
+  __shared__ float wsm[SMALL_MAX_O * SMALL_MAX_K];
+  __shared__ float4 tab[SMALL_MAX_K];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < a.O * a.K; i += blockDim.x) wsm[i] = ld_any(a.weight, i, a.weight_dtype);
+  build_prologue_table(a, b, tab);
+  __syncthreads();
+  const int P = a.P_out;
+  const int groups = P >> 3;
+  const int taps = a.kh * a.kw;
+  float ssum = 0.f, ssq = 0.f, vmax = 0.f, vmin = __int_as_float(0x7f800000);
+  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += gridDim.x * blockDim.x) {
+    const int q0 = gi << 3;
+    const int oy = q0 / a.W_out, ox0 = q0 - oy * a.W_out;
+    float acc[MAXO][8];
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[o][j] = 0.f;
+    for (int c = 0; c < a.Cin; ++c) {
+      const int s = a.chan_src ? a.chan_src[c] : c;
+      const TS* plane = (s < a.C0) ? reinterpret_cast<const TS*>(a.src0) + (int64_t)b * a.src0_bstride + (int64_t)s * a.P_in
+                                   : reinterpret_cast<const TS*>(a.src1) + (int64_t)b * a.src1_bstride + (int64_t)(s - a.C0) * a.P_in;
+      const float4 t = tab[c];
+      for (int ky = 0; ky < a.kh; ++ky) {
+        const int iy = oy - a.pad + ky;
+        if (iy < 0 || iy >= a.H_in) continue;
+        const TS* row = plane + (int64_t)iy * a.W_in;
+        const int ix0 = ox0 - a.pad;
+        float win[8 + 6];                                    // kw <= 7
+#pragma unroll
+        for (int j = 0; j < 8 + 6; ++j) {
+          win[j] = 0.f;
+          if (j < 8 + a.kw - 1) {
+            const int ix = ix0 + j;
+            if (ix >= 0 && ix < a.W_in) {
+              const float x = (float)row[ix];
+              float z = fmaf(x, t.x, t.y);
+              if (a.has_gate) z *= sigmoidf_exact(fmaf(t.z, x, t.w));
+              win[j] = z;
+            }
+          }
+        }
+        const float* wrow = wsm + c * taps + ky * a.kw;
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          if (kx < a.kw) {
+#pragma unroll
+            for (int o = 0; o < MAXO; ++o) {
+              if (o < a.O) {
+                const float wv = wrow[o * a.K + kx];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[o][j] = fmaf(wv, win[j + kx], acc[o][j]);
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o) {
+      if (o < a.O) {
+        const EpiCoef ec = load_epi(a, o);
+        float r[8], y[8];
+        if (a.res) load8_any(a.res, ((int64_t)b * a.O + o) * P + q0, a.res_dtype, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          y[j] = epilogue_value(acc[o][j], ec, a.act, a.res ? r[j] : 0.f);
+          ssum += y[j]; ssq = fmaf(y[j], y[j], ssq);
+          vmax = fmaxf(vmax, y[j]); vmin = fminf(vmin, y[j]);
+        }
+        if (o < a.O_split) store8_any(a.out, ((int64_t)b * a.O_split + o) * P + q0, a.out_dtype, y);
+        else store8_any(a.out2, ((int64_t)b * (a.O - a.O_split) + (o - a.O_split)) * P + q0, a.out2_dtype, y);
+      }
+    }
+  }
+  emit_side_stats(a, b, ssum, ssq, vmax, vmin);
+}
+
 bool conv_small_supported(const ConvArgs& a) { return a.O <= SMALL_MAX_O && a.K <= SMALL_MAX_K && a.k_order == 0; }
 
 int launch_conv_small(const ConvArgs& a, cudaStream_t st) {
+  const bool same_dt = a.C1 == 0 || a.src1_dtype == a.src0_dtype;
+  const bool vec = a.stride == 1 && a.dil == 1 && a.W_out % 8 == 0 && a.kw <= 7 && same_dt && a.vec_out;
+  if (vec) {
+    int bx = (int)cdiv(a.P_out / 8, SMALL_THREADS);
+    if (bx > 2048) bx = 2048;
+    dim3 grid(bx, a.B);
+    const bool f32 = a.src0_dtype == VRCOC_F32;
+    if (a.O <= 4) {
+      if (f32) conv_small_vec_kernel<float, 4><<<grid, SMALL_THREADS, 0, st>>>(a);
+      else conv_small_vec_kernel<__nv_bfloat16, 4><<<grid, SMALL_THREADS, 0, st>>>(a);
+    } else {
+      if (f32) conv_small_vec_kernel<float, 8><<<grid, SMALL_THREADS, 0, st>>>(a);
+      else conv_small_vec_kernel<__nv_bfloat16, 8><<<grid, SMALL_THREADS, 0, st>>>(a);
+    }
+    return check_launch("conv_small_vec");
+  }
   int bx = (int)cdiv(a.P_out, SMALL_THREADS);
   if (bx > 1024) bx = 1024;
   conv_small_kernel<<<dim3(bx, a.B), SMALL_THREADS, 0, st>>>(a);

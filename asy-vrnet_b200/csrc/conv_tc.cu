@@ -627,6 +627,185 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_xform_kernel(ConvArgs a
   tc_teardown(L, tmem_base);
 }
 
+// ---- kernel 3: persistent GroupNorm/table-prologue projection ------------------------------------------------------------------
+// For 1x1 projections with a prologue and K <= 384 (GroupNorm -> fc1|fc_v, GroupNorm -> mlp.fc1 + GELU): one CTA owns one
+// 128-point tile and a range of output channels.
+//   * threads 0..255 build the normalised bf16 A operand ONCE (all K slabs resident in shared memory), then become the 8
+//     epilogue warps;
+//   * warp 8 lane 0 streams weight slabs by TMA through a 4-deep ring (starts before A is ready);
+//   * warp 9 lane 0 issues tcgen05.mma for N tile j into TMEM buffer j&1 while the epilogue warps drain buffer (j-1)&1:
+//     the activation epilogue (the issue-bound part, profiles/) overlaps the tensor work and the weight traffic, and the A
+//     transform is not repeated per N tile as in conv_tc_xform_kernel.
+constexpr int TP_THREADS = 320;
+constexpr int TP_STAGES = 4;
+
+struct TpLayout {
+  int nt;            // N tile width (TMEM buffer = nt columns, two buffers)
+  int tiles;         // N tiles per CTA
+  int n_range;       // output channels per CTA = tiles * nt (last CTA / tile clipped by O)
+  int nslabs;        // K slabs (resident A)
+  int tmem_cols;
+  int b_bytes;       // nt * 128
+  int off_a, off_b, off_tab, off_epi, off_bar, total;
+};
+
+template <typename TS>
+__global__ void __launch_bounds__(TP_THREADS, 1) conv_tc_persist_kernel(ConvArgs a, TpLayout L, const __grid_constant__ CUtensorMap tmapB) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  unsigned char* smem = smem_raw + pad;
+  unsigned char* sA = smem + L.off_a;                                // [nslabs][16 KB]
+  unsigned char* sB = smem + L.off_b;                                // [TP_STAGES][b_bytes]
+  float4* tab = reinterpret_cast<float4*>(smem + L.off_tab);
+  float* epi = reinterpret_cast<float*>(smem + L.off_epi);           // [2][n_range]: scale, shift
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  uint64_t* bar_free = bar_full + TP_STAGES;
+  uint64_t* acc_full = bar_free + TP_STAGES;                         // [2]
+  uint64_t* acc_empty = acc_full + 2;                                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, p0 = blockIdx.x * TC_BM;
+  const int n_begin = blockIdx.y * L.n_range;
+  const int P = a.P_out;
+  int tiles = L.tiles;
+  if (n_begin + tiles * L.nt > a.O) tiles = (a.O - n_begin + L.nt - 1) / L.nt;
+
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)L.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 256) {
+    for (int i = 0; i < TP_STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_free[i], 1); }
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 8); mbar_init(&acc_empty[1], 8);      // one arrival per epilogue warp
+    mbar_fence_init();
+    tma_prefetch_desc(&tmapB);
+  }
+  build_prologue_table(a, b, tab);                                     // strides by blockDim.x: every thread takes part
+  if (tid < 256) {
+    for (int n = tid; n < L.n_range; n += 256) {
+      const int o = n_begin + n;
+      const bool in = o < a.O;
+      epi[n] = (in && a.e_scale) ? a.e_scale[o] : 1.f;
+      epi[L.n_range + n] = (in && a.e_shift) ? a.e_shift[o] : 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();                                                     // barriers + TMEM slot + tables visible
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int nk = L.nslabs;
+
+  if (warp == 8) {
+    // ---- weight producer --------------------------------------------------------------------------------------------
+    // the first TP_STAGES slabs need no free-slot wait and are issued before (A), i.e. while the other warps still build
+    // the A operand; everything after that depends on MMA progress and therefore has to come after the barrier
+    const int total = tiles * nk;
+    auto issue = [&](int it) {
+      const int s = it % TP_STAGES;
+      const int j = it / nk, kc = it - j * nk;
+      if (it >= TP_STAGES) mbar_wait(&bar_free[s], (uint32_t)((it / TP_STAGES) - 1) & 1);
+      mbar_expect_tx(&bar_full[s], (uint32_t)L.b_bytes);
+      tma_load_2d(sB + s * L.b_bytes, &tmapB, kc * TC_BK, n_begin + j * L.nt, &bar_full[s]);
+    };
+    if (lane == 0)
+      for (int it = 0; it < total && it < TP_STAGES; ++it) issue(it);
+    __syncwarp();
+    __syncthreads();                                                   // (A) the A operand is complete
+    if (lane == 0)
+      for (int it = TP_STAGES; it < total; ++it) issue(it);
+    __syncwarp();
+  } else if (warp == 9) {
+    __syncthreads();                                                   // (A)
+    // ---- MMA issuer ---------------------------------------------------------------------------------------------------
+    if (lane == 0) {
+      tc_fence_after();
+      const uint32_t idesc = make_idesc(L.nt);
+      int it = 0;
+      for (int j = 0; j < tiles; ++j) {
+        const int buf = j & 1;
+        if (j >= 2) { mbar_wait(&acc_empty[buf], (uint32_t)((j >> 1) - 1) & 1); tc_fence_after(); }
+        const uint32_t tacc = tmem_base + (uint32_t)(buf * L.nt);
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int s = it % TP_STAGES;
+          mbar_wait(&bar_full[s], (uint32_t)(it / TP_STAGES) & 1);
+          tc_fence_after();
+          const int ksteps = (min(TC_BK, a.K - kc * TC_BK) + 15) >> 4;
+          issue_slab_mmas(tacc, smem_u32(sA + kc * TC_A_BYTES), smem_u32(sB + s * L.b_bytes), idesc, ksteps, kc == 0);
+          tc_commit(&bar_free[s]);
+        }
+        tc_commit(&acc_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- A operand: transform on load, all K slabs resident -----------------------------------------------------------------
+    const int a_chunk = tid & 15, a_krow0 = tid >> 4, a_blk = a_chunk >> 3, a_c = a_chunk & 7;
+    const int q0 = p0 + a_chunk * 8;
+    RawSlab<TS> raw;
+    slab_gload<TS, true>(a, b, 0, a_krow0, q0, P, 1, raw);
+    for (int kc = 0; kc < nk; ++kc) {
+      const int ksteps = (min(TC_BK, a.K - kc * TC_BK) + 15) >> 4;
+      RawSlab<TS> cur = raw;
+      if (kc + 1 < nk) slab_gload<TS, true>(a, b, kc + 1, a_krow0, q0, P, 1, raw);
+      if (a.has_gate) slab_sstore<TS, true, true>(kc, ksteps, a_krow0, a_blk, a_c, 1, 0, a.Cin, tab, cur, sA + kc * TC_A_BYTES);
+      else slab_sstore<TS, true, false>(kc, ksteps, a_krow0, a_blk, a_c, 1, 0, a.Cin, tab, cur, sA + kc * TC_A_BYTES);
+    }
+    fence_async_smem();
+    __syncthreads();                                                   // (A)
+
+    // ---- epilogue warps ---------------------------------------------------------------------------------------------------------
+    const int lq = warp & 3, chalf = warp >> 2;
+    const int q = p0 + lq * 32 + lane;
+    const bool valid = q < P;
+    const bool all_valid = __all_sync(0xffffffffu, valid);
+    const int ncols = L.nt >> 1;
+    for (int j = 0; j < tiles; ++j) {
+      const int buf = j & 1;
+      mbar_wait(&acc_full[buf], (uint32_t)(j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * L.nt);
+      const int nloc = j * L.nt;                                       // tile offset inside the CTA's range
+      int c_end = (chalf + 1) * ncols;
+      if (c_end > a.O - n_begin - nloc) c_end = a.O - n_begin - nloc;
+      for (int c0 = chalf * ncols; c0 < c_end; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tbase + (uint32_t)c0, r);
+        const int o0 = n_begin + nloc + c0;
+        const int lim = min(16, a.O - o0);
+        const bool fast = lim == 16 && all_valid;
+        const bool second = o0 >= a.O_split;
+        const int odt = second ? a.out2_dtype : a.out_dtype;
+        void* obase = second ? a.out2 : a.out;
+        const int64_t oidx = (second ? ((int64_t)b * (a.O - a.O_split) + (o0 - a.O_split)) : ((int64_t)b * a.O_split + o0)) * P + q;
+        const float* es = epi + nloc + c0;
+        const float* eh = epi + L.n_range + nloc + c0;
+#define TP_EPI(ACTV)                                                                                                             \
+  if (odt == VRCOC_BF16) epi_plain_group<ACTV, __nv_bfloat16>(r, es, eh, reinterpret_cast<__nv_bfloat16*>(obase) + oidx, P, lim, valid, fast); \
+  else epi_plain_group<ACTV, float>(r, es, eh, reinterpret_cast<float*>(obase) + oidx, P, lim, valid, fast)
+        switch (a.act) {
+          case VRCOC_ACT_NONE: TP_EPI(VRCOC_ACT_NONE); break;
+          case VRCOC_ACT_RELU: TP_EPI(VRCOC_ACT_RELU); break;
+          case VRCOC_ACT_GELU: TP_EPI(VRCOC_ACT_GELU); break;
+          case VRCOC_ACT_SILU: TP_EPI(VRCOC_ACT_SILU); break;
+          default: TP_EPI(VRCOC_ACT_LRELU); break;
+        }
+#undef TP_EPI
+      }
+      // this warp is done reading TMEM buffer `buf`
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L.tmem_cols));
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------
 static bool tma_a_eligible(const ConvArgs& a) {
   return a.fast1x1 && a.src0_dtype == VRCOC_BF16 && !a.gn_sums && !a.table && !a.chan_src && a.C1 == 0 && (a.K % 8 == 0) &&
@@ -693,6 +872,43 @@ static TcLayout tc_layout(const ConvArgs& a) {
   return L;
 }
 
+static TpLayout tp_layout(const ConvArgs& a) {
+  TpLayout T{};
+  T.nslabs = (a.K + TC_BK - 1) / TC_BK;
+  T.nt = a.O >= 128 ? 128 : (int)cdiv(a.O, 32) * 32;
+  const int64_t m_tiles = cdiv(a.P_out, TC_BM) * a.B;
+  const int n_tiles_total = (int)cdiv(a.O, T.nt);
+  // resident CTAs per SM by shared memory / TMEM (2 x nt columns each)
+  const int smem1 = T.nslabs * TC_A_BYTES + TP_STAGES * T.nt * 128 + a.Cin * 16 + 2048;
+  int res = (220 * 1024) / (smem1 + 2 * n_tiles_total * T.nt * 4);
+  if (res > 2) res = 2;
+  if (res < 1) res = 1;
+  const int64_t slots = (int64_t)sm_count() * res;
+  // split the output channels over as many CTAs as it takes to fill the chip once, but never re-build A more than needed
+  int splits = (int)cdiv(slots, m_tiles);
+  if (splits > n_tiles_total) splits = n_tiles_total;
+  if (splits < 1) splits = 1;
+  T.tiles = (int)cdiv(n_tiles_total, splits);
+  T.n_range = T.tiles * T.nt;
+  T.tmem_cols = 32;
+  while (T.tmem_cols < 2 * T.nt) T.tmem_cols *= 2;
+  T.b_bytes = T.nt * 128;
+  T.off_b = 0;
+  T.off_a = TP_STAGES * T.b_bytes;
+  T.off_tab = T.off_a + T.nslabs * TC_A_BYTES;
+  T.off_epi = T.off_tab + a.Cin * 16;
+  T.off_bar = (T.off_epi + 2 * T.n_range * 4 + 15) & ~15;
+  T.total = T.off_bar + (2 * TP_STAGES + 4) * 8 + 16 + 1024;
+  return T;
+}
+
+static bool persist_eligible(const ConvArgs& a, const TcLayout& L) {
+  if (!a.fast1x1 || !L.plain_epi || !L.use_tma_b || a.chan_src || a.C1 != 0) return false;
+  if (!(a.gn_sums || a.table)) return false;             // prologue-free projections take the TMA-only kernel
+  if (a.K > 384 || a.O < 32) return false;
+  return tp_layout(a).total <= 220 * 1024;
+}
+
 bool conv_tc_supported(const ConvArgs& a) {
   if (a.weight_dtype != VRCOC_BF16) return false;
   if (a.C1 > 0 && a.src1_dtype != a.src0_dtype) return false;
@@ -755,6 +971,24 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     return check_launch("conv_tc_tma");
   }
   const bool f32 = a.src0_dtype == VRCOC_F32;
+  if (persist_eligible(a, L)) {
+    TpLayout T = tp_layout(a);
+    dim3 pgrid((unsigned)cdiv(a.P_out, TC_BM), (unsigned)cdiv(a.O, T.n_range), (unsigned)a.B);
+    // the weight box is nt rows here, not L.n_tile
+    cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.O};
+    cuuint64_t strides[1] = {(cuuint64_t)a.K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)T.nt};
+    int rc = encode(&tmB, a.weight, 2, dims, strides, box);
+    if (rc) return rc;
+    if (f32) {
+      set_smem(conv_tc_persist_kernel<float>, T.total);
+      conv_tc_persist_kernel<float><<<pgrid, TP_THREADS, T.total, st>>>(a, T, tmB);
+    } else {
+      set_smem(conv_tc_persist_kernel<__nv_bfloat16>, T.total);
+      conv_tc_persist_kernel<__nv_bfloat16><<<pgrid, TP_THREADS, T.total, st>>>(a, T, tmB);
+    }
+    return check_launch("conv_tc_persist");
+  }
 #define LAUNCH(TS, FASTV)                                                        \
   do {                                                                           \
     set_smem(conv_tc_xform_kernel<TS, FASTV>, L.total);                          \
