@@ -650,7 +650,7 @@ struct TpLayout {
 };
 
 template <typename TS>
-__global__ void __launch_bounds__(TP_THREADS, 1) conv_tc_persist_kernel(ConvArgs a, TpLayout L, const __grid_constant__ CUtensorMap tmapB) {
+__global__ void __launch_bounds__(TP_THREADS, 2) conv_tc_persist_kernel(ConvArgs a, TpLayout L, const __grid_constant__ CUtensorMap tmapB) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
   unsigned char* smem = smem_raw + pad;
@@ -893,9 +893,9 @@ static TpLayout tp_layout(const ConvArgs& a) {
   T.tmem_cols = 32;
   while (T.tmem_cols < 2 * T.nt) T.tmem_cols *= 2;
   T.b_bytes = T.nt * 128;
-  T.off_b = 0;
-  T.off_a = TP_STAGES * T.b_bytes;
-  T.off_tab = T.off_a + T.nslabs * TC_A_BYTES;
+  T.off_a = 0;
+  T.off_b = T.nslabs * TC_A_BYTES;
+  T.off_tab = T.off_b + TP_STAGES * T.b_bytes;
   T.off_epi = T.off_tab + a.Cin * 16;
   T.off_bar = (T.off_epi + 2 * T.n_range * 4 + 15) & ~15;
   T.total = T.off_bar + (2 * TP_STAGES + 4) * 8 + 16 + 1024;
@@ -923,7 +923,11 @@ static int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t*
 }
 
 template <typename K>
-static void set_smem(K kern, int bytes) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
+static void set_smem(K kern, int bytes) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  // ask for the largest shared-memory carve-out: residency (CTAs/SM) must not depend on the driver's L1/smem heuristic
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 
 }  // namespace vrcoc
 extern "C" int vrcoc_debug_set_trace(unsigned long long* buf) {
