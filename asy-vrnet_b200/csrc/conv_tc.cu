@@ -682,6 +682,7 @@ __global__ void __launch_bounds__(TP_THREADS, 2) conv_tc_persist_kernel(ConvArgs
     mbar_fence_init();
     tma_prefetch_desc(&tmapB);
   }
+  if (tid == 0) trace(0);
   build_prologue_table(a, b, tab);                                     // strides by blockDim.x: every thread takes part
   if (tid < 256) {
     for (int n = tid; n < L.n_range; n += 256) {
@@ -744,6 +745,7 @@ __global__ void __launch_bounds__(TP_THREADS, 2) conv_tc_persist_kernel(ConvArgs
     const int a_chunk = tid & 15, a_krow0 = tid >> 4, a_blk = a_chunk >> 3, a_c = a_chunk & 7;
     const int q0 = p0 + a_chunk * 8;
     RawSlab<TS> raw;
+    if (tid == 0) trace(1);
     slab_gload<TS, true>(a, b, 0, a_krow0, q0, P, 1, raw);
     for (int kc = 0; kc < nk; ++kc) {
       const int ksteps = (min(TC_BK, a.K - kc * TC_BK) + 15) >> 4;
@@ -753,6 +755,7 @@ __global__ void __launch_bounds__(TP_THREADS, 2) conv_tc_persist_kernel(ConvArgs
       else slab_sstore<TS, true, false>(kc, ksteps, a_krow0, a_blk, a_c, 1, 0, a.Cin, tab, cur, sA + kc * TC_A_BYTES);
     }
     fence_async_smem();
+    if (tid == 0) trace(2);
     __syncthreads();                                                   // (A)
 
     // ---- epilogue warps ---------------------------------------------------------------------------------------------------------
@@ -765,6 +768,7 @@ __global__ void __launch_bounds__(TP_THREADS, 2) conv_tc_persist_kernel(ConvArgs
       const int buf = j & 1;
       mbar_wait(&acc_full[buf], (uint32_t)(j >> 1) & 1);
       tc_fence_after();
+      if (tid == 0 && j == 0) trace(3);
       const uint32_t tbase = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * L.nt);
       const int nloc = j * L.nt;                                       // tile offset inside the CTA's range
       int c_end = (chalf + 1) * ncols;
@@ -798,13 +802,19 @@ __global__ void __launch_bounds__(TP_THREADS, 2) conv_tc_persist_kernel(ConvArgs
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
     }
+    if (tid == 0) trace(4);
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) trace(5);
   if (warp == 9) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L.tmem_cols));
   }
 }
+
+}  // namespace vrcoc
+#include "conv_tc_cm.cuh"
+namespace vrcoc {
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
 static bool tma_a_eligible(const ConvArgs& a) {
@@ -909,6 +919,71 @@ static bool persist_eligible(const ConvArgs& a, const TcLayout& L) {
   return tp_layout(a).total <= 220 * 1024;
 }
 
+// channel-major kernel: operand sourcing, ring depth and output tiles per CTA from a small cost model (time unit ~ us)
+struct CmPlan { TqLayout T; int xmode; double cost; };
+
+static bool cm_plan(const ConvArgs& a, CmPlan& best) {
+  if (!a.fast1x1 || !a.vec_out || a.chan_src || a.C1 != 0) return false;
+  if (a.weight_dtype != VRCOC_BF16 || (a.K % 8) != 0 || (reinterpret_cast<uintptr_t>(a.weight) & 15) != 0 || !tma_encode_fn()) return false;
+  // outputs / residual travel as TMA boxes of 32 channels: 16-byte aligned bases, the split on a 32-channel boundary,
+  // bf16 residual, and no residual into fp32 outputs (the staging region holds one or the other)
+  if (a.O_split != a.O && (a.O_split % 32) != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(a.out) & 15) != 0 || (a.O_split != a.O && (reinterpret_cast<uintptr_t>(a.out2) & 15) != 0)) return false;
+  if (a.res && (a.res_dtype != VRCOC_BF16 || (reinterpret_cast<uintptr_t>(a.res) & 15) != 0 || a.out_dtype != VRCOC_BF16 ||
+                (a.O_split != a.O && a.out2_dtype != VRCOC_BF16)))
+    return false;
+  const bool prologue = a.gn_sums || a.table || a.has_gate;
+  const bool tma_x = !prologue && a.src0_dtype == VRCOC_BF16 && (reinterpret_cast<uintptr_t>(a.src0) & 15) == 0 &&
+                     (a.src0_bstride % 8) == 0;
+  const int nslabs = (a.K + TC_BK - 1) / TC_BK;
+  const int n_tiles = (int)cdiv(a.O, TQ_MT);
+  const int64_t m_tiles = cdiv(a.P_out, TQ_NP) * a.B;
+  const bool plain = !(a.post_scale || a.res || a.f_scale || a.f_shift || a.out_sample_sums || a.out_minmax);
+  // measured (tools/microbench.py, B200): with both operands by TMA the point-major kernel keeps 3 CTAs per SM and wins
+  // whenever the last 128-channel tile would be partly empty (O = 64, 320); the channel-major kernel wins on full tiles
+  if (tma_x && (a.O % TQ_MT) != 0) return false;
+  const double epi_us = a.act == VRCOC_ACT_GELU || a.act == VRCOC_ACT_SILU ? 1.6 : (plain ? 0.5 : 0.8);
+  bool found = false;
+  const int modes[6] = {1, 1, 1, 0, 0, 0}, depth[6] = {2, 3, 4, 2, 3, 4};
+  for (int cand = 0; cand < (tma_x ? 6 : 3); ++cand) {
+    const int mode = tma_x ? modes[cand] : 2, st = depth[cand];
+    const int x_bytes = mode == 0 ? st * TQ_X_BYTES : nslabs * TQ_X_BYTES;
+    const int tab_bytes = mode == 2 ? a.Cin * 16 : 0;
+    const int total = x_bytes + st * TQ_W_BYTES + 8 * 4096 + tab_bytes + 256 + 1024;
+    if (total > 220 * 1024) continue;
+    const int res = (227 * 1024) / (total + 1024) >= 2 ? 2 : 1;
+    const int64_t slots = (int64_t)sm_count() * res;
+    const double x_us = mode == 2 ? 1.1 * nslabs : 0.6;
+    const double mma_us = nslabs * (mode == 0 ? 0.28 : 0.16) * (st == 2 ? 1.3 : (st == 3 ? 1.05 : 1.0));
+    for (int t = 1; t <= n_tiles; ++t) {
+      const int64_t ctas = m_tiles * cdiv(n_tiles, t);
+      const int64_t waves = cdiv(ctas, slots);
+      // co-resident CTAs share the SM's issue slots and fill bandwidth, but one's latency-bound phases (set-up, operand
+      // build, pipeline fill) hide behind the other's epilogue: 1.6x, not 2x, and only on the steady-state part
+      const double share = (res == 2 && ctas > (int64_t)sm_count()) ? 1.6 : 1.0;
+      const double tile_us = share * (mma_us > epi_us ? mma_us : epi_us);
+      const double cost = waves * (2.0 + x_us + t * tile_us + (mma_us < epi_us ? mma_us : epi_us));
+      if (!found || cost < best.cost - 1e-9) {
+        found = true;
+        best.cost = cost;
+        best.xmode = mode;
+        TqLayout& T = best.T;
+        T.stages = st;
+        T.nslabs = nslabs;
+        T.tiles = t;
+        T.plain = plain ? 1 : 0;
+        T.off_x = 0;
+        T.off_w = x_bytes;
+        T.off_stage = T.off_w + st * TQ_W_BYTES;
+        T.off_tab = T.off_stage + 8 * 4096;
+        T.off_bar = T.off_tab + tab_bytes;
+        T.total = total;
+      }
+    }
+  }
+  return found;
+}
+
 bool conv_tc_supported(const ConvArgs& a) {
   if (a.weight_dtype != VRCOC_BF16) return false;
   if (a.C1 > 0 && a.src1_dtype != a.src0_dtype) return false;
@@ -929,7 +1004,11 @@ static void set_smem(K kern, int bytes) {
   cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
+static int g_tc_use_cm = 1;
+
 }  // namespace vrcoc
+// debug / A-B switch: 0 routes 1x1 projections to the point-major kernels (tools/microbench.py --no-cm)
+extern "C" int vrcoc_debug_set_cm(int on) { vrcoc::g_tc_use_cm = on; return 0; }
 extern "C" int vrcoc_debug_set_trace(unsigned long long* buf) {
   return cudaMemcpyToSymbol(vrcoc::g_tc_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -2;
 }
@@ -962,6 +1041,66 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     int rc = encode(&tmB, a.weight, 2, dims, strides, box);
     if (rc) return rc;
   }
+  const bool f32 = a.src0_dtype == VRCOC_F32;
+  CmPlan cm;
+  if (g_tc_use_cm && cm_plan(a, cm)) {
+    const TqLayout& T = cm.T;
+    dim3 cgrid((unsigned)cdiv(a.P_out, TQ_NP), (unsigned)cdiv(a.O, T.tiles * TQ_MT), (unsigned)a.B);
+    CUtensorMap tmW, tmX, tmO1, tmO2, tmRes;
+    memset(&tmX, 0, sizeof(tmX));
+    memset(&tmO2, 0, sizeof(tmO2));
+    memset(&tmRes, 0, sizeof(tmRes));
+    {
+      // outputs [B][C][P]: box = one 128-byte row segment (64 bf16 / 32 fp32 points) x 32 channels, 128-byte swizzle
+      const int c1 = a.O_split, c2 = a.O - a.O_split;
+      const int e1 = a.out_dtype == VRCOC_BF16 ? 2 : 4;
+      cuuint64_t dims[3] = {(cuuint64_t)a.P_out, (cuuint64_t)c1, (cuuint64_t)a.B};
+      cuuint64_t strides[2] = {(cuuint64_t)a.P_out * e1, (cuuint64_t)c1 * a.P_out * e1};
+      cuuint32_t box[3] = {(cuuint32_t)(128 / e1), 32, 1};
+      int rc = tma_encode(&tmO1, a.out_dtype, a.out, 3, dims, strides, box, true);
+      if (rc) return rc;
+      if (c2 > 0) {
+        const int e2 = a.out2_dtype == VRCOC_BF16 ? 2 : 4;
+        cuuint64_t dims2[3] = {(cuuint64_t)a.P_out, (cuuint64_t)c2, (cuuint64_t)a.B};
+        cuuint64_t strides2[2] = {(cuuint64_t)a.P_out * e2, (cuuint64_t)c2 * a.P_out * e2};
+        cuuint32_t box2[3] = {(cuuint32_t)(128 / e2), 32, 1};
+        rc = tma_encode(&tmO2, a.out2_dtype, a.out2, 3, dims2, strides2, box2, true);
+        if (rc) return rc;
+      }
+      if (a.res) {
+        cuuint64_t dimsr[3] = {(cuuint64_t)a.P_out, (cuuint64_t)a.O, (cuuint64_t)a.B};
+        cuuint64_t stridesr[2] = {(cuuint64_t)a.P_out * 2, (cuuint64_t)a.O * a.P_out * 2};
+        cuuint32_t boxr[3] = {64, 32, 1};
+        rc = tma_encode(&tmRes, VRCOC_BF16, a.res, 3, dimsr, stridesr, boxr, true);
+        if (rc) return rc;
+      }
+    }
+    {
+      cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.O};
+      cuuint64_t strides[1] = {(cuuint64_t)a.K * 2};
+      cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TQ_MT};
+      int rc = encode(&tmW, a.weight, 2, dims, strides, box);
+      if (rc) return rc;
+    }
+    if (cm.xmode != 2) {
+      cuuint64_t dims[3] = {(cuuint64_t)a.P_in, (cuuint64_t)a.C0, (cuuint64_t)a.B};
+      cuuint64_t strides[2] = {(cuuint64_t)a.P_in * 2, (cuuint64_t)a.src0_bstride * 2};
+      cuuint32_t box[3] = {64, (cuuint32_t)TC_BK, 1};
+      int rc = encode(&tmX, a.src0, 3, dims, strides, box);
+      if (rc) return rc;
+    }
+#define LAUNCH_CM(TS, MODE)                                                                     \
+  do {                                                                                          \
+    set_smem(conv_tc_cm_kernel<TS, MODE>, T.total);                                             \
+    conv_tc_cm_kernel<TS, MODE><<<cgrid, TQ_THREADS, T.total, st>>>(a, T, tmW, tmX, tmO1, tmO2, tmRes); \
+  } while (0)
+    if (cm.xmode == 0) LAUNCH_CM(__nv_bfloat16, 0);
+    else if (cm.xmode == 1) LAUNCH_CM(__nv_bfloat16, 1);
+    else if (f32) LAUNCH_CM(float, 2);
+    else LAUNCH_CM(__nv_bfloat16, 2);
+#undef LAUNCH_CM
+    return check_launch("conv_tc_cm");
+  }
   dim3 grid((unsigned)cdiv(a.P_out, TC_BM), (unsigned)cdiv(a.O, L.n_tile), (unsigned)a.B);
   if (tma_a_eligible(a)) {
     // activations [B][C][P] bf16; box = 64 points (128 B) x 64 channels, lands as one MN-major SW128 block
@@ -974,7 +1113,6 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     conv_tc_tma_kernel<<<grid, TC_THREADS, L.total, st>>>(a, L, tmA, tmB, tmR, tmO);
     return check_launch("conv_tc_tma");
   }
-  const bool f32 = a.src0_dtype == VRCOC_F32;
   if (persist_eligible(a, L)) {
     TpLayout T = tp_layout(a);
     dim3 pgrid((unsigned)cdiv(a.P_out, TC_BM), (unsigned)cdiv(a.O, T.n_range), (unsigned)a.B);

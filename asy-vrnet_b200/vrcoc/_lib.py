@@ -60,6 +60,7 @@ SIGNATURES = {
     "vrcoc_chan_affine": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
     "vrcoc_img_enh_finish": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P, _P]),
     "vrcoc_debug_set_trace": (_I, [_P]),
+    "vrcoc_debug_set_cm": (_I, [_I]),
     "vrcoc_im2col": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vrcoc_dwconv": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vrcoc_upsample_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -191,6 +191,10 @@ int vrcoc_img_enh_finish(const void* k, int k_dtype, const void* image, int imag
  * (start, setup done, first operands landed, last MMA committed, epilogue done, TMEM released); NULL switches it off. */
 int vrcoc_debug_set_trace(unsigned long long* buf);
 
+/* Debug / A-B switch: on = 0 routes 1x1 projections to the point-major tcgen05 kernels instead of the channel-major one
+ * (conv_tc_cm.cuh); results are identical up to fp32 summation order.  Default 1. */
+int vrcoc_debug_set_cm(int on);
+
 /* Explicit tap-major im2col: col[b][(ky*kw+kx)*C + c][oy][ox] = x[b][c][oy*s-p+ky*d][ox*s-p+kx*d] (zero outside).  Feeds the
  * TMA-only tcgen05 kernel for k x k convolutions with many channels on small maps (vr_coc.py:99-102,313; coc_fpn_dual.py:55-67). */
 int vrcoc_im2col(const void* x, void* col, int dtype, int B, int C, int H, int W, int kh, int kw, int stride, int pad, int dil,
