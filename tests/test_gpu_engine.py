@@ -127,3 +127,59 @@ def test_auto_engine_picks_tcgen05_for_bf16_weights(env):
     assert rel_err(simt, ref) < 1e-6
     e = rel_err(auto, ref)
     assert 1e-4 < e < 6e-3, e
+
+
+CM_CASES = [  # B, C, O, H, W, split, act, mode
+    (2, 64, 256, 32, 32, 128, "none", "gn"),       # S1 fc1|fc_v: fp32 | bf16 split outputs, GroupNorm prologue
+    (2, 128, 1024, 32, 32, 0, "gelu", "gn"),       # S2 mlp.fc1: 8 output tiles per CTA range
+    (2, 320, 512, 32, 32, 256, "none", "gn"),      # 5 resident k-slabs
+    (2, 1024, 128, 32, 32, 0, "none", "res"),      # S2 mlp.fc2: both operands by TMA, residual + layer scale + statistics
+    (2, 2048, 512, 16, 16, 0, "none", "res"),      # streamed X, 32 k-slabs
+    (1, 4608, 512, 16, 16, 0, "relu", "plain"),    # ASPP branch GEMM
+    (2, 64, 72, 16, 24, 0, "none", "gn"),          # O not a multiple of 32: clipped TMA store rows
+    (3, 136, 200, 8, 24, 0, "gelu", "gn"),         # K = 2.1 slabs, 192 points: clipped point columns
+    (2, 64, 48, 5, 8, 0, "none", "gn"),            # 40 points: one partial tile
+]
+
+
+@pytest.mark.parametrize("case", CM_CASES, ids=[f"C{c[1]}_O{c[2]}_{c[3]}x{c[4]}_{c[7]}" for c in CM_CASES])
+def test_channel_major_kernel_matches_point_major(env, case):
+    """conv_tc_cm_kernel (weights as the M operand, TMA-staged epilogue) against the point-major tcgen05 kernels (switched
+    with vrcoc_debug_set_cm) and the CUDA-core engine: same bf16 operands, fp32 accumulation."""
+    ops = env
+    from vrcoc._lib import ACT_GELU, ACT_NONE, ACT_RELU, lib
+    B, C, O, H, W, split, act_name, mode = case
+    act = {"none": ACT_NONE, "gelu": ACT_GELU, "relu": ACT_RELU}[act_name]
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(B, C, H, W, generator=g) * 1.3 + 0.2).bfloat16().cuda()
+    w = (torch.randn(O, C, generator=g) / C ** 0.5).bfloat16().cuda()
+    kw = dict(e_shift=(torch.randn(O, generator=g) * 0.1).cuda(), e_scale=(torch.rand(O, generator=g) + 0.5).cuda(), act=act)
+    if mode == "gn":
+        _, sums = ops.channel_sums(x, want_chan=False, want_sample=True)
+        kw["gn"] = (sums, (torch.rand(C, generator=g) + 0.5).cuda(), (torch.randn(C, generator=g) * 0.1).cuda(), 1e-5)
+    if mode == "res":
+        kw.update(res=torch.randn(B, O, H, W, generator=g).bfloat16().cuda(), post_scale=(torch.rand(O, generator=g) + 0.5).cuda())
+    outs, stats, mm = {}, {}, {}
+    try:
+        for name, engine, cm in (("simt", 1, 1), ("cm", 2, 1), ("pm", 2, 0)):
+            lib.vrcoc_debug_set_cm(cm)
+            if split:
+                o1 = torch.full((B, split, H, W), float("nan"), device="cuda")
+                o2 = torch.full((B, O - split, H, W), float("nan"), device="cuda", dtype=torch.bfloat16)
+            else:
+                o1, o2 = torch.full((B, O, H, W), float("nan"), device="cuda", dtype=torch.bfloat16), None
+            k2 = dict(kw)
+            if mode == "res":
+                k2["out_sample_sums"] = ops.new_sample_sums(B, "cuda")
+            ops.conv_fwd(ops.conv_desc(x, w, o1, out2=o2, engine=engine, **k2))
+            torch.cuda.synchronize()
+            outs[name] = torch.cat([o1.float(), o2.float()], 1) if split else o1.float()
+            if mode == "res":
+                stats[name] = k2["out_sample_sums"].sum(1)
+    finally:
+        lib.vrcoc_debug_set_cm(1)
+    assert torch.isfinite(outs["cm"]).all(), "channel-major kernel left part of the output unwritten"
+    assert rel_err(outs["cm"], outs["pm"]) < 1e-5          # same operands, same accumulation: rounding-order noise only
+    assert rel_err(outs["cm"], outs["simt"]) < (6e-3 if mode == "gn" else 3e-3)   # GN(x) rounded to bf16 before the MMA
+    if stats:
+        assert rel_err(stats["cm"], stats["simt"]) < 1e-4
