@@ -26,6 +26,9 @@
 //   64/128-byte store per warp.  ncu (profiles/) showed the first version of this epilogue was issue-bound at ~160 SASS
 //   instructions per output column; pointers are therefore hoisted, coefficients read with ld.shared, the activation is
 //   a template parameter and GELU uses a branch-free erfc (|err| < 2e-7, bf16 outputs).
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "conv_common.cuh"
 #include "tma.cuh"
 
@@ -93,8 +96,12 @@ __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
   return r;
 }
 
-// branch-free GELU: 0.5 x (1 + erf(x/sqrt2)) through erfc(|z|) ~ poly(t) exp(-z^2), t = 1/(1 + p|z|)  (A&S 7.1.26,
-// |erfc error| < 1.5e-7); the two tails are formed without cancellation.
+// branch-free exact-erf GELU with ONE special-function op:
+//   gelu(x) = max(x, 0) - a * 2^P(a),   a = min(|x|, 6.0811),   2^P(a) ~ 0.5 erfc(a / sqrt 2)
+// P is a degree-6 fit of -(log2(e) * -ln erfc(a/sqrt2)) - 1 on [0, 6.0811] (weighted for the error of a * 0.5 erfc; beyond the
+// clamp the true term is < 4e-9).  |gelu error| < 3e-7 over the whole line, evaluated in fp32 (tools/fit_gelu.py).  The MUFU
+// pipe (16 lanes / clk / SM) is what bounds a GELU epilogue on sm_100a: the earlier A&S 7.1.26 form needed a reciprocal as
+// well as the exponential and ran at half the rate.
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -105,18 +112,23 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-// (the first version used __frcp_rn / __expf: ncu + SASS showed a guarded Newton reciprocal with a CALL slow path and a
-// denormal-range fix-up around every exponential, ~35 instructions per output; this form is 16, all single-issue)
+#define VRCOC_GELU_AMAX 6.081118f
+#define VRCOC_GELU_C0 -9.999930859e-01f
+#define VRCOC_GELU_C1 -1.151201725e+00f
+#define VRCOC_GELU_C2 -4.587709606e-01f
+#define VRCOC_GELU_C3 -5.341212451e-02f
+#define VRCOC_GELU_C4 8.080728352e-03f
+#define VRCOC_GELU_C5 -7.692232612e-04f
+#define VRCOC_GELU_C6 3.309320891e-05f
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);   // 0.5 * erfc polynomial
-  p = fmaf(p, t, 0.5f * 1.421413741f);
-  p = fmaf(p, t, 0.5f * -0.284496736f);
-  p = fmaf(p, t, 0.5f * 0.254829592f);
-  const float half_u = p * t * ex2_approx(z * z * -1.4426950408889634f);   // 0.5 * erfc(|z|)
-  const float r = x * half_u;
-  return x >= 0.f ? x - r : r;
+  const float a = fminf(fabsf(x), VRCOC_GELU_AMAX);
+  float p = fmaf(VRCOC_GELU_C6, a, VRCOC_GELU_C5);
+  p = fmaf(p, a, VRCOC_GELU_C4);
+  p = fmaf(p, a, VRCOC_GELU_C3);
+  p = fmaf(p, a, VRCOC_GELU_C2);
+  p = fmaf(p, a, VRCOC_GELU_C1);
+  p = fmaf(p, a, VRCOC_GELU_C0);
+  return fmaf(-a, ex2_approx(p), fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f)); }
 
@@ -944,25 +956,32 @@ static bool cm_plan(const ConvArgs& a, CmPlan& best) {
   if (tma_x && (a.O % TQ_MT) != 0) return false;
   const double epi_us = a.act == VRCOC_ACT_GELU || a.act == VRCOC_ACT_SILU ? 1.6 : (plain ? 0.5 : 0.8);
   bool found = false;
-  const int modes[6] = {1, 1, 1, 0, 0, 0}, depth[6] = {2, 3, 4, 2, 3, 4};
-  for (int cand = 0; cand < (tma_x ? 6 : 3); ++cand) {
-    const int mode = tma_x ? modes[cand] : 2, st = depth[cand];
+  const int modes[10] = {1, 1, 1, 1, 1, 0, 0, 0, 0, 0}, depth[10] = {2, 3, 4, 6, 8, 2, 3, 4, 5, 6};
+  // a bf16 source with a prologue can still come in by TMA and be normalised in place (XMODE 3)
+  const bool tma_x3 = prologue && a.src0_dtype == VRCOC_BF16 && (reinterpret_cast<uintptr_t>(a.src0) & 15) == 0 &&
+                      (a.src0_bstride % 8) == 0 && nslabs <= TQ_MAX_SLABS3;
+  for (int cand = 0; cand < (tma_x ? 10 : 5); ++cand) {
+    const int bufs = 1;       // a second staging buffer was measured: no gain (the bulk-store drain is not on the critical path)
+    const int mode = tma_x ? modes[cand] : (tma_x3 ? 3 : 2), st = depth[cand];
     const int x_bytes = mode == 0 ? st * TQ_X_BYTES : nslabs * TQ_X_BYTES;
-    const int tab_bytes = mode == 2 ? a.Cin * 16 : 0;
-    const int total = x_bytes + st * TQ_W_BYTES + 8 * 4096 + tab_bytes + 256 + 1024;
+    const int tab_bytes = mode >= 2 ? a.Cin * 16 : 0;
+    const int total = x_bytes + st * TQ_W_BYTES + bufs * 8 * 4096 + tab_bytes + 512 + 1024;
     if (total > 220 * 1024) continue;
     const int res = (227 * 1024) / (total + 1024) >= 2 ? 2 : 1;
     const int64_t slots = (int64_t)sm_count() * res;
-    const double x_us = mode == 2 ? 1.1 * nslabs : 0.6;
-    const double mma_us = nslabs * (mode == 0 ? 0.28 : 0.16) * (st == 2 ? 1.3 : (st == 3 ? 1.05 : 1.0));
+    const double x_us = mode == 2 ? 1.1 * nslabs : (mode == 3 ? 1.5 + 0.2 * nslabs : 0.6);
+    // one k-slab: four MMAs (0.14 us) or, when the ring is shallow, the L2 -> shared latency of a TMA box (~1 us) / depth
+    const double mma_bw_us = nslabs * (mode == 0 ? 0.28 : 0.14);    // bandwidth part: shared by co-resident CTAs
+    const double mma_lat_us = nslabs * 1.0 / st;                     // latency part: every CTA has its own ring
     for (int t = 1; t <= n_tiles; ++t) {
       const int64_t ctas = m_tiles * cdiv(n_tiles, t);
       const int64_t waves = cdiv(ctas, slots);
       // co-resident CTAs share the SM's issue slots and fill bandwidth, but one's latency-bound phases (set-up, operand
       // build, pipeline fill) hide behind the other's epilogue: 1.6x, not 2x, and only on the steady-state part
       const double share = (res == 2 && ctas > (int64_t)sm_count()) ? 1.6 : 1.0;
-      const double tile_us = share * (mma_us > epi_us ? mma_us : epi_us);
-      const double cost = waves * (2.0 + x_us + t * tile_us + (mma_us < epi_us ? mma_us : epi_us));
+      double tile_us = share * (mma_bw_us > epi_us ? mma_bw_us : epi_us);
+      if (mma_lat_us > tile_us) tile_us = mma_lat_us;
+      const double cost = waves * (2.0 + x_us + t * tile_us + (mma_bw_us < epi_us ? mma_bw_us : epi_us));
       if (!found || cost < best.cost - 1e-9) {
         found = true;
         best.cost = cost;
@@ -975,7 +994,8 @@ static bool cm_plan(const ConvArgs& a, CmPlan& best) {
         T.off_x = 0;
         T.off_w = x_bytes;
         T.off_stage = T.off_w + st * TQ_W_BYTES;
-        T.off_tab = T.off_stage + 8 * 4096;
+        T.stage_bufs = bufs;
+        T.off_tab = T.off_stage + bufs * 8 * 4096;
         T.off_bar = T.off_tab + tab_bytes;
         T.total = total;
       }
@@ -1045,6 +1065,10 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   CmPlan cm;
   if (g_tc_use_cm && cm_plan(a, cm)) {
     const TqLayout& T = cm.T;
+    static const bool dbg = getenv("VRCOC_DEBUG_PLAN") != nullptr;
+    if (dbg)
+      fprintf(stderr, "[vrcoc] cm plan K=%d O=%d P=%d B=%d: xmode=%d stages=%d tiles=%d smem=%d cost=%.1f\n", a.K, a.O, a.P_out, a.B,
+              cm.xmode, T.stages, T.tiles, T.total, cm.cost);
     dim3 cgrid((unsigned)cdiv(a.P_out, TQ_NP), (unsigned)cdiv(a.O, T.tiles * TQ_MT), (unsigned)a.B);
     CUtensorMap tmW, tmX, tmO1, tmO2, tmRes;
     memset(&tmX, 0, sizeof(tmX));
@@ -1096,6 +1120,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   } while (0)
     if (cm.xmode == 0) LAUNCH_CM(__nv_bfloat16, 0);
     else if (cm.xmode == 1) LAUNCH_CM(__nv_bfloat16, 1);
+    else if (cm.xmode == 3) LAUNCH_CM(__nv_bfloat16, 3);
     else if (f32) LAUNCH_CM(float, 2);
     else LAUNCH_CM(__nv_bfloat16, 2);
 #undef LAUNCH_CM

@@ -16,7 +16,10 @@
 //   warp 8     lane 0 runs the TMA ring (weights, and X when it comes by TMA);
 //   warp 9     lane 0 issues tcgen05.mma into TMEM buffer j&1 while the epilogue warps drain buffer (j-1)&1.
 // XMODE 0: X streamed with the weights (K too large to keep);  1: X resident, fetched by TMA with the first output tile;
-//       2: X resident, built by the CTA's threads through the prologue table (GroupNorm / gate / plain fp32 sources).
+//       2: X resident, built by the CTA's threads through the prologue table (GroupNorm / gate / plain fp32 sources);
+//       3: X resident, bf16 source with a prologue: the RAW slabs arrive by TMA already in the operand layout (all of them in
+//          flight at once) and warps 0-7 normalise / gate them IN PLACE — the prologue is per channel = per k-row, so the
+//          layout does not change; slab by slab, so the first MMAs start while later slabs are still being transformed.
 #pragma once
 
 namespace vrcoc {
@@ -26,13 +29,15 @@ constexpr int TQ_NP = 128;                          // points per tile  (MMA N)
 constexpr int TQ_MT = 128;                          // outputs per tile (MMA M)
 constexpr int TQ_W_BYTES = TQ_MT * TC_BK * 2;       // 16 KB
 constexpr int TQ_X_BYTES = TQ_NP * TC_BK * 2;       // 16 KB
-constexpr int TQ_MAX_STAGES = 4;
+constexpr int TQ_MAX_STAGES = 8;
+constexpr int TQ_MAX_SLABS3 = 9;                    // XMODE 3: per-slab barriers
 
 struct TqLayout {
   int stages;        // ring depth
   int nslabs;        // K slabs
   int tiles;         // output tiles per CTA
   int plain;         // epilogue is act(acc*es + eh) only
+  int stage_bufs;    // 1 or 2 epilogue staging buffers of 8 x 4 KB
   int off_x, off_w, off_stage, off_tab, off_bar, total;
 };
 
@@ -42,6 +47,68 @@ __host__ __device__ constexpr uint32_t make_idesc_cm(int n) {
 }
 
 struct CmCoef { float es, eh, ps, fs, fh; };
+
+// split tcgen05.ld: the destination registers are only defined after tmem_ld_wait, which takes them as in/out operands so
+// that the compiler orders every use after the wait
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
+// ---- packed fp32x2 arithmetic (FFMA2: two lanes' worth of FMA per issue slot; ncu showed the GELU epilogue bound by the
+// FMA pipe, not by issue) ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// gelu_fast (conv_tc.cu) on two values
+__device__ __forceinline__ uint64_t gelu2(uint64_t x) {
+  float x0, x1;
+  upk2(x, x0, x1);
+  const float a0 = fminf(fabsf(x0), VRCOC_GELU_AMAX), a1 = fminf(fabsf(x1), VRCOC_GELU_AMAX);
+  const uint64_t a = pk2(a0, a1);
+  uint64_t p = fma2(pk2(VRCOC_GELU_C6, VRCOC_GELU_C6), a, pk2(VRCOC_GELU_C5, VRCOC_GELU_C5));
+  p = fma2(p, a, pk2(VRCOC_GELU_C4, VRCOC_GELU_C4));
+  p = fma2(p, a, pk2(VRCOC_GELU_C3, VRCOC_GELU_C3));
+  p = fma2(p, a, pk2(VRCOC_GELU_C2, VRCOC_GELU_C2));
+  p = fma2(p, a, pk2(VRCOC_GELU_C1, VRCOC_GELU_C1));
+  p = fma2(p, a, pk2(VRCOC_GELU_C0, VRCOC_GELU_C0));
+  float p0, p1;
+  upk2(p, p0, p1);
+  return fma2(pk2(-a0, -a1), pk2(ex2_approx(p0), ex2_approx(p1)), pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+}
+
+template <int ACT>
+__device__ __forceinline__ uint64_t act2(uint64_t v) {
+  if (ACT == VRCOC_ACT_NONE) return v;
+  if (ACT == VRCOC_ACT_GELU) return gelu2(v);
+  float a, b;
+  upk2(v, a, b);
+  return pk2(act_tc<ACT>(a), act_tc<ACT>(b));
+}
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
@@ -65,7 +132,7 @@ __device__ __forceinline__ void unpack8_bf16(const uint4& u, float* f) {
 // fp32 outputs (the similarity half of fc1|fc_v) go through the same region in two 32-point passes.
 template <int ACT, bool PLAIN>
 __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty, uint64_t* rbar,
-                                            unsigned char* region, const CUtensorMap* tmO1, const CUtensorMap* tmO2,
+                                            unsigned char* region0, int buf_stride, const CUtensorMap* tmO1, const CUtensorMap* tmO2,
                                             const CUtensorMap* tmR, int b, int p0, int o_begin, int tiles) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lq = warp & 3, ch = warp >> 2;
@@ -74,9 +141,9 @@ __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_bas
   const bool has_res = !PLAIN && a.res != nullptr;
   const bool want_sums = !PLAIN && a.out_sample_sums != nullptr;
   const bool want_mm = !PLAIN && a.out_minmax != nullptr;
-  const uint32_t rbase = smem_u32(region) + lane * 128;
   const int sw = lane & 7;
   uint32_t res_phase = 0;
+  unsigned long long t_wait = 0, t_comp = 0;       // debug trace: warp 0's time waiting for accumulators / draining them
   float ssum = 0.f, ssq = 0.f, vmax = 0.f, vmin = __int_as_float(0x7f800000);
   for (int j = 0; j < tiles; ++j) {
     const int buf = j & 1;
@@ -84,8 +151,14 @@ __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_bas
     const int o = o_row0 + lane;
     const bool ok = o < a.O;
     const bool row_live = o_row0 < a.O;                              // warp-uniform
-    if (j > 0) {                                                     // the previous tile's store has finished reading the region
-      if (lane == 0) tma_store_wait_read();
+    // staging buffer j&1 (when there are two): its previous store — tile j-2's — must have finished reading it
+    unsigned char* region = region0 + (j & 1) * buf_stride;
+    const uint32_t rbase = smem_u32(region) + lane * 128;
+    if (j > 0) {
+      if (lane == 0) {
+        if (buf_stride) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else tma_store_wait_read();
+      }
       __syncwarp();
     }
     if (has_res && row_live && lane == 0) {
@@ -102,44 +175,57 @@ __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_bas
     const int odt = second ? a.out2_dtype : a.out_dtype;
     const CUtensorMap* tmO = second ? tmO2 : tmO1;
     const int ochan0 = second ? o_row0 - a.O_split : o_row0;
+    const bool tr = g_tc_trace != nullptr && threadIdx.x == 0;
+    unsigned long long t0 = 0, t1 = 0;
+    if (tr) t0 = gtime();
     mbar_wait(&acc_full[buf], (uint32_t)(j >> 1) & 1);
     tc_fence_after();
     if (threadIdx.x == 0 && j == 0) trace(3);
+    if (tr) { t1 = gtime(); t_wait += t1 - t0; }
     if (has_res && row_live) { mbar_wait(rbar, res_phase); res_phase ^= 1u; }
     const uint32_t tbase = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TQ_NP + ch * (TQ_NP / 2));
+    // the TMEM read of group c+1 is in flight while group c is processed
+    uint32_t rn[16];
+    tmem_ld16_issue(tbase, rn);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint32_t r[16];
-      tmem_ld16(tbase + (uint32_t)(16 * c), r);
+      tmem_ld_wait(rn);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = rn[i];
+      if (c < 3) tmem_ld16_issue(tbase + (uint32_t)(16 * (c + 1)), rn);
       if (row_live) {
         const int q0 = q_base + 16 * c;
         float y[16];
-        if (PLAIN) {
+        {
+          const uint64_t es2 = pk2(k.es, k.es), eh2 = pk2(k.eh, k.eh);
+          uint64_t v[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) y[i] = act_tc<ACT>(fmaf(__uint_as_float(r[i]), k.es, k.eh));
-        } else {
-          float res[16];
-          if (has_res) {
-            unpack8_bf16(lds128(rbase + (uint32_t)(((2 * c) ^ sw) << 4)), res);
-            unpack8_bf16(lds128(rbase + (uint32_t)(((2 * c + 1) ^ sw) << 4)), res + 8);
-          } else {
+          for (int i = 0; i < 8; ++i)
+            v[i] = act2<ACT>(fma2(pk2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), es2, eh2));
+          if (!PLAIN) {
+            const uint64_t ps2 = pk2(k.ps, k.ps), fs2 = pk2(k.fs, k.fs), fh2 = pk2(k.fh, k.fh);
+            if (has_res) {
+              float res[16];
+              unpack8_bf16(lds128(rbase + (uint32_t)(((2 * c) ^ sw) << 4)), res);
+              unpack8_bf16(lds128(rbase + (uint32_t)(((2 * c + 1) ^ sw) << 4)), res + 8);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) res[i] = 0.f;
+              for (int i = 0; i < 8; ++i) v[i] = fma2(fma2(v[i], ps2, pk2(res[2 * i], res[2 * i + 1])), fs2, fh2);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fma2(mul2(v[i], ps2), fs2, fh2);
+            }
           }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) upk2(v[i], y[2 * i], y[2 * i + 1]);
+        }
+        if (!PLAIN && (want_sums || want_mm)) {
+          const bool whole = ok && q0 + 16 <= P;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float v = act_tc<ACT>(fmaf(__uint_as_float(r[i]), k.es, k.eh));
-            v = fmaf(v, k.ps, res[i]);
-            y[i] = fmaf(v, k.fs, k.fh);
-          }
-          if (want_sums || want_mm) {
-            const bool whole = ok && q0 + 16 <= P;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (whole || (ok && q0 + i < P)) {
-                ssum += y[i]; ssq = fmaf(y[i], y[i], ssq);
-                vmax = fmaxf(vmax, y[i]); vmin = fminf(vmin, y[i]);
-              }
+            if (whole || (ok && q0 + i < P)) {
+              ssum += y[i]; ssq = fmaf(y[i], y[i], ssq);
+              vmax = fmaxf(vmax, y[i]); vmin = fminf(vmin, y[i]);
             }
           }
         }
@@ -176,6 +262,12 @@ __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_bas
     tc_fence_before();
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
+    if (tr) t_comp += gtime() - t1;
+  }
+  if (g_tc_trace != nullptr && threadIdx.x == 0) {
+    unsigned long long* trp = g_tc_trace + ((blockIdx.z * gridDim.y + blockIdx.y) * (size_t)gridDim.x + blockIdx.x) * 8;
+    trp[6] = t_wait;
+    trp[7] = t_comp;
   }
   if (lane == 0) tma_store_wait_read();                            // shared memory must outlive the bulk stores' reads
   if (want_sums) {
@@ -219,7 +311,9 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
   uint64_t* acc_full = bar_free + TQ_MAX_STAGES;                     // [2]
   uint64_t* acc_empty = acc_full + 2;                                // [2]
   uint64_t* res_bar = acc_empty + 2;                                 // [8] one per epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
+  uint64_t* x_full = res_bar + 8;                                    // [9] XMODE 3: raw slab landed
+  uint64_t* x_ready = x_full + TQ_MAX_SLABS3;                        // [9] XMODE 3: slab transformed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_ready + TQ_MAX_SLABS3);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, p0 = blockIdx.x * TQ_NP;
@@ -240,12 +334,14 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     mbar_init(&acc_empty[0], 8); mbar_init(&acc_empty[1], 8);      // one arrival per epilogue warp
     for (int i = 0; i < 8; ++i) mbar_init(&res_bar[i], 1);
+    if (XMODE == 3)
+      for (int i = 0; i < TQ_MAX_SLABS3; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_ready[i], 8); }
     mbar_fence_init();
     tma_prefetch_desc(&tmapW);
     if (XMODE != 2) tma_prefetch_desc(&tmapX);
     tma_prefetch_desc(&tmapO1);
   }
-  if (XMODE == 2) build_prologue_table(a, b, tab);                   // strides by blockDim.x: every thread takes part
+  if (XMODE >= 2) build_prologue_table(a, b, tab);                   // strides by blockDim.x: every thread takes part
   tc_fence_before();
   __syncthreads();                                                     // barriers + TMEM slot + table visible
   tc_fence_after();
@@ -267,6 +363,13 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
         tma_load_3d(dst + TC_A_LBO, &tmapX, p0 + 64, kc * TC_BK, b, &bar_full[s]);
       }
     };
+    if (XMODE == 3 && lane == 0) {
+      for (int kc = 0; kc < nk; ++kc) {                                // every raw slab in flight at once
+        mbar_expect_tx(&x_full[kc], (uint32_t)TQ_X_BYTES);
+        tma_load_3d(sX + kc * TQ_X_BYTES, &tmapX, p0, kc * TC_BK, b, &x_full[kc]);
+        tma_load_3d(sX + kc * TQ_X_BYTES + TC_A_LBO, &tmapX, p0 + 64, kc * TC_BK, b, &x_full[kc]);
+      }
+    }
     if (XMODE == 2) {
       // the first ST slabs need no free-slot wait and go out while the other warps still build X; the rest depends on
       // MMA progress and therefore has to come after barrier (A)
@@ -294,6 +397,7 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
         for (int kc = 0; kc < nk; ++kc, ++it) {
           const int s = it % ST;
           mbar_wait(&bar_full[s], (uint32_t)(it / ST) & 1);
+          if (XMODE == 3 && j == 0) mbar_wait(&x_ready[kc], 0);
           tc_fence_after();
           const int ksteps = (min(TC_BK, a.K - kc * TC_BK) + 15) >> 4;
           const uint32_t w_addr = smem_u32(sW + s * TQ_W_BYTES);
@@ -328,8 +432,39 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
       if (tid == 0) trace(2);
       __syncthreads();                                                 // (A)
     }
+    if (XMODE == 3) {
+      // ---- X operand: in-place prologue on the TMA-landed raw slabs -----------------------------------------------------------
+      if (tid == 0) trace(1);
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(&x_full[kc], 0);
+        const uint32_t slab = smem_u32(sX + kc * TQ_X_BYTES);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int u = tid + 256 * i;                                   // 16-byte chunk of the slab; k-row = (u >> 3) & 63
+          const int chn = kc * TC_BK + ((u >> 3) & 63);
+          if (chn < a.Cin) {                                             // rows past Cin stay zero (TMA fill)
+            const float4 t = tab[chn];
+            float f[8];
+            unpack8_bf16(lds128(slab + (uint32_t)u * 16u), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float x = f[e];
+              float y = fmaf(x, t.x, t.y);
+              if (a.has_gate) y *= sigmoid_fast(fmaf(t.z, x, t.w));
+              f[e] = y;
+            }
+            sts128(slab + (uint32_t)u * 16u, pack8_bf16(f));
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&x_ready[kc])) : "memory");
+      }
+      if (tid == 0) trace(2);
+    }
 #define CM_EPI(ACTV, PL)                                                                                                  \
-  cm_epilogue<ACTV, PL>(a, tmem_base, acc_full, acc_empty, &res_bar[warp], stage + warp * 4096, &tmapO1, &tmapO2, &tmapR, b, p0, \
+  cm_epilogue<ACTV, PL>(a, tmem_base, acc_full, acc_empty, &res_bar[warp], stage + warp * 4096, L.stage_bufs == 2 ? 8 * 4096 : 0, \
+                        &tmapO1, &tmapO2, &tmapR, b, p0, \
                         o_begin, tiles)
     if (L.plain) {
       switch (a.act) {

@@ -1,0 +1,34 @@
+"""Coefficients of the one-MUFU GELU used by the tcgen05 epilogues (csrc/conv_tc.cu: gelu_fast / gelu2).
+    gelu(x) = max(x, 0) - a * 2^P(a),  a = min(|x|, AMAX),  2^P(a) ~ 0.5 * erfc(a / sqrt 2)
+P = degree-6 reweighted least-squares (Remez-like) fit, checked in emulated fp32 Horner arithmetic.  python tools/fit_gelu.py"""
+import numpy as np
+from numpy.polynomial import chebyshev as C, polynomial as Pn
+from scipy.special import erf, erfc
+
+ZMAX, DEG = 4.3, 6
+z = np.linspace(0, ZMAX, 400001)
+q = -np.log(erfc(z))
+w = z * np.sqrt(2) * 0.5 * erfc(z) + 1e-12          # sensitivity of a * 0.5 erfc to an error in q
+for _ in range(60):
+    c = C.chebfit(2 * z / ZMAX - 1, q, DEG, w=w)
+    err = np.abs(z * np.sqrt(2) * 0.5 * (np.exp(-C.chebval(2 * z / ZMAX - 1, c)) - erfc(z)))
+    w = w * (1 + 3 * err / err.max())
+    w /= w.max()
+mono = np.zeros(1)
+for k, ck in enumerate(C.cheb2poly(c)):
+    mono = Pn.polyadd(mono, ck * Pn.polypow(np.array([-1.0, 2 / ZMAX]), k))
+coef = np.array([-(np.log2(np.e) * mono[k] / np.sqrt(2) ** k) for k in range(DEG + 1)])
+coef[0] -= 1.0
+c32 = coef.astype(np.float32)
+amax = np.float32(ZMAX * np.sqrt(2))
+print("AMAX", amax)
+print("C0..C6:", ", ".join("%.9ef" % v for v in c32))
+x = np.linspace(-8, 8, 2000001).astype(np.float32)
+a = np.minimum(np.abs(x), amax).astype(np.float32)
+acc = np.full_like(a, c32[-1])
+for ck in c32[-2::-1]:
+    acc = (acc * a + ck).astype(np.float32)
+g = (np.maximum(x, 0) - a * np.exp2(acc.astype(np.float64)).astype(np.float32)).astype(np.float32)
+ref = 0.5 * x.astype(np.float64) * (1 + erf(x.astype(np.float64) / np.sqrt(2)))
+d = np.abs(g - ref)
+print("max |gelu error| %.3e at x = %.3f" % (d.max(), x[d.argmax()]))

@@ -37,4 +37,5 @@ names = ["start", "setup", "A_built", "acc0_full", "epi_done", "exit"]
 d_ = rel[:, 1:] - rel[:, :-1]
 for i in range(5):
     print(f"  {names[i]:>9s} -> {names[i + 1]:<9s} mean {d_[:, i].mean():7.2f} us   p90 {d_[:, i].quantile(0.9):7.2f}   max {d_[:, i].max():7.2f}")
+print(f"  warp 0: waiting for accumulators {t[:, 6].double().mean() / 1e3:.2f} us, draining them {t[:, 7].double().mean() / 1e3:.2f} us (sum over the CTA's tiles)")
 print(f"  CTA lifetime mean {(rel[:, 5] - rel[:, 0]).mean():.2f} us; start times: p50 {rel[:, 0].median():.1f} us, max {rel[:, 0].max():.1f} us")
