@@ -185,9 +185,11 @@ __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_bas
     if (has_res && row_live) { mbar_wait(rbar, res_phase); res_phase ^= 1u; }
     const uint32_t tbase = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TQ_NP + ch * (TQ_NP / 2));
     // the TMEM read of group c+1 is in flight while group c is processed
+    // (not unrolled: a CTA often drains a single tile, i.e. runs this code once, from a cold instruction cache — ncu showed
+    // instruction fetch, not issue, bounding the fully unrolled version)
     uint32_t rn[16];
     tmem_ld16_issue(tbase, rn);
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t r[16];
       tmem_ld_wait(rn);
