@@ -426,6 +426,61 @@ dwconv_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __r
   }
 }
 
+// 3x3 / stride 1 / pad 1 fast path (every depthwise conv of the decoupled head): one thread = 8 columns x R output rows.
+// Each input row is fetched once per thread as one 16-byte vector plus its two halo elements and feeds up to three output
+// rows; R + 2 row fetches per R output rows instead of 3R, no per-tap predicates.  Requires W % 8 == 0 and 16-byte aligned
+// planes (host-checked).
+template <typename T, int R>
+__global__ void __launch_bounds__(256)
+dwconv3_s1_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out, int planes, int C,
+                  int H, int W) {
+  const int cols8 = W >> 3;
+  const int rgroups = (H + R - 1) / R;
+  const int64_t total = (int64_t)planes * rgroups * cols8;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(t % cols8);
+    const int64_t rest = t / cols8;
+    const int rg = (int)(rest % rgroups);
+    const int64_t plane = rest / rgroups;
+    const int c = (int)(plane % C);
+    float wk[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) wk[i] = ldf<T>(w + (int64_t)c * 9 + i);
+    const float b0 = bias ? bias[c] : 0.f;
+    float acc[R][8];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[r][j] = b0;
+    const int oy0 = rg * R, x0 = c8 * 8;
+    const T* px = x + plane * (int64_t)H * W;
+#pragma unroll
+    for (int r = -1; r <= R; ++r) {
+      const int iy = oy0 + r;
+      if (iy < 0 || iy >= H) continue;
+      const T* row = px + (int64_t)iy * W;
+      float v[10], mid[8];
+      ld8<T>(row + x0, mid);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j + 1] = mid[j];
+      v[0] = x0 > 0 ? ldf<T>(row + x0 - 1) : 0.f;
+      v[9] = x0 + 8 < W ? ldf<T>(row + x0 + 8) : 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int rel = r - ky + 1;                 // output row (relative) this input row feeds through tap row ky
+        if (rel < 0 || rel >= R) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          acc[rel][j] = fmaf(wk[ky * 3 + 2], v[j + 2], fmaf(wk[ky * 3 + 1], v[j + 1], fmaf(wk[ky * 3], v[j], acc[rel][j])));
+      }
+    }
+    T* po = out + plane * (int64_t)H * W + x0;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (oy0 + r < H) st8<T>(po + (int64_t)(oy0 + r) * W, acc[r]);
+  }
+}
+
 template <typename F>
 static int by_dtype(int dt, F&& f) {
   if (dt == VRCOC_F32) return f((float*)nullptr);
@@ -595,6 +650,15 @@ extern "C" int vrcoc_dwconv(const void* x, const void* weight, const float* bias
   int blocks = (int)(cdiv(total, 256) < 148 * 32 ? cdiv(total, 256) : 148 * 32);
   return by_dtype(dtype, [&](auto* t) {
     using T = typename std::remove_pointer<decltype(t)>::type;
+    const int es = (int)sizeof(T);
+    if (k == 3 && stride == 1 && pad == 1 && W % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 &&
+        ((int64_t)H * W * es) % 16 == 0) {
+      constexpr int R = 4;
+      const int64_t tot = (int64_t)B * C * ((H + R - 1) / R) * (W / 8);
+      const int nb = (int)(cdiv(tot, 256) < 148 * 32 ? cdiv(tot, 256) : 148 * 32);
+      dwconv3_s1_kernel<T, R><<<nb, 256, 0, st>>>((const T*)x, (const T*)weight, bias, (T*)out, B * C, C, H, W);
+      return check_launch("dwconv3");
+    }
     if (k == 3) dwconv_kernel<T, 3><<<blocks, 256, 0, st>>>((const T*)x, (const T*)weight, bias, (T*)out, B * C, C, H, W, Ho, Wo, stride, pad);
     else dwconv_kernel<T, 5><<<blocks, 256, 0, st>>>((const T*)x, (const T*)weight, bias, (T*)out, B * C, C, H, W, Ho, Wo, stride, pad);
     return check_launch("dwconv");

@@ -183,3 +183,22 @@ def test_channel_major_kernel_matches_point_major(env, case):
     assert rel_err(outs["cm"], outs["simt"]) < (6e-3 if mode == "gn" else 3e-3)   # GN(x) rounded to bf16 before the MMA
     if stats:
         assert rel_err(stats["cm"], stats["simt"]) < 1e-4
+
+
+@pytest.mark.parametrize("case", [(2, 256, 64, 64, 3, 1, 1), (2, 16, 22, 24, 3, 1, 1), (1, 8, 9, 10, 3, 1, 1), (2, 12, 16, 16, 3, 2, 1),
+                                  (1, 6, 12, 16, 5, 1, 2)], ids=lambda c: "x".join(map(str, c)))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_depthwise_conv(env, case, dtype):
+    """vrcoc_dwconv (DWConv.dconv, normal_conv.py:26-27): 3x3/s1 fast path (8 columns x 4 rows per thread) and the generic one"""
+    from vrcoc._lib import check, lib
+    B, C, H, W, k, stride, pad = case
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, C, H, W, generator=g).to(dtype).cuda()
+    w = (torch.randn(C, 1, k, k, generator=g) / k).to(dtype).cuda()
+    bias = torch.randn(C, generator=g).cuda()
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    y = torch.full((B, C, Ho, Wo), float("nan"), device="cuda", dtype=dtype)
+    check(lib.vrcoc_dwconv(x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), 0 if dtype == torch.float32 else 1, B, C, H, W, k,
+                           stride, pad, torch.cuda.current_stream().cuda_stream), "dwconv")
+    ref = F.conv2d(x.float(), w.float(), bias, stride=stride, padding=pad, groups=C)
+    assert rel_err(y.float(), ref) < (1e-5 if dtype == torch.float32 else 4e-3)
