@@ -168,18 +168,29 @@ class CoCFpnDual(nn.Module):
         self.p4_3_det = CoCUpsample(in_channels=in_channels[-2], out_channels=in_channels[-3])
         self.p3_out_det = Conv(in_channels=in_channels[-3] * 2, out_channels=in_channels[-3])
 
-    def forward(self, x, x_radar):
+    def forward(self, x, x_radar, det_tail=None):
+        """det_tail (optional, not in the reference signature): a callable applied to (p3, p4, p5) inside the detection
+        branch — EfficientVRNet passes its head so that it overlaps the segmentation branch as well."""
         x_out, x_radar_out = self.backbone(x, x_radar)
         s2, s3, s4, s5 = x_out
         r2, r3, r4, r5 = x_radar_out
-        s5 = self.aspp(s5)
-        # segmentation branch (image features)
-        t = self.sc_attn_seg4(cat_shuffle(s4, self.upsample5_4(s5)))
-        t = self.sc_attn_seg3(cat_shuffle(self.upsample4_3(t), s3))
-        t = self.sc_attn_seg2(cat_shuffle(self.upsample3_2(t), s2))
-        seg = self.upsample2_0(t)
-        # detection branch (radar features)
-        p5 = self.p5_out_det(r5)
-        p4 = self.p4_out_det(torch.cat([r4, self.p5_4_det(p5)], dim=1))
-        p3 = self.p3_out_det(torch.cat([r3, self.p4_3_det(p4)], dim=1))
-        return (p3, p4, p5), seg
+
+        def seg_branch():          # image features
+            t = self.aspp(s5)
+            t = self.sc_attn_seg4(cat_shuffle(s4, self.upsample5_4(t)))
+            t = self.sc_attn_seg3(cat_shuffle(self.upsample4_3(t), s3))
+            t = self.sc_attn_seg2(cat_shuffle(self.upsample3_2(t), s2))
+            return self.upsample2_0(t)
+
+        def det_branch():          # radar features
+            p5 = self.p5_out_det(r5)
+            p4 = self.p4_out_det(torch.cat([r4, self.p5_4_det(p5)], dim=1))
+            p3 = self.p3_out_det(torch.cat([r3, self.p4_3_det(p4)], dim=1))
+            return det_tail((p3, p4, p5)) if det_tail is not None else (p3, p4, p5)
+
+        if x.is_cuda:
+            det, seg = ops.run_pair(det_branch, seg_branch)
+        else:
+            seg = seg_branch()
+            det = det_branch()
+        return det, seg

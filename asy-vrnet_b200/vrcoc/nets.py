@@ -15,6 +15,5 @@ class EfficientVRNet(nn.Module):
         self.head = DecoupleHead(num_classes, width, depthwise=True)
 
     def forward(self, x, x_radar):
-        fpn_outs, seg_outputs = self.backbone.forward(x, x_radar)
-        det_outputs = self.head.forward(fpn_outs)
+        det_outputs, seg_outputs = self.backbone.forward(x, x_radar, det_tail=self.head.forward)
         return det_outputs, seg_outputs

@@ -35,6 +35,34 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_SIDE_STREAMS = {}
+PAIR_STREAMS = True          # set False to serialise the two modality branches (debug / A-B)
+
+
+def run_pair(f_main, f_side):
+    """Run two INDEPENDENT closures concurrently: f_main on the current stream, f_side on a per-device side stream, joined
+    before returning.  The image and the radar halves of VRCoC (vr_coc.py:589-675) and the segmentation / detection halves of
+    the neck (coc_fpn_dual.py:199-224) do not depend on each other between fusion points; at the deep stages one half fills
+    less than half of the 148 SMs, so the halves are launched side by side (inside a CUDA-graph capture the fork/join becomes
+    two parallel branches of the graph).  Only without autograd; the caller keeps the closures' inputs alive until the join,
+    which is what makes cross-stream use of caching-allocator blocks safe."""
+    main = torch.cuda.current_stream()
+    if not PAIR_STREAMS or torch.is_grad_enabled():
+        return f_main(), f_side()
+    key = main.device.index
+    side = _SIDE_STREAMS.get(key)
+    if side is None:
+        side = _SIDE_STREAMS[key] = torch.cuda.Stream(device=main.device)
+    if side == main:            # nested call from inside a side branch: nothing left to overlap with
+        return f_main(), f_side()
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        b = f_side()
+    a = f_main()
+    main.wait_stream(side)
+    return a, b
+
+
 def _f32(t):
     """Small parameter vectors are always consumed as fp32.  The converted copy is memoised on the tensor object and
     keyed on (storage pointer, version counter): optimizer steps / load_state_dict / .to() invalidate it, so inference

@@ -115,33 +115,34 @@ class VRCoC(nn.Module):
     def forward_embeddings(self, x, x_radar):
         """reference :575-587.  The cat([x, pos]) tensors are never built: the patch-embed kernel reads the position
         grid as a second, batch-broadcast source."""
-        x = self.image_initial(x)
-        x_radar = self.radar_initial(x_radar)
+        from . import ops
+        pair = ops.run_pair if x.is_cuda else (lambda f, g: (f(), g()))
+        x_in, r_in = x, x_radar
+        x, x_radar = pair(lambda: self.image_initial(x_in), lambda: self.radar_initial(r_in))
         x = self.image_enhance_by_radar1(x, x_radar)
         x_radar = self.radar_enhance_by_image1(x, x_radar)
-        from . import ops
         pos = ops.cached(self, "pos_" + str(x.dtype), [self.fea_pos], lambda: self.fea_pos.permute(2, 0, 1).to(x.dtype).contiguous())
         if pos.shape[-2:] != x.shape[-2:]:
             raise RuntimeError(f"Sizes of tensors must match: fea_pos is {tuple(pos.shape[-2:])}, input is {tuple(x.shape[-2:])}")
-        x = self.patch_embed(x, extra=pos)
-        x_radar = self.patch_embed_radar(x_radar, extra=pos)
-        return x, x_radar
+        x_e, r_e = x, x_radar
+        return pair(lambda: self.patch_embed(x_e, extra=pos), lambda: self.patch_embed_radar(r_e, extra=pos))
 
     def forward_tokens(self, x, x_radar):
         """reference :589-675."""
         outs, outs_radar = [], []
         nstage = (len(self.network) + 1) // 3
+        from . import ops
+        pair = ops.run_pair if x.is_cuda else (lambda f, g: (f(), g()))
         for i in range(nstage):
-            x = self.network[3 * i](x)
-            x_radar = self.network_radar[3 * i](x_radar)
+            # the two modality stacks are independent between fusion points: side by side on two streams
+            x, x_radar = pair(lambda x=x: self.network[3 * i](x), lambda r=x_radar: self.network_radar[3 * i](r))
             x = self.network[3 * i + 1](x, x_radar)
             x_radar = self.network_radar[3 * i + 1](x, x_radar)
             if i in (0, nstage - 1):
                 outs.append(x)
                 outs_radar.append(x_radar)
             if i < nstage - 1:
-                x = self.network[3 * i + 2](x)
-                x_radar = self.network_radar[3 * i + 2](x_radar)
+                x, x_radar = pair(lambda x=x: self.network[3 * i + 2](x), lambda r=x_radar: self.network_radar[3 * i + 2](r))
                 if i in (0, 1):
                     outs.append(x)
                     outs_radar.append(x_radar)
