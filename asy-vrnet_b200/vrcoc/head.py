@@ -28,14 +28,20 @@ class DecoupleHead(nn.Module):
             self.reg_preds.append(nn.Conv2d(c, 4, kernel_size=1, stride=1, padding=0))
             self.obj_preds.append(nn.Conv2d(c, 1, kernel_size=1, stride=1, padding=0))
 
+    def forward_level(self, k, x):
+        """one pyramid level (reference decouplehead.py:70-88 loop body); the classification tower runs on a side stream
+        next to the regression tower when there is no autograd"""
+        from . import ops
+        x = self.stems[k](x)
+        if x.is_cuda and not torch.is_grad_enabled():
+            cls = ops.Fork(lambda: self.cls_preds[k](self.cls_convs[k](x)), lane=5 + k)
+        else:
+            cls = None
+        reg_feat = self.reg_convs[k](x)
+        reg_output = self.reg_preds[k](reg_feat)
+        obj_output = self.obj_preds[k](reg_feat)
+        cls_output = cls.join() if cls is not None else self.cls_preds[k](self.cls_convs[k](x))
+        return torch.cat([reg_output, obj_output, cls_output], 1)
+
     def forward(self, inputs):
-        outputs = []
-        for k, x in enumerate(inputs):
-            x = self.stems[k](x)
-            cls_feat = self.cls_convs[k](x)
-            cls_output = self.cls_preds[k](cls_feat)
-            reg_feat = self.reg_convs[k](x)
-            reg_output = self.reg_preds[k](reg_feat)
-            obj_output = self.obj_preds[k](reg_feat)
-            outputs.append(torch.cat([reg_output, obj_output, cls_output], 1))
-        return outputs
+        return [self.forward_level(k, x) for k, x in enumerate(inputs)]

@@ -97,7 +97,10 @@ class ASPP(nn.Module):
         native = x.is_cuda and not torch.is_grad_enabled() and not self.training and x.dtype in (torch.float32, torch.bfloat16)
         if native:     # eval, no autograd: every conv+BN+ReLU is one implicit-GEMM launch (dilation in the im2col gather)
             from .fusion import conv_bn_relu_infer
-            feats = [conv_bn_relu_infer(x, br[0], br[1]) for br in (self.branch1, self.branch2, self.branch3, self.branch4)]
+            # the dilated branches are independent and each fills only part of the chip at 16x16: three of them on side streams
+            forks = [ops.Fork(lambda br=br: conv_bn_relu_infer(x, br[0], br[1]), lane=8 + i)
+                     for i, br in enumerate((self.branch2, self.branch3, self.branch4))]
+            feats = [conv_bn_relu_infer(x, self.branch1[0], self.branch1[1])] + [f.join() for f in forks]
         else:
             feats = [self.branch1(x), self.branch2(x), self.branch3(x), self.branch4(x)]
         g = torch.mean(torch.mean(x, 2, True), 3, True)
@@ -168,9 +171,10 @@ class CoCFpnDual(nn.Module):
         self.p4_3_det = CoCUpsample(in_channels=in_channels[-2], out_channels=in_channels[-3])
         self.p3_out_det = Conv(in_channels=in_channels[-3] * 2, out_channels=in_channels[-3])
 
-    def forward(self, x, x_radar, det_tail=None):
-        """det_tail (optional, not in the reference signature): a callable applied to (p3, p4, p5) inside the detection
-        branch — EfficientVRNet passes its head so that it overlaps the segmentation branch as well."""
+    def forward(self, x, x_radar, det_level=None):
+        """det_level (optional, not in the reference signature): a callable (k, p_k) applied to each detection map as soon
+        as it exists — EfficientVRNet passes DecoupleHead.forward_level, so that the head of a coarse level runs next to the
+        neck of the finer ones and the whole detection half next to the segmentation half."""
         x_out, x_radar_out = self.backbone(x, x_radar)
         s2, s3, s4, s5 = x_out
         r2, r3, r4, r5 = x_radar_out
@@ -184,9 +188,16 @@ class CoCFpnDual(nn.Module):
 
         def det_branch():          # radar features
             p5 = self.p5_out_det(r5)
+            if det_level is None:
+                p4 = self.p4_out_det(torch.cat([r4, self.p5_4_det(p5)], dim=1))
+                p3 = self.p3_out_det(torch.cat([r3, self.p4_3_det(p4)], dim=1))
+                return p3, p4, p5
+            o5 = ops.Fork(lambda: det_level(2, p5), lane=2)
             p4 = self.p4_out_det(torch.cat([r4, self.p5_4_det(p5)], dim=1))
+            o4 = ops.Fork(lambda: det_level(1, p4), lane=3)
             p3 = self.p3_out_det(torch.cat([r3, self.p4_3_det(p4)], dim=1))
-            return det_tail((p3, p4, p5)) if det_tail is not None else (p3, p4, p5)
+            o3 = det_level(0, p3)
+            return [o3, o4.join(), o5.join()]
 
         if x.is_cuda:
             det, seg = ops.run_pair(det_branch, seg_branch)

@@ -15,5 +15,5 @@ class EfficientVRNet(nn.Module):
         self.head = DecoupleHead(num_classes, width, depthwise=True)
 
     def forward(self, x, x_radar):
-        det_outputs, seg_outputs = self.backbone.forward(x, x_radar, det_tail=self.head.forward)
+        det_outputs, seg_outputs = self.backbone.forward(x, x_radar, det_level=self.head.forward_level)
         return det_outputs, seg_outputs

@@ -63,6 +63,37 @@ def run_pair(f_main, f_side):
     return a, b
 
 
+class Fork:
+    """f() on side stream number `lane` (>= 1) of the current device, ordered after everything already queued on the
+    current stream; join() orders the current stream after it and returns f's result.  Same liveness rule as run_pair: the
+    object keeps the closure (and so its inputs) alive until the join.  Without CUDA / with autograd it degenerates to a
+    plain call."""
+
+    def __init__(self, f, lane):
+        main = torch.cuda.current_stream() if torch.cuda.is_available() else None
+        self.side = None
+        if main is not None and PAIR_STREAMS and not torch.is_grad_enabled():
+            key = (main.device.index, lane)
+            side = _SIDE_STREAMS.get(key)
+            if side is None:
+                side = _SIDE_STREAMS[key] = torch.cuda.Stream(device=main.device)
+            if side != main:
+                self.side = side
+        self.f = f
+        if self.side is None:
+            self.value = f()
+        else:
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                self.value = f()
+
+    def join(self):
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        self.f = None
+        return self.value
+
+
 def _f32(t):
     """Small parameter vectors are always consumed as fp32.  The converted copy is memoised on the tensor object and
     keyed on (storage pointer, version counter): optimizer steps / load_state_dict / .to() invalidate it, so inference
