@@ -826,6 +826,7 @@ __global__ void __launch_bounds__(TP_THREADS, 2) conv_tc_persist_kernel(ConvArgs
 
 }  // namespace vrcoc
 #include "conv_tc_cm.cuh"
+#include "mlp_fused.cuh"
 namespace vrcoc {
 
 // ---- host side ---------------------------------------------------------------------------------------------------------
@@ -1168,3 +1169,66 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
 }
 
 }  // namespace vrcoc
+
+// ---- fused channel MLP ------------------------------------------------------------------------------------------------------
+extern "C" int vrcoc_mlp_fused_supported(int dtype, int C, int hidden, int P) {
+  return dtype == VRCOC_BF16 && (C == 64 || C == 128) && hidden > 0 && hidden % vrcoc::TQ_MT == 0 && P > 0 && P % 8 == 0 &&
+         vrcoc::tma_encode_fn() != nullptr;
+}
+
+extern "C" int vrcoc_mlp_fused_fwd(const void* x, const double* gn_sums, const float* gamma, const float* beta, float eps, const void* w1,
+                                   const float* b1, const void* w2, const float* b2, const float* layer_scale, void* out,
+                                   double* out_sample_sums, int B, int C, int hidden, int P, void* stream) {
+  using namespace vrcoc;
+  VRCOC_REQUIRE(x && gn_sums && gamma && beta && w1 && b1 && w2 && out && B > 0, "mlp_fused: bad argument");
+  VRCOC_REQUIRE(vrcoc_mlp_fused_supported(VRCOC_BF16, C, hidden, P), "mlp_fused: unsupported shape C=%d hidden=%d P=%d", C, hidden, P);
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  VRCOC_REQUIRE(al(x) && al(w1) && al(w2) && al(out), "mlp_fused: pointers must be 16-byte aligned");
+  ConvArgs a1, a2;
+  memset(&a1, 0, sizeof(a1));
+  memset(&a2, 0, sizeof(a2));
+  a1.B = B; a1.C0 = a1.Cin = a1.K = C; a1.O = hidden; a1.P_in = a1.P_out = P;
+  a1.src0 = x; a1.src0_dtype = VRCOC_BF16; a1.src0_bstride = (int64_t)C * P;
+  a1.gn_sums = gn_sums; a1.gn_gamma = gamma; a1.gn_beta = beta; a1.gn_eps = eps;
+  a2.B = B; a2.C0 = a2.Cin = a2.K = hidden; a2.O = a2.O_split = C; a2.P_in = a2.P_out = P;
+  a2.e_shift = b2; a2.post_scale = layer_scale; a2.act = VRCOC_ACT_NONE;
+  a2.res = x; a2.res_dtype = VRCOC_BF16;
+  a2.out = out; a2.out_dtype = a2.out2_dtype = VRCOC_BF16;
+  a2.out_sample_sums = out_sample_sums;
+  MlpLayout L;
+  L.nk1 = C / TC_BK;
+  L.nh = hidden / TQ_MT;
+  // ring depth: as deep as two resident CTAs per SM allow (227 KB, 1 KB reserved per CTA)
+  L.stages = 2;
+  for (int stg = MF_MAX_STAGES; stg >= 2; --stg) {
+    const int tot = L.nk1 * TQ_X_BYTES + stg * TQ_W_BYTES + 2 * TQ_X_BYTES + C * 16 + 512 + 1024;
+    if (2 * (tot + 1024) <= 227 * 1024) { L.stages = stg; break; }
+  }
+  L.off_ring = L.nk1 * TQ_X_BYTES;
+  L.off_h = L.off_ring + L.stages * TQ_W_BYTES;
+  L.off_tab = L.off_h + 2 * TQ_X_BYTES;
+  L.off_bar = L.off_tab + C * 16;
+  L.total = L.off_bar + 512 + 1024;
+  CUtensorMap tmX, tmW1, tmW2, tmO, tmR;
+  int rc;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)P, (cuuint64_t)C, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)P * 2, (cuuint64_t)C * P * 2};
+    cuuint32_t boxx[3] = {64, (cuuint32_t)TC_BK, 1}, boxo[3] = {64, 32, 1};
+    if ((rc = tma_encode(&tmX, VRCOC_BF16, x, 3, dims, strides, boxx, true))) return rc;
+    if ((rc = tma_encode(&tmR, VRCOC_BF16, x, 3, dims, strides, boxo, true))) return rc;
+    if ((rc = tma_encode(&tmO, VRCOC_BF16, out, 3, dims, strides, boxo, true))) return rc;
+  }
+  {
+    cuuint64_t d1[2] = {(cuuint64_t)C, (cuuint64_t)hidden}, s1[1] = {(cuuint64_t)C * 2};
+    cuuint64_t d2[2] = {(cuuint64_t)hidden, (cuuint64_t)C}, s2[1] = {(cuuint64_t)hidden * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TQ_MT};
+    if ((rc = tma_encode(&tmW1, VRCOC_BF16, w1, 2, d1, s1, box, true))) return rc;
+    if ((rc = tma_encode(&tmW2, VRCOC_BF16, w2, 2, d2, s2, box, true))) return rc;
+  }
+  set_smem(mlp_fused_kernel, L.total);
+  dim3 grid((unsigned)cdiv(P, TQ_NP), 1, (unsigned)B);
+  mlp_fused_kernel<<<grid, MF_THREADS, L.total, (cudaStream_t)stream>>>(a1, a2, L, b1, tmX, tmW1, tmW2, tmO, tmR);
+  return check_launch("mlp_fused");
+}
+

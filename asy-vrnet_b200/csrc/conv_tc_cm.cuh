@@ -130,7 +130,7 @@ __device__ __forceinline__ void unpack8_bf16(const uint4& u, float* f) {
 // residual lands there by TMA, is replaced in place by the result, and leaves by TMA store — global memory only ever sees
 // whole 128-byte rows, and the clipping of the boxes to the tensors replaces every edge predicate on the stores.
 // fp32 outputs (the similarity half of fc1|fc_v) go through the same region in two 32-point passes.
-template <int ACT, bool PLAIN>
+template <int ACT, bool PLAIN, bool LATE_RES = false>
 __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty, uint64_t* rbar,
                                             unsigned char* region0, int buf_stride, const CUtensorMap* tmO1, const CUtensorMap* tmO2,
                                             const CUtensorMap* tmR, int b, int p0, int o_begin, int tiles) {
@@ -161,7 +161,7 @@ __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_bas
       }
       __syncwarp();
     }
-    if (has_res && row_live && lane == 0) {
+    if (!LATE_RES && has_res && row_live && lane == 0) {
       mbar_expect_tx(rbar, 4096u);
       tma_load_3d(region, tmR, q_base, o_row0, b, rbar);
     }
@@ -182,6 +182,10 @@ __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_bas
     tc_fence_after();
     if (threadIdx.x == 0 && j == 0) trace(3);
     if (tr) { t1 = gtime(); t_wait += t1 - t0; }
+    if (LATE_RES && has_res && row_live && lane == 0) {              // the region only becomes free with the accumulator
+      mbar_expect_tx(rbar, 4096u);
+      tma_load_3d(region, tmR, q_base, o_row0, b, rbar);
+    }
     if (has_res && row_live) { mbar_wait(rbar, res_phase); res_phase ^= 1u; }
     const uint32_t tbase = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TQ_NP + ch * (TQ_NP / 2));
     // the TMEM read of group c+1 is in flight while group c is processed

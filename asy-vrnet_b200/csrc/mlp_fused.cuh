@@ -1,0 +1,224 @@
+// tcgen05 path, kernel 5: the channel MLP of a ClusterBlock in ONE kernel (included by conv_tc.cu)
+//
+//   out = x + ls * ( W2 . gelu( W1 . GN(x) + b1 ) + b2 )          (reference vr_coc.py:208-228 Mlp, :264-275 ClusterBlock)
+//
+// As two launches the hidden activation (mlp_ratio 8: 512 / 1024 channels at the two large stages) is written to and read
+// back from HBM — 2 x 134 MB per block at stage 1, more than everything else the block moves.  Here it never leaves the SM:
+//   * one CTA owns a 128-point tile; X (C <= 128 channels) arrives by TMA and is GroupNorm'ed in place (XMODE 3 of
+//     conv_tc_cm.cuh);
+//   * the hidden layer is produced 128 channels at a time:  acc1[128 hid x 128 pts] = W1 chunk . X  (tcgen05, TMEM cols 0-127);
+//     the 8 epilogue warps read it, add b1, apply the erf GELU and write it as bf16 straight into the MN-major SW128 operand
+//     layout (lane = hidden channel = k-row of the second GEMM, 16 consecutive points = two 16-byte chunks);
+//   * acc2[C x 128 pts] += W2 chunk . H  (TMEM cols 128-255) accumulates over the chunks;
+//   * the last epilogue is cm_epilogue: + b2, layer scale, residual (TMA), GroupNorm statistics of the result for the next
+//     block, TMA store.
+// Both weight matrices stream through one TMA ring in the order the MMA thread consumes them.  TMEM: 256 columns, so two
+// CTAs share an SM and one's GELU overlaps the other's loads.
+#pragma once
+
+namespace vrcoc {
+
+constexpr int MF_THREADS = 320;
+constexpr int MF_MAX_STAGES = 6;
+
+struct MlpLayout {
+  int nk1;           // k-slabs of the first GEMM  (C / 64, 1..2)
+  int nh;            // hidden chunks of 128
+  int stages;        // weight ring depth
+  int off_ring, off_h, off_tab, off_bar, total;
+};
+
+__global__ void __launch_bounds__(MF_THREADS, 2)
+mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict__ b1, const __grid_constant__ CUtensorMap tmapX,
+                 const __grid_constant__ CUtensorMap tmapW1, const __grid_constant__ CUtensorMap tmapW2,
+                 const __grid_constant__ CUtensorMap tmapO, const __grid_constant__ CUtensorMap tmapR) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  unsigned char* smem = smem_raw + pad;
+  unsigned char* sX = smem;                                          // [nk1][16 KB]
+  unsigned char* ring = smem + L.off_ring;                           // [stages][16 KB]
+  unsigned char* sH = smem + L.off_h;                                // [2][16 KB] hidden chunk; later the epilogue staging
+  float4* tab = reinterpret_cast<float4*>(smem + L.off_tab);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  uint64_t* bar_free = bar_full + MF_MAX_STAGES;
+  uint64_t* x_full = bar_free + MF_MAX_STAGES;                       // [2]
+  uint64_t* x_ready = x_full + 2;                                    // [2]
+  uint64_t* acc1_full = x_ready + 2;
+  uint64_t* acc1_empty = acc1_full + 1;
+  uint64_t* h_full = acc1_empty + 1;
+  uint64_t* h_empty = h_full + 1;
+  uint64_t* acc2_full = h_empty + 1;
+  uint64_t* acc2_empty = acc2_full + 1;                              // never waited for (single output tile)
+  uint64_t* res_bar = acc2_empty + 1;                                // [8]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, p0 = blockIdx.x * TQ_NP;
+  const int nk1 = L.nk1, nh = L.nh, ST = L.stages;
+
+  if (tid == 0) trace(0);
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 256) {
+    for (int i = 0; i < ST; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_free[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_ready[i], 8); }
+    mbar_init(acc1_full, 1); mbar_init(acc1_empty, 8);
+    mbar_init(h_full, 8); mbar_init(h_empty, 1);
+    mbar_init(acc2_full, 1); mbar_init(acc2_empty, 8);
+    for (int i = 0; i < 8; ++i) mbar_init(&res_bar[i], 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmapX); tma_prefetch_desc(&tmapW1); tma_prefetch_desc(&tmapW2);
+    tma_prefetch_desc(&tmapO); tma_prefetch_desc(&tmapR);
+  }
+  build_prologue_table(a1, b, tab);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ---- TMA producer: X slabs, then the weight slabs in MMA order ------------------------------------------------------------
+    if (lane == 0) {
+      for (int kc = 0; kc < nk1; ++kc) {
+        mbar_expect_tx(&x_full[kc], (uint32_t)TQ_X_BYTES);
+        tma_load_3d(sX + kc * TQ_X_BYTES, &tmapX, p0, kc * TC_BK, b, &x_full[kc]);
+        tma_load_3d(sX + kc * TQ_X_BYTES + TC_A_LBO, &tmapX, p0 + 64, kc * TC_BK, b, &x_full[kc]);
+      }
+      int it = 0;
+      auto put = [&](const CUtensorMap* map, int x, int y) {
+        const int s = it % ST;
+        if (it >= ST) mbar_wait(&bar_free[s], (uint32_t)((it / ST) - 1) & 1);
+        mbar_expect_tx(&bar_full[s], (uint32_t)TQ_W_BYTES);
+        tma_load_2d(ring + s * TQ_W_BYTES, map, x, y, &bar_full[s]);
+        ++it;
+      };
+      for (int kc = 0; kc < nk1; ++kc) put(&tmapW1, kc * TC_BK, 0);
+      for (int j = 0; j < nh; ++j) {
+        if (j + 1 < nh)
+          for (int kc = 0; kc < nk1; ++kc) put(&tmapW1, kc * TC_BK, (j + 1) * TQ_MT);
+        put(&tmapW2, j * TQ_MT, 0);
+        put(&tmapW2, j * TQ_MT + TC_BK, 0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ---- MMA issuer -----------------------------------------------------------------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_cm(TQ_NP);
+      const uint32_t acc1 = tmem_base, acc2 = tmem_base + TQ_NP;
+      int it = 0;
+      auto slab = [&](uint32_t tacc, uint32_t x_addr, bool first) {
+        const int s = it % ST;
+        mbar_wait(&bar_full[s], (uint32_t)(it / ST) & 1);
+        tc_fence_after();
+        const uint32_t w_addr = smem_u32(ring + s * TQ_W_BYTES);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          tc_mma(tacc, make_desc(w_addr + t * 32, 16, 1024), make_desc(x_addr + t * 2048, TC_A_LBO, 1024), idesc, (!first || t > 0) ? 1u : 0u);
+        tc_commit(&bar_free[s]);
+        ++it;
+      };
+      auto gemm1 = [&](int j) {
+        for (int kc = 0; kc < nk1; ++kc) {
+          if (j == 0) mbar_wait(&x_ready[kc], 0);
+          slab(acc1, smem_u32(sX + kc * TQ_X_BYTES), kc == 0);
+        }
+        tc_commit(acc1_full);
+      };
+      gemm1(0);
+      for (int j = 0; j < nh; ++j) {
+        if (j + 1 < nh) {
+          mbar_wait(acc1_empty, (uint32_t)j & 1);                      // the epilogue warps have read hidden chunk j out of TMEM
+          tc_fence_after();
+          gemm1(j + 1);
+        }
+        mbar_wait(h_full, (uint32_t)j & 1);                            // hidden chunk j is in shared memory (bf16 operand layout)
+        tc_fence_after();
+        slab(acc2, smem_u32(sH), j == 0);
+        slab(acc2, smem_u32(sH + TQ_X_BYTES), false);
+        tc_commit(h_empty);
+        if (j == nh - 1) tc_commit(acc2_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- GroupNorm in place on the TMA-landed X slabs ---------------------------------------------------------------------------
+    if (tid == 0) trace(1);
+    for (int kc = 0; kc < nk1; ++kc) {
+      mbar_wait(&x_full[kc], 0);
+      const uint32_t sl = smem_u32(sX + kc * TQ_X_BYTES);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int u = tid + 256 * i;
+        const int chn = kc * TC_BK + ((u >> 3) & 63);
+        if (chn < a1.Cin) {
+          const float4 t = tab[chn];
+          float f[8];
+          unpack8_bf16(lds128(sl + (uint32_t)u * 16u), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], t.x, t.y);
+          sts128(sl + (uint32_t)u * 16u, pack8_bf16(f));
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&x_ready[kc])) : "memory");
+    }
+    if (tid == 0) trace(2);
+
+    // ---- hidden layer: TMEM -> + b1 -> GELU -> bf16 -> operand layout of the second GEMM ------------------------------------------
+    const int lq = warp & 3, ch = warp >> 2;
+    const int hrow = 32 * (lq & 1) + lane;                             // k-row inside the 64-row slab
+    const uint32_t hbase = smem_u32(sH) + (uint32_t)((lq >> 1) * TQ_X_BYTES + ch * TC_A_LBO + hrow * 128);
+    const int sw = lane & 7;
+    const uint32_t tbase = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * (TQ_NP / 2));
+    for (int j = 0; j < nh; ++j) {
+      const float bias = __ldg(b1 + j * TQ_MT + lq * 32 + lane);
+      const uint64_t one2 = pk2(1.f, 1.f), bias2 = pk2(bias, bias);
+      mbar_wait(acc1_full, (uint32_t)j & 1);
+      tc_fence_after();
+      if (tid == 0 && j == 0) trace(3);
+      if (j > 0) mbar_wait(h_empty, (uint32_t)(j - 1) & 1);            // the second GEMM of chunk j-1 has read sH
+      uint32_t rn[16];
+      tmem_ld16_issue(tbase, rn);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[16];
+        tmem_ld_wait(rn);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = rn[i];
+        if (c < 3) {
+          tmem_ld16_issue(tbase + (uint32_t)(16 * (c + 1)), rn);
+        } else {
+          tc_fence_before();                                           // all of acc1 is in registers: the next chunk may overwrite it
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc1_empty)) : "memory");
+        }
+        float y[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          upk2(gelu2(fma2(pk2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), one2, bias2)), y[2 * i], y[2 * i + 1]);
+        float lo[8], hi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { lo[i] = y[i]; hi[i] = y[8 + i]; }
+        sts128(hbase + (uint32_t)(((2 * c) ^ sw) << 4), pack8_bf16(lo));
+        sts128(hbase + (uint32_t)(((2 * c + 1) ^ sw) << 4), pack8_bf16(hi));
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(h_full)) : "memory");
+    }
+    // ---- output: + b2, layer scale, residual, statistics, TMA store (staging aliases sH: free once acc2 is complete) ---------------
+    cm_epilogue<VRCOC_ACT_NONE, false, true>(a2, tmem_base + TQ_NP, acc2_full, acc2_empty, &res_bar[warp], sH + warp * 4096, 0, &tmapO, &tmapO,
+                                             &tmapR, b, p0, 0, 1);
+    if (tid == 0) trace(4);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) trace(5);
+  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+}
+
+}  // namespace vrcoc

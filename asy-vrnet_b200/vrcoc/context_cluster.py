@@ -215,6 +215,12 @@ class ClusterBlock(nn.Module):
         ops.conv_fwd(ops.conv_desc(o, tm.fc2.weight.detach().reshape(C, ED), x1, e_shift=f32(tm.fc2.bias), post_scale=ls1, res=x,
                                    out_sample_sums=sums[0]))
         hid = mlp.fc1.weight.shape[0]
+        if ops.mlp_fused_ok(x1, hid) and mlp.fc1.weight.dtype == dt and mlp.fc2.weight.dtype == dt:
+            # both large stages: the hidden activation (8 x C channels) stays on chip
+            x2 = ops.mlp_fused_fwd(x1, sums[0], f32(n2.weight), f32(n2.bias), n2.eps, mlp.fc1.weight.detach().reshape(hid, C),
+                                   f32(mlp.fc1.bias), mlp.fc2.weight.detach().reshape(C, hid), f32(mlp.fc2.bias), ls2, sums[1])
+            x2._vrcoc_sums = sums[1]
+            return x2
         h = torch.empty(B, hid, H, W, device=dev, dtype=dt)
         ops.conv_fwd(ops.conv_desc(x1, mlp.fc1.weight.detach().reshape(hid, C), h, gn=(sums[0], f32(n2.weight), f32(n2.bias), n2.eps),
                                    e_shift=f32(mlp.fc1.bias), act=ACT_GELU))

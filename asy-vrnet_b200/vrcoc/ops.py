@@ -63,6 +63,24 @@ def run_pair(f_main, f_side):
     return a, b
 
 
+FUSED_MLP = True             # set False to run the channel MLP as two GEMM launches (debug / A-B)
+
+
+def mlp_fused_ok(x, hidden):
+    B, C, H, W = x.shape
+    return FUSED_MLP and x.dtype == torch.bfloat16 and bool(lib.vrcoc_mlp_fused_supported(1, C, hidden, H * W))
+
+
+def mlp_fused_fwd(x, sums, gamma, beta, eps, w1, b1, w2, b2, ls, out_sums):
+    """out = x + ls * (W2 . gelu(W1 . GN(x) + b1) + b2) in one launch (csrc/mlp_fused.cuh; reference vr_coc.py:208-228, :270-275)"""
+    B, C, H, W = x.shape
+    hid = w1.shape[0]
+    out = torch.empty_like(x)
+    check(lib.vrcoc_mlp_fused_fwd(_ptr(x), _ptr(sums), _ptr(gamma), _ptr(beta), float(eps), _ptr(w1), _ptr(b1), _ptr(w2), _ptr(b2),
+                                  _ptr(ls), _ptr(out), _ptr(out_sums), B, C, hid, H * W, _stream()), "mlp_fused_fwd")
+    return out
+
+
 class Fork:
     """f() on side stream number `lane` (>= 1) of the current device, ordered after everything already queued on the
     current stream; join() orders the current stream after it and returns f's result.  Same liveness rule as run_pair: the

@@ -191,6 +191,17 @@ int vrcoc_img_enh_finish(const void* k, int k_dtype, const void* image, int imag
  * (start, setup done, first operands landed, last MMA committed, epilogue done, TMEM released); NULL switches it off. */
 int vrcoc_debug_set_trace(unsigned long long* buf);
 
+/* Fused channel MLP of a ClusterBlock (reference vr_coc.py:208-228 Mlp inside :264-275), inference, bf16:
+ *   out = x + layer_scale * ( W2 . gelu( W1 . GroupNorm1(x) + b1 ) + b2 ),   hidden never leaves the SM (csrc/mlp_fused.cuh).
+ * x, out: [B][C][P] bf16; gn_sums: per-sample slot sums of x (vrcoc_channel_sums / a producer's out_sample_sums); w1 [hidden][C],
+ * w2 [C][hidden] bf16; b1, b2, layer_scale (may be NULL = 1), gamma, beta fp32; out_sample_sums (may be NULL, else zeroed by the
+ * caller) receives the slot sums of `out`.  vrcoc_mlp_fused_supported tells whether a shape is covered (C in {64, 128},
+ * hidden % 128 == 0, P % 8 == 0); other shapes use two vrcoc_conv_fwd calls. */
+int vrcoc_mlp_fused_supported(int dtype, int C, int hidden, int P);
+int vrcoc_mlp_fused_fwd(const void* x, const double* gn_sums, const float* gamma, const float* beta, float eps, const void* w1,
+                        const float* b1, const void* w2, const float* b2, const float* layer_scale, void* out,
+                        double* out_sample_sums, int B, int C, int hidden, int P, void* stream);
+
 /* Debug / A-B switch: on = 0 routes 1x1 projections to the point-major tcgen05 kernels instead of the channel-major one
  * (conv_tc_cm.cuh); results are identical up to fp32 summation order.  Default 1. */
 int vrcoc_debug_set_cm(int on);

@@ -202,3 +202,37 @@ def test_depthwise_conv(env, case, dtype):
                            stride, pad, torch.cuda.current_stream().cuda_stream), "dwconv")
     ref = F.conv2d(x.float(), w.float(), bias, stride=stride, padding=pad, groups=C)
     assert rel_err(y.float(), ref) < (1e-5 if dtype == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("case", [(2, 64, 512, 32, 32), (1, 128, 1024, 16, 24), (2, 64, 256, 5, 8), (3, 128, 128, 8, 8)],
+                         ids=lambda c: "x".join(map(str, c)))
+def test_fused_mlp_matches_two_launches(env, case):
+    """vrcoc_mlp_fused_fwd (hidden layer kept on chip) against the two-GEMM path and an fp32 torch restatement of
+    x + ls * fc2(gelu(fc1(GroupNorm(1, C)(x))))  (reference vr_coc.py:208-228, :270-275)"""
+    ops = env
+    from vrcoc._lib import ACT_GELU
+    B, C, hid, H, W = case
+    g = torch.Generator().manual_seed(9)
+    x = (torch.randn(B, C, H, W, generator=g) * 1.2 + 0.1).bfloat16().cuda()
+    w1 = (torch.randn(hid, C, generator=g) / C ** 0.5).bfloat16().cuda()
+    w2 = (torch.randn(C, hid, generator=g) / hid ** 0.5).bfloat16().cuda()
+    b1, b2 = (torch.randn(hid, generator=g) * 0.1).cuda(), (torch.randn(C, generator=g) * 0.1).cuda()
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).cuda(), (torch.randn(C, generator=g) * 0.1).cuda()
+    ls = (torch.rand(C, generator=g) + 0.5).cuda()
+    sums = ops.sample_sums_of(x)
+    assert ops.mlp_fused_ok(x, hid)
+    s_f = ops.new_sample_sums(B, "cuda")
+    fused = ops.mlp_fused_fwd(x, sums, gamma, beta, 1e-5, w1, b1, w2, b2, ls, s_f)
+    h = torch.empty(B, hid, H, W, device="cuda", dtype=torch.bfloat16)
+    ops.conv_fwd(ops.conv_desc(x, w1, h, gn=(sums, gamma, beta, 1e-5), e_shift=b1, act=ACT_GELU))
+    two = torch.empty_like(x)
+    s_t = ops.new_sample_sums(B, "cuda")
+    ops.conv_fwd(ops.conv_desc(h, w2, two, e_shift=b2, post_scale=ls, res=x, out_sample_sums=s_t))
+    torch.cuda.synchronize()
+    xf = x.float()
+    ref = xf + ls.view(1, -1, 1, 1) * F.conv2d(F.gelu(F.conv2d(F.group_norm(xf, 1, gamma, beta, 1e-5), w1.float().view(hid, C, 1, 1), b1)),
+                                              w2.float().view(C, hid, 1, 1), b2)
+    assert torch.isfinite(fused.float()).all()
+    assert rel_err(fused.float(), two.float()) < 2e-3            # same arithmetic; both round the hidden layer to bf16
+    assert rel_err(fused.float(), ref) < 8e-3                    # bf16 GN(x), bf16 hidden, bf16 output
+    assert rel_err(s_f.sum(1), s_t.sum(1)) < 2e-3

@@ -25,6 +25,8 @@ CASES = {
     "s3_mlp2": ("projres", 1280, 320, 32, {}),
     "s4_mlp1": ("gnproj", 512, 2048, 16, dict(act=ACT_GELU)),
     "s4_mlp2": ("projres", 2048, 512, 16, {}),
+    "s1_mlpf": ("mlpf", 64, 512, 128, {}),
+    "s2_mlpf": ("mlpf", 128, 1024, 64, {}),
     "s1_core": ("core", 128, 0, 128, dict(E=4, fold=8)),
     "s2_core": ("core", 128, 0, 64, dict(E=4, fold=4)),
     "s3_core": ("core", 256, 0, 32, dict(E=8, fold=2)),
@@ -76,6 +78,16 @@ def main():
             d = ops.conv_desc(x, w, out, e_shift=bias, post_scale=ls, res=res, out_sample_sums=sums)
             fn = lambda: ops.conv_fwd(d)
             by, fl = B * P * (C + 2 * O) * es, 2.0 * B * P * C * O
+        elif kind == "mlpf":
+            x = torch.randn(B, C, H, H, device=dev, generator=g).to(dt)
+            w1 = (torch.randn(O, C, device=dev, generator=g) / C ** 0.5).to(dt)
+            w2 = (torch.randn(C, O, device=dev, generator=g) / O ** 0.5).to(dt)
+            b1, b2, ls = torch.zeros(O, device=dev), torch.zeros(C, device=dev), torch.ones(C, device=dev)
+            gamma, beta = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+            sums = ops.sample_sums_of(x)
+            osum = ops.new_sample_sums(B, dev)
+            fn = lambda: ops.mlp_fused_fwd(x, sums, gamma, beta, 1e-5, w1, b1, w2, b2, ls, osum)
+            by, fl = B * P * 3 * C * es, 4.0 * B * P * C * O
         elif kind == "conv3":
             x = torch.randn(B, C, H, H, device=dev, generator=g).to(dt)
             w = (torch.randn(O, C * 9, device=dev, generator=g) / (C * 9) ** 0.5).to(dt)
