@@ -243,6 +243,95 @@ __global__ void __launch_bounds__(SMALL_THREADS) conv_small_kernel(ConvArgs a) {
 // Vectorised variant (stride 1, W_out % 8 == 0, one source dtype): one thread = 8 consecutive output pixels of a row x all
 // output channels; per (channel, ky) it loads the 8 + kw - 1 input window once (one 128-bit load + edge scalars) and reuses it
 // for the kw taps; outputs leave as 128-bit stores.
+// "Same" k x k convolution (k = KW in {1, 3}, stride 1, pad (k-1)/2) on rows that are a multiple of 8 wide and 16-byte
+// aligned — every ingest convolution of the model (512 x 512 frames, 3..7 channels).  Compile-time taps: the 8 centre pixels
+// of a row are ONE 128-bit load, the halo two scalars; no per-tap predicates.  Bandwidth-bound by construction.
+template <typename TS, int MAXO, int KW>
+__global__ void __launch_bounds__(SMALL_THREADS) conv_small_same_kernel(ConvArgs a) {
+  constexpr int PAD = (KW - 1) / 2;
+  __shared__ float wsm[SMALL_MAX_O * SMALL_MAX_K];
+  __shared__ float4 tab[SMALL_MAX_K];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < a.O * a.K; i += blockDim.x) wsm[i] = ld_any(a.weight, i, a.weight_dtype);
+  build_prologue_table(a, b, tab);
+  __syncthreads();
+  const int P = a.P_out, W = a.W_in;
+  const int groups = P >> 3;
+  float ssum = 0.f, ssq = 0.f, vmax = 0.f, vmin = __int_as_float(0x7f800000);
+  for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += gridDim.x * blockDim.x) {
+    const int q0 = gi << 3;
+    const int oy = q0 / W, ox0 = q0 - oy * W;
+    float acc[MAXO][8];
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[o][j] = 0.f;
+    for (int c = 0; c < a.Cin; ++c) {
+      const int s = a.chan_src ? a.chan_src[c] : c;
+      const TS* plane = (s < a.C0) ? reinterpret_cast<const TS*>(a.src0) + (int64_t)b * a.src0_bstride + (int64_t)s * a.P_in
+                                   : reinterpret_cast<const TS*>(a.src1) + (int64_t)b * a.src1_bstride + (int64_t)(s - a.C0) * a.P_in;
+      const float4 t = tab[c];
+#pragma unroll
+      for (int ky = 0; ky < KW; ++ky) {
+        const int iy = oy - PAD + ky;
+        if (iy < 0 || iy >= a.H_in) continue;
+        const TS* row = plane + (int64_t)iy * W;
+        float win[8 + 2 * PAD];
+        {
+          float ctr[8];
+          ld8<TS>(row + ox0, ctr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) win[PAD + j] = ctr[j];
+          if (PAD) {
+            win[0] = ox0 > 0 ? (float)row[ox0 - 1] : 0.f;
+            win[8 + 2 * PAD - 1] = ox0 + 8 < W ? (float)row[ox0 + 8] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8 + 2 * PAD; ++j) {
+          const float x = win[j];
+          float z = fmaf(x, t.x, t.y);
+          if (a.has_gate) z *= sigmoidf_exact(fmaf(t.z, x, t.w));
+          win[j] = z;
+        }
+        if (PAD) {                                            // zero padding is applied AFTER the prologue
+          if (ox0 == 0) win[0] = 0.f;
+          if (ox0 + 8 >= W) win[8 + 2 * PAD - 1] = 0.f;
+        }
+        const float* wrow = wsm + c * KW * KW + ky * KW;
+#pragma unroll
+        for (int kx = 0; kx < KW; ++kx) {
+#pragma unroll
+          for (int o = 0; o < MAXO; ++o) {
+            if (o < a.O) {
+              const float wv = wrow[o * a.K + kx];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[o][j] = fmaf(wv, win[j + kx], acc[o][j]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < MAXO; ++o) {
+      if (o < a.O) {
+        const EpiCoef ec = load_epi(a, o);
+        float r[8], y[8];
+        if (a.res) load8_any(a.res, ((int64_t)b * a.O + o) * P + q0, a.res_dtype, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          y[j] = epilogue_value(acc[o][j], ec, a.act, a.res ? r[j] : 0.f);
+          ssum += y[j]; ssq = fmaf(y[j], y[j], ssq);
+          vmax = fmaxf(vmax, y[j]); vmin = fminf(vmin, y[j]);
+        }
+        if (o < a.O_split) store8_any(a.out, ((int64_t)b * a.O_split + o) * P + q0, a.out_dtype, y);
+        else store8_any(a.out2, ((int64_t)b * (a.O - a.O_split) + (o - a.O_split)) * P + q0, a.out2_dtype, y);
+      }
+    }
+  }
+  emit_side_stats(a, b, ssum, ssq, vmax, vmin);
+}
+
 template <typename TS, int MAXO>
 __global__ void __launch_bounds__(SMALL_THREADS) conv_small_vec_kernel(ConvArgs a) {
   __shared__ float wsm[SMALL_MAX_O * SMALL_MAX_K];
@@ -333,6 +422,24 @@ int launch_conv_small(const ConvArgs& a, cudaStream_t st) {
     if (bx > 2048) bx = 2048;
     dim3 grid(bx, a.B);
     const bool f32 = a.src0_dtype == VRCOC_F32;
+    const int es = f32 ? 4 : 2;
+    auto al = [&](const void* p, int64_t bstride) {
+      return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (bstride * es) % 16 == 0 && ((int64_t)a.P_in * es) % 16 == 0;
+    };
+    const bool same = a.kh == a.kw && (a.kw == 1 || a.kw == 3) && a.pad == (a.kw - 1) / 2 && a.W_in == a.W_out && a.H_in == a.H_out &&
+                      a.W_in % 8 == 0 && al(a.src0, a.src0_bstride) && (a.C1 == 0 || al(a.src1, a.src1_bstride));
+    if (same) {
+#define SAME(TS, MO, KWV) conv_small_same_kernel<TS, MO, KWV><<<grid, SMALL_THREADS, 0, st>>>(a)
+      if (a.O <= 4) {
+        if (a.kw == 1) { if (f32) SAME(float, 4, 1); else SAME(__nv_bfloat16, 4, 1); }
+        else           { if (f32) SAME(float, 4, 3); else SAME(__nv_bfloat16, 4, 3); }
+      } else {
+        if (a.kw == 1) { if (f32) SAME(float, 8, 1); else SAME(__nv_bfloat16, 8, 1); }
+        else           { if (f32) SAME(float, 8, 3); else SAME(__nv_bfloat16, 8, 3); }
+      }
+#undef SAME
+      return check_launch("conv_small_same");
+    }
     if (a.O <= 4) {
       if (f32) conv_small_vec_kernel<float, 4><<<grid, SMALL_THREADS, 0, st>>>(a);
       else conv_small_vec_kernel<__nv_bfloat16, 4><<<grid, SMALL_THREADS, 0, st>>>(a);

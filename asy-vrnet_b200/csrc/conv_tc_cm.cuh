@@ -57,6 +57,17 @@ __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
+      "%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
@@ -130,7 +141,9 @@ __device__ __forceinline__ void unpack8_bf16(const uint4& u, float* f) {
 // residual lands there by TMA, is replaced in place by the result, and leaves by TMA store — global memory only ever sees
 // whole 128-byte rows, and the clipping of the boxes to the tensors replaces every edge predicate on the stores.
 // fp32 outputs (the similarity half of fc1|fc_v) go through the same region in two 32-point passes.
-template <int ACT, bool PLAIN, bool LATE_RES = false>
+// RES_MODE: 0 = the residual box is requested on entry; 1 = after the accumulator wait (region busy until then);
+//           2 = the caller has already requested it on `rbar` (first phase)
+template <int ACT, bool PLAIN, int RES_MODE = 0>
 __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty, uint64_t* rbar,
                                             unsigned char* region0, int buf_stride, const CUtensorMap* tmO1, const CUtensorMap* tmO2,
                                             const CUtensorMap* tmR, int b, int p0, int o_begin, int tiles) {
@@ -161,7 +174,7 @@ __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_bas
       }
       __syncwarp();
     }
-    if (!LATE_RES && has_res && row_live && lane == 0) {
+    if (RES_MODE == 0 && has_res && row_live && lane == 0) {
       mbar_expect_tx(rbar, 4096u);
       tma_load_3d(region, tmR, q_base, o_row0, b, rbar);
     }
@@ -182,7 +195,7 @@ __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_bas
     tc_fence_after();
     if (threadIdx.x == 0 && j == 0) trace(3);
     if (tr) { t1 = gtime(); t_wait += t1 - t0; }
-    if (LATE_RES && has_res && row_live && lane == 0) {              // the region only becomes free with the accumulator
+    if (RES_MODE == 1 && has_res && row_live && lane == 0) {         // the region only becomes free with the accumulator
       mbar_expect_tx(rbar, 4096u);
       tma_load_3d(region, tmR, q_base, o_row0, b, rbar);
     }

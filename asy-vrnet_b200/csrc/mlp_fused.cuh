@@ -173,6 +173,7 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
     const int hrow = 32 * (lq & 1) + lane;                             // k-row inside the 64-row slab
     const uint32_t hbase = smem_u32(sH) + (uint32_t)((lq >> 1) * TQ_X_BYTES + ch * TC_A_LBO + hrow * 128);
     const int sw = lane & 7;
+    unsigned char* out_region = sX + (lq >> 1) * TQ_X_BYTES + ch * TC_A_LBO + (lq & 1) * 4096;   // [32 channels][64 points] of X
     const uint32_t tbase = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * (TQ_NP / 2));
     for (int j = 0; j < nh; ++j) {
       const float bias = __ldg(b1 + j * TQ_MT + lq * 32 + lane);
@@ -180,39 +181,47 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
       mbar_wait(acc1_full, (uint32_t)j & 1);
       tc_fence_after();
       if (tid == 0 && j == 0) trace(3);
-      if (j > 0) mbar_wait(h_empty, (uint32_t)(j - 1) & 1);            // the second GEMM of chunk j-1 has read sH
-      uint32_t rn[16];
-      tmem_ld16_issue(tbase, rn);
+      if (j == nh - 1 && lq * 32 < a2.O && lane == 0) {
+        // the last first-GEMM has read X: its slab becomes the staging region of the output epilogue and the residual (the raw
+        // x again) is fetched into it now, under the last GELU pass
+        mbar_expect_tx(&res_bar[warp], 4096u);
+        tma_load_3d(out_region, &tmapR, p0 + ch * (TQ_NP / 2), lq * 32, b, &res_bar[warp]);
+      }
+      // two 32-column reads; after the second one acc1 is free, so the next chunk's first GEMM runs under the second half of
+      // the GELU work.  sH is first written after the first 16 values are computed: by then the previous chunk's second GEMM
+      // (which reads it) has normally completed.
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[16];
-        tmem_ld_wait(rn);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = rn[i];
-        if (c < 3) {
-          tmem_ld16_issue(tbase + (uint32_t)(16 * (c + 1)), rn);
-        } else {
-          tc_fence_before();                                           // all of acc1 is in registers: the next chunk may overwrite it
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t r[32];
+        tmem_ld32(tbase + (uint32_t)(32 * hh), r);
+        if (hh == 1) {
+          tc_fence_before();
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc1_empty)) : "memory");
         }
-        float y[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          upk2(gelu2(fma2(pk2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), one2, bias2)), y[2 * i], y[2 * i + 1]);
-        float lo[8], hi[8];
+        for (int sub = 0; sub < 2; ++sub) {
+          const int c = 2 * hh + sub;
+          float y[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { lo[i] = y[i]; hi[i] = y[8 + i]; }
-        sts128(hbase + (uint32_t)(((2 * c) ^ sw) << 4), pack8_bf16(lo));
-        sts128(hbase + (uint32_t)(((2 * c + 1) ^ sw) << 4), pack8_bf16(hi));
+          for (int i = 0; i < 8; ++i)
+            upk2(gelu2(fma2(pk2(__uint_as_float(r[16 * sub + 2 * i]), __uint_as_float(r[16 * sub + 2 * i + 1])), one2, bias2)), y[2 * i],
+                 y[2 * i + 1]);
+          float lo[8], hi[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { lo[i] = y[i]; hi[i] = y[8 + i]; }
+          if (c == 0 && j > 0) mbar_wait(h_empty, (uint32_t)(j - 1) & 1);   // the second GEMM of chunk j-1 has read sH
+          sts128(hbase + (uint32_t)(((2 * c) ^ sw) << 4), pack8_bf16(lo));
+          sts128(hbase + (uint32_t)(((2 * c + 1) ^ sw) << 4), pack8_bf16(hi));
+        }
       }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(h_full)) : "memory");
     }
-    // ---- output: + b2, layer scale, residual, statistics, TMA store (staging aliases sH: free once acc2 is complete) ---------------
-    cm_epilogue<VRCOC_ACT_NONE, false, true>(a2, tmem_base + TQ_NP, acc2_full, acc2_empty, &res_bar[warp], sH + warp * 4096, 0, &tmapO, &tmapO,
-                                             &tmapR, b, p0, 0, 1);
+    // ---- output: + b2, layer scale, residual, statistics, TMA store (staged in the warp's part of the X slab) ----------------------
+    cm_epilogue<VRCOC_ACT_NONE, false, 2>(a2, tmem_base + TQ_NP, acc2_full, acc2_empty, &res_bar[warp], out_region, 0, &tmapO, &tmapO,
+                                          &tmapR, b, p0, 0, 1);
     if (tid == 0) trace(4);
   }
   tc_fence_before();
