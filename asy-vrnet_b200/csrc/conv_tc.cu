@@ -1172,7 +1172,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
 
 // ---- fused channel MLP ------------------------------------------------------------------------------------------------------
 extern "C" int vrcoc_mlp_fused_supported(int dtype, int C, int hidden, int P) {
-  return dtype == VRCOC_BF16 && (C == 64 || C == 128) && hidden > 0 && hidden % vrcoc::TQ_MT == 0 && P > 0 && P % 8 == 0 &&
+  return dtype == VRCOC_BF16 && C >= 64 && C % 64 == 0 && C <= 384 && hidden > 0 && hidden % vrcoc::TQ_MT == 0 && P > 0 && P % 8 == 0 &&
          vrcoc::tma_encode_fn() != nullptr;
 }
 
@@ -1198,15 +1198,19 @@ extern "C" int vrcoc_mlp_fused_fwd(const void* x, const double* gn_sums, const f
   MlpLayout L;
   L.nk1 = C / TC_BK;
   L.nh = hidden / TQ_MT;
-  // ring depth: as deep as two resident CTAs per SM allow (227 KB, 1 KB reserved per CTA)
+  L.mt2 = (C + TQ_MT - 1) / TQ_MT;
+  L.h_bufs = L.mt2 == 1 ? 1 : 2;
+  L.tmem_cols = L.mt2 == 1 ? 256 : 512;
+  // ring depth: C <= 128: as deep as two resident CTAs per SM allow (227 KB, 1 KB reserved per CTA); else one CTA per SM
+  const int budget = L.mt2 == 1 ? (227 * 1024) / 2 - 1024 : 220 * 1024;
   L.stages = 2;
   for (int stg = MF_MAX_STAGES; stg >= 2; --stg) {
-    const int tot = L.nk1 * TQ_X_BYTES + stg * TQ_W_BYTES + 2 * TQ_X_BYTES + C * 16 + 512 + 1024;
-    if (2 * (tot + 1024) <= 227 * 1024) { L.stages = stg; break; }
+    const int tot = L.nk1 * TQ_X_BYTES + stg * TQ_W_BYTES + L.h_bufs * 2 * TQ_X_BYTES + C * 16 + 512 + 1024;
+    if (tot <= budget) { L.stages = stg; break; }
   }
   L.off_ring = L.nk1 * TQ_X_BYTES;
   L.off_h = L.off_ring + L.stages * TQ_W_BYTES;
-  L.off_tab = L.off_h + 2 * TQ_X_BYTES;
+  L.off_tab = L.off_h + L.h_bufs * 2 * TQ_X_BYTES;
   L.off_bar = L.off_tab + C * 16;
   L.total = L.off_bar + 512 + 1024;
   CUtensorMap tmX, tmW1, tmW2, tmO, tmR;
@@ -1226,9 +1230,14 @@ extern "C" int vrcoc_mlp_fused_fwd(const void* x, const double* gn_sums, const f
     if ((rc = tma_encode(&tmW1, VRCOC_BF16, w1, 2, d1, s1, box, true))) return rc;
     if ((rc = tma_encode(&tmW2, VRCOC_BF16, w2, 2, d2, s2, box, true))) return rc;
   }
-  set_smem(mlp_fused_kernel, L.total);
   dim3 grid((unsigned)cdiv(P, TQ_NP), 1, (unsigned)B);
-  mlp_fused_kernel<<<grid, MF_THREADS, L.total, (cudaStream_t)stream>>>(a1, a2, L, b1, tmX, tmW1, tmW2, tmO, tmR);
+  if (L.mt2 == 1) {
+    set_smem(mlp_fused_kernel<true>, L.total);
+    mlp_fused_kernel<true><<<grid, MF_THREADS, L.total, (cudaStream_t)stream>>>(a1, a2, L, b1, tmX, tmW1, tmW2, tmO, tmR);
+  } else {
+    set_smem(mlp_fused_kernel<false>, L.total);
+    mlp_fused_kernel<false><<<grid, MF_THREADS, L.total, (cudaStream_t)stream>>>(a1, a2, L, b1, tmX, tmW1, tmW2, tmO, tmR);
+  }
   return check_launch("mlp_fused");
 }
 

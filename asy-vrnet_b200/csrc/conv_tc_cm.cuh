@@ -142,8 +142,11 @@ __device__ __forceinline__ void unpack8_bf16(const uint4& u, float* f) {
 // whole 128-byte rows, and the clipping of the boxes to the tensors replaces every edge predicate on the stores.
 // fp32 outputs (the similarity half of fc1|fc_v) go through the same region in two 32-point passes.
 // RES_MODE: 0 = the residual box is requested on entry; 1 = after the accumulator wait (region busy until then);
-//           2 = the caller has already requested it on `rbar` (first phase)
-template <int ACT, bool PLAIN, int RES_MODE = 0>
+//           2 = the caller has already requested it on `rbar` (first phase);
+//           3 = LINEAR only: the boxes of all tiles are requested on entry (one barrier phase; every tile has its own region)
+// LINEAR: the `tiles` accumulators are all complete when acc_full[0] fires and sit side by side in TMEM (tile j at column
+//         j * 128); tile j is staged in region0 + j * buf_stride (the fused MLP's output epilogue)
+template <int ACT, bool PLAIN, int RES_MODE = 0, bool LINEAR = false>
 __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_base, uint64_t* acc_full, uint64_t* acc_empty, uint64_t* rbar,
                                             unsigned char* region0, int buf_stride, const CUtensorMap* tmO1, const CUtensorMap* tmO2,
                                             const CUtensorMap* tmR, int b, int p0, int o_begin, int tiles) {
@@ -158,16 +161,22 @@ __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_bas
   uint32_t res_phase = 0;
   unsigned long long t_wait = 0, t_comp = 0;       // debug trace: warp 0's time waiting for accumulators / draining them
   float ssum = 0.f, ssq = 0.f, vmax = 0.f, vmin = __int_as_float(0x7f800000);
+  if (RES_MODE == 3 && has_res && lane == 0) {
+    int live = 0;
+    for (int j = 0; j < tiles; ++j) live += (o_begin + j * TQ_MT + lq * 32 < a.O) ? 1 : 0;
+    if (live) mbar_expect_tx(rbar, 4096u * (uint32_t)live);
+    for (int j = 0; j < live; ++j) tma_load_3d(region0 + j * buf_stride, tmR, q_base, o_begin + j * TQ_MT + lq * 32, b, rbar);
+  }
   for (int j = 0; j < tiles; ++j) {
-    const int buf = j & 1;
+    const int buf = LINEAR ? 0 : (j & 1);
     const int o_row0 = o_begin + j * TQ_MT + lq * 32;
     const int o = o_row0 + lane;
     const bool ok = o < a.O;
     const bool row_live = o_row0 < a.O;                              // warp-uniform
     // staging buffer j&1 (when there are two): its previous store — tile j-2's — must have finished reading it
-    unsigned char* region = region0 + (j & 1) * buf_stride;
+    unsigned char* region = region0 + (LINEAR ? j : (j & 1)) * buf_stride;
     const uint32_t rbase = smem_u32(region) + lane * 128;
-    if (j > 0) {
+    if (j > 0 && !LINEAR) {
       if (lane == 0) {
         if (buf_stride) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         else tma_store_wait_read();
@@ -191,7 +200,7 @@ __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_bas
     const bool tr = g_tc_trace != nullptr && threadIdx.x == 0;
     unsigned long long t0 = 0, t1 = 0;
     if (tr) t0 = gtime();
-    mbar_wait(&acc_full[buf], (uint32_t)(j >> 1) & 1);
+    mbar_wait(&acc_full[buf], LINEAR ? 0u : ((uint32_t)(j >> 1) & 1));
     tc_fence_after();
     if (threadIdx.x == 0 && j == 0) trace(3);
     if (tr) { t1 = gtime(); t_wait += t1 - t0; }
@@ -199,8 +208,11 @@ __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_bas
       mbar_expect_tx(rbar, 4096u);
       tma_load_3d(region, tmR, q_base, o_row0, b, rbar);
     }
-    if (has_res && row_live) { mbar_wait(rbar, res_phase); res_phase ^= 1u; }
-    const uint32_t tbase = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TQ_NP + ch * (TQ_NP / 2));
+    if (has_res && row_live) {
+      if (RES_MODE == 3) mbar_wait(rbar, 0);
+      else { mbar_wait(rbar, res_phase); res_phase ^= 1u; }
+    }
+    const uint32_t tbase = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)((LINEAR ? j : buf) * TQ_NP + ch * (TQ_NP / 2));
     // the TMEM read of group c+1 is in flight while group c is processed
     // (not unrolled: a CTA often drains a single tile, i.e. runs this code once, from a cold instruction cache — ncu showed
     // instruction fetch, not issue, bounding the fully unrolled version)

@@ -12,22 +12,29 @@
 //   * acc2[C x 128 pts] += W2 chunk . H  (TMEM cols 128-255) accumulates over the chunks;
 //   * the last epilogue is cm_epilogue: + b2, layer scale, residual (TMA), GroupNorm statistics of the result for the next
 //     block, TMA store.
-// Both weight matrices stream through one TMA ring in the order the MMA thread consumes them.  TMEM: 256 columns, so two
-// CTAs share an SM and one's GELU overlaps the other's loads.
+// Both weight matrices stream through one TMA ring in the order the MMA thread consumes them.
+// C <= 128 (stages 1, 2): TMEM 256 columns, one hidden buffer, two CTAs per SM (one's GELU overlaps the other's loads).
+// C <= 384 (stage 3):     acc2 is ceil(C/128) tiles side by side (TMEM 512 columns), two hidden buffers so that the second GEMM
+//                         of chunk j runs under the GELU of chunk j+1, one CTA per SM.
 #pragma once
 
 namespace vrcoc {
 
 constexpr int MF_THREADS = 320;
 constexpr int MF_MAX_STAGES = 6;
+constexpr int MF_MAX_NK1 = 6;
 
 struct MlpLayout {
   int nk1;           // k-slabs of the first GEMM  (C / 64, 1..2)
   int nh;            // hidden chunks of 128
   int stages;        // weight ring depth
+  int mt2;           // output tiles of 128 channels (ceil(C / 128), 1..3)
+  int h_bufs;        // hidden buffers in shared memory (1 or 2)
+  int tmem_cols;     // 256 or 512
   int off_ring, off_h, off_tab, off_bar, total;
 };
 
+template <bool SINGLE>      // SINGLE: C <= 128 — one output tile, one hidden buffer (compile-time, the hot configuration)
 __global__ void __launch_bounds__(MF_THREADS, 2)
 mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict__ b1, const __grid_constant__ CUtensorMap tmapX,
                  const __grid_constant__ CUtensorMap tmapW1, const __grid_constant__ CUtensorMap tmapW2,
@@ -37,17 +44,17 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
   unsigned char* smem = smem_raw + pad;
   unsigned char* sX = smem;                                          // [nk1][16 KB]
   unsigned char* ring = smem + L.off_ring;                           // [stages][16 KB]
-  unsigned char* sH = smem + L.off_h;                                // [2][16 KB] hidden chunk; later the epilogue staging
+  unsigned char* sH = smem + L.off_h;                                // [h_bufs][2][16 KB] hidden chunk(s), bf16 operand layout
   float4* tab = reinterpret_cast<float4*>(smem + L.off_tab);
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   uint64_t* bar_free = bar_full + MF_MAX_STAGES;
-  uint64_t* x_full = bar_free + MF_MAX_STAGES;                       // [2]
-  uint64_t* x_ready = x_full + 2;                                    // [2]
-  uint64_t* acc1_full = x_ready + 2;
+  uint64_t* x_full = bar_free + MF_MAX_STAGES;                       // [MF_MAX_NK1]
+  uint64_t* x_ready = x_full + MF_MAX_NK1;                           // [MF_MAX_NK1]
+  uint64_t* acc1_full = x_ready + MF_MAX_NK1;
   uint64_t* acc1_empty = acc1_full + 1;
-  uint64_t* h_full = acc1_empty + 1;
-  uint64_t* h_empty = h_full + 1;
-  uint64_t* acc2_full = h_empty + 1;
+  uint64_t* h_full = acc1_empty + 1;                                 // [2]
+  uint64_t* h_empty = h_full + 2;                                    // [2]
+  uint64_t* acc2_full = h_empty + 2;
   uint64_t* acc2_empty = acc2_full + 1;                              // never waited for (single output tile)
   uint64_t* res_bar = acc2_empty + 1;                                // [8]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
@@ -55,17 +62,18 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, p0 = blockIdx.x * TQ_NP;
   const int nk1 = L.nk1, nh = L.nh, ST = L.stages;
+  const int MT2 = SINGLE ? 1 : L.mt2, HB = SINGLE ? 1 : L.h_bufs;
 
   if (tid == 0) trace(0);
   if (warp == 9) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)L.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 256) {
     for (int i = 0; i < ST; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_free[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_ready[i], 8); }
+    for (int i = 0; i < MF_MAX_NK1; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_ready[i], 8); }
     mbar_init(acc1_full, 1); mbar_init(acc1_empty, 8);
-    mbar_init(h_full, 8); mbar_init(h_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&h_full[i], 8); mbar_init(&h_empty[i], 1); }
     mbar_init(acc2_full, 1); mbar_init(acc2_empty, 8);
     for (int i = 0; i < 8; ++i) mbar_init(&res_bar[i], 1);
     mbar_fence_init();
@@ -98,8 +106,10 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
       for (int j = 0; j < nh; ++j) {
         if (j + 1 < nh)
           for (int kc = 0; kc < nk1; ++kc) put(&tmapW1, kc * TC_BK, (j + 1) * TQ_MT);
-        put(&tmapW2, j * TQ_MT, 0);
-        put(&tmapW2, j * TQ_MT + TC_BK, 0);
+        for (int m = 0; m < MT2; ++m) {
+          put(&tmapW2, j * TQ_MT, m * TQ_MT);
+          put(&tmapW2, j * TQ_MT + TC_BK, m * TQ_MT);
+        }
       }
     }
     __syncwarp();
@@ -134,11 +144,15 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
           tc_fence_after();
           gemm1(j + 1);
         }
-        mbar_wait(h_full, (uint32_t)j & 1);                            // hidden chunk j is in shared memory (bf16 operand layout)
+        const int hb = j % HB;
+        mbar_wait(&h_full[hb], (uint32_t)(j / HB) & 1);                // hidden chunk j is in shared memory (bf16 operand layout)
         tc_fence_after();
-        slab(acc2, smem_u32(sH), j == 0);
-        slab(acc2, smem_u32(sH + TQ_X_BYTES), false);
-        tc_commit(h_empty);
+        unsigned char* hbuf = sH + hb * 2 * TQ_X_BYTES;
+        for (int m = 0; m < MT2; ++m) {
+          slab(acc2 + (uint32_t)(m * TQ_NP), smem_u32(hbuf), j == 0);
+          slab(acc2 + (uint32_t)(m * TQ_NP), smem_u32(hbuf + TQ_X_BYTES), false);
+        }
+        tc_commit(&h_empty[hb]);
         if (j == nh - 1) tc_commit(acc2_full);
       }
     }
@@ -171,17 +185,19 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
     // ---- hidden layer: TMEM -> + b1 -> GELU -> bf16 -> operand layout of the second GEMM ------------------------------------------
     const int lq = warp & 3, ch = warp >> 2;
     const int hrow = 32 * (lq & 1) + lane;                             // k-row inside the 64-row slab
-    const uint32_t hbase = smem_u32(sH) + (uint32_t)((lq >> 1) * TQ_X_BYTES + ch * TC_A_LBO + hrow * 128);
+    const uint32_t hbase0 = smem_u32(sH) + (uint32_t)((lq >> 1) * TQ_X_BYTES + ch * TC_A_LBO + hrow * 128);
     const int sw = lane & 7;
     unsigned char* out_region = sX + (lq >> 1) * TQ_X_BYTES + ch * TC_A_LBO + (lq & 1) * 4096;   // [32 channels][64 points] of X
     const uint32_t tbase = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * (TQ_NP / 2));
     for (int j = 0; j < nh; ++j) {
       const float bias = __ldg(b1 + j * TQ_MT + lq * 32 + lane);
+      const int hb = j % HB;
+      const uint32_t hbase = hbase0 + (uint32_t)(hb * 2 * TQ_X_BYTES);
       const uint64_t one2 = pk2(1.f, 1.f), bias2 = pk2(bias, bias);
       mbar_wait(acc1_full, (uint32_t)j & 1);
       tc_fence_after();
       if (tid == 0 && j == 0) trace(3);
-      if (j == nh - 1 && lq * 32 < a2.O && lane == 0) {
+      if (MT2 == 1 && j == nh - 1 && lq * 32 < a2.O && lane == 0) {
         // the last first-GEMM has read X: its slab becomes the staging region of the output epilogue and the residual (the raw
         // x again) is fetched into it now, under the last GELU pass
         mbar_expect_tx(&res_bar[warp], 4096u);
@@ -210,24 +226,28 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
           float lo[8], hi[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) { lo[i] = y[i]; hi[i] = y[8 + i]; }
-          if (c == 0 && j > 0) mbar_wait(h_empty, (uint32_t)(j - 1) & 1);   // the second GEMM of chunk j-1 has read sH
+          if (c == 0 && j >= HB) mbar_wait(&h_empty[hb], (uint32_t)(j / HB - 1) & 1);   // the second GEMM of chunk j-HB has read it
           sts128(hbase + (uint32_t)(((2 * c) ^ sw) << 4), pack8_bf16(lo));
           sts128(hbase + (uint32_t)(((2 * c + 1) ^ sw) << 4), pack8_bf16(hi));
         }
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(h_full)) : "memory");
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&h_full[hb])) : "memory");
     }
     // ---- output: + b2, layer scale, residual, statistics, TMA store (staged in the warp's part of the X slab) ----------------------
-    cm_epilogue<VRCOC_ACT_NONE, false, 2>(a2, tmem_base + TQ_NP, acc2_full, acc2_empty, &res_bar[warp], out_region, 0, &tmapO, &tmapO,
-                                          &tmapR, b, p0, 0, 1);
+    if (MT2 == 1)
+      cm_epilogue<VRCOC_ACT_NONE, false, 2>(a2, tmem_base + TQ_NP, acc2_full, acc2_empty, &res_bar[warp], out_region, 0, &tmapO, &tmapO,
+                                            &tmapR, b, p0, 0, 1);
+    else   // output tile m is staged in X slabs 2m, 2m+1 (its own 128 channels); all residual boxes requested at once
+      cm_epilogue<VRCOC_ACT_NONE, false, 3, true>(a2, tmem_base + TQ_NP, acc2_full, acc2_empty, &res_bar[warp], out_region, 2 * TQ_X_BYTES,
+                                                  &tmapO, &tmapO, &tmapR, b, p0, 0, MT2);
     if (tid == 0) trace(4);
   }
   tc_fence_before();
   __syncthreads();
   if (tid == 0) trace(5);
-  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+  if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L.tmem_cols));
 }
 
 }  // namespace vrcoc

@@ -63,12 +63,15 @@ def run_pair(f_main, f_side):
     return a, b
 
 
+FUSED_MLP_MAX_C = 128
 FUSED_MLP = True             # set False to run the channel MLP as two GEMM launches (debug / A-B)
 
 
 def mlp_fused_ok(x, hidden):
     B, C, H, W = x.shape
-    return FUSED_MLP and x.dtype == torch.bfloat16 and bool(lib.vrcoc_mlp_fused_supported(1, C, hidden, H * W))
+    # policy: the kernel covers C <= 384, but past 128 channels (stage 3: 64 point tiles, 1.6 MB of weights streamed per CTA)
+    # it is bound by the per-SM weight stream and two launches spread over more SMs are faster (tools/microbench.py s3_mlpf)
+    return FUSED_MLP and C <= FUSED_MLP_MAX_C and x.dtype == torch.bfloat16 and bool(lib.vrcoc_mlp_fused_supported(1, C, hidden, H * W))
 
 
 def mlp_fused_fwd(x, sums, gamma, beta, eps, w1, b1, w2, b2, ls, out_sums):

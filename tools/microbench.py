@@ -27,6 +27,7 @@ CASES = {
     "s4_mlp2": ("projres", 2048, 512, 16, {}),
     "s1_mlpf": ("mlpf", 64, 512, 128, {}),
     "s2_mlpf": ("mlpf", 128, 1024, 64, {}),
+    "s3_mlpf": ("mlpf", 320, 1280, 32, {}),
     "s1_core": ("core", 128, 0, 128, dict(E=4, fold=8)),
     "s2_core": ("core", 128, 0, 64, dict(E=4, fold=4)),
     "s3_core": ("core", 256, 0, 32, dict(E=8, fold=2)),
