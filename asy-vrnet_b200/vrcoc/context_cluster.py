@@ -219,7 +219,7 @@ class ClusterBlock(nn.Module):
             # both large stages: the hidden activation (8 x C channels) stays on chip
             x2 = ops.mlp_fused_fwd(x1, sums[0], f32(n2.weight), f32(n2.bias), n2.eps, mlp.fc1.weight.detach().reshape(hid, C),
                                    f32(mlp.fc1.bias), mlp.fc2.weight.detach().reshape(C, hid), f32(mlp.fc2.bias), ls2, sums[1])
-            x2._vrcoc_sums = sums[1]
+            x2._vrcoc_sums = ops.tag_like(sums[1], sums)
             return x2
         h = torch.empty(B, hid, H, W, device=dev, dtype=dt)
         ops.conv_fwd(ops.conv_desc(x1, mlp.fc1.weight.detach().reshape(hid, C), h, gn=(sums[0], f32(n2.weight), f32(n2.bias), n2.eps),
@@ -227,7 +227,7 @@ class ClusterBlock(nn.Module):
         x2 = torch.empty_like(x)
         ops.conv_fwd(ops.conv_desc(h, mlp.fc2.weight.detach().reshape(C, hid), x2, e_shift=f32(mlp.fc2.bias), post_scale=ls2, res=x1,
                                    out_sample_sums=sums[1]))
-        x2._vrcoc_sums = sums[1]
+        x2._vrcoc_sums = ops.tag_like(sums[1], sums)
         return x2
 
     def forward(self, x):

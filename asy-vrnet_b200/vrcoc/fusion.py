@@ -92,7 +92,7 @@ def _fold_bn(mean, var, w, b, eps):
 def conv2d_native(x, weight, bias=None, stride=1, pad=0, extra=None, extra_bstride=None, act=ACT_NONE,
                   e_scale=None, out_minmax=None, out_dtype=None):
     """Dense (groups=1) k x k convolution on the implicit-GEMM engine.  Differentiable through `_ConvFn`."""
-    return _ConvFn.apply(x, weight, bias, stride, pad, extra, extra_bstride, act, e_scale, out_minmax, out_dtype)
+    return _apply(_ConvFn, x, weight, bias, stride, pad, extra, extra_bstride, act, e_scale, out_minmax, out_dtype)
 
 
 def _conv_launch(x, weight, bias32, stride, pad, extra, extra_bstride, act, e_scale, out_minmax, out_dtype, dil=1):
@@ -240,7 +240,7 @@ class BaseConv(nn.Module):
             return self.act(self.bn(self.conv(x)))        # training / other configurations: library path (out of scope §8f)
         if not x.is_cuda:
             raise VrcocError("vrcoc BaseConv needs a CUDA tensor (no CPU fallback exists)")
-        return _BaseConvFn.apply(x, self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias, self, out_minmax)
+        return _apply(_BaseConvFn, x, self.conv.weight, self.conv.bias, self.bn.weight, self.bn.bias, self, out_minmax)
 
     def fuseforward(self, x):
         return self.act(self.conv(x))
@@ -265,14 +265,32 @@ def _base_conv_forward(mod, x, out_minmax):
     return _conv_launch(x, conv.weight, sh, stride, pad, None, None, act, sc, out_minmax, None)
 
 
+class _NoGradCtx:
+    """stand-in for the autograd context when a Function's forward body is run without autograd"""
+    needs_input_grad = (False,) * 32
+
+    def save_for_backward(self, *tensors):
+        pass
+
+
+def _apply(fn, *args):
+    """fn.apply(*args) — or, without autograd, fn.forward alone: inside Function.apply `ctx.needs_input_grad` still reports
+    the parameters' requires_grad, which made every gradient-free call clone the BatchNorm statistics it would need for
+    backward (64 copy kernels per forward, profiles/)"""
+    if torch.is_grad_enabled():
+        return fn.apply(*args)
+    return fn.forward(_NoGradCtx(), *args)
+
+
 class _BaseConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, bn_w, bn_b, mod, out_minmax):
         training = mod.bn.training or not mod.bn.track_running_stats
-        rm = None if training else mod.bn.running_mean.detach().clone()
-        rv = None if training else mod.bn.running_var.detach().clone()
+        need_bwd = any(ctx.needs_input_grad)
+        rm = None if training or not need_bwd else mod.bn.running_mean.detach().clone()
+        rv = None if training or not need_bwd else mod.bn.running_var.detach().clone()
         out = _base_conv_forward(mod, x, out_minmax)
-        if any(ctx.needs_input_grad):
+        if need_bwd:
             ctx.save_for_backward(x, weight, bias, bn_w, bn_b, rm, rv)
             ctx.meta = (mod.conv.stride[0], mod.conv.padding[0], mod._act_name, mod.bn.eps, training)
         return out
@@ -344,7 +362,7 @@ class ShuffleAttention(nn.Module):
     def forward(self, x):
         if not x.is_cuda:
             raise VrcocError("vrcoc ShuffleAttention needs a CUDA tensor (no CPU fallback exists)")
-        return _ShuffleAttentionFn.apply(x, self.cweight, self.cbias, self.sweight, self.sbias, self.gn.weight, self.gn.bias, self)
+        return _apply(_ShuffleAttentionFn, x, self.cweight, self.cbias, self.sweight, self.sbias, self.gn.weight, self.gn.bias, self)
 
 
 def _group_norm_maybe_empty(q):
@@ -396,7 +414,7 @@ class eca_block(nn.Module):
     def forward(self, x):
         if not x.is_cuda:
             raise VrcocError("vrcoc eca_block needs a CUDA tensor (no CPU fallback exists)")
-        return _EcaFn.apply(x, self.conv.weight)
+        return _apply(_EcaFn, x, self.conv.weight)
 
 
 class _EcaFn(torch.autograd.Function):
@@ -445,7 +463,7 @@ class ImageEnhanceByRadar(nn.Module):
         if not image_map.is_cuda:
             raise VrcocError("vrcoc ImageEnhanceByRadar needs CUDA tensors (no CPU fallback exists)")
         rp = self.radar_projection
-        return _ImageEnhanceFn.apply(image_map, radar_map, rp.conv.weight, rp.bn.weight, rp.bn.bias,
+        return _apply(_ImageEnhanceFn, image_map, radar_map, rp.conv.weight, rp.bn.weight, rp.bn.bias,
                                      self.norm.weight, self.norm.bias, self)
 
 
@@ -515,7 +533,7 @@ class RadarEnhanceByImage(nn.Module):
         if not image_map.is_cuda:
             raise VrcocError("vrcoc RadarEnhanceByImage needs CUDA tensors (no CPU fallback exists)")
         ip, sa = self.inverse_projection, self.image_attn
-        return _RadarEnhanceFn.apply(image_map, radar_map, ip.conv.weight, ip.bn.weight, ip.bn.bias, self.norm.weight,
+        return _apply(_RadarEnhanceFn, image_map, radar_map, ip.conv.weight, ip.bn.weight, ip.bn.bias, self.norm.weight,
                                      self.norm.bias, self.channel_attn.conv.weight, sa.cweight, sa.cbias, sa.sweight,
                                      sa.sbias, sa.gn.weight, sa.gn.bias, self)
 

@@ -44,6 +44,8 @@ class BilinearUpsample(nn.Upsample):
 
     def forward(self, x):
         if x.is_cuda and self.mode == "bilinear" and self.align_corners and x.dtype in (torch.float32, torch.bfloat16):
+            if not torch.is_grad_enabled():
+                return _UpsampleFn.forward(type("_Ctx", (), {})(), x, float(self.scale_factor))
             return _UpsampleFn.apply(x, float(self.scale_factor))
         return super().forward(x)
 
@@ -175,6 +177,10 @@ class CoCFpnDual(nn.Module):
         """det_level (optional, not in the reference signature): a callable (k, p_k) applied to each detection map as soon
         as it exists — EfficientVRNet passes DecoupleHead.forward_level, so that the head of a coarse level runs next to the
         neck of the finer ones and the whole detection half next to the segmentation half."""
+        with ops.sums_arena(x.shape[0], x.device):
+            return self._forward(x, x_radar, det_level)
+
+    def _forward(self, x, x_radar, det_level):
         x_out, x_radar_out = self.backbone(x, x_radar)
         s2, s3, s4, s5 = x_out
         r2, r3, r4, r5 = x_radar_out

@@ -167,8 +167,78 @@ def channel_sums(x, want_chan=True, want_sample=False):
 STAT_SLOTS = 32      # == VRCOC_STAT_SLOTS (include/vrcoc.h)
 
 
+class sums_arena:
+    """Context manager around one gradient-free model forward: all statistics buffers of the forward come out of ONE
+    device buffer that is zeroed once on entry (one fill kernel instead of ~40 per forward; they sit on the critical path of
+    the launch chain).  Slices carry the arena generation; a statistics tensor that rode along on an activation from an
+    earlier forward is recognised as stale by sample_sums_of and recomputed.  Nested uses share the outermost arena."""
+    _state = {}      # device index -> [buffer, next_free, generation, depth]
+    SLOTS = 128
+
+    def __init__(self, B, device):
+        self.key = None
+        if device.type == "cuda" and not torch.is_grad_enabled():
+            self.key, self.B, self.device = (device.index if device.index is not None else torch.cuda.current_device()), B, device
+
+    def __enter__(self):
+        if self.key is None:
+            return self
+        st = sums_arena._state.get(self.key)
+        if st is None or st[0].shape[1] != self.B:
+            if st is not None and st[3] > 0:
+                self.key = None          # a different batch size inside an open arena: leave it alone
+                return self
+            st = sums_arena._state[self.key] = [torch.empty(sums_arena.SLOTS, self.B, STAT_SLOTS, 2, device=self.device, dtype=torch.float64), 0, 0, 0]
+        if st[3] == 0:
+            st[0].zero_()
+            st[1] = 0
+            st[2] += 1
+        st[3] += 1
+        return self
+
+    def __exit__(self, *exc):
+        if self.key is not None:
+            sums_arena._state[self.key][3] -= 1
+        return False
+
+    @staticmethod
+    def take(B, device, n):
+        if device.type != "cuda" or torch.is_grad_enabled():
+            return None
+        st = sums_arena._state.get(device.index if device.index is not None else torch.cuda.current_device())
+        k = 1 if n is None else n
+        if st is None or st[3] == 0 or st[0].shape[1] != B or st[1] + k > sums_arena.SLOTS:
+            return None
+        out = st[0][st[1]:st[1] + k] if n is not None else st[0][st[1]]
+        st[1] += k
+        out._vrcoc_arena = (st[0], st[2])
+        return out
+
+    @staticmethod
+    def stale(ss):
+        tag = getattr(ss, "_vrcoc_arena", None)
+        if tag is None:
+            return False
+        for st in sums_arena._state.values():
+            if st[0] is tag[0]:
+                return st[2] != tag[1]
+        return True
+
+
+def tag_like(view, parent):
+    """carry the arena tag of `parent` over to a view of it"""
+    tag = getattr(parent, "_vrcoc_arena", None)
+    if tag is not None:
+        view._vrcoc_arena = tag
+    return view
+
+
 def new_sample_sums(B, device, n=None):
     """zeroed slot-wise GroupNorm statistics buffer(s): [B, STAT_SLOTS, 2] (or [n, B, STAT_SLOTS, 2]) float64"""
+    device = torch.device(device)
+    got = sums_arena.take(B, device, n)
+    if got is not None:
+        return got
     shape = (B, STAT_SLOTS, 2) if n is None else (n, B, STAT_SLOTS, 2)
     return torch.zeros(shape, device=device, dtype=torch.float64)
 
@@ -176,7 +246,7 @@ def new_sample_sums(B, device, n=None):
 def sample_sums_of(x):
     """GroupNorm(1,C) statistics of x: reuse the producer's side output when it rode along on the tensor."""
     ss = getattr(x, "_vrcoc_sums", None)
-    if ss is not None and ss.shape[0] == x.shape[0]:
+    if ss is not None and ss.shape[0] == x.shape[0] and not sums_arena.stale(ss):
         return ss
     return channel_sums(x, want_chan=False, want_sample=True)[1]
 

@@ -149,6 +149,11 @@ class VRCoC(nn.Module):
         return outs, outs_radar
 
     def forward(self, x, x_radar):
+        from . import ops
+        with ops.sums_arena(x.shape[0], x.device):
+            return self._forward(x, x_radar)
+
+    def _forward(self, x, x_radar):
         x, x_radar = self.forward_embeddings(x, x_radar)
         x, x_radar = self.forward_tokens(x, x_radar)
         if self.fork_feat:
