@@ -23,6 +23,9 @@ namespace vrcoc {
 int cluster_core_fwd_fast(const void* feat, int fdt, const void* value, int vdt, void* out, int odt, uint8_t* idx, float* smax,
                           const float* alpha, const float* beta, int B, int E, int D, int H, int W, int F1, int F2, int pw, int ph,
                           int64_t bs_f, int64_t bs_v, int64_t bs_o, cudaStream_t st);   // cluster_core_fast.cu
+int cluster_core_fwd_fast2(const void* feat, int fdt, const void* value, int vdt, void* out, int odt, uint8_t* idx, float* smax,
+                           const float* alpha, const float* beta, int B, int E, int D, int H, int W, int F1, int F2, int pw, int ph,
+                           int64_t bs_f, int64_t bs_v, int64_t bs_o, cudaStream_t st);  // cluster_core_fast2.cu
 
 constexpr int CORE_THREADS = 256;
 constexpr float NORM_EPS = 1e-12f;  // F.normalize eps (vr_coc.py:121-122)
@@ -612,7 +615,11 @@ extern "C" int vrcoc_cluster_core_fwd(const void* feat, int feat_dtype, const vo
   q.bs_o = out_bstride ? out_bstride : dense;
   q.bs_df = q.bs_dv = dense;
   cudaStream_t st = (cudaStream_t)stream;
-  // TMA fast path for 2x2 proposals on power-of-two regions (every live configuration); 1 = not covered -> generic kernel
+  // compile-time path for 16x16 regions / 2x2 proposals / D in {24, 32}, then the TMA fast path for 2x2 proposals on
+  // power-of-two regions (every live configuration); 1 = not covered -> next kernel
+  rc = cluster_core_fwd_fast2(feat, feat_dtype, value, value_dtype, out, out_dtype, idx, sim_max, alpha, beta, B, E, D, H, W, q.F1,
+                              q.F2, proposal_w, proposal_h, q.bs_f, q.bs_v, q.bs_o, st);
+  if (rc != 1) return rc;
   rc = cluster_core_fwd_fast(feat, feat_dtype, value, value_dtype, out, out_dtype, idx, sim_max, alpha, beta, B, E, D, H, W, q.F1,
                              q.F2, proposal_w, proposal_h, q.bs_f, q.bs_v, q.bs_o, st);
   if (rc != 1) return rc;

@@ -93,12 +93,13 @@ def main():
     from einops import rearrange
 
     gen = torch.Generator().manual_seed(20261017)
+    stream = {"gen": gen}                                            # the extra cases at the end draw from their own stream
 
     def randn(*s):
-        return f32(torch.randn(*s, generator=gen, dtype=torch.double))
+        return f32(torch.randn(*s, generator=stream["gen"], dtype=torch.double))
 
     def rand(*s):
-        return f32(torch.rand(*s, generator=gen, dtype=torch.double))
+        return f32(torch.rand(*s, generator=stream["gen"], dtype=torch.double))
 
     # ---- cluster core (the part of Cluster.forward between fc1/fc_v and fc2), via the reference module with
     #      identity projections so that the module's own code computes it -------------------------------------
@@ -110,7 +111,15 @@ def main():
         dict(name="core_8x8_d24", B=2, E=4, D=24, H=16, W=16, fold_w=2, fold_h=2, proposal_w=2, proposal_h=2),
         dict(name="core_p4_m16", B=1, E=2, D=16, H=32, W=16, fold_w=2, fold_h=1, proposal_w=4, proposal_h=4),
     ]
-    for c in core_cases:
+    # added after the first fixtures were committed: own random stream (so the files above never change) and, with
+    # `--extra-only`, generated alone.  D=24 on 16x16 regions = neck level p4, the second shape of the compile-time kernel.
+    extra_core_cases = [
+        dict(name="core_16x16_d24", B=1, E=2, D=24, H=32, W=32, fold_w=2, fold_h=2, proposal_w=2, proposal_h=2),
+    ]
+    extra_only = "--extra-only" in sys.argv
+    if extra_only:
+        stream["gen"] = torch.Generator().manual_seed(20261018)
+    for c in (extra_core_cases if extra_only else core_cases):
         ED = c["E"] * c["D"]
         m = R.Cluster(ED, ED, c["proposal_w"], c["proposal_h"], c["fold_w"], c["fold_h"], c["E"], c["D"]).double()
         alpha, beta = f32(rand(1) * 1.5 + 0.5), f32(rand(1) - 0.5)
@@ -157,6 +166,8 @@ def main():
         save(c["name"], cfg, rec_in, None,
              {"y": out, "idx": idx.to(torch.int32), "sim_max": smax, "margin": margin},
              {"feat": feat.grad, "value": value.grad, "alpha": m.sim_alpha.grad, "beta": m.sim_beta.grad})
+    if extra_only:
+        return
 
     # ---- Cluster / Mlp / ClusterBlock modules -----------------------------------------------------------------
     mod_cases = [

@@ -62,7 +62,7 @@ def test_core_golden_fp32(V, name):
     assert abs(dab[1].item() - fx.grad_in["beta"].item()) <= FP32_TOL * max(1.0, abs(fx.grad_in["beta"].item())) * 10
 
 
-@pytest.mark.parametrize("name", ["core_16x16_f2_p2", "core_live_s1", "core_8x8_d24"])
+@pytest.mark.parametrize("name", ["core_16x16_f2_p2", "core_live_s1", "core_8x8_d24", "core_16x16_d24"])
 def test_core_golden_bf16_storage(V, name):
     """bf16 value/out storage with fp32 similarity operand (the layout the bf16 block uses): same assignments as the
     fp32 reference because feat is untouched; outputs within the bf16 gate."""
@@ -300,6 +300,37 @@ def test_core_properties_full_size(V):
         if sel.shape[1] > 1:
             assert (sel - sel[:, :1]).abs().max() < 1e-4 * sel.abs().max()
     assert int(idx.max()) <= 3
+
+
+@pytest.mark.parametrize("E,D,H,fold", [(4, 32, 128, 8), (8, 32, 32, 2), (8, 32, 16, 1), (4, 24, 32, 2)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_core_compile_time_kernel_vs_general_fast_path(V, E, D, H, fold, dtype):
+    """The compile-time 16x16 kernel (cluster_core_fast2.cu) against the run-time-geometry TMA kernel it replaces, at the
+    live sizes S1 / S3 / S4 / N4 with B=8 (S1: several region-heads per persistent CTA): identical assignments, same
+    sim_max and outputs up to summation order / 3-ulp sigmoid."""
+    import os
+    from vrcoc import ops
+    torch.manual_seed(11)
+    B = 8
+    feat = torch.randn(B, E * D, H, H, device="cuda")
+    value = torch.randn(B, E * D, H, H, device="cuda").to(dtype)
+    a = torch.tensor([0.9], device="cuda")
+    b = torch.tensor([0.15], device="cuda")
+    args = (E, fold, fold, 2, 2)
+    assert os.environ.get("VRCOC_CORE_FAST2") is None
+    o_new, idx_new, s_new = ops.cluster_core_fwd(feat, value, a, b, *args, save_aux=True)
+    o_inf, _, _ = ops.cluster_core_fwd(feat, value, a, b, *args)            # without the auxiliary outputs
+    os.environ["VRCOC_CORE_FAST2"] = "0"
+    try:
+        o_old, idx_old, s_old = ops.cluster_core_fwd(feat, value, a, b, *args, save_aux=True)
+    finally:
+        del os.environ["VRCOC_CORE_FAST2"]
+    torch.cuda.synchronize()
+    assert torch.equal(o_new, o_inf)
+    assert torch.equal(idx_new, idx_old)
+    assert rel_err(s_new, s_old) < 1e-6
+    assert rel_err(o_new.float(), o_old.float()) < (1e-5 if dtype == torch.float32 else 4e-3)
+    assert (o_new.float() - o_old.float()).abs().max() <= (1e-5 if dtype == torch.float32 else 2 ** -7) * o_old.float().abs().max()
 
 
 def test_reference_assert_is_mirrored(V):

@@ -31,6 +31,12 @@ CASES = {
     "s1_core": ("core", 128, 0, 128, dict(E=4, fold=8)),
     "s2_core": ("core", 128, 0, 64, dict(E=4, fold=4)),
     "s3_core": ("core", 256, 0, 32, dict(E=8, fold=2)),
+    "s4_core": ("core", 256, 0, 16, dict(E=8, fold=1)),
+    "n4_core": ("core", 96, 0, 32, dict(E=4, fold=2)),
+    # the same launches through the run-time-geometry TMA kernel (VRCOC_CORE_FAST2=0), for A/B
+    "s1_core_rt": ("core", 128, 0, 128, dict(E=4, fold=8, rt=True)),
+    "s2_core_rt": ("core", 128, 0, 64, dict(E=4, fold=4, rt=True)),
+    "s3_core_rt": ("core", 256, 0, 32, dict(E=8, fold=2, rt=True)),
     "s3_conv3": ("conv3", 320, 320, 32, {}),
     "s1_conv3": ("conv3", 64, 64, 128, {}),
 }
@@ -101,7 +107,15 @@ def main():
             feat = torch.randn(B, C, H, H, device=dev, generator=g)
             value = torch.randn(B, C, H, H, device=dev, generator=g).to(dt)
             a, b_ = torch.ones(1, device=dev), torch.zeros(1, device=dev)
-            fn = lambda: ops.cluster_core_fwd(feat, value, a, b_, E, fold, fold, 2, 2)
+            if kw.get("rt"):
+                def fn():
+                    os.environ["VRCOC_CORE_FAST2"] = "0"
+                    try:
+                        ops.cluster_core_fwd(feat, value, a, b_, E, fold, fold, 2, 2)
+                    finally:
+                        del os.environ["VRCOC_CORE_FAST2"]
+            else:
+                fn = lambda: ops.cluster_core_fwd(feat, value, a, b_, E, fold, fold, 2, 2)
             by, fl = B * P * C * (4 + 2 * es), 13.0 * B * P * C
         for _ in range(3):
             fn()
