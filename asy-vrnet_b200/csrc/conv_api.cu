@@ -176,6 +176,29 @@ __global__ void __launch_bounds__(256) table_apply_kernel(ConvArgs a) {
   if (s < a.C0) base = (int64_t)b * a.src0_bstride + (int64_t)s * P;
   else { src = a.src1; dt = a.src1_dtype; base = (int64_t)b * a.src1_bstride + (int64_t)(s - a.C0) * P; }
   const int64_t obase = ((int64_t)b * a.Cin + k) * P;
+  if (dt == VRCOC_BF16 && a.out_dtype == VRCOC_BF16 && (P & 7) == 0 && ((base | obase) & 7) == 0 &&
+      ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(a.out)) & 15) == 0) {
+    // bf16 planes (the neck's cat + shuffle copies, the attention gates): 128-bit loads / stores, 8 points per thread
+    const __nv_bfloat16* sp = reinterpret_cast<const __nv_bfloat16*>(src) + base;
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + obase;
+    const bool ident = t.x == 1.f && t.y == 0.f && !a.has_gate;
+    for (int i = threadIdx.x * 8; i < P; i += blockDim.x * 8) {
+      if (ident) {
+        *reinterpret_cast<uint4*>(op + i) = __ldg(reinterpret_cast<const uint4*>(sp + i));
+      } else {
+        float v[8];
+        ld8<__nv_bfloat16>(sp + i, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float y = fmaf(v[e], t.x, t.y);
+          if (a.has_gate) y *= sigmoidf_exact(fmaf(t.z, v[e], t.w));
+          v[e] = y;
+        }
+        st8<__nv_bfloat16>(op + i, v);
+      }
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
     float x = ld_any(src, base + i, dt);
     float y = fmaf(x, t.x, t.y);

@@ -157,7 +157,7 @@ img_enh_finish_kernel(const T* __restrict__ k, const T* __restrict__ img, T* __r
   const int plane = blockIdx.y, c = plane % C;
   const int lo = blockIdx.x * PLANE_CHUNK, hi = min(HW, lo + PLANE_CHUNK);
   const float mx = __uint_as_float(minmax[0]), mn = __uint_as_float(~minmax[1]);
-  const float dst = mx - mn;               // 0/0 -> NaN, like the reference's true_divide (vr_coc.py:66)
+  const float inv_dst = 1.0f / (mx - mn);  // constant map: 0 * inf -> NaN, like the reference's 0/0 true_divide (vr_coc.py:66)
   const float a = sc ? sc[c] : 1.f, b = sh ? sh[c] : 0.f;
   const int64_t base = (int64_t)plane * HW;
   float s = 0.f, sq = 0.f;
@@ -169,7 +169,7 @@ img_enh_finish_kernel(const T* __restrict__ k, const T* __restrict__ img, T* __r
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (j < n) {
-        float t = (1.0f + (v[j] - mn) / dst) * im[j];
+        float t = fmaf(v[j] - mn, inv_dst, 1.0f) * im[j];
         t = fmaf(t, a, b);
         y[j] = t;
         s += t; sq = fmaf(t, t, sq);
@@ -210,9 +210,19 @@ sa_gate_sums_kernel(const T* __restrict__ img, int Ci, int HW, int G, const floa
       gc = fmaf(sw[j], gb[j] - gw[j] * mean * rstd, sb[j]);
       const T* p = img + (int64_t)plane * HW;
       float s = 0.f, dummy = 0.f;
-      for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-        float x = ldf<T>(p + i);
-        s = fmaf(x, sigmoidf_exact(fmaf(ga, x, gc)), s);
+      if ((HW & 7) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        // 128-bit loads; MUFU sigmoid (ex2 + rcp, ~3 ulp): this sum only feeds the ECA channel mean
+        for (int i = threadIdx.x * 8; i < HW; i += blockDim.x * 8) {
+          float v[8];
+          ld8<T>(p + i, v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) s = fmaf(v[e], __fdividef(1.0f, 1.0f + __expf(-fmaf(ga, v[e], gc))), s);
+        }
+      } else {
+        for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+          float x = ldf<T>(p + i);
+          s = fmaf(x, sigmoidf_exact(fmaf(ga, x, gc)), s);
+        }
       }
       block_sum2(s, dummy, red);
       amean = s * inv_hw;

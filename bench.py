@@ -409,6 +409,15 @@ def run_ours(args):
     roof.update({"traffic": traffic, "kernel": top_label, "launches_timed": n, "avg_us": 1e3 * t_ms / n,
                  "share_of_native_time": t_ms / total_ms, "peak_source": pk["source"],
                  "hbm_frac": hbm_frac, "tensor_frac": tc_frac})
+    # the HBM-bound kernel of the CoC block (the cluster core, ~1 flop/byte), reported beside the dominant one
+    core = [(k, v) for k, v in table.items() if k.startswith("cluster_core_fwd")]
+    roof_core = None
+    if core:
+        c_label, (c_n, c_ms, c_by, c_fl) = max(core, key=lambda kv: kv[1][1])
+        c_hbm = c_by / (c_ms / 1e3) / 1e9
+        roof_core = {"bound": "hbm", "achieved": c_hbm, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": c_hbm / pk["hbm_gbs"],
+                     "kernel": c_label, "launches_timed": c_n, "avg_us": 1e3 * c_ms / c_n,
+                     "share_of_native_time": sum(v[1] for _, v in core) / total_ms, "peak_source": pk["source"]}
     if args.profile_kernels and rank == 0:
         for label, (cnt, t, b_, f_) in sorted(table.items(), key=lambda kv: -kv[1][1]):
             print(f"  {label:44s} n={cnt:4d} {t / cnt * 1e3:9.1f} us/launch  {b_ / (t / 1e3) / 1e9 if t else 0:8.1f} GB/s "
@@ -428,6 +437,7 @@ def run_ours(args):
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clk.summary(),
         "roofline": roof,
+        "roofline_coc_core": roof_core,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, model)
