@@ -151,9 +151,6 @@ struct TcLayout {
   int res_tma;      // residual epilogue through a TMA-staged [n_tile][128] bf16 tile (fetched at kernel start, rewritten in
                     // place, stored by TMA): no per-thread global access, full memory-level parallelism
   int off_b, off_tab, off_epi, off_res, off_bar, total;
-  int imp;          // implicit k x k "same" convolution: the A slab of (tap, 64 channels) is a TMA box of the NCHW map shifted
-                    // by the tap offset; the zero padding is the TMA out-of-bounds fill (no im2col matrix, no gather)
-  int imp_bw;       // columns per 64-point block (the block is imp_bw x 64/imp_bw points of the map)
 };
 
 struct TcSmem {
@@ -441,18 +438,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_tma_kernel(ConvArgs a, 
       if (kc >= NS) mbar_wait(&S.bar_free[s], (uint32_t)((kc / NS) - 1) & 1);
       mbar_expect_tx(&S.bar_full[s], (uint32_t)(TC_A_BYTES + L.b_bytes));
       unsigned char* As = S.sA + s * TC_A_BYTES;
-      if (L.imp) {
-        // k = tap * Cin + c (tap-major weights): slab kc = 64 channels of one tap; both 64-point blocks of the tile are
-        // boxes of the [B][C][H][W] map displaced by (dy, dx)
-        const int cpt = a.Cin / TC_BK, tap = kc / cpt, c0 = (kc - tap * cpt) * TC_BK;
-        const int dy = (tap / a.kw) * a.dil - a.pad, dx = (tap % a.kw) * a.dil - a.pad;
-        const int q1 = p0 + 64;
-        tma_load_4d(As, &tmapA, p0 % a.W_in + dx, p0 / a.W_in + dy, c0, b, &S.bar_full[s]);
-        tma_load_4d(As + TC_A_LBO, &tmapA, q1 % a.W_in + dx, q1 / a.W_in + dy, c0, b, &S.bar_full[s]);
-      } else {
-        tma_load_3d(As, &tmapA, p0, kc * TC_BK, b, &S.bar_full[s]);
-        tma_load_3d(As + TC_A_LBO, &tmapA, p0 + 64, kc * TC_BK, b, &S.bar_full[s]);
-      }
+      tma_load_3d(As, &tmapA, p0, kc * TC_BK, b, &S.bar_full[s]);
+      tma_load_3d(As + TC_A_LBO, &tmapA, p0 + 64, kc * TC_BK, b, &S.bar_full[s]);
       tma_load_2d(S.sB + s * L.b_bytes, &tmapB, kc * TC_BK, n0, &S.bar_full[s]);
     }
   } else if (tid == 32) {
@@ -848,19 +835,6 @@ static bool tma_a_eligible(const ConvArgs& a) {
          ((reinterpret_cast<uintptr_t>(a.weight) & 15) == 0) && tma_encode_fn() != nullptr;
 }
 
-// k x k "same" convolution (stride 1, output map = input map) with tap-major weights whose 64-wide k slabs are 64 channels
-// of ONE tap, on maps whose 64-point blocks are rectangles (rows of 16 / 32 points, or multiples of 64): the im2col rows of
-// a slab are then a shifted box of the input map, which TMA fetches with its zero fill as the padding.
-static bool implicit_eligible(const ConvArgs& a) {
-  static const bool off = [] { const char* e = getenv("VRCOC_CONV_IMPLICIT"); return e && e[0] == '0'; }();
-  if (off || a.kh * a.kw <= 1 || a.stride != 1 || a.k_order != 1 || a.H_out != a.H_in || a.W_out != a.W_in) return false;
-  if (a.src0_dtype != VRCOC_BF16 || a.weight_dtype != VRCOC_BF16 || a.gn_sums || a.table || a.chan_src || a.has_gate || a.C1 != 0) return false;
-  if ((a.Cin % TC_BK) != 0 || (a.P_out % TC_BM) != 0) return false;
-  if (!(a.W_in == 16 || a.W_in == 32 || (a.W_in % 64) == 0)) return false;
-  if ((reinterpret_cast<uintptr_t>(a.src0) & 15) != 0 || (a.src0_bstride % 8) != 0 || (reinterpret_cast<uintptr_t>(a.weight) & 15) != 0) return false;
-  return tma_encode_fn() != nullptr;
-}
-
 static bool res_tma_eligible(const ConvArgs& a) {
   return a.res && a.res_dtype == VRCOC_BF16 && a.out_dtype == VRCOC_BF16 && a.O_split == a.O && a.P_out % 8 == 0 &&
          ((reinterpret_cast<uintptr_t>(a.res) | reinterpret_cast<uintptr_t>(a.out)) & 15) == 0 && tma_encode_fn() != nullptr &&
@@ -1154,20 +1128,6 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     return check_launch("conv_tc_cm");
   }
   dim3 grid((unsigned)cdiv(a.P_out, TC_BM), (unsigned)cdiv(a.O, L.n_tile), (unsigned)a.B);
-  if (L.use_tma_b && implicit_eligible(a)) {
-    // activations [B][C][H][W] bf16; box = one 64-point block (bw columns x 64/bw rows) x 64 channels: lands as the same
-    // MN-major SW128 block as the 1x1 case (a channel's 64 points are 128 contiguous bytes)
-    L.imp = 1;
-    L.imp_bw = a.W_in < 64 ? a.W_in : 64;
-    cuuint64_t dims[4] = {(cuuint64_t)a.W_in, (cuuint64_t)a.H_in, (cuuint64_t)a.C0, (cuuint64_t)a.B};
-    cuuint64_t strides[3] = {(cuuint64_t)a.W_in * 2, (cuuint64_t)a.P_in * 2, (cuuint64_t)a.src0_bstride * 2};
-    cuuint32_t box[4] = {(cuuint32_t)L.imp_bw, (cuuint32_t)(64 / L.imp_bw), (cuuint32_t)TC_BK, 1};
-    int rc = encode(&tmA, a.src0, 4, dims, strides, box);
-    if (rc) return rc;
-    set_smem(conv_tc_tma_kernel, L.total);
-    conv_tc_tma_kernel<<<grid, TC_THREADS, L.total, st>>>(a, L, tmA, tmB, tmR, tmO);
-    return check_launch("conv_tc_tma(implicit)");
-  }
   if (tma_a_eligible(a)) {
     // activations [B][C][P] bf16; box = 64 points (128 B) x 64 channels, lands as one MN-major SW128 block
     cuuint64_t dims[3] = {(cuuint64_t)a.P_in, (cuuint64_t)a.C0, (cuuint64_t)a.B};

@@ -394,6 +394,54 @@ im2col_kernel(const T* __restrict__ x, T* __restrict__ col, int B, int C, int H,
   }
 }
 
+// 3x3 / pad 1 / dilation 1 / stride 1 or 2 on bf16 maps (every im2col launch of the backbone): one thread = 8 consecutive
+// output columns of one (plane, output row) for ALL nine taps.  The three input rows are fetched once with 128-bit loads
+// (+ one or two halo elements), the column shifts are funnel shifts / byte permutes on the packed bf16 words, and every
+// tap leaves as one 16-byte store: 9 or 12 loads and 9 stores per thread instead of 72 scalar loads, and one index
+// decode per nine outputs (the generic kernel above reached 1.1-1.5 TB/s, profiles/r01_kernel_table.txt).
+template <int STRIDE>
+__global__ void __launch_bounds__(256)
+im2col3_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, uint32_t total, int C, int H, int W, int Ho,
+                    int Wo) {
+  const uint32_t cols8 = (uint32_t)Wo >> 3;
+  const int64_t Po = (int64_t)Ho * Wo;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t c8 = t % cols8, r = t / cols8;
+    const int oy = (int)(r % (uint32_t)Ho);
+    const uint32_t plane = r / (uint32_t)Ho;                          // b * C + c
+    const uint32_t b = plane / (uint32_t)C, c = plane - b * (uint32_t)C;
+    const int x0 = (int)c8 * 8 * STRIDE;                               // first input column of the centre tap
+    const __nv_bfloat16* xp = x + (int64_t)plane * H * W;
+    __nv_bfloat16* op = col + ((int64_t)b * 9 * C + c) * Po + (int64_t)oy * Wo + c8 * 8;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * STRIDE - 1 + ky;
+      uint4 o0 = make_uint4(0u, 0u, 0u, 0u), o1 = o0, o2 = o0;
+      if (iy >= 0 && iy < H) {
+        const __nv_bfloat16* row = xp + (int64_t)iy * W;
+        const uint32_t left = x0 > 0 ? (uint32_t)__bfloat16_as_ushort(row[x0 - 1]) : 0u;
+        if (STRIDE == 1) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + x0));
+          const uint32_t right = x0 + 8 < W ? (uint32_t)__bfloat16_as_ushort(row[x0 + 8]) : 0u;
+          o1 = v;
+          o0 = make_uint4((v.x << 16) | left, __funnelshift_l(v.x, v.y, 16), __funnelshift_l(v.y, v.z, 16), __funnelshift_l(v.z, v.w, 16));
+          o2 = make_uint4(__funnelshift_r(v.x, v.y, 16), __funnelshift_r(v.y, v.z, 16), __funnelshift_r(v.z, v.w, 16), (v.w >> 16) | (right << 16));
+        } else {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + x0)), u = __ldg(reinterpret_cast<const uint4*>(row + x0 + 8));
+          // centre tap: even elements; right tap: odd elements; left tap: odd elements one word earlier
+          o1 = make_uint4(__byte_perm(v.x, v.y, 0x5410), __byte_perm(v.z, v.w, 0x5410), __byte_perm(u.x, u.y, 0x5410), __byte_perm(u.z, u.w, 0x5410));
+          o2 = make_uint4(__byte_perm(v.x, v.y, 0x7632), __byte_perm(v.z, v.w, 0x7632), __byte_perm(u.x, u.y, 0x7632), __byte_perm(u.z, u.w, 0x7632));
+          o0 = make_uint4(left | (v.x & 0xffff0000u), __byte_perm(v.y, v.z, 0x7632), __byte_perm(v.w, u.x, 0x7632), __byte_perm(u.y, u.z, 0x7632));
+        }
+      }
+      __nv_bfloat16* ot = op + (int64_t)(3 * ky) * C * Po;
+      *reinterpret_cast<uint4*>(ot) = o0;
+      *reinterpret_cast<uint4*>(ot + (int64_t)C * Po) = o1;
+      *reinterpret_cast<uint4*>(ot + 2 * (int64_t)C * Po) = o2;
+    }
+  }
+}
+
 // ---- depthwise k x k convolution (DWConv.dconv of the decoupled head, reference normal_conv.py:26-27) -------------------
 // one thread = 8 consecutive output columns of one (plane, row); weights of the plane in registers; bandwidth-bound.
 template <typename T, int K>
@@ -643,6 +691,17 @@ extern "C" int vrcoc_im2col(const void* x, void* col, int dtype, int B, int C, i
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t total = (int64_t)B * kh * kw * C * Ho * ((Wo + 7) / 8);
   int blocks = (int)(cdiv(total, 256) < 148 * 32 ? cdiv(total, 256) : 148 * 32);
+  const int64_t fast_total = (int64_t)B * C * Ho * (Wo / 8);
+  if (dtype == VRCOC_BF16 && kh == 3 && kw == 3 && pad == 1 && dil == 1 && (stride == 1 || stride == 2) && (Wo % 8) == 0 &&
+      (W % (8 * stride)) == 0 && Wo * stride == W && fast_total < (1ll << 31) &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(col)) & 15) == 0) {
+    const int nb = (int)cdiv(fast_total, 256);
+    if (stride == 1)
+      im2col3_bf16_kernel<1><<<nb, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, (uint32_t)fast_total, C, H, W, Ho, Wo);
+    else
+      im2col3_bf16_kernel<2><<<nb, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, (uint32_t)fast_total, C, H, W, Ho, Wo);
+    return check_launch("im2col3");
+  }
   return by_dtype(dtype, [&](auto* t) {
     using T = typename std::remove_pointer<decltype(t)>::type;
     im2col_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, (T*)col, B, C, H, W, Ho, Wo, kh, kw, stride, pad, dil);

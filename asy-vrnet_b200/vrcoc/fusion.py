@@ -116,13 +116,11 @@ def _conv_launch(x, weight, bias32, stride, pad, extra, extra_bstride, act, e_sc
     # run on the streaming kernel, which takes the PyTorch order
     tapm = kh * kw > 1 and weight.dtype == torch.bfloat16 and not (O <= 8 and Cin * kh * kw <= 64)
     w2 = ops.tap_major(weight) if tapm else weight.detach().reshape(O, -1).contiguous()
-    # "same" k x k convs on maps whose 64-point blocks are rectangles: the engine fetches the im2col rows of a k slab as a
-    # shifted TMA box of x (zero fill = padding) - nothing is materialised (csrc/conv_tc.cu: implicit_eligible)
-    implicit = (tapm and extra is None and x.dtype == torch.bfloat16 and stride == 1 and (Ho, Wo) == (H, W) and Cin % 64 == 0 and
-                (W in (16, 32) or W % 64 == 0) and (H * W) % 128 == 0)
-    if tapm and not implicit and extra is None and Cin >= 32 and x.dtype == torch.bfloat16 and (Ho * Wo) % 8 == 0:
+    if tapm and extra is None and Cin >= 32 and x.dtype == torch.bfloat16 and (Ho * Wo) % 8 == 0:
         # many channels: materialise the tap-major im2col matrix once and run the TMA-only 1x1 kernel on it, instead of
-        # re-gathering the same rows in every N-tile CTA (9x the input: a few MB on the 16x16..64x64 maps where this is used)
+        # re-gathering the same rows in every N-tile CTA (9x the input: a few MB on the 16x16..64x64 maps where this is used).
+        # (Fetching the rows as shifted TMA boxes of x instead does not work in NCHW: the innermost box coordinate must be
+        # 16-byte aligned, so the +-1 column taps fault - measured with tools/tma_probe.cu)
         col = torch.empty(B, kh * kw * Cin, Ho, Wo, device=x.device, dtype=x.dtype)
         check(lib.vrcoc_im2col(_ptr(x), _ptr(col), _dt(x), B, Cin, H, W, kh, kw, stride, pad, dil, _stream()), "im2col")
         d = conv_desc(col, w2, out, e_scale=e_scale, e_shift=bias32, act=act, out_minmax=out_minmax)

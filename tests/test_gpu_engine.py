@@ -99,10 +99,10 @@ def test_tcgen05_full_epilogue_and_prologue(env):
 
 @pytest.mark.parametrize("shape", [(2, 64, 96, 16, 16, 3, 1, 1, 1), (1, 128, 64, 32, 32, 3, 2, 1, 1), (2, 64, 64, 16, 16, 3, 1, 6, 6),
                                    (1, 320, 128, 16, 16, 3, 1, 12, 12), (2, 4, 3, 64, 64, 3, 1, 1, 1), (2, 7, 4, 64, 64, 1, 1, 0, 1),
-                                   # implicit "same" convs (shifted TMA boxes): block = 64x1, 64x1 (two per row), 32x2, 16x4 points
+                                   # the 3x3 im2col fast path (stride 1 / 2) + GEMM at the live map sizes, 5x5 and odd maps on the generic one
                                    (1, 64, 64, 128, 128, 3, 1, 1, 1), (2, 128, 128, 64, 64, 3, 1, 1, 1), (2, 320, 320, 32, 32, 3, 1, 1, 1),
                                    (2, 512, 512, 16, 16, 3, 1, 1, 1), (1, 64, 192, 32, 32, 3, 1, 2, 2), (1, 64, 96, 64, 64, 5, 1, 2, 1),
-                                   (1, 128, 64, 8, 16, 3, 1, 1, 1)])
+                                   (1, 128, 64, 8, 16, 3, 1, 1, 1), (2, 64, 128, 64, 64, 3, 2, 1, 1), (1, 320, 512, 32, 32, 3, 2, 1, 1)])
 def test_tap_major_dilation_and_small_kernel(env, shape):
     """fusion._conv_launch picks: tap-major K order on the tensor-core path for k x k convs, dilation (ASPP), and the
     few-channel streaming kernel for the ingest convs; all against torch conv2d on the same bf16 operands"""
