@@ -355,6 +355,23 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
   const int nk = L.nslabs;
   const int ST = L.stages;
 
+  // one ring step = the weight slab (tile j, k-slab kc) and, when X is streamed / fetched with the first tile, its X slab
+  const int total_steps = tiles * nk;
+  auto issue = [&](int it) {
+    const int s = it % ST;
+    const int j = it / nk, kc = it - j * nk;
+    if (it >= ST) mbar_wait(&bar_free[s], (uint32_t)((it / ST) - 1) & 1);
+    const bool need_x = XMODE == 0 || (XMODE == 1 && j == 0);
+    mbar_expect_tx(&bar_full[s], (uint32_t)(TQ_W_BYTES + (need_x ? TQ_X_BYTES : 0)));
+    tma_load_2d(sW + s * TQ_W_BYTES, &tmapW, kc * TC_BK, o_begin + j * TQ_MT, &bar_full[s]);
+    if (need_x) {
+      unsigned char* dst = sX + (XMODE == 0 ? s : kc) * TQ_X_BYTES;
+      tma_load_3d(dst, &tmapX, p0, kc * TC_BK, b, &bar_full[s]);
+      tma_load_3d(dst + TC_A_LBO, &tmapX, p0 + 64, kc * TC_BK, b, &bar_full[s]);
+    }
+  };
+  const int early_steps = total_steps < ST ? total_steps : ST;       // need no free-slot wait
+
   if (tid == 0) trace(0);
   if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * TQ_NP)));
@@ -368,8 +385,18 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
     if (XMODE == 3)
       for (int i = 0; i < TQ_MAX_SLABS3; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_ready[i], 8); }
     mbar_fence_init();
-    tma_prefetch_desc(&tmapW);
-    if (XMODE != 2) tma_prefetch_desc(&tmapX);
+    fence_async_smem();
+    // this thread is the TMA producer: everything that depends on nothing goes out NOW, under the prologue-table build and
+    // the TMEM allocation (the per-CTA trace showed 1.1 us of set-up before the first request and the CTA then waiting
+    // ~2 us for it): every raw X slab (XMODE 3) and the first ring-depth weight slabs
+    if (XMODE == 3) {
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_expect_tx(&x_full[kc], (uint32_t)TQ_X_BYTES);
+        tma_load_3d(sX + kc * TQ_X_BYTES, &tmapX, p0, kc * TC_BK, b, &x_full[kc]);
+        tma_load_3d(sX + kc * TQ_X_BYTES + TC_A_LBO, &tmapX, p0 + 64, kc * TC_BK, b, &x_full[kc]);
+      }
+    }
+    for (int it = 0; it < early_steps; ++it) issue(it);
     tma_prefetch_desc(&tmapO1);
   }
   if (XMODE >= 2) build_prologue_table(a, b, tab);                   // strides by blockDim.x: every thread takes part
@@ -379,40 +406,10 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 8) {
-    // ---- TMA producer ---------------------------------------------------------------------------------------------------
-    const int total = tiles * nk;
-    auto issue = [&](int it) {
-      const int s = it % ST;
-      const int j = it / nk, kc = it - j * nk;
-      if (it >= ST) mbar_wait(&bar_free[s], (uint32_t)((it / ST) - 1) & 1);
-      const bool need_x = XMODE == 0 || (XMODE == 1 && j == 0);
-      mbar_expect_tx(&bar_full[s], (uint32_t)(TQ_W_BYTES + (need_x ? TQ_X_BYTES : 0)));
-      tma_load_2d(sW + s * TQ_W_BYTES, &tmapW, kc * TC_BK, o_begin + j * TQ_MT, &bar_full[s]);
-      if (need_x) {
-        unsigned char* dst = sX + (XMODE == 0 ? s : kc) * TQ_X_BYTES;
-        tma_load_3d(dst, &tmapX, p0, kc * TC_BK, b, &bar_full[s]);
-        tma_load_3d(dst + TC_A_LBO, &tmapX, p0 + 64, kc * TC_BK, b, &bar_full[s]);
-      }
-    };
-    if (XMODE == 3 && lane == 0) {
-      for (int kc = 0; kc < nk; ++kc) {                                // every raw slab in flight at once
-        mbar_expect_tx(&x_full[kc], (uint32_t)TQ_X_BYTES);
-        tma_load_3d(sX + kc * TQ_X_BYTES, &tmapX, p0, kc * TC_BK, b, &x_full[kc]);
-        tma_load_3d(sX + kc * TQ_X_BYTES + TC_A_LBO, &tmapX, p0 + 64, kc * TC_BK, b, &x_full[kc]);
-      }
-    }
-    if (XMODE == 2) {
-      // the first ST slabs need no free-slot wait and go out while the other warps still build X; the rest depends on
-      // MMA progress and therefore has to come after barrier (A)
-      if (lane == 0)
-        for (int it = 0; it < total && it < ST; ++it) issue(it);
-      __syncwarp();
-      __syncthreads();                                                 // (A)
-      if (lane == 0)
-        for (int it = ST; it < total; ++it) issue(it);
-    } else if (lane == 0) {
-      for (int it = 0; it < total; ++it) issue(it);
-    }
+    // ---- TMA producer: the rest of the ring (every step from here on waits for a slot the MMAs have released) -------------
+    if (XMODE == 2) __syncthreads();                                   // (A)
+    if (lane == 0)
+      for (int it = early_steps; it < total_steps; ++it) issue(it);
     __syncwarp();
   } else if (warp == 9) {
     if (XMODE == 2) __syncthreads();                                   // (A)
