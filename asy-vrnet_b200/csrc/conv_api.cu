@@ -207,6 +207,9 @@ __global__ void __launch_bounds__(256) table_apply_kernel(ConvArgs a) {
   }
 }
 
+int64_t wgrad_tc_workspace(const ConvArgs& a, int dy_dtype);                                   // wgrad_tc.cu
+int launch_wgrad_tc(const ConvArgs& a, const void* dy, int dy_dtype, float* dW, float* db, float* ws, cudaStream_t st);
+
 static int wgrad_splits(const ConvArgs& a, int& slabs_per_sample, int& units_per_split) {
   slabs_per_sample = (int)cdiv(a.P_out, WG_P);
   int units = a.B * slabs_per_sample;
@@ -256,7 +259,10 @@ extern "C" int64_t vrcoc_conv1x1_wgrad_workspace(const vrcoc_conv_desc* d) {
   if (fill_args(d, a)) return -1;
   int sps, ups;
   int splits = wgrad_splits(a, sps, ups);
-  return (int64_t)splits * ((int64_t)a.O * a.Cin + a.O);
+  const int64_t simt = (int64_t)splits * ((int64_t)a.O * a.Cin + a.O);
+  // the descriptor's `out` stands for dy (same shape and dtype): enough for whichever path vrcoc_conv1x1_wgrad takes
+  const int64_t tc = wgrad_tc_workspace(a, a.out_dtype);
+  return tc > simt ? tc : simt;
 }
 
 extern "C" int vrcoc_conv1x1_wgrad(const vrcoc_conv_desc* d, const void* dy, int dy_dtype, float* dW, float* db,
@@ -272,6 +278,12 @@ extern "C" int vrcoc_conv1x1_wgrad(const vrcoc_conv_desc* d, const void* dy, int
   VRCOC_REQUIRE(workspace_floats >= need, "wgrad: workspace too small (%lld < %lld floats)", (long long)workspace_floats,
                 (long long)need);
   cudaStream_t st = (cudaStream_t)stream;
+  // bf16 operands: tensor-core path on the raw activations, prologue applied to the per-sample partials (wgrad_tc.cu)
+  const int64_t tc_need = wgrad_tc_workspace(a, dy_dtype);
+  if (tc_need >= 0 && workspace_floats >= tc_need) {
+    rc = launch_wgrad_tc(a, dy, dy_dtype, dW, db, workspace, st);
+    if (rc != 1) return rc;
+  }
   float* ws = workspace;
   float* ws_db = workspace + (int64_t)splits * a.O * a.Cin;
   size_t smem = (size_t)2 * WG_P * WG_RS * sizeof(float) + (size_t)a.Cin * sizeof(float4);

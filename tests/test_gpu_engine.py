@@ -241,3 +241,42 @@ def test_fused_mlp_matches_two_launches(env, case):
     assert rel_err(fused.float(), two.float()) < 2e-3            # same arithmetic; both round the hidden layer to bf16
     assert rel_err(fused.float(), ref) < 8e-3                    # bf16 GN(x), bf16 hidden, bf16 output
     assert rel_err(s_f.sum(1), s_t.sum(1)) < 2e-3
+
+
+@pytest.mark.parametrize("case", [(8, 64, 512, 32, 32, True), (2, 320, 1280, 32, 32, True), (2, 128, 64, 64, 64, False),
+                                  (3, 72, 96, 10, 20, True), (1, 640, 200, 8, 8, False), (4, 512, 64, 128, 128, False)],
+                         ids=lambda c: f"B{c[0]}_C{c[1]}_O{c[2]}_{c[3]}x{c[4]}_{'gn' if c[5] else 'plain'}")
+def test_wgrad_tensor_core_matches_reference_and_cuda_core(env, case):
+    """dW = dY . prologue(x)^T, db = sum dY: the tcgen05 path (raw bf16 operands by TMA, GroupNorm coefficients applied to
+    the per-sample partials) against fp64 torch on the same bf16 values and against the CUDA-core path it replaces"""
+    import os
+    ops = env
+    B, C, O, H, W, use_gn = case
+    g = torch.Generator().manual_seed(21)
+    x = (torch.randn(B, C, H, W, generator=g) * 1.7 + 0.6).to(torch.bfloat16).cuda()
+    dy = torch.randn(B, O, H, W, generator=g).to(torch.bfloat16).cuda()
+    w = torch.zeros(O, C, dtype=torch.bfloat16, device="cuda")
+    gamma = (torch.rand(C, generator=g) + 0.5).cuda()
+    beta = torch.randn(C, generator=g).cuda()
+    gn = None
+    xh = x.double()
+    if use_gn:
+        _, sums = ops.channel_sums(x, want_chan=False, want_sample=True)
+        gn = (sums, gamma, beta, 1e-5)
+        mu = xh.mean(dim=(1, 2, 3), keepdim=True)
+        var = xh.var(dim=(1, 2, 3), unbiased=False, keepdim=True)
+        xh = (xh - mu) / torch.sqrt(var + 1e-5) * gamma.double().view(1, C, 1, 1) + beta.double().view(1, C, 1, 1)
+    ref_w = torch.einsum("bop,bcp->oc", dy.double().flatten(2), xh.flatten(2))
+    ref_b = dy.double().sum(dim=(0, 2, 3))
+    assert os.environ.get("VRCOC_WGRAD_TC") is None
+    dW, db = ops.conv1x1_wgrad(ops.conv_desc(x, w, dy, gn=gn), dy)
+    os.environ["VRCOC_WGRAD_TC"] = "0"
+    try:
+        dW0, db0 = ops.conv1x1_wgrad(ops.conv_desc(x, w, dy, gn=gn), dy)
+    finally:
+        del os.environ["VRCOC_WGRAD_TC"]
+    assert rel_err(dW0, ref_w) < 1e-5 and rel_err(db0, ref_b) < 1e-5
+    assert rel_err(dW, ref_w) < 2e-5, "tensor-core weight gradient disagrees with the fp64 reference"
+    assert rel_err(db, ref_b) < 1e-5
+    dW2, _ = ops.conv1x1_wgrad(ops.conv_desc(x, w, dy, gn=gn), dy)
+    assert torch.equal(dW, dW2), "the tensor-core weight gradient must be deterministic"
