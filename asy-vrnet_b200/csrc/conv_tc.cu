@@ -936,7 +936,13 @@ static bool persist_eligible(const ConvArgs& a, const TcLayout& L) {
 struct CmPlan { TqLayout T; int xmode; double cost; };
 
 static bool cm_plan(const ConvArgs& a, CmPlan& best) {
-  if (!a.fast1x1 || !a.vec_out || a.chan_src || a.C1 != 0) return false;
+  if (!a.fast1x1 || !a.vec_out || a.chan_src) return false;
+  // a second source (virtual concat, RadarEnhanceByImage) only through the TMA + in-place prologue mode: bf16, the boundary
+  // on a k-slab, and no second output (its tensor-map slot carries the second source)
+  const bool two_src = a.C1 != 0;
+  if (two_src && (!(a.table || a.gn_sums || a.has_gate) || a.src1_dtype != VRCOC_BF16 || a.src0_dtype != VRCOC_BF16 || (a.C0 % TC_BK) != 0 ||
+                  a.src1_bstride == 0 || (a.src1_bstride % 8) != 0 || (reinterpret_cast<uintptr_t>(a.src1) & 15) != 0 || a.O_split != a.O))
+    return false;
   if (a.weight_dtype != VRCOC_BF16 || (a.K % 8) != 0 || (reinterpret_cast<uintptr_t>(a.weight) & 15) != 0 || !tma_encode_fn()) return false;
   // outputs / residual travel as TMA boxes of 32 channels: 16-byte aligned bases, the split on a 32-channel boundary,
   // bf16 residual, and no residual into fp32 outputs (the staging region holds one or the other)
@@ -961,6 +967,7 @@ static bool cm_plan(const ConvArgs& a, CmPlan& best) {
   // a bf16 source with a prologue can still come in by TMA and be normalised in place (XMODE 3)
   const bool tma_x3 = prologue && a.src0_dtype == VRCOC_BF16 && (reinterpret_cast<uintptr_t>(a.src0) & 15) == 0 &&
                       (a.src0_bstride % 8) == 0 && nslabs <= TQ_MAX_SLABS3;
+  if (two_src && !tma_x3) return false;
   for (int cand = 0; cand < (tma_x ? 10 : 5); ++cand) {
     const int bufs = 1;       // a second staging buffer was measured: no gain (the bulk-store drain is not on the critical path)
     const int mode = tma_x ? modes[cand] : (tma_x3 ? 3 : 2), st = depth[cand];
@@ -1113,6 +1120,12 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
       cuuint32_t box[3] = {64, (cuuint32_t)TC_BK, 1};
       int rc = encode(&tmX, a.src0, 3, dims, strides, box);
       if (rc) return rc;
+      if (a.C1 > 0) {                                                  // second source, in the second-output slot (cm_plan)
+        cuuint64_t dims1[3] = {(cuuint64_t)a.P_in, (cuuint64_t)a.C1, (cuuint64_t)a.B};
+        cuuint64_t strides1[2] = {(cuuint64_t)a.P_in * 2, (cuuint64_t)a.src1_bstride * 2};
+        rc = encode(&tmO2, a.src1, 3, dims1, strides1, box);
+        if (rc) return rc;
+      }
     }
 #define LAUNCH_CM(TS, MODE)                                                                     \
   do {                                                                                          \

@@ -391,9 +391,14 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
     // ~2 us for it): every raw X slab (XMODE 3) and the first ring-depth weight slabs
     if (XMODE == 3) {
       for (int kc = 0; kc < nk; ++kc) {
+        // two-source input (virtual concat [src0 | src1], C0 a multiple of 64): the second source's map rides in the slot of
+        // the second output, which such launches do not have
+        const bool second = a.C1 > 0 && kc * TC_BK >= a.C0;
+        const CUtensorMap* tx = second ? &tmapO2 : &tmapX;
+        const int ch = kc * TC_BK - (second ? a.C0 : 0);
         mbar_expect_tx(&x_full[kc], (uint32_t)TQ_X_BYTES);
-        tma_load_3d(sX + kc * TQ_X_BYTES, &tmapX, p0, kc * TC_BK, b, &x_full[kc]);
-        tma_load_3d(sX + kc * TQ_X_BYTES + TC_A_LBO, &tmapX, p0 + 64, kc * TC_BK, b, &x_full[kc]);
+        tma_load_3d(sX + kc * TQ_X_BYTES, tx, p0, ch, b, &x_full[kc]);
+        tma_load_3d(sX + kc * TQ_X_BYTES + TC_A_LBO, tx, p0 + 64, ch, b, &x_full[kc]);
       }
     }
     for (int it = 0; it < early_steps; ++it) issue(it);

@@ -239,7 +239,7 @@ sa_gate_sums_kernel(const T* __restrict__ img, int Ci, int HW, int G, const floa
 // (< Ci: attended image channel, else radar channel).  table[b][k] = {scale*eca, 0, gate_a, gate_c}
 __global__ void radar_enh_table_kernel(const float* __restrict__ attn, const float* __restrict__ cs_radar,
                                        const int32_t* __restrict__ chan_src, const float* __restrict__ eca_w, int eca_k, int Ci,
-                                       int Cr, int HW, float* __restrict__ table) {
+                                       int Cr, int HW, float* __restrict__ table, int concat_order) {
   extern __shared__ float means[];   // [Ci+Cr] logical-channel means
   const int b = blockIdx.x, K = Ci + Cr;
   const float inv_hw = 1.0f / (float)HW;
@@ -264,7 +264,9 @@ __global__ void radar_enh_table_kernel(const float* __restrict__ attn, const flo
     } else {
       o = make_float4(eca, 0.f, 0.f, 88.f);
     }
-    reinterpret_cast<float4*>(table)[(int64_t)b * K + k] = o;
+    // concat_order: row = channel of the virtual concat [image | radar] (the GEMM then runs on the sources in memory order
+    // with its weight columns permuted instead, and both sources can come in by TMA)
+    reinterpret_cast<float4*>(table)[(int64_t)b * K + (concat_order ? s : k)] = o;
   }
 }
 
@@ -633,8 +635,20 @@ extern "C" int vrcoc_radar_enh_table(const float* attn, const float* chan_sums_r
   int K = Ci + Cr;
   VRCOC_REQUIRE(K * 4 <= 48 * 1024, "radar_enh_table: too many channels (%d)", K);
   radar_enh_table_kernel<<<B, 256, K * sizeof(float), (cudaStream_t)stream>>>(attn, chan_sums_radar, chan_src, eca_weight,
-                                                                              eca_k, Ci, Cr, HW, table);
+                                                                              eca_k, Ci, Cr, HW, table, 0);
   return check_launch("radar_enh_table");
+}
+
+extern "C" int vrcoc_radar_enh_table_concat_order(const float* attn, const float* chan_sums_radar, const int32_t* chan_src,
+                                                  const float* eca_weight, int eca_k, int B, int Ci, int Cr, int HW, float* table,
+                                                  void* stream) {
+  VRCOC_REQUIRE(attn && chan_sums_radar && eca_weight && table && chan_src, "radar_enh_table_concat_order: null pointer");
+  VRCOC_REQUIRE(B > 0 && Ci > 0 && Cr > 0 && HW > 0 && eca_k > 0 && (eca_k & 1), "radar_enh_table_concat_order: bad dimension");
+  int K = Ci + Cr;
+  VRCOC_REQUIRE(K * 4 <= 48 * 1024, "radar_enh_table_concat_order: too many channels (%d)", K);
+  radar_enh_table_kernel<<<B, 256, K * sizeof(float), (cudaStream_t)stream>>>(attn, chan_sums_radar, chan_src, eca_weight,
+                                                                              eca_k, Ci, Cr, HW, table, 1);
+  return check_launch("radar_enh_table_concat_order");
 }
 
 extern "C" int vrcoc_gelu_bwd(const void* dy, const void* u, void* out, int dtype, int64_t n, void* stream) {

@@ -57,6 +57,7 @@ SIGNATURES = {
     "vrcoc_cluster_core_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P] + [_I] * 9 + [_L] * 5 + [_P]),
     "vrcoc_sa_gate_sums": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vrcoc_radar_enh_table": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "vrcoc_radar_enh_table_concat_order": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "vrcoc_chan_affine": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
     "vrcoc_img_enh_finish": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _P, _P]),
     "vrcoc_debug_set_trace": (_I, [_P]),

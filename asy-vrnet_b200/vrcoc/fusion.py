@@ -540,6 +540,13 @@ class RadarEnhanceByImage(nn.Module):
                                      sa.sbias, sa.gn.weight, sa.gn.bias, self)
 
 
+def _concat_order_weight(w2, chan_src):
+    """W'[:, chan_src[k]] = W[:, k]: the projection weight for inputs in the memory order of the virtual concat"""
+    wn = torch.empty_like(w2)
+    wn[:, chan_src.long()] = w2
+    return wn.contiguous()
+
+
 class _RadarEnhanceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image, radar, w, g1, b1, g2, b2, eca_w, cw, cb, sw, sb, gw, gb, mod):
@@ -571,11 +578,25 @@ class _RadarEnhanceFn(torch.autograd.Function):
                                          _ptr(attn), _stream()), "sa_gate_sums")
         table = torch.empty(B, Ci + Cr, 4, device=dev, dtype=torch.float32)
         ew = _f32(eca_w).reshape(-1)
-        check(lib.vrcoc_radar_enh_table(_ptr(attn), _ptr(cs_rad), _ptr(mod._chan_src), _ptr(ew), ew.numel(), B, Ci, Cr, HW,
-                                        _ptr(table), _stream()), "radar_enh_table")
         w2 = w.detach().reshape(Cr, -1).contiguous()
         out = torch.empty_like(radar)
         gate = not mod.initial
+        # eval, bf16, the image/radar boundary on a 64-channel k slab: the contraction does not care about the order of k, so the
+        # shuffle moves from the activations to the weight columns (W'[:, chan_src[k]] = W[:, k], memoised) and the GEMM reads
+        # [image | radar] in memory order - both sources by TMA, attention / ECA applied in place (channel-major kernel)
+        concat_order = (not (train1 or train2) and not any(ctx.needs_input_grad) and image.dtype == torch.bfloat16 and Ci % 64 == 0
+                        and w2.dtype == torch.bfloat16 and HW % 8 == 0)
+        if concat_order:
+            check(lib.vrcoc_radar_enh_table_concat_order(_ptr(attn), _ptr(cs_rad), _ptr(mod._chan_src), _ptr(ew), ew.numel(), B, Ci,
+                                                         Cr, HW, _ptr(table), _stream()), "radar_enh_table_concat_order")
+            w_nat = ops.cached(mod, "w_concat_order", [w], lambda: _concat_order_weight(w2, mod._chan_src))
+            s1, t1 = _bn_affine(ip.bn)
+            s2, t2 = _bn_affine(bn2)
+            conv_fwd(conv_desc(image, w_nat, out, src1=radar, table=table, has_gate=gate,
+                               e_scale=s1, e_shift=t1, act=ACT_RELU, res=radar, f_scale=s2, f_shift=t2))
+            return out
+        check(lib.vrcoc_radar_enh_table(_ptr(attn), _ptr(cs_rad), _ptr(mod._chan_src), _ptr(ew), ew.numel(), B, Ci, Cr, HW,
+                                        _ptr(table), _stream()), "radar_enh_table")
         if train1 or train2:
             u = torch.empty_like(radar)
             conv_fwd(conv_desc(image, w2, u, src1=radar, chan_src=mod._chan_src, table=table, has_gate=gate))

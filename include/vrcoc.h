@@ -166,6 +166,11 @@ int vrcoc_radar_enh_table(const float* attn /*[B][Ci][4]*/, const float* chan_su
                                                     include ShuffleAttention's own channel_shuffle*/,
                           const float* eca_weight, int eca_k, int B, int Ci, int Cr, int HW,
                           float* table /*[B][Ci+Cr][4]*/, void* stream);
+/* Same table with its rows in the channel order of the virtual concat [image | radar] (row chan_src[k] instead of k): for
+ * running the projection on the two sources in memory order with permuted weight columns, W'[:, chan_src[k]] = W[:, k]. */
+int vrcoc_radar_enh_table_concat_order(const float* attn, const float* chan_sums_radar, const int32_t* chan_src,
+                                       const float* eca_weight, int eca_k, int B, int Ci, int Cr, int HW, float* table,
+                                       void* stream);
 
 /* Stand-alone application of a conv prologue (no contraction): out[b,k,p] = T(src[b, chan_src[k], p]) with T taken
  * from desc->gn_* or desc->table exactly as in vrcoc_conv_fwd (weight/epilogue fields are ignored, O must equal

@@ -202,6 +202,37 @@ def test_fusion_golden(V, name):
         _check_grads(mod, fx, xs, ["image", "radar"], y, FP32_TOL)
 
 
+@pytest.mark.parametrize("Ci,Cr,H,W,B", [(64, 64, 32, 32, 2), (128, 128, 16, 24, 3), (320, 320, 8, 8, 2), (64, 128, 16, 16, 1)])
+def test_radar_enhance_concat_order_path_vs_oracle(V, Ci, Cr, H, W, B):
+    """gradient-free bf16 RadarEnhanceByImage with the image/radar boundary on a 64-channel slab: the shuffle is moved to the
+    weight columns and the projection reads [image | radar] in memory order (channel-major tcgen05 kernel, both sources by
+    TMA; 640 input channels: the transform-on-load kernel on the same formulation) - against the fp64 oracle on the same
+    bf16-rounded weights and inputs"""
+    from oracle import coc_oracle as O
+    torch.manual_seed(5)
+    m = V.RadarEnhanceByImage(radar_in_channels=Cr, image_in_channels=Ci).eval()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.numel() and n.split(".")[-1] in ("cweight", "cbias", "sweight", "sbias"):
+                p.normal_()
+        for n, b in m.named_buffers():
+            if n.endswith("running_var"):
+                b.uniform_(0.5, 1.5)
+            elif n.endswith("running_mean"):
+                b.normal_(0, 0.2)
+    m = m.to(torch.bfloat16)
+    img = torch.randn(B, Ci, H, W).to(torch.bfloat16)
+    rad = torch.rand(B, Cr, H, W).to(torch.bfloat16)
+    sd = {k: v.double() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        ref = O.radar_enhance_by_image(img.double(), rad.double(), sd, "")
+        got = m.cuda()(img.cuda(), rad.cuda())
+        got2 = m(img.cuda(), rad.cuda())
+    assert got.dtype == torch.bfloat16
+    assert rel_err(got.float(), ref) < BF16_TOL
+    assert torch.equal(got, got2)
+
+
 def test_vrcoc_mini_golden(V):
     fx = Fixture("vrcoc_mini_eval")
     m = V.VRCoC(norm_layer=V.GroupNorm, **fx.cfg).to("cuda").eval()
