@@ -384,10 +384,18 @@ def run_ours(args):
         forward(sx, sr)
         acct.stop()
         launches_per_step = acct.count
+        # per-launch timing: one stream, and the stream is held while the host queues the whole eager forward, so that the
+        # event pairs bracket kernels running back to back (an eager launch otherwise starts on an idle GPU and its pair
+        # also measures ~5 us of launch latency; concurrent branches would measure each other)
+        from vrcoc import ops as _ops
+        pair_streams, _ops.PAIR_STREAMS = _ops.PAIR_STREAMS, False
         acct.start("time")
         for _ in range(3):
+            torch.cuda._sleep(int(1.9e6 * 40))
             forward(sx, sr)
+            torch.cuda.synchronize()
         acct.stop()
+        _ops.PAIR_STREAMS = pair_streams
     table = acct.table()
     total_ms = sum(v[1] for v in table.values())
     pk = peaks()
