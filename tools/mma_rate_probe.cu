@@ -1,0 +1,85 @@
+// Stand-alone probe: tcgen05.mma issue rate for the operand layouts the projection kernels use.
+//   D[128 x N] (TMEM) += A[128 x 16] * B[N x 16]^T, bf16, fp32 accumulate; operands stay in shared memory (no loads in the
+//   timed loop), one thread issues `iters` x 4 MMAs (one 64-deep slab) and commits once per slab, as the kernels do.
+//   variants: A K-major / B K-major (wgrad_tc), A K-major / B MN-major (channel-major kernel), A MN-major / B K-major
+//   (point-major kernels); N = 64, 128, 256.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -I asy-vrnet_b200/csrc tools/mma_rate_probe.cu -o tools/mma_rate_probe -lcuda
+#include "tma.cuh"
+namespace vrcoc { char* err_buf() { static char b[256]; return b; } int fail(int c, const char* f, ...) { printf("fail: %s\n", f); return c; } int check_launch(const char*) { return 0; } }
+using namespace vrcoc;
+
+__device__ __forceinline__ uint64_t desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b),
+               "r"(idesc), "r"(acc)
+               : "memory");
+}
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// amaj / bmaj: 0 = K-major, 1 = MN-major
+__global__ void __launch_bounds__(128) mma_kernel(int n, int amaj, int bmaj, int iters, long long* cycles) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  unsigned char* sA = smem;                 // 16 KB: 128 rows x 64 k (either layout)
+  unsigned char* sB = smem + 16384;         // up to 32 KB: 256 rows x 64 k
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(256u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (threadIdx.x == 0) { mbar_init(&bar, (uint32_t)iters + 1u); mbar_fence_init(); }
+  fence_async_smem();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)amaj << 15) | ((uint32_t)bmaj << 16) | ((uint32_t)(n >> 3) << 17) | (8u << 24);
+    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t ad = amaj ? desc(a0 + j * 2048, 8192, 1024) : desc(a0 + j * 32, 16, 1024);
+        const uint64_t bd = bmaj ? desc(b0 + j * 2048, 8192, 1024) : desc(b0 + j * 32, 16, 1024);
+        mma(tmem, ad, bd, idesc, (it | j) ? 1u : 0u);
+      }
+      commit(&bar);                                      // one arrival per slab; the barrier expects iters + 1 of them
+    }
+    commit(&bar);
+    mbar_wait(&bar, 0);
+    cycles[blockIdx.x] = clock64() - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u));
+}
+
+int main() {
+  long long* d;
+  cudaMalloc(&d, 148 * 8);
+  cudaFuncSetAttribute(mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024);
+  printf("%4s %6s %6s | %12s %14s %10s\n", "N", "A", "B", "clk / MMA", "flop/clk/SM", "of 8192");
+  for (int n : {64, 128, 256})
+    for (int v = 0; v < 3; ++v) {
+      const int amaj = v == 2, bmaj = v == 1, iters = 4000;
+      mma_kernel<<<148, 128, 52 * 1024>>>(n, amaj, bmaj, 64, d);
+      mma_kernel<<<148, 128, 52 * 1024>>>(n, amaj, bmaj, iters, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
+      long long h[148];
+      cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+      double c = 0;
+      for (int i = 0; i < 148; ++i) c += (double)h[i];
+      c /= 148.0 * iters * 4;
+      const double fl = 2.0 * 128 * n * 16 / c;
+      printf("%4d %6s %6s | %12.1f %14.0f %9.1f%%\n", n, amaj ? "MN" : "K", bmaj ? "MN" : "K", c, fl, 100.0 * fl / 8192.0);
+    }
+  return 0;
+}
