@@ -280,3 +280,35 @@ def test_wgrad_tensor_core_matches_reference_and_cuda_core(env, case):
     assert rel_err(db, ref_b) < 1e-5
     dW2, _ = ops.conv1x1_wgrad(ops.conv_desc(x, w, dy, gn=gn), dy)
     assert torch.equal(dW, dW2), "the tensor-core weight gradient must be deterministic"
+
+
+@pytest.mark.parametrize("case", [(3, 4, 3, True, True), (1, 7, 4, True, False), (1, 3, 3, False, False), (1, 4, 4, False, True)],
+                         ids=lambda c: f"k{c[0]}_{c[1]}to{c[2]}_{'relu' if c[3] else 'none'}_{'stats' if c[4] else 'plain'}")
+def test_ingest_convs_compile_time_kernel(env, case):
+    """the four ingest shapes (conv_ingest_kernel: bf16 in / out, compile-time channel counts, BN-style affine, ReLU, residual,
+    whole-batch min/max side output) against torch conv2d in fp32 on the same bf16 operands; frames wide enough for several
+    8-pixel groups per row and rows that touch both borders"""
+    ops = env
+    k, C, O, relu, stats = case
+    B, H, W = 2, 24, 64
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, C, H, W, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(O, C, k, k, generator=g) / (C * k * k) ** 0.5).to(torch.bfloat16).cuda()
+    es, eh = (torch.rand(O, generator=g) + 0.5).cuda(), torch.randn(O, generator=g).cuda()
+    res = torch.randn(B, O, H, W, generator=g).to(torch.bfloat16).cuda() if not stats else None
+    ref = F.conv2d(x.float(), w.float(), None, padding=(k - 1) // 2) * es.view(1, O, 1, 1) + eh.view(1, O, 1, 1)
+    if relu:
+        ref = ref.relu()
+    if res is not None:
+        ref = ref + res.float()
+    out = torch.empty(B, O, H, W, device="cuda", dtype=torch.bfloat16)
+    mm = torch.tensor([0, 0], dtype=torch.int32, device="cuda") if stats else None       # {max bits, ~min bits} (atomicMax on both)
+    from vrcoc._lib import ACT_RELU, ACT_NONE
+    d = ops.conv_desc(x, w.reshape(O, -1).contiguous(), out, kh=k, kw=k, stride=1, pad=(k - 1) // 2, e_scale=es, e_shift=eh,
+                      act=ACT_RELU if relu else ACT_NONE, res=res, out_minmax=mm)
+    ops.conv_fwd(d)
+    assert rel_err(out.float(), ref) < 4e-3                     # one bf16 rounding of the result
+    assert (out.float() - ref).abs().max() <= 2 ** -7 * ref.abs().max()
+    if stats and relu:
+        got_max = torch.tensor([mm[0].item()], dtype=torch.int32).view(torch.float32).item()
+        assert abs(got_max - ref.max().item()) <= 2 ** -7 * abs(ref.max().item())
