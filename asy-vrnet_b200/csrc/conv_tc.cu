@@ -69,14 +69,61 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
       : "memory");
 }
 
-// issue the K=16 MMAs of one slab
+// ---- lean MMA issue ---------------------------------------------------------------------------------------------------
+// ONE thread issues every tcgen05.mma of a CTA, and its instruction stream is on the critical path: the per-tile timestamp trace
+// of the channel-major kernel showed the issue loop taking 2.8 us for the 20 MMAs of a 128x128x320 tile (245 clk per MMA, the
+// tensor pipe needs 64) - rebuilding two 64-bit descriptors with shifts / masks, run-time accumulate flags and loop control per
+// MMA, in a single dependent chain that also competes for issue slots with two epilogue warps.  Here a descriptor is a
+// {lo, hi} register pair: hi (SBO, version, swizzle) is a constant, lo (address and LBO in 16-byte units) advances by an
+// immediate per k-step; the four k-steps of a 64-deep slab are straight-line code.
+constexpr uint32_t TC_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);          // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t tc_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+template <bool ACC>
+__device__ __forceinline__ void tc_mma_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate = 1u) {
+  if (ACC) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.eq.u32 p, 0, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(TC_DESC_HI), "r"(idesc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(TC_DESC_HI), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// the k-steps of one slab: operand A advances by a_step, B by b_step (16-byte units) per 16 k; `acc0` = accumulate flag of the
+// first MMA (0 only for the first slab of a tile)
+template <int A_STEP, int B_STEP>
+__device__ __forceinline__ void tc_issue_slab(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc0, int ksteps) {
+  if (ksteps == 4) {
+    tc_mma_lo<false>(tmem_d, a_lo, b_lo, idesc, acc0);
+    tc_mma_lo<true>(tmem_d, a_lo + A_STEP, b_lo + B_STEP, idesc);
+    tc_mma_lo<true>(tmem_d, a_lo + 2 * A_STEP, b_lo + 2 * B_STEP, idesc);
+    tc_mma_lo<true>(tmem_d, a_lo + 3 * A_STEP, b_lo + 3 * B_STEP, idesc);
+  } else {
+    for (int j = 0; j < ksteps; ++j) tc_mma_lo<false>(tmem_d, a_lo + j * A_STEP, b_lo + j * B_STEP, idesc, (acc0 || j > 0) ? 1u : 0u);
+  }
+}
+
+// issue the K=16 MMAs of one slab: A MN-major (16 k-rows = two 8-row groups = 2048 B), B K-major (16 k = 32 B inside the row)
 __device__ __forceinline__ void issue_slab_mmas(uint32_t tmem_base, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, int ksteps,
                                                 bool first_slab) {
-  for (int j = 0; j < ksteps; ++j) {
-    const uint64_t ad = make_desc(a_addr + j * 2048, TC_A_LBO, 1024);   // 16 k-rows = two 8-row groups
-    const uint64_t bd = make_desc(b_addr + j * 32, 16, 1024);           // 16 k = 32 B inside the 128 B row
-    tc_mma(tmem_base, ad, bd, idesc, (!first_slab || j > 0) ? 1u : 0u);
-  }
+  tc_issue_slab<2048 / 16, 32 / 16>(tmem_base, tc_desc_lo(a_addr, TC_A_LBO), tc_desc_lo(b_addr, 16), idesc, first_slab ? 0u : 1u, ksteps);
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {

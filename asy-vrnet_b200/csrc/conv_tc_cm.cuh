@@ -435,11 +435,8 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
           const int ksteps = (min(TC_BK, a.K - kc * TC_BK) + 15) >> 4;
           const uint32_t w_addr = smem_u32(sW + s * TQ_W_BYTES);
           const uint32_t x_addr = smem_u32(sX + (XMODE == 0 ? s : kc) * TQ_X_BYTES);
-          for (int t = 0; t < ksteps; ++t) {
-            const uint64_t wd = make_desc(w_addr + t * 32, 16, 1024);            // 16 k = 32 B inside the 128 B row
-            const uint64_t xd = make_desc(x_addr + t * 2048, TC_A_LBO, 1024);    // 16 k-rows = two 8-row groups
-            tc_mma(tacc, wd, xd, idesc, (kc > 0 || t > 0) ? 1u : 0u);
-          }
+          // A = weights, K-major: 16 k = 32 B inside the 128 B row; B = activations, MN-major: 16 k-rows = two 8-row groups
+          tc_issue_slab<32 / 16, 2048 / 16>(tacc, tc_desc_lo(w_addr, 16), tc_desc_lo(x_addr, TC_A_LBO), idesc, kc > 0 ? 1u : 0u, ksteps);
           tc_commit(&bar_free[s]);
         }
         tc_commit(&acc_full[buf]);

@@ -124,9 +124,7 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
         mbar_wait(&bar_full[s], (uint32_t)(it / ST) & 1);
         tc_fence_after();
         const uint32_t w_addr = smem_u32(ring + s * TQ_W_BYTES);
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-          tc_mma(tacc, make_desc(w_addr + t * 32, 16, 1024), make_desc(x_addr + t * 2048, TC_A_LBO, 1024), idesc, (!first || t > 0) ? 1u : 0u);
+        tc_issue_slab<32 / 16, 2048 / 16>(tacc, tc_desc_lo(w_addr, 16), tc_desc_lo(x_addr, TC_A_LBO), idesc, first ? 0u : 1u, 4);
         tc_commit(&bar_free[s]);
         ++it;
       };

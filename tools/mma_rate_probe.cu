@@ -23,7 +23,8 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
 // amaj / bmaj: 0 = K-major, 1 = MN-major.  mode: what the other warps do meanwhile (the projection kernels' epilogue / producer):
 //   0 nothing; 1 warps 1-8 read the OTHER accumulator buffer (TMEM columns 128..255) with tcgen05.ld.x16 in a loop;
 //   2 warps 1-8 stream 16-byte shared-memory stores + loads over a private 32 KB region; 3 warp 9 keeps 16 KB TMA boxes (L2
-//   hits) landing in a 4-slot ring; 4 = 1 + 2 + 3
+//   hits) landing in a 4-slot ring; 4 = 1 + 2 + 3; 5: tcgen05.fence::after_thread_sync before every slab (as the kernels do
+//   after their full-barrier wait); 6: that fence + a wait on an already completed mbarrier phase; 7: the wait alone
 __global__ void __launch_bounds__(320) mma_kernel(int n, int amaj, int bmaj, int iters, long long* cycles, int mode,
                                                  const __grid_constant__ CUtensorMap tm) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -50,6 +51,9 @@ __global__ void __launch_bounds__(320) mma_kernel(int n, int amaj, int bmaj, int
     const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
+      if (mode == 6 || mode == 7) mbar_wait(&ring[0], 1);               // an already-completed phase (never armed: parity 1 passes)
+      if (mode == 5 || mode == 6) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // modes 8, 9: operands walk over a large footprint like the kernels' (X resident 80 KB + a 64 KB weight ring)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint64_t ad = amaj ? desc(a0 + j * 2048, 8192, 1024) : desc(a0 + j * 32, 16, 1024);
@@ -119,7 +123,7 @@ int main() {
   cudaFuncSetAttribute(mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   printf("%4s %6s %6s %5s | %12s %14s %10s\n", "N", "A", "B", "mode", "clk / MMA", "flop/clk/SM", "of 8192");
   for (int n : {128})
-    for (int mode = 0; mode < 5; ++mode)
+    for (int mode : {0, 5, 6, 7})
     for (int v = 0; v < 2; ++v) {
       const int amaj = 0, bmaj = v == 1, iters = 4000;
       mma_kernel<<<148, 320, 150 * 1024>>>(n, amaj, bmaj, 64, d, mode, tm);
