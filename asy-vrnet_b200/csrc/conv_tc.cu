@@ -492,15 +492,17 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_tma_kernel(ConvArgs a, 
   } else if (tid == 32) {
     // MMA issuer
     const uint32_t idesc = make_idesc(L.n_tile);
+    int s = 0;
+    uint32_t ph = 0;
     for (int kc = 0; kc < nk; ++kc) {
-      const int s = kc % NS;
-      mbar_wait(&S.bar_full[s], (uint32_t)(kc / NS) & 1);
+      mbar_wait(&S.bar_full[s], ph);
       if (kc == 0) trace(2);
       tc_fence_after();
       const int ksteps = (min(TC_BK, a.K - kc * TC_BK) + 15) >> 4;
       issue_slab_mmas(tmem_base, smem_u32(S.sA + s * TC_A_BYTES), smem_u32(S.sB + s * L.b_bytes), idesc, ksteps, kc == 0);
       tc_commit(&S.bar_free[s]);
       if (kc == nk - 1) { tc_commit(S.bar_acc); trace(3); }
+      if (++s == NS) { s = 0; ph ^= 1u; }
     }
   }
   __syncwarp();

@@ -422,14 +422,14 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
     if (lane == 0) {
       tc_fence_after();
       const uint32_t idesc = make_idesc_cm(TQ_NP);
-      int it = 0;
+      int s = 0;                                                       // ring slot and its phase, advanced without divisions:
+      uint32_t ph = 0;                                                 // this loop is the critical path of the CTA
       for (int j = 0; j < tiles; ++j) {
         const int buf = j & 1;
         if (j >= 2) { mbar_wait(&acc_empty[buf], (uint32_t)((j >> 1) - 1) & 1); tc_fence_after(); }
         const uint32_t tacc = tmem_base + (uint32_t)(buf * TQ_NP);
-        for (int kc = 0; kc < nk; ++kc, ++it) {
-          const int s = it % ST;
-          mbar_wait(&bar_full[s], (uint32_t)(it / ST) & 1);
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(&bar_full[s], ph);
           if (XMODE == 3 && j == 0) mbar_wait(&x_ready[kc], 0);
           tc_fence_after();
           const int ksteps = (min(TC_BK, a.K - kc * TC_BK) + 15) >> 4;
@@ -438,6 +438,7 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
           // A = weights, K-major: 16 k = 32 B inside the 128 B row; B = activations, MN-major: 16 k-rows = two 8-row groups
           tc_issue_slab<32 / 16, 2048 / 16>(tacc, tc_desc_lo(w_addr, 16), tc_desc_lo(x_addr, TC_A_LBO), idesc, kc > 0 ? 1u : 0u, ksteps);
           tc_commit(&bar_free[s]);
+          if (++s == ST) { s = 0; ph ^= 1u; }
         }
         tc_commit(&acc_full[buf]);
       }

@@ -118,15 +118,15 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
     if (lane == 0) {
       const uint32_t idesc = make_idesc_cm(TQ_NP);
       const uint32_t acc1 = tmem_base, acc2 = tmem_base + TQ_NP;
-      int it = 0;
+      int s = 0;                                                       // ring slot and phase, advanced without divisions
+      uint32_t ph = 0;
       auto slab = [&](uint32_t tacc, uint32_t x_addr, bool first) {
-        const int s = it % ST;
-        mbar_wait(&bar_full[s], (uint32_t)(it / ST) & 1);
+        mbar_wait(&bar_full[s], ph);
         tc_fence_after();
         const uint32_t w_addr = smem_u32(ring + s * TQ_W_BYTES);
         tc_issue_slab<32 / 16, 2048 / 16>(tacc, tc_desc_lo(w_addr, 16), tc_desc_lo(x_addr, TC_A_LBO), idesc, first ? 0u : 1u, 4);
         tc_commit(&bar_free[s]);
-        ++it;
+        if (++s == ST) { s = 0; ph ^= 1u; }
       };
       auto gemm1 = [&](int j) {
         for (int kc = 0; kc < nk1; ++kc) {
