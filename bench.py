@@ -41,6 +41,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train", "block-sweep"],
+                    help="infer: BASELINE configs[2] (the driver's line); train: configs[3] (training step, NCCL gradient all-reduce); "
+                         "block-sweep: configs[1] (tools/block_sweep.py; extra flags after --)")
+    ap.add_argument("--img", type=int, default=512, help="frame side (1024: BASELINE configs[4], fea_pos buffers replaced)")
+    ap.add_argument("--no-check", action="store_true", help="skip the pre-timing oracle spot check of the benched outputs")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the unmodified reference eager on the GPU")
     ap.add_argument("--phi", default="l")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="frames per GPU per step")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
@@ -50,7 +56,11 @@ def parse():
     ap.add_argument("--ncu-pass", action="store_true",
                     help="profiling aid: run warmup+steps eager forwards (no CUDA graph, no timing, no JSON) and exit; used "
                          "under `ncu --metrics gpu__time_duration.sum` to produce profiles/*launches*.csv")
-    return ap.parse_args()
+    args, rest = ap.parse_known_args()
+    args.rest = [r for r in rest if r != "--"]
+    if args.mode != "block-sweep" and args.rest:
+        ap.error(f"unrecognized arguments: {args.rest}")
+    return args
 
 
 def peaks():
@@ -232,51 +242,172 @@ def synth_batch(batch, seed, dtype):
     return x, r
 
 
+def load_reference():
+    """The UNMODIFIED reference (vendored to git-ignored baseline/_ref/ by __graft_entry__.build()) through its own public
+    API: nets/efficient_vrnet.py:EfficientVRNet + nets/yolo_training.py:weights_init (train.py:297-298).  No product module
+    is imported on this path.  Returns None when the vendored tree is absent (then the oracle port stands in)."""
+    from oracle import ref_shim
+    if not ref_shim.available(ref_shim.VENDORED):
+        return None
+    ref_shim.install(ref_shim.VENDORED)
+    import contextlib
+    import io
+    from nets.efficient_vrnet import EfficientVRNet as RefNet
+    from nets.yolo_training import weights_init
+
+    def make(phi, seed=0):
+        torch.manual_seed(seed)
+        m = RefNet(4, 9, phi)
+        with contextlib.redirect_stdout(io.StringIO()):
+            weights_init(m)
+        return m.eval()
+    return make
+
+
+def _time_cpu_forward(fwd, x, r, n, warm):
+    with torch.no_grad():
+        for _ in range(warm):
+            fwd(x, r)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fwd(x, r)
+        return time.perf_counter() - t0
+
+
 def run_reference(args):
-    """CPU arm: the oracle port of the reference's implementation of this path, all host threads, 1 frame / step."""
+    """CPU arm: the reference's own EfficientVRNet (BASELINE.json configs[0]: batch 1, fp32, 512x512 RGB + 4x512x512 radar,
+    random init) on all host threads, 1 frame / step.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import coc_oracle as O
-    import vrcoc
     torch.set_num_threads(os.cpu_count() or 1)
-    torch.manual_seed(0)
-    model = vrcoc.EfficientVRNet(4, 9, args.phi).eval()
-    sd = {k: v.float() for k, v in model.state_dict().items()}
     x, r = synth_batch(1, 100, torch.float32)
-    with torch.no_grad():
-        for _ in range(max(1, min(args.warmup, 3))):
-            O.efficient_vrnet_forward(x, r, sd, args.phi)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            O.efficient_vrnet_forward(x, r, sd, args.phi)
-        dt = time.perf_counter() - t0
+    make = load_reference()
+    if make is not None:
+        model = make(args.phi)
+        fwd, kind = (lambda a, b: model(a, b)), "reference"
+        what = "the reference's own nets/efficient_vrnet.py:EfficientVRNet, unmodified (baseline/_ref)"
+    else:
+        # only when the vendored reference is missing: the oracle port needs a state dict of the right shapes, and the product's
+        # module tree (CPU tensors, no kernel runs) is the one place left to get it from
+        from oracle import coc_oracle as O
+        import vrcoc
+        torch.manual_seed(0)
+        sd = {k: v.float() for k, v in vrcoc.EfficientVRNet(4, 9, args.phi).state_dict().items()}
+        fwd, kind = (lambda a, b: O.efficient_vrnet_forward(a, b, sd, args.phi)), "port"
+        what = "oracle port of the reference (baseline/_ref absent)"
+    dt = _time_cpu_forward(fwd, x, r, args.steps, max(1, min(args.warmup, 3)))
     fps = args.steps / dt
     sample = f"1 frame/step (one frame of the {args.batch}-frame per-GPU batch), fp32, phi={args.phi}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ASY-VRNet(phi={args.phi}) multi-task inference fwd, 512x512 RGB + 4x512x512 radar (CPU, oracle port of the reference)"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "config": {"workload": f"ASY-VRNet(phi={args.phi}) multi-task inference fwd, 512x512 RGB + 4x512x512 radar (CPU: {what})"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
 
 def cpu_baseline(args, model):
-    from oracle import coc_oracle as O
+    """Rank 0, N=1: the reference's own model (strict-loaded with the benched weights: the drop-in contract at work) timed on
+    the host cores over a bounded sample."""
     torch.set_num_threads(os.cpu_count() or 1)
     sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
     x, r = synth_batch(1, 100, torch.float32)
-    n = 48                                     # ~10-15 s of host time at the ~4 frames/s this port reaches on 16 threads
+    make = load_reference()
+    if make is not None:
+        ref = make(args.phi)
+        ref.load_state_dict(sd, strict=True)
+        fwd, kind = (lambda a, b: ref(a, b)), "reference"
+    else:
+        from oracle import coc_oracle as O
+        fwd, kind = (lambda a, b: O.efficient_vrnet_forward(a, b, sd, args.phi)), "port"
+    dt1 = _time_cpu_forward(fwd, x, r, 1, 1)
+    n = max(4, min(64, int(12.0 / max(dt1, 1e-3))))          # ~12 s of host time
+    dt = _time_cpu_forward(fwd, x, r, n, 0)
+    return {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{n} frames, batch 1, fp32, phi={args.phi}, after 2 warm-up frames"}
+
+
+def reference_eager_gpu(args, model, dev):
+    """Secondary baseline ('the honest kernel to beat'): the UNMODIFIED reference running eager on this B200 with
+    the benched weights and batch — fp32 with TF32 off (the valid fp32 oracle setting), fp32 with TF32 on (PyTorch's
+    default for cuDNN), and under bf16 autocast.  cuDNN/cuBLAS/ATen kernels; no product code."""
+    make = load_reference()
+    if make is None:
+        return None
+    ref = make(args.phi)
+    ref.load_state_dict({k: v.detach().float().cpu() for k, v in model.state_dict().items()}, strict=True)
+    ref = ref.to(dev)
+    x, r = (t.to(dev) for t in synth_batch(args.batch, 100, torch.float32))
+    out = {}
+
+    def run(name, tf32, autocast):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        ctx = torch.autocast("cuda", dtype=torch.bfloat16) if autocast else torch.autocast("cuda", enabled=False)
+        try:
+            with torch.no_grad(), ctx:
+                for _ in range(3):
+                    ref(x, r)
+                torch.cuda.synchronize()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n = 10
+                s.record()
+                for _ in range(n):
+                    ref(x, r)
+                e.record()
+                torch.cuda.synchronize()
+            out[name] = {"value": args.batch * n / (s.elapsed_time(e) / 1e3), "unit": UNIT, "batch": args.batch}
+        except Exception as ex:       # e.g. out of memory for the [R,M,N,D] temporaries
+            out[name] = {"error": str(ex)[:120]}
+    run("fp32_tf32_off", False, False)
+    run("fp32_tf32_on", True, False)
+    run("bf16_autocast", True, True)
+    del ref
+    torch.cuda.empty_cache()
+    return out
+
+
+def oracle_spot_check(args, model, static_in, batch, graph, graph_outs):
+    """Before any timing: the benched configuration (bf16 weights, batch B, CUDA graph replay, side-stream branches) must
+    produce finite outputs that agree with the CPU oracle evaluated in fp64 on the SAME bf16-rounded weights and inputs
+    (whole batch: data_normal couples the samples).  Gated: rel. L2 error of each detection map as the GRAPH REPLAY
+    produced it and of the segmentation logits (eager pass of the same modules; the graph only keeps the class map)
+    <= tol; the graph's per-pixel class map must agree with the oracle's arg-max on >= 99 % of the pixels."""
+    from oracle import coc_oracle as O
+    tol = 3e-2 if args.dtype == "bf16" else 2e-3
+    sx, sr = static_in
     with torch.no_grad():
-        O.efficient_vrnet_forward(x, r, sd, args.phi)
+        sx.copy_(batch[0]); sr.copy_(batch[1])
+        if graph is not None:
+            graph.replay()
+            det = [d.double().cpu() for d in graph_outs[0]]
+            cls = graph_outs[1].cpu().long()
+            _, seg_logits = model(sx, sr)
+        else:
+            det, seg_logits = model(sx, sr)
+            det = [d.double().cpu() for d in det]
+            cls = seg_logits.argmax(1).cpu().long()
+        seg_logits = seg_logits.double().cpu()
+        sd = {k: v.detach().double().cpu() for k, v in model.state_dict().items()}
         t0 = time.perf_counter()
-        for _ in range(n):
-            O.efficient_vrnet_forward(x, r, sd, args.phi)
-        dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} frames, batch 1, fp32, phi={args.phi}, after 1 warm-up frame"}
+        rdet, rseg = O.efficient_vrnet_forward(batch[0].double().cpu(), batch[1].double().cpu(), sd, args.phi)
+        dt_oracle = time.perf_counter() - t0
+
+    def rel(a, b):
+        return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+    errs = {f"det{i}": rel(a, b) for i, (a, b) in enumerate(zip(det, rdet))}
+    errs["seg_logits"] = rel(seg_logits, rseg)
+    finite = all(torch.isfinite(t).all().item() for t in det + [seg_logits])
+    agree = (cls == rseg.argmax(1)).double().mean().item()
+    ok = finite and max(errs.values()) <= tol and agree >= 0.99
+    res = {"ok": ok, "finite": finite, "rel_err": errs, "seg_class_agreement": agree, "tol": tol, "through_cuda_graph": graph is not None,
+           "oracle": f"oracle/coc_oracle.py fp64 on the {args.dtype}-rounded weights and inputs, batch {batch[0].shape[0]}, {dt_oracle:.1f} s"}
+    if not ok:
+        raise SystemExit("bench.py: the benched configuration fails its oracle spot check: " + json.dumps(res))
+    return res
 
 
 def run_ours(args):
@@ -420,9 +551,15 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    with ClockSampler(local) as clk:
+    check = None
+    if rank == 0 and not args.no_check:
+        check = oracle_spot_check(args, model, (sx, sr), devb[0], graph, (det_out, seg_out))
+    with ClockSampler(local) as clk:                  # started before the warm-up steps so that a 60 ms timed region has samples
+        for i in range(20):
+            step_resident(i)
+        torch.cuda.synchronize()
         ms_res = timed(step_resident)
-    ms_e2e = timed(step_e2e, drain_e2e)
+        ms_e2e = timed(step_e2e, drain_e2e)
     frames = B * world * args.steps
     value = frames / (ms_res / 1e3)
     e2e = frames / (ms_e2e / 1e3)
@@ -498,7 +635,20 @@ def run_ours(args):
         "clocks": clk.summary(),
         "roofline": roof,
         "roofline_coc_core": roof_core,
+        "output_check": check,
     }
+    # whole-step fractions on SURVEY 8d's per-frame figures for the 27 ClusterBlocks (bf16: 101 MB, 66.6 GFLOP per frame at phi='l',
+    # 512x512): what fraction of the HBM / tensor peak the CoC path of the step amounts to
+    if args.phi == "l" and args.img == 512 and args.dtype == "bf16":
+        fps_gpu = value / world
+        line["roofline_step"] = {"coc_alg_MB_per_frame": 100.7, "coc_GFLOP_per_frame": 66.6,
+                                 "hbm_frac": 100.7e6 * fps_gpu / 1e9 / pk["hbm_gbs"], "tc_frac": 66.6e9 * fps_gpu / 1e12 / pk["bf16_tflops"]}
+    if rank == 0 and world == 1:
+        from tools import block_sweep
+        with torch.no_grad():
+            line["roofline_block"] = block_sweep.live_rows(B, dtype, iters=10)      # per live row: all launches of one ClusterBlock fwd
+        if not args.no_ref_gpu:
+            line["reference_eager_gpu"] = reference_eager_gpu(args, model, dev)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, model)
     if rank == 0:
@@ -509,6 +659,9 @@ def run_ours(args):
 
 def main():
     args = parse()
+    if args.mode == "block-sweep":
+        from tools import block_sweep
+        return block_sweep.main(args.rest)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -1,9 +1,11 @@
 """
 Import shim for the UNMODIFIED reference under /root/reference.   *** TEST INFRASTRUCTURE ONLY ***
 
-Used by `oracle/make_golden.py` (fixture generation) and by `tests/test_oracle_vs_reference.py`
-(live re-check when the read-only reference mount is present).  Nothing under `-m gpu`, `smoke()` or
-`bench.py` may call this: /root/reference does not exist on the GPU box.
+Used by `oracle/make_golden.py` (fixture generation), by `tests/test_oracle_vs_reference.py` (live re-check when
+the read-only reference mount is present) and by the BASELINE legs of `bench.py` (`--impl reference`, `cpu_baseline`,
+`reference_eager_gpu`), which import the unmodified reference from the git-ignored copy `baseline/_ref/` that
+`__graft_entry__.build()` vendors (it travels to the GPU box; /root/reference does not exist there).  Nothing under
+`asy-vrnet_b200/` imports it.
 
 What it does: stubs the python packages the reference imports but this image lacks
 (timm, thop, torchinfo), tolerates the `nn.GroupNorm(0, 0)` that `RadarEnhanceByImage(image_in_channels=3)`
@@ -20,8 +22,11 @@ import torch.nn as nn
 REF_ROOT = os.environ.get("VRCOC_REFERENCE_ROOT", "/root/reference")
 
 
-def available():
-    return os.path.isdir(os.path.join(REF_ROOT, "backbone", "fusion"))
+VENDORED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def available(root=None):
+    return os.path.isdir(os.path.join(root or REF_ROOT, "backbone", "fusion"))
 
 
 def _stub(name, **attrs):
@@ -45,10 +50,11 @@ class _DropPath(nn.Module):
         return x * mask / keep
 
 
-def install():
-    """Idempotent.  Returns the reference root."""
-    if not available():
-        raise RuntimeError(f"reference not mounted at {REF_ROOT}")
+def install(root=None):
+    """Idempotent.  Returns the reference root (default: the read-only mount; bench.py passes the vendored copy)."""
+    root = root or REF_ROOT
+    if not available(root):
+        raise RuntimeError(f"reference not found at {root}")
     if "timm" not in sys.modules:
         def to_2tuple(v):
             return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
@@ -77,6 +83,6 @@ def install():
 
         nn.GroupNorm.__init__ = init
         nn.GroupNorm._vrcoc_zero_ok = True
-    if REF_ROOT not in sys.path:
-        sys.path.insert(0, REF_ROOT)
-    return REF_ROOT
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    return root

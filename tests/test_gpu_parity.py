@@ -288,7 +288,7 @@ def test_live_block_vs_oracle_fp32(V, cid):
     assert rel_err(got, ref) < FP32_TOL
 
 
-@pytest.mark.parametrize("cid", ["S1", "S3", "N5"])
+@pytest.mark.parametrize("cid", list(LIVE))
 def test_live_block_vs_oracle_bf16(V, cid):
     from oracle import coc_oracle as O
     m, x, (heads, fw, fh, pw, ph) = _seeded_block(V, cid)
