@@ -21,7 +21,12 @@ static int fill_args(const vrcoc_conv_desc* d, ConvArgs& a) {
   VRCOC_REQUIRE(d->C1 == 0 || d->src1, "conv: C1 > 0 but src1 is null");
   VRCOC_REQUIRE(d->O_split > 0 && d->O_split <= d->O && (d->O_split == d->O || d->out2), "conv: bad O_split / out2");
   VRCOC_REQUIRE(!(d->gn_sums && d->table), "conv: gn_sums and table are mutually exclusive");
-  VRCOC_REQUIRE(!d->gn_sums || (d->gn_gamma && d->gn_beta && d->C1 == 0 && !d->chan_src), "conv: GroupNorm prologue needs gamma/beta and a single source");
+  VRCOC_REQUIRE(!d->gn_sums || d->gn_fold_k1 || (d->gn_gamma && d->gn_beta && d->C1 == 0 && !d->chan_src),
+                "conv: GroupNorm prologue needs gamma/beta and a single source");
+  VRCOC_REQUIRE(!d->gn_fold_k1 || (d->gn_sums && !d->gn_gamma && !d->gn_beta && !d->e_scale && d->e_shift && d->C1 == 0 && !d->chan_src &&
+                                   !d->table && d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0 && (d->C0 % 64) == 0 &&
+                                   d->weight_dtype == VRCOC_BF16 && d->src0_dtype == VRCOC_BF16),
+                "conv: folded GroupNorm needs gn_sums, e_shift (k0), a bf16 1x1 projection of a single bf16 source with C0 %% 64 == 0");
   auto okdt = [](int t) { return t == VRCOC_F32 || t == VRCOC_BF16; };
   VRCOC_REQUIRE(okdt(d->src0_dtype) && okdt(d->weight_dtype) && okdt(d->out_dtype) && (d->C1 == 0 || okdt(d->src1_dtype)) &&
                     (!d->res || okdt(d->res_dtype)) && (d->O_split == d->O || okdt(d->out2_dtype)),
@@ -35,6 +40,7 @@ static int fill_args(const vrcoc_conv_desc* d, ConvArgs& a) {
   a.src1 = d->src1; a.src1_dtype = d->src1_dtype; a.src1_bstride = d->src1_bstride;
   a.chan_src = d->chan_src;
   a.gn_sums = d->gn_sums; a.gn_gamma = d->gn_gamma; a.gn_beta = d->gn_beta; a.gn_eps = d->gn_eps;
+  a.gn_fold_k1 = d->gn_fold_k1;
   a.table = d->table; a.has_gate = d->has_gate;
   a.weight = d->weight; a.weight_dtype = d->weight_dtype;
   a.e_scale = d->e_scale; a.e_shift = d->e_shift; a.act = d->act; a.post_scale = d->post_scale;
@@ -230,6 +236,7 @@ extern "C" int vrcoc_conv_fwd(const vrcoc_conv_desc* d, void* stream) {
   int rc = fill_args(d, a);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (a.gn_fold_k1) return launch_conv_tc(a, st);        // only the channel-major tcgen05 kernel implements the fold
   if (d->engine == 2) {
     VRCOC_REQUIRE(conv_tc_supported(a), "conv: tcgen05 engine forced but the problem is not supported by it");
     return launch_conv_tc(a, st);

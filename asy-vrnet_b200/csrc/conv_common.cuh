@@ -14,6 +14,7 @@ struct ConvArgs {
   const void* src1; int src1_dtype; int64_t src1_bstride;
   const int32_t* chan_src;
   const double* gn_sums; const float* gn_gamma; const float* gn_beta; float gn_eps;
+  const float* gn_fold_k1;   // GroupNorm folded into the weights ([O][2K] = hi|lo), statistics applied in the epilogue (vrcoc.h)
   const float* table; int has_gate;
   const void* weight; int weight_dtype;
   const float* e_scale; const float* e_shift; int act; const float* post_scale;

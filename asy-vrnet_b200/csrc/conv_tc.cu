@@ -1000,16 +1000,19 @@ static bool cm_plan(const ConvArgs& a, CmPlan& best) {
   if (a.res && (a.res_dtype != VRCOC_BF16 || (reinterpret_cast<uintptr_t>(a.res) & 15) != 0 || a.out_dtype != VRCOC_BF16 ||
                 (a.O_split != a.O && a.out2_dtype != VRCOC_BF16)))
     return false;
-  const bool prologue = a.gn_sums || a.table || a.has_gate;
+  const bool fold = a.gn_fold_k1 != nullptr;                // GroupNorm folded into [hi | lo] weights: raw X by TMA, no prologue
+  const bool prologue = !fold && (a.gn_sums || a.table || a.has_gate);
   const bool tma_x = !prologue && a.src0_dtype == VRCOC_BF16 && (reinterpret_cast<uintptr_t>(a.src0) & 15) == 0 &&
                      (a.src0_bstride % 8) == 0;
-  const int nslabs = (a.K + TC_BK - 1) / TC_BK;
+  if (fold && (!tma_x || two_src)) return false;
+  const int nx = (a.K + TC_BK - 1) / TC_BK;                 // X slabs
+  const int nslabs = fold ? 2 * nx : nx;                    // weight slabs of a (feat) tile
   const int n_tiles = (int)cdiv(a.O, TQ_MT);
   const int64_t m_tiles = cdiv(a.P_out, TQ_NP) * a.B;
   const bool plain = !(a.post_scale || a.res || a.f_scale || a.f_shift || a.out_sample_sums || a.out_minmax);
   // measured (tools/microbench.py, B200): with both operands by TMA the point-major kernel keeps 3 CTAs per SM and wins
   // whenever the last 128-channel tile would be partly empty (O = 64, 320); the channel-major kernel wins on full tiles
-  if (tma_x && (a.O % TQ_MT) != 0) return false;
+  if (tma_x && !fold && (a.O % TQ_MT) != 0) return false;
   const double epi_us = a.act == VRCOC_ACT_GELU || a.act == VRCOC_ACT_SILU ? 1.6 : (plain ? 0.5 : 0.8);
   bool found = false;
   const int modes[10] = {1, 1, 1, 1, 1, 0, 0, 0, 0, 0}, depth[10] = {2, 3, 4, 6, 8, 2, 3, 4, 5, 6};
@@ -1017,10 +1020,10 @@ static bool cm_plan(const ConvArgs& a, CmPlan& best) {
   const bool tma_x3 = prologue && a.src0_dtype == VRCOC_BF16 && (reinterpret_cast<uintptr_t>(a.src0) & 15) == 0 &&
                       (a.src0_bstride % 8) == 0 && nslabs <= TQ_MAX_SLABS3;
   if (two_src && !tma_x3) return false;
-  for (int cand = 0; cand < (tma_x ? 10 : 5); ++cand) {
+  for (int cand = 0; cand < (tma_x ? (fold ? 5 : 10) : 5); ++cand) {
     const int bufs = 1;       // a second staging buffer was measured: no gain (the bulk-store drain is not on the critical path)
     const int mode = tma_x ? modes[cand] : (tma_x3 ? 3 : 2), st = depth[cand];
-    const int x_bytes = mode == 0 ? st * TQ_X_BYTES : nslabs * TQ_X_BYTES;
+    const int x_bytes = mode == 0 ? st * TQ_X_BYTES : nx * TQ_X_BYTES;
     const int tab_bytes = mode >= 2 ? a.Cin * 16 : 0;
     const int total = x_bytes + st * TQ_W_BYTES + bufs * 8 * 4096 + tab_bytes + 512 + 1024;
     if (total > 220 * 1024) continue;
@@ -1046,6 +1049,7 @@ static bool cm_plan(const ConvArgs& a, CmPlan& best) {
         TqLayout& T = best.T;
         T.stages = st;
         T.nslabs = nslabs;
+        T.nx = nx;
         T.tiles = t;
         T.plain = plain ? 1 : 0;
         T.off_x = 0;
@@ -1157,8 +1161,9 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
       }
     }
     {
-      cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.O};
-      cuuint64_t strides[1] = {(cuuint64_t)a.K * 2};
+      const int wk = a.gn_fold_k1 ? 2 * a.K : a.K;                     // folded GroupNorm: rows are [hi | lo]
+      cuuint64_t dims[2] = {(cuuint64_t)wk, (cuuint64_t)a.O};
+      cuuint64_t strides[1] = {(cuuint64_t)wk * 2};
       cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TQ_MT};
       int rc = encode(&tmW, a.weight, 2, dims, strides, box);
       if (rc) return rc;
@@ -1189,6 +1194,8 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
 #undef LAUNCH_CM
     return check_launch("conv_tc_cm");
   }
+  VRCOC_REQUIRE(!a.gn_fold_k1, "conv(tcgen05): the folded-GroupNorm projection needs the channel-major kernel (P %% 8 == 0, aligned "
+                               "bf16 tensors, O_split %% 128 == 0, C0 %% 64 == 0); this problem is not covered");
   dim3 grid((unsigned)cdiv(a.P_out, TC_BM), (unsigned)cdiv(a.O, L.n_tile), (unsigned)a.B);
   if (tma_a_eligible(a)) {
     // activations [B][C][P] bf16; box = 64 points (128 B) x 64 channels, lands as one MN-major SW128 block
@@ -1231,6 +1238,26 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
 }
 
 }  // namespace vrcoc
+
+// Is the folded-GroupNorm projection (vrcoc.h, gn_fold_k1) available for this shape?  Runs the channel-major planner on a
+// synthetic problem (aligned pointers), so the host side can decide before it builds the [hi | lo] weights.
+extern "C" int vrcoc_gn_fold_supported(int B, int C, int O, int O_split, int P) {
+  using namespace vrcoc;
+  if (B <= 0 || C <= 0 || (C % 64) != 0 || O <= 0 || O_split <= 0 || O_split > O || P <= 0 || (P % 8) != 0 || !tma_encode_fn()) return 0;
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.C0 = a.Cin = a.K = C; a.O = O; a.O_split = O_split; a.P_in = a.P_out = P; a.kh = a.kw = a.stride = a.dil = 1;
+  a.H_in = a.H_out = 1; a.W_in = a.W_out = P;
+  void* fake = reinterpret_cast<void*>(uintptr_t(1) << 20);
+  a.src0 = fake; a.src0_dtype = VRCOC_BF16; a.src0_bstride = (int64_t)C * P;
+  a.weight = fake; a.weight_dtype = VRCOC_BF16;
+  a.out = fake; a.out_dtype = VRCOC_F32; a.out2 = fake; a.out2_dtype = VRCOC_BF16;
+  a.gn_sums = reinterpret_cast<const double*>(fake); a.gn_fold_k1 = reinterpret_cast<const float*>(fake);
+  a.e_shift = reinterpret_cast<const float*>(fake);
+  a.fast1x1 = 1; a.vec_out = 1;
+  CmPlan cm;
+  return cm_plan(a, cm) ? 1 : 0;
+}
 
 // ---- fused channel MLP ------------------------------------------------------------------------------------------------------
 extern "C" int vrcoc_mlp_fused_supported(int dtype, int C, int hidden, int P) {

@@ -35,6 +35,7 @@ constexpr int TQ_MAX_SLABS3 = 9;                    // XMODE 3: per-slab barrier
 struct TqLayout {
   int stages;        // ring depth
   int nslabs;        // K slabs
+  int nx;            // X slabs (== nslabs, except with the folded GroupNorm: the weights are [hi | lo], 2 * nx slabs per feat tile)
   int tiles;         // output tiles per CTA
   int plain;         // epilogue is act(acc*es + eh) only
   int stage_bufs;    // 1 or 2 epilogue staging buffers of 8 x 4 KB
@@ -161,6 +162,9 @@ __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_bas
   uint32_t res_phase = 0;
   unsigned long long t_wait = 0, t_comp = 0;       // debug trace: warp 0's time waiting for accumulators / draining them
   float ssum = 0.f, ssq = 0.f, vmax = 0.f, vmin = __int_as_float(0x7f800000);
+  // folded GroupNorm (vrcoc.h, gn_fold_k1): y = rstd_b * acc + (k0[o] - rstd_b * mean_b * k1[o])
+  float fold_mu = 0.f, fold_rstd = 1.f;
+  if (a.gn_fold_k1) gn_mean_rstd(a.gn_sums, b, (double)a.C0 * (double)a.P_in, a.gn_eps, fold_mu, fold_rstd);
   if (RES_MODE == 3 && has_res && lane == 0) {
     int live = 0;
     for (int j = 0; j < tiles; ++j) live += (o_begin + j * TQ_MT + lq * 32 < a.O) ? 1 : 0;
@@ -190,6 +194,10 @@ __device__ __forceinline__ void cm_epilogue(const ConvArgs& a, uint32_t tmem_bas
     CmCoef k;
     k.es = (ok && a.e_scale) ? __ldg(a.e_scale + o) : 1.f;
     k.eh = (ok && a.e_shift) ? __ldg(a.e_shift + o) : 0.f;
+    if (a.gn_fold_k1) {
+      k.es = fold_rstd;
+      k.eh = ok ? fmaf(-fold_rstd * fold_mu, __ldg(a.gn_fold_k1 + o), k.eh) : 0.f;
+    }
     k.ps = (!PLAIN && ok && a.post_scale) ? __ldg(a.post_scale + o) : 1.f;
     k.fs = (!PLAIN && ok && a.f_scale) ? __ldg(a.f_scale + o) : 1.f;
     k.fh = (!PLAIN && ok && a.f_shift) ? __ldg(a.f_shift + o) : 0.f;
@@ -353,15 +361,27 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
   int tiles = (a.O - o_begin + TQ_MT - 1) / TQ_MT;
   if (tiles > L.tiles) tiles = L.tiles;
   const int nk = L.nslabs;
+  const int nkx = L.nx;
   const int ST = L.stages;
+  // folded GroupNorm: the weight rows are [hi | lo]; a feat tile (rows < O_split) contracts both halves against the same nkx
+  // raw X slabs, a value tile only the hi half
+  const bool fold = XMODE == 1 && a.gn_fold_k1 != nullptr;
+  // (when the feat | value boundary is not on a tile boundary every tile contracts both halves: the caller then supplies a lo half
+  // for the value rows as well)
+  const bool value_hi_only = (a.O_split % TQ_MT) == 0;
+  auto slabs_of = [&](int j) { return fold ? ((value_hi_only && o_begin + j * TQ_MT >= a.O_split) ? nkx : 2 * nkx) : nk; };
+  int total_steps = 0;
+  for (int j = 0; j < tiles; ++j) total_steps += slabs_of(j);
 
-  // one ring step = the weight slab (tile j, k-slab kc) and, when X is streamed / fetched with the first tile, its X slab
-  const int total_steps = tiles * nk;
+  // one ring step = the weight slab (tile j, k-slab kc) and, when X is streamed / fetched with the first tile, its X slab.
+  // Steps are issued in order by ONE thread (tid 256): (pj, pkc) walk the (tile, slab) pairs.
+  int pj = 0, pkc = 0;
   auto issue = [&](int it) {
     const int s = it % ST;
-    const int j = it / nk, kc = it - j * nk;
+    const int j = pj, kc = pkc;
+    if (++pkc == slabs_of(pj)) { pkc = 0; ++pj; }
     if (it >= ST) mbar_wait(&bar_free[s], (uint32_t)((it / ST) - 1) & 1);
-    const bool need_x = XMODE == 0 || (XMODE == 1 && j == 0);
+    const bool need_x = XMODE == 0 || (XMODE == 1 && j == 0 && kc < nkx);
     mbar_expect_tx(&bar_full[s], (uint32_t)(TQ_W_BYTES + (need_x ? TQ_X_BYTES : 0)));
     tma_load_2d(sW + s * TQ_W_BYTES, &tmapW, kc * TC_BK, o_begin + j * TQ_MT, &bar_full[s]);
     if (need_x) {
@@ -428,13 +448,15 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
         const int buf = j & 1;
         if (j >= 2) { mbar_wait(&acc_empty[buf], (uint32_t)((j >> 1) - 1) & 1); tc_fence_after(); }
         const uint32_t tacc = tmem_base + (uint32_t)(buf * TQ_NP);
-        for (int kc = 0; kc < nk; ++kc) {
+        const int nkj = slabs_of(j);
+        for (int kc = 0; kc < nkj; ++kc) {
           mbar_wait(&bar_full[s], ph);
           if (XMODE == 3 && j == 0) mbar_wait(&x_ready[kc], 0);
           tc_fence_after();
-          const int ksteps = (min(TC_BK, a.K - kc * TC_BK) + 15) >> 4;
+          const int kx = (XMODE == 1 && kc >= nkx) ? kc - nkx : kc;       // X slab (the lo half of the fold re-reads the slabs)
+          const int ksteps = (min(TC_BK, a.K - kx * TC_BK) + 15) >> 4;
           const uint32_t w_addr = smem_u32(sW + s * TQ_W_BYTES);
-          const uint32_t x_addr = smem_u32(sX + (XMODE == 0 ? s : kc) * TQ_X_BYTES);
+          const uint32_t x_addr = smem_u32(sX + (XMODE == 0 ? s : kx) * TQ_X_BYTES);
           // A = weights, K-major: 16 k = 32 B inside the 128 B row; B = activations, MN-major: 16 k-rows = two 8-row groups
           tc_issue_slab<32 / 16, 2048 / 16>(tacc, tc_desc_lo(w_addr, 16), tc_desc_lo(x_addr, TC_A_LBO), idesc, kc > 0 ? 1u : 0u, ksteps);
           tc_commit(&bar_free[s]);

@@ -38,6 +38,7 @@ class ConvDesc(C.Structure):
         ("out2", C.c_void_p), ("out2_dtype", C.c_int32), ("O_split", C.c_int32),
         ("out_sample_sums", C.c_void_p), ("out_minmax", C.c_void_p),
         ("engine", C.c_int32), ("dil", C.c_int32), ("k_order", C.c_int32),
+        ("gn_fold_k1", C.c_void_p),
     ]
 
 
@@ -50,6 +51,7 @@ SIGNATURES = {
     "vrcoc_device_ok": (_I, []),
     "vrcoc_channel_sums": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "vrcoc_conv_fwd": (_I, [C.POINTER(ConvDesc), _P]),
+    "vrcoc_gn_fold_supported": (_I, [_I, _I, _I, _I, _I]),
     "vrcoc_table_apply": (_I, [C.POINTER(ConvDesc), _P]),
     "vrcoc_conv1x1_wgrad": (_I, [C.POINTER(ConvDesc), _P, _I, _P, _P, _P, _L, _P]),
     "vrcoc_conv1x1_wgrad_workspace": (_L, [C.POINTER(ConvDesc)]),

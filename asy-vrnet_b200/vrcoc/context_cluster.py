@@ -108,7 +108,7 @@ class Cluster(nn.Module):
             y = ops.GNProjFn.apply(x, None, None, None, 0.0, w, b, ACT_NONE, ED)
         else:
             sums, norm = gn
-            y = ops.GNProjFn.apply(x, sums, norm.weight, norm.bias, norm.eps, w, b, ACT_NONE, ED)
+            y = ops.GNProjFn.apply(x, sums, norm.weight, norm.bias, norm.eps, w, b, ACT_NONE, ED)       # folds GN when it can
         if isinstance(y, tuple):          # bf16 storage: similarity operand stays fp32
             return y
         return y[:, :ED], y[:, ED:]
@@ -199,7 +199,13 @@ class ClusterBlock(nn.Module):
         ls2 = f32(self.layer_scale_2) if self.use_layer_scale else None
         dev, dt = x.device, x.dtype
         sums0 = ops.sample_sums_of(x)
-        if dt == torch.float32:
+        if ops.gn_fold_ok(x, 2 * ED, ED) and tm.fc1.weight.dtype == dt:
+            w_fold, k0, k1 = ops.cached(self, "w_fold", [tm.fc1.weight, tm.fc1.bias, tm.fc_v.weight, tm.fc_v.bias, n1.weight, n1.bias],
+                                        lambda: ops.fold_gn_weights(tm.fc1.weight, tm.fc1.bias, tm.fc_v.weight, tm.fc_v.bias, n1.weight, n1.bias))
+            feat = torch.empty(B, ED, H, W, device=dev, dtype=torch.float32)
+            value = torch.empty(B, ED, H, W, device=dev, dtype=dt)
+            ops.conv_fwd(ops.conv_desc(x, w_fold, feat, gn_fold=(sums0, k1, n1.eps), e_shift=k0, out2=value))
+        elif dt == torch.float32:
             y = torch.empty(B, 2 * ED, H, W, device=dev, dtype=dt)
             ops.conv_fwd(ops.conv_desc(x, w_in, y, gn=(sums0, f32(n1.weight), f32(n1.bias), n1.eps), e_shift=b_in))
             feat, value = y[:, :ED], y[:, ED:]

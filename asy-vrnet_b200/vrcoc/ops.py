@@ -257,7 +257,7 @@ def sample_sums_of(x):
 def conv_desc(src0, weight, out, *, src1=None, src0_bstride=None, src1_bstride=None, chan_src=None,
               gn=None, table=None, has_gate=False, kh=1, kw=1, stride=1, pad=0,
               e_scale=None, e_shift=None, act=ACT_NONE, post_scale=None, res=None, f_scale=None, f_shift=None,
-              out2=None, out_sample_sums=None, out_minmax=None, engine=ENGINE_AUTO, keep=None, dil=1, k_order=0):
+              out2=None, out_sample_sums=None, out_minmax=None, engine=ENGINE_AUTO, keep=None, dil=1, k_order=0, gn_fold=None):
     """Fill a ConvDesc from tensors.  `keep` collects temporaries that must outlive the launch call."""
     d = ConvDesc()
     B = out.shape[0]
@@ -275,7 +275,11 @@ def conv_desc(src0, weight, out, *, src1=None, src0_bstride=None, src1_bstride=N
         d.src1, d.src1_dtype = _ptr(src1), _dt(src1)
         d.src1_bstride = C1 * H_in * W_in if src1_bstride is None else src1_bstride
     d.chan_src = _ptr(chan_src)
-    if gn is not None:
+    if gn_fold is not None:
+        # GroupNorm folded into the weights: `weight` is [O][2*C0] = [hi | lo], e_shift = k0, statistics enter in the epilogue
+        sums, k1, eps = gn_fold
+        d.gn_sums, d.gn_eps, d.gn_fold_k1 = _ptr(sums), eps, _ptr(k1)
+    elif gn is not None:
         sums, gamma, beta, eps = gn
         d.gn_sums, d.gn_gamma, d.gn_beta, d.gn_eps = _ptr(sums), _ptr(gamma), _ptr(beta), eps
     d.table, d.has_gate = _ptr(table), int(has_gate)
@@ -292,6 +296,38 @@ def conv_desc(src0, weight, out, *, src1=None, src0_bstride=None, src1_bstride=N
     d.engine = engine
     d.dil, d.k_order = dil, k_order
     return d
+
+
+FOLD_GN = True              # set False to run GN -> fc1|fc_v with the in-place prologue (bf16-rounded GN(x) operand; debug / A-B)
+
+
+def gn_fold_ok(x, O, O_split):
+    """Can the GN -> fc1|fc_v projection of this activation run in the folded form (include/vrcoc.h, gn_fold_k1)?"""
+    B, C, H, W = x.shape
+    return FOLD_GN and x.dtype == torch.bfloat16 and bool(lib.vrcoc_gn_fold_supported(B, C, O, O_split, H * W))
+
+
+def fold_gn_weights(w_feat, b_feat, w_value, b_value, gamma, beta):
+    """GroupNorm(1,C) folded into the concatenated fc1 | fc_v projection (reference vr_coc.py:156-157 after :265):
+
+        W.GN(x) + b = rstd * ((W diag(gamma)) . x) - rstd * mean * k1 + k0,   k1 = (W diag(gamma)) . 1,  k0 = b + W . beta
+
+    so the tensor core contracts the RAW bf16 activations and nothing is rounded before the similarity: W diag(gamma) is
+    split into two bf16 terms hi + lo (error 2^-17).  Rounding GN(x) itself to bf16 — the only alternative for a bf16
+    operand — flips ~0.05 % of the arg-max assignments and moves the Cluster output by ~2e-2.
+    Returns (w_fold [2ED][2C] bf16, k0 [2ED] fp32, k1 [2ED] fp32).  The fc_v rows carry a lo half only when the feat | value
+    boundary is not on a 128-row tile boundary (neck: ED = 96), where every tile contracts both halves; otherwise `value`
+    (stored as bf16 anyway) is computed from the hi half alone and its lo half is zero."""
+    w = torch.cat([w_feat, w_value], 0).float().reshape(w_feat.shape[0] + w_value.shape[0], -1)      # [2ED][C], bf16-exact values
+    wg = w * gamma.float()[None, :]
+    hi = wg.to(torch.bfloat16)
+    lo = (wg - hi.float()).to(torch.bfloat16)
+    ED = w_feat.shape[0]
+    if ED % 128 == 0:
+        lo[ED:] = 0                                   # value rows contract the hi half only (their tiles stop after C)
+    k1 = (hi.double() + lo.double()).sum(1).float()
+    k0 = (torch.cat([b_feat, b_value], 0).double() + (w.double() * beta.double()[None, :]).sum(1)).float()
+    return torch.cat([hi, lo], 1).contiguous(), k0.contiguous(), k1.contiguous()
 
 
 def tap_major(weight):
@@ -449,7 +485,13 @@ class GNProjFn(torch.autograd.Function):
             out = torch.empty(B, O, H, W, device=x.device, dtype=x.dtype)
             out2 = None
         gn = None if sums is None else (sums, g32, b32, eps)
-        d = conv_desc(x, w2, out, gn=gn, e_shift=bias32, act=act, out2=out2)
+        if gn is not None and out2 is not None and act == ACT_NONE and w2.dtype == torch.bfloat16 and gn_fold_ok(x, O, split_fp32):
+            # fc1 | fc_v after norm1: GroupNorm folded into split-bf16 weights, `feat` exact to 2^-17 (see fold_gn_weights)
+            bz = bias32 if bias32 is not None else torch.zeros(O, device=x.device)
+            w_fold, k0, k1 = fold_gn_weights(w2[:split_fp32], bz[:split_fp32], w2[split_fp32:], bz[split_fp32:], g32, b32)
+            d = conv_desc(x, w_fold, out, gn_fold=(sums, k1, eps), e_shift=k0, out2=out2)
+        else:
+            d = conv_desc(x, w2, out, gn=gn, e_shift=bias32, act=act, out2=out2)
         conv_fwd(d)
         if any(ctx.needs_input_grad):
             ctx.save_for_backward(x, sums, g32, b32, w2, bias32)

@@ -110,9 +110,20 @@ typedef struct vrcoc_conv_desc {
   int32_t dil;     /* dilation (0 or 1 = dense); ASPP branches use 6/12/18 (neck/coc_fpn_dual.py:55-67) */
   int32_t k_order; /* 0: weight[o][c][ky][kx] (PyTorch); 1: weight[o][ky][kx][c] (tap-major: the im2col rows of one k slab
                       are consecutive channels of one tap -> cheap gathers on the tcgen05 path) */
+  /* GroupNorm(1,C0) FOLDED into a 1x1 projection (bf16 tcgen05 path; Cluster.fc1|fc_v after norm1, vr_coc.py:156-157,265):
+   *   W.GN(x) + b  =  rstd_b * ((W diag(gamma)) . x)  -  rstd_b * mean_b * k1[o]  +  k0[o]
+   * so the tensor core consumes the RAW activations and the per-sample statistics enter in the epilogue only.  When
+   * gn_fold_k1 != NULL: weight is [O][2*C0] bf16 = [hi | lo], the two-term bf16 split of W diag(gamma) (rows >= O_split use
+   * the hi half only); e_shift = k0[o] = b[o] + sum_c W[o,c] beta[c]; gn_fold_k1[o] = sum_c (hi + lo)[o,c]; gn_sums gives
+   * the statistics; gn_gamma / gn_beta / e_scale must be NULL.  The split keeps the similarity operand `feat` exact to
+   * ~2^-17: rounding GN(x) itself to bf16 flips ~0.05 % of the hard assignments and moves the Cluster output by ~2e-2. */
+  const float* gn_fold_k1;
 } vrcoc_conv_desc;
 
 int vrcoc_conv_fwd(const vrcoc_conv_desc* d, void* stream);
+/* 1 when the folded-GroupNorm form of a bf16 1x1 projection (gn_fold_k1 above) is available for [B][C][P] -> O channels
+ * (first O_split of them fp32 `feat`); the host side asks before it builds the [hi | lo] weights. */
+int vrcoc_gn_fold_supported(int B, int C, int O, int O_split, int P);
 
 /* Backward helpers of the 1x1 projections (training path of vr_coc.py:156-157,191,217-223).
  *   wgrad: dW[o][k] (+)= sum_{b,p} dy[b,o,p] * z[b,k,p],  db[o] (+)= sum dy      (z = prologue(src), as in fwd)

@@ -148,3 +148,40 @@ def test_fusion_train_mode_bf16_vs_oracle(V, C, H):
     for k, v in up1.items():
         if k.endswith("running_mean") or k.endswith("running_var"):
             assert rel_err(ier.state_dict()[k].float(), v) < BF16_TOL, k
+
+
+@pytest.mark.parametrize("cid", list(LIVE))
+def test_folded_groupnorm_projection_keeps_feat_exact(V, cid):
+    """GN -> fc1|fc_v in the folded form (include/vrcoc.h gn_fold_k1): `feat` (the similarity operand) must match the fp64
+    evaluation of W.GN(x)+b on the bf16-rounded weights/inputs to ~1e-5 (it decides the hard assignments), `value` to bf16
+    rounding.  Rows the planner does not cover fall back to the in-place GroupNorm prologue (reported, not failed)."""
+    from vrcoc import ops
+    C, H, fold, heads, hd, r = LIVE[cid]
+    ED = heads * hd
+    B = 2
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(B, C, H, H, generator=g) * 1.7 + 0.6).to(torch.bfloat16)            # non-zero mean: exercises the -rstd*mu*k1 term
+    w1 = (torch.randn(ED, C, generator=g) / C ** 0.5).to(torch.bfloat16)
+    wv = (torch.randn(ED, C, generator=g) / C ** 0.5).to(torch.bfloat16)
+    b1, bv = torch.randn(ED, generator=g) * 0.1, torch.randn(ED, generator=g) * 0.1
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    xd = x.double()
+    mu = xd.mean(dim=(1, 2, 3), keepdim=True)
+    var = xd.var(dim=(1, 2, 3), unbiased=False, keepdim=True)
+    xh = (xd - mu) / torch.sqrt(var + 1e-5) * gamma.double().view(1, -1, 1, 1) + beta.double().view(1, -1, 1, 1)
+    feat_ref = torch.einsum("oc,bchw->bohw", w1.double(), xh) + b1.double().view(1, -1, 1, 1)
+    val_ref = torch.einsum("oc,bchw->bohw", wv.double(), xh) + bv.double().view(1, -1, 1, 1)
+    xc = x.cuda()
+    ok = ops.gn_fold_ok(xc, 2 * ED, ED)
+    print(cid, "folded GroupNorm projection supported:", ok)
+    if not ok:
+        assert cid in ("N4",), f"{cid}: the folded projection should cover this row"
+        return
+    sums = ops.channel_sums(xc, want_chan=False, want_sample=True)[1]
+    w_fold, k0, k1 = ops.fold_gn_weights(w1.cuda(), b1.cuda(), wv.cuda(), bv.cuda(), gamma.cuda(), beta.cuda())
+    feat = torch.empty(B, ED, H, H, device="cuda", dtype=torch.float32)
+    value = torch.empty(B, ED, H, H, device="cuda", dtype=torch.bfloat16)
+    ops.conv_fwd(ops.conv_desc(xc, w_fold, feat, gn_fold=(sums, k1, 1e-5), e_shift=k0, out2=value))
+    e_f, e_v = rel_err(feat, feat_ref), rel_err(value.float(), val_ref)
+    print(f"{cid}: feat {e_f:.2e}  value {e_v:.2e}")
+    assert e_f < 2e-5 and e_v < 6e-3
