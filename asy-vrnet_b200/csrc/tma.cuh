@@ -84,19 +84,25 @@ static inline EncodeTiledFn tma_encode_fn() {
   return fn;
 }
 
-// dims / box innermost first; strides_bytes for dims 1..rank-1
-static inline int tma_encode(CUtensorMap* tm, int dtype, const void* base, int rank, const cuuint64_t* dims,
-                             const cuuint64_t* strides_bytes, const cuuint32_t* box, bool swizzle128) {
+// dims / box innermost first; strides_bytes for dims 1..rank-1; swizzle_bytes in {0, 32, 64, 128}
+static inline int tma_encode_sw(CUtensorMap* tm, int dtype, const void* base, int rank, const cuuint64_t* dims,
+                                const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle_bytes) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   memset(tm, 0, sizeof(*tm));
   EncodeTiledFn fn = tma_encode_fn();
   if (!fn) return fail(VRCOC_ECUDA, "cuTensorMapEncodeTiled is not available");
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = fn(tm, dtype == VRCOC_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
-                  const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  const_cast<void*>(base), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(VRCOC_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return VRCOC_OK;
+}
+static inline int tma_encode(CUtensorMap* tm, int dtype, const void* base, int rank, const cuuint64_t* dims,
+                             const cuuint64_t* strides_bytes, const cuuint32_t* box, bool swizzle128) {
+  return tma_encode_sw(tm, dtype, base, rank, dims, strides_bytes, box, swizzle128 ? 128 : 0);
 }
 
 static inline int sm_count() {

@@ -199,9 +199,20 @@ class ClusterBlock(nn.Module):
         ls2 = f32(self.layer_scale_2) if self.use_layer_scale else None
         dev, dt = x.device, x.dtype
         sums0 = ops.sample_sums_of(x)
+        pw, ph = tm._proposal()
+        fold_w = None
         if ops.gn_fold_ok(x, 2 * ED, ED) and tm.fc1.weight.dtype == dt:
-            w_fold, k0, k1 = ops.cached(self, "w_fold", [tm.fc1.weight, tm.fc1.bias, tm.fc_v.weight, tm.fc_v.bias, n1.weight, n1.bias],
-                                        lambda: ops.fold_gn_weights(tm.fc1.weight, tm.fc1.bias, tm.fc_v.weight, tm.fc_v.bias, n1.weight, n1.bias))
+            fold_w = ops.cached(self, "w_fold", [tm.fc1.weight, tm.fc1.bias, tm.fc_v.weight, tm.fc_v.bias, n1.weight, n1.bias],
+                                lambda: ops.fold_gn_weights(tm.fc1.weight, tm.fc1.bias, tm.fc_v.weight, tm.fc_v.bias, n1.weight, n1.bias))
+        x1 = None
+        if fold_w is not None and tm.fc2.weight.dtype == dt and ops.token_mixer_fused_ok(x, tm.heads, tm.head_dim, tm.fold_w, tm.fold_h, pw, ph):
+            # stages 1 and 2: the whole token-mixer half in one persistent kernel (feat / value / core output stay on chip)
+            sums = ops.new_sample_sums(B, dev, n=2)
+            x1, _, _ = ops.token_mixer_fused_fwd(x, sums0, n1.eps, fold_w[0], fold_w[1], fold_w[2], f32(tm.sim_alpha), f32(tm.sim_beta),
+                                                 tm.fc2.weight.detach().reshape(C, ED), f32(tm.fc2.bias), ls1, sums[0],
+                                                 tm.heads, tm.head_dim, tm.fold_w, tm.fold_h)
+        elif fold_w is not None:
+            w_fold, k0, k1 = fold_w
             feat = torch.empty(B, ED, H, W, device=dev, dtype=torch.float32)
             value = torch.empty(B, ED, H, W, device=dev, dtype=dt)
             ops.conv_fwd(ops.conv_desc(x, w_fold, feat, gn_fold=(sums0, k1, n1.eps), e_shift=k0, out2=value))
@@ -213,13 +224,13 @@ class ClusterBlock(nn.Module):
             feat = torch.empty(B, ED, H, W, device=dev, dtype=torch.float32)
             value = torch.empty(B, ED, H, W, device=dev, dtype=dt)
             ops.conv_fwd(ops.conv_desc(x, w_in, feat, gn=(sums0, f32(n1.weight), f32(n1.bias), n1.eps), e_shift=b_in, out2=value))
-        pw, ph = tm._proposal()
-        o, _, _ = ops.cluster_core_fwd(feat, value, f32(tm.sim_alpha), f32(tm.sim_beta), tm.heads, tm.fold_w, tm.fold_h, pw, ph,
-                                       out_dtype=dt)
-        sums = ops.new_sample_sums(B, dev, n=2)
-        x1 = torch.empty_like(x)
-        ops.conv_fwd(ops.conv_desc(o, tm.fc2.weight.detach().reshape(C, ED), x1, e_shift=f32(tm.fc2.bias), post_scale=ls1, res=x,
-                                   out_sample_sums=sums[0]))
+        if x1 is None:
+            o, _, _ = ops.cluster_core_fwd(feat, value, f32(tm.sim_alpha), f32(tm.sim_beta), tm.heads, tm.fold_w, tm.fold_h, pw, ph,
+                                           out_dtype=dt)
+            sums = ops.new_sample_sums(B, dev, n=2)
+            x1 = torch.empty_like(x)
+            ops.conv_fwd(ops.conv_desc(o, tm.fc2.weight.detach().reshape(C, ED), x1, e_shift=f32(tm.fc2.bias), post_scale=ls1, res=x,
+                                       out_sample_sums=sums[0]))
         hid = mlp.fc1.weight.shape[0]
         if ops.mlp_fused_ok(x1, hid) and mlp.fc1.weight.dtype == dt and mlp.fc2.weight.dtype == dt:
             # both large stages: the hidden activation (8 x C channels) stays on chip

@@ -84,6 +84,28 @@ def mlp_fused_fwd(x, sums, gamma, beta, eps, w1, b1, w2, b2, ls, out_sums):
     return out
 
 
+FUSED_TOKEN_MIXER = True     # set False to run the token-mixer half as three launches (debug / A-B)
+
+
+def token_mixer_fused_ok(x, heads, head_dim, fold_w, fold_h, pw, ph):
+    B, C, H, W = x.shape
+    return FUSED_TOKEN_MIXER and x.dtype == torch.bfloat16 and \
+        bool(lib.vrcoc_token_mixer_supported(BF16, C, H, W, heads, head_dim, fold_w, fold_h, pw, ph))
+
+
+def token_mixer_fused_fwd(x, sums, eps, w_fold, k0, k1, alpha, beta, w2, b2, ls, out_sums, heads, head_dim, fold_w, fold_h, save_aux=False):
+    """out = x + ls * (W2 . cluster_core(fc1(GN(x)), fc_v(GN(x))) + b2) in one launch (csrc/token_mixer_fused.cu;
+    reference vr_coc.py:155-192 inside :264-267).  Returns (out, idx, sim_max)."""
+    B, C, H, W = x.shape
+    out = torch.empty_like(x)
+    idx = torch.empty(B, heads, H, W, device=x.device, dtype=torch.uint8) if save_aux else None
+    smax = torch.empty(B, heads, H, W, device=x.device, dtype=torch.float32) if save_aux else None
+    check(lib.vrcoc_token_mixer_fwd(_ptr(x), _ptr(sums), float(eps), _ptr(w_fold), _ptr(k0), _ptr(k1), _ptr(alpha), _ptr(beta), _ptr(w2),
+                                    _ptr(b2), _ptr(ls), _ptr(out), _ptr(out_sums), _ptr(idx), _ptr(smax), B, C, H, W, heads, head_dim,
+                                    fold_w, fold_h, _stream()), "token_mixer_fwd")
+    return out, idx, smax
+
+
 class Fork:
     """f() on side stream number `lane` (>= 1) of the current device, ordered after everything already queued on the
     current stream; join() orders the current stream after it and returns f's result.  Same liveness rule as run_pair: the

@@ -218,6 +218,22 @@ int vrcoc_mlp_fused_fwd(const void* x, const double* gn_sums, const float* gamma
                         const float* b1, const void* w2, const float* b2, const float* layer_scale, void* out,
                         double* out_sample_sums, int B, int C, int hidden, int P, void* stream);
 
+/* Fused token-mixer half of a ClusterBlock (reference vr_coc.py:155-192 Cluster.forward inside :264-267), inference, bf16:
+ *   out = x + layer_scale * ( W2 . cluster_core( fc1(GN(x)), fc_v(GN(x)) ) + b2 )
+ * in ONE persistent kernel (csrc/token_mixer_fused.cu): one CTA per 16x16 region, feat / value / core output never leave the
+ * SM.  GroupNorm is folded into the projection weights exactly as for vrcoc_conv_fwd with gn_fold_k1: w_fold [2*E*D][2*C]
+ * bf16 = [hi | lo], k0 / k1 [2*E*D] fp32.  x, out [B][C][H][W] bf16; w2 [C][E*D] bf16; b2, layer_scale (nullable = 1) fp32;
+ * gn_sums = slot sums of x; out_sample_sums (nullable, caller zeroes) receives the slot sums of out; idx (uint8 [B][E][H][W])
+ * and sim_max (float [B][E][H][W]) are optional outputs as in vrcoc_cluster_core_fwd.  Covered: C in {64, 128}, 4 heads x 32,
+ * 16x16 regions (H / fold_w = W / fold_h = 16), 2x2 proposals = stages 1 and 2 of the backbone; vrcoc_token_mixer_supported
+ * tells; everything else runs the three-launch path. */
+int vrcoc_token_mixer_supported(int dtype, int C, int H, int W, int heads, int head_dim, int fold_w, int fold_h, int proposal_w,
+                                int proposal_h);
+int vrcoc_token_mixer_fwd(const void* x, const double* gn_sums, float gn_eps, const void* w_fold, const float* k0, const float* k1,
+                          const float* alpha, const float* beta, const void* w2, const float* b2, const float* layer_scale, void* out,
+                          double* out_sample_sums, uint8_t* idx, float* sim_max, int B, int C, int H, int W, int heads, int head_dim,
+                          int fold_w, int fold_h, void* stream);
+
 /* Debug / A-B switch: on = 0 routes 1x1 projections to the point-major tcgen05 kernels instead of the channel-major one
  * (conv_tc_cm.cuh); results are identical up to fp32 summation order.  Default 1. */
 int vrcoc_debug_set_cm(int on);
