@@ -1020,7 +1020,7 @@ static bool cm_plan(const ConvArgs& a, CmPlan& best) {
   const bool tma_x3 = prologue && a.src0_dtype == VRCOC_BF16 && (reinterpret_cast<uintptr_t>(a.src0) & 15) == 0 &&
                       (a.src0_bstride % 8) == 0 && nslabs <= TQ_MAX_SLABS3;
   if (two_src && !tma_x3) return false;
-  for (int cand = 0; cand < (tma_x ? (fold ? 5 : 10) : 5); ++cand) {
+  for (int cand = 0; cand < (tma_x ? 10 : 5); ++cand) {
     const int bufs = 1;       // a second staging buffer was measured: no gain (the bulk-store drain is not on the critical path)
     const int mode = tma_x ? modes[cand] : (tma_x3 ? 3 : 2), st = depth[cand];
     const int x_bytes = mode == 0 ? st * TQ_X_BYTES : nx * TQ_X_BYTES;

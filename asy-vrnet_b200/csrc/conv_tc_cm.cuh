@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
   const int ST = L.stages;
   // folded GroupNorm: the weight rows are [hi | lo]; a feat tile (rows < O_split) contracts both halves against the same nkx
   // raw X slabs, a value tile only the hi half
-  const bool fold = XMODE == 1 && a.gn_fold_k1 != nullptr;
+  const bool fold = XMODE <= 1 && a.gn_fold_k1 != nullptr;        // X resident (1) or streamed with the weights (0: large C)
   // (when the feat | value boundary is not on a tile boundary every tile contracts both halves: the caller then supplies a lo half
   // for the value rows as well)
   const bool value_hi_only = (a.O_split % TQ_MT) == 0;
@@ -385,9 +385,10 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
     mbar_expect_tx(&bar_full[s], (uint32_t)(TQ_W_BYTES + (need_x ? TQ_X_BYTES : 0)));
     tma_load_2d(sW + s * TQ_W_BYTES, &tmapW, kc * TC_BK, o_begin + j * TQ_MT, &bar_full[s]);
     if (need_x) {
+      const int kx = (fold && kc >= nkx) ? kc - nkx : kc;               // the lo half of the fold contracts the same x slabs again
       unsigned char* dst = sX + (XMODE == 0 ? s : kc) * TQ_X_BYTES;
-      tma_load_3d(dst, &tmapX, p0, kc * TC_BK, b, &bar_full[s]);
-      tma_load_3d(dst + TC_A_LBO, &tmapX, p0 + 64, kc * TC_BK, b, &bar_full[s]);
+      tma_load_3d(dst, &tmapX, p0, kx * TC_BK, b, &bar_full[s]);
+      tma_load_3d(dst + TC_A_LBO, &tmapX, p0 + 64, kx * TC_BK, b, &bar_full[s]);
     }
   };
   const int early_steps = total_steps < ST ? total_steps : ST;       // need no free-slot wait
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
           mbar_wait(&bar_full[s], ph);
           if (XMODE == 3 && j == 0) mbar_wait(&x_ready[kc], 0);
           tc_fence_after();
-          const int kx = (XMODE == 1 && kc >= nkx) ? kc - nkx : kc;       // X slab (the lo half of the fold re-reads the slabs)
+          const int kx = (fold && kc >= nkx) ? kc - nkx : kc;             // X slab (the lo half of the fold re-reads the slabs)
           const int ksteps = (min(TC_BK, a.K - kx * TC_BK) + 15) >> 4;
           const uint32_t w_addr = smem_u32(sW + s * TQ_W_BYTES);
           const uint32_t x_addr = smem_u32(sX + (XMODE == 0 ? s : kx) * TQ_X_BYTES);

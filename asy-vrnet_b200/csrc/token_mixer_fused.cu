@@ -17,13 +17,14 @@
 //          TMEM: feat = columns 0-255 (lane = channel e*32+d), value = columns 256-511.
 //   core   16 warps; warp (e, j) = head e (its TMEM lane quarter), points 64j..64j+63 (region rows 4j..4j+3):
 //            pass 1  quadrant sums of feat straight from TMEM registers (lane = channel) -> centres, normalised per warp;
-//            pass 2  32-point chunks of feat transposed through a 4 KB swizzled scratch: a lane owns 2 points x 16 channels,
-//                    FFMA2 streams for |f|^2 and the 4 centre dot products, one shuffle step, arg-max, sigmoid gate ->
-//                    one-hot weights w[n][m] in smem, member counts;
-//            pass 3  value from TMEM (lane = channel): A[m] += w[n][m] * v[n] with broadcast weight reads, quadrant sums;
+//            pass 2  32-point chunks of feat transposed through a 4 KB swizzled scratch: a lane then owns 4 channels x 8 points with
+//                    its centres in registers (no broadcast loads), FFMA2 streams for |f|^2 and the 4 centre dot products, a
+//                    transpose-reduce over 8 lanes leaves lane L with point L: arg-max, sigmoid gate -> (gate | centre) word;
+//            pass 3  value from TMEM (lane = channel): A[k_n] += g_n * v[n] with one 16-byte broadcast read per 4 points;
 //                    partials of the four warps of a head combined through smem;
-//            pass 4  o[n] = sum_m w[n][m] * a[m], rounded to bf16 and written as the MN-major SW128 B operand of GEMM 2
-//                    (the 4 KB chunk a warp writes is the one its scratch lived in).
+//            pass 4  lane = point: o[n][:] = g_n * a[k_n][:], rounded to bf16 and written as the K-major SW128 B operand of GEMM 2
+//                    (row = point; the first version kept lane = channel everywhere and was bound by the shared-memory pipe:
+//                    broadcast LDS.128 of one-hot weights, 4 cycles per point and warp, 12.5 us per region).
 //   GEMM 2 tcgen05  D2[C][256] = W2[C][128] . o   into the dead feat columns.
 //   epilogue        + b2, * ls1, + x (from the tile), statistics for the next GroupNorm, bf16, in place; one TMA store.
 //
@@ -39,7 +40,9 @@ namespace {
 
 constexpr int TM_E = 4, TM_D = 32, TM_ED = 128, TM_RS = 16, TM_N = 256;
 constexpr int TM_CWARPS = 16;
-constexpr int TM_THREADS = (TM_CWARPS + 1) * 32;
+constexpr int TM_THREADS = (TM_CWARPS + 4) * 32;                     // + one warpgroup: warp 16 = TMA / MMA issue, warps 17-19 idle
+constexpr int TM_REGS_COMPUTE = 104, TM_REGS_AUX = 56;               // setmaxnreg re-divides the CTA's OWN launch pool (640 x 96 = 61440 registers):
+                                                                     // 16*32*104 + 4*32*56 = 60416 fits (120 would dead-lock the last warpgroup; at 24 the MMA-issuing thread spills and crawls)
 constexpr float TM_EPS = 1e-12f;
 
 // ---- tcgen05 / packed-math helpers (same encodings as conv_tc.cu) ---------------------------------------------------------------
@@ -56,6 +59,12 @@ __device__ __forceinline__ uint32_t tm_desc_lo(uint32_t saddr, uint32_t lbo_byte
 }
 // D[128 x 256] (+)= A[128 x 16] (K-major, SW128) . B[16 x 256] (MN-major): kind::f16, bf16 operands, fp32 accumulate
 constexpr uint32_t TM_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(TM_N >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t TM_IDESC_KK = TM_IDESC & ~(1u << 16);             // the same with a K-major B operand (GEMM 2: rows = points)
+// aggregation GEMM (pass 3): D[128 x 48] = V[128 x 256 points] (bf16 in TMEM) . WB[256 points x 48] (K-major smem)
+constexpr int TM_NW = 48;                                            // 16 (gate hi) + 16 (gate lo) + 4 quadrant means + 12 zero rows
+constexpr uint32_t TM_IDESC_AGG = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TM_NW >> 3) << 17) | ((128u >> 4) << 24);
+constexpr int TM_WB_SLAB = TM_NW * 128;                              // bytes of one 64-point k-slab of WB
+template <uint32_t IDESC = TM_IDESC>
 __device__ __forceinline__ void tm_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -65,9 +74,44 @@ __device__ __forceinline__ void tm_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t 
       "mov.b64 da, {%1, %2};\n\t"
       "mov.b64 db, {%3, %4};\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-      "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(TM_IDESC), "r"(accumulate)
+      "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(IDESC), "r"(accumulate)
       : "memory");
 }
+// D[128 x N] (+)= A[128 x 16] (bf16 pairs in TMEM, lane = row, 8 columns) . B[16 x N] (smem, K-major SW128): pass 3 on the tensor core
+__device__ __forceinline__ void tm_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "}" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tm_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+      "%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+      "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tm_ld4_issue(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+// the destination registers of the split loads are only defined after the wait: they are in/out operands of it so that the
+// compiler orders every use after it
+__device__ __forceinline__ void tm_ld_wait12(uint32_t (&a)[4], uint32_t (&b)[4], uint32_t (&c)[4]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(c[0]), "+r"(c[1]),
+                 "+r"(c[2]), "+r"(c[3])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory"); }
 __device__ __forceinline__ void tm_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,"
@@ -132,6 +176,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// debug trace (vrcoc_debug_set_tm_trace): per CTA and region iteration 16 u64 %globaltimer stamps
+//   producer: 0 x+W1 landed, 1 GEMM 1 issued, 2 GEMM 1 done, 3 o ready seen, 4 GEMM 2 done, 5 epilogue done seen, 6 store issued
+//   warp 0:   8 GEMM 1 seen, 9 pass 1, 10 pass 2, 11 pass 3, 12 pass 4, 13 GEMM 2 seen, 14 epilogue written
+__device__ unsigned long long* g_tm_trace = nullptr;
+constexpr int TM_TRACE_ITERS = 4;
+__device__ __forceinline__ unsigned long long tm_time() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void tm_trace(unsigned long long* tr, int it, int slot) {
+  if (tr && it < TM_TRACE_ITERS) tr[((size_t)blockIdx.x * TM_TRACE_ITERS + it) * 16 + slot] = tm_time();
+}
+
 struct TmArgs {
   const double* gn_sums; float gn_eps;          // per-sample slot sums of x (GroupNorm 1)
   const float* k0; const float* k1;             // [2*ED] folded GroupNorm constants (ops.fold_gn_weights)
@@ -149,12 +207,12 @@ template <int C> struct TmSmem {
   static constexpr int off_x = 0;
   static constexpr int off_o = off_x + NXB * XB;                       // 64 KB: W1 (feat hi|lo [, value hi]) / scratch / o operand
   static constexpr int off_d = off_o + 65536;                          // 32 KB: W2 (C = 128: value hi of W1 before it)
-  static constexpr int off_wq = off_d + 32768;                         // [E][128 point pairs][4 centres][2] fp32
-  static constexpr int off_cd = off_wq + 16384;                        // [16 warps][32 d][4 centres][2] fp32 normalised centres (dup)
-  static constexpr int off_p1 = off_cd + 16384;                        // [E][4 j][2][32] feat quadrant partial sums
-  static constexpr int off_p3 = off_p1 + 4096;                         // [E][4 j][4 m][32] aggregation partials
-  static constexpr int off_pq = off_p3 + 8192;                         // [E][4 j][2][32] value quadrant partial sums
-  static constexpr int off_cnt = off_pq + 4096;                        // [E][4 j][4] member counts
+  static constexpr int off_wq = off_d + 32768;                         // [E][256 points] u32: (gate bits & ~3) | centre index
+  static constexpr int off_cd = off_wq + 4096;                         // [16 warps][4 centres][36] fp32 centre aggregates a[m][d]
+  static constexpr int off_p1 = off_cd + 16 * 4 * 36 * 4;              // [E][4 j][2][32] feat quadrant partial sums
+  static constexpr int off_wb = off_p1 + 4096;                         // [4 k-slabs][48 rows][128 B] bf16: B operand of the aggregation GEMM
+  static constexpr int off_stat = off_wb + 4 * TM_WB_SLAB;             // [256 samples] float2 (mean, rstd) of GroupNorm 1
+  static constexpr int off_cnt = off_stat + 2048;                      // [E][4 j][4] member counts
   static constexpr int off_bar = off_cnt + 256;
   static constexpr int total = off_bar + 256 + 1024;                   // + alignment slack
   static constexpr bool W2_RESIDENT = C == 64;                         // C = 128: region d holds value-W1 until GEMM 1 is done
@@ -174,10 +232,8 @@ token_mixer_fused_kernel(TmArgs A, const __grid_constant__ CUtensorMap tmX, cons
   unsigned char* sX = smem + S::off_x;
   unsigned char* sO = smem + S::off_o;
   unsigned char* sD = smem + S::off_d;
-  float* wq = reinterpret_cast<float*>(smem + S::off_wq);
   float* part1 = reinterpret_cast<float*>(smem + S::off_p1);
-  float* part3 = reinterpret_cast<float*>(smem + S::off_p3);
-  float* partq = reinterpret_cast<float*>(smem + S::off_pq);
+  float2* stat = reinterpret_cast<float2*>(smem + S::off_stat);
   int* cntp = reinterpret_cast<int*>(smem + S::off_cnt);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::off_bar);
   uint64_t* x_full = bars;              // [2]
@@ -187,11 +243,17 @@ token_mixer_fused_kernel(TmArgs A, const __grid_constant__ CUtensorMap tmX, cons
   uint64_t* o_ready = bars + 5;
   uint64_t* acc2_full = bars + 6;
   uint64_t* epi_done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* va_ready = bars + 8;
+  uint64_t* accA_full = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned long long* const tr = (tid == 0 || tid == TM_CWARPS * 32) ? g_tm_trace : nullptr;
+  if (tid == 0) tm_trace(tr, 0, 15);                                   // kernel entry
   const int regions_per_sample = A.F1 * A.F2;
-  const int n_mine = ((int)blockIdx.x < A.regions) ? (A.regions - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // a CTA owns a contiguous range of regions (mostly one sample: statistics look-ups and flushes stay rare, neighbours share L2 lines)
+  const int rg_begin = (int)(((long long)blockIdx.x * A.regions) / gridDim.x);
+  const int n_mine = (int)(((long long)(blockIdx.x + 1) * A.regions) / gridDim.x) - rg_begin;
 
   if (warp == TM_CWARPS) {
     if (lane == 0) {
@@ -199,12 +261,40 @@ token_mixer_fused_kernel(TmArgs A, const __grid_constant__ CUtensorMap tmX, cons
       mbar_init(w1_full, 1); mbar_init(w2_full, 1);
       mbar_init(acc1_full, 1); mbar_init(acc2_full, 1);
       mbar_init(o_ready, TM_CWARPS); mbar_init(epi_done, TM_CWARPS);
+      mbar_init(va_ready, TM_CWARPS); mbar_init(accA_full, 1);
       mbar_fence_init();
       tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmOut); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2);
     }
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (warp < TM_CWARPS) {
+    // per-sample GroupNorm statistics, once (fp64 reduction of the slot sums: 16 warps, sample b = warp, warp + 16, ...)
+    for (int b = warp; b < A.B; b += TM_CWARPS) {
+      float mu, rstd;
+      gn_mean_rstd(A.gn_sums, b, (double)C * (double)A.H * (double)A.W, A.gn_eps, mu, rstd);
+      if (lane == 0) stat[b] = make_float2(mu, rstd);
+    }
+    // constant rows of WB: 32 + m = quadrant-mean weights (1/64 on the 64 points of quadrant m), 36..47 = 0.  One 16-byte chunk
+    // (8 points of one row of one slab) per thread: 4 slabs x 16 rows x 8 chunks = 512.
+    {
+      const int slab = tid >> 7, r = 32 + ((tid >> 3) & 15), c = tid & 7;
+      uint32_t w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int n = slab * 64 + c * 8 + 2 * i + hf;
+          const int qd = 2 * ((n >> 4) >= 8) + ((n & 15) >= 8);
+          if (r < 36 && qd == r - 32) v |= 0x3C80u << (16 * hf);            // bf16(1/64)
+        }
+        w[i] = v;
+      }
+      sts128(smem_u32(smem + S::off_wb) + (uint32_t)(slab * TM_WB_SLAB + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)), w[0], w[1], w[2], w[3]);
+    }
+    fence_async_smem();
   }
   tm_fence_before();
   __syncthreads();
@@ -219,12 +309,13 @@ token_mixer_fused_kernel(TmArgs A, const __grid_constant__ CUtensorMap tmX, cons
     col0 = (q % A.F2) * TM_RS;
   };
 
-  if (warp == TM_CWARPS) {
+  if (warp >= TM_CWARPS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TM_REGS_AUX));
     // ================================ producer: TMA + MMA issue (one thread) ==================================================
-    if (lane == 0 && n_mine > 0) {
+    if (warp == TM_CWARPS && lane == 0 && n_mine > 0) {
       auto load_x = [&](int it) {
         int b, row0, col0;
-        region_coords((int)blockIdx.x + it * (int)gridDim.x, b, row0, col0);
+        region_coords(rg_begin + it, b, row0, col0);
         const int buf = it % NXB;
         mbar_expect_tx(&x_full[buf], (uint32_t)S::XB);
         tma_load_4d(sX + buf * S::XB, &tmX, col0, 0, row0, b, &x_full[buf]);
@@ -258,6 +349,7 @@ token_mixer_fused_kernel(TmArgs A, const __grid_constant__ CUtensorMap tmX, cons
         mbar_wait(&x_full[buf], xph);
         mbar_wait(w1_full, ph);
         tm_fence_after();
+        tm_trace(tr, it, 0);
         // ---- GEMM 1: feat (hi then lo against the same x slabs) -> columns 0-255, value (hi) -> columns 256-511 ----------------
         {
           const uint32_t x_addr = smem_u32(xt);
@@ -279,33 +371,50 @@ token_mixer_fused_kernel(TmArgs A, const __grid_constant__ CUtensorMap tmX, cons
           }
           tm_commit(acc1_full);
         }
+        tm_trace(tr, it, 1);
         mbar_wait(acc1_full, ph);                                          // W1 consumed: operand region free for the scratch / o
+        tm_trace(tr, it, 2);
         if (!S::W2_RESIDENT) load_w2();
+        // ---- aggregation GEMM (pass 3): [gate-weighted sums | quadrant means] of value, A operand = bf16 value in TMEM -------------
+        mbar_wait(va_ready, ph);
+        tm_fence_after();
+        {
+          const uint32_t wb_addr = smem_u32(smem + S::off_wb);
+#pragma unroll 4
+          for (int ks = 0; ks < 16; ++ks)
+            tm_mma_ts(T_FEAT + 128u, T_FEAT + (uint32_t)(8 * ks), tm_desc_lo(wb_addr + (ks >> 2) * TM_WB_SLAB + (ks & 3) * 32, 16), TM_HI_SW128,
+                      TM_IDESC_AGG, ks > 0 ? 1u : 0u);
+          tm_commit(accA_full);
+        }
         // ---- GEMM 2: D2[C x 256] = W2 . o   into the feat columns ----------------------------------------------------------------
         mbar_wait(o_ready, ph);
         if (!S::W2_RESIDENT || it == 0) { mbar_wait(w2_full, w2_phase); w2_phase ^= 1u; }
         tm_fence_after();
+        tm_trace(tr, it, 3);
         {
           const uint32_t o_addr = smem_u32(sO);
           for (int s = 0; s < 2; ++s) {
             const uint32_t w_addr = smem_u32(sD + s * 16384);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              tm_mma(T_FEAT, tm_desc_lo(w_addr + ks * 32, 16), TM_HI_SW128, tm_desc_lo(o_addr + (s * 4 + ks) * 2048, 16384), TM_HI_SW128,
-                     (s > 0 || ks > 0) ? 1u : 0u);
+              tm_mma<TM_IDESC_KK>(T_FEAT, tm_desc_lo(w_addr + ks * 32, 16), TM_HI_SW128, tm_desc_lo(o_addr + s * 32768 + ks * 32, 16), TM_HI_SW128,
+                                  (s > 0 || ks > 0) ? 1u : 0u);
           }
           tm_commit(acc2_full);
         }
         mbar_wait(acc2_full, ph);                                          // o and W2 consumed
+        tm_trace(tr, it, 4);
         if (it + 1 < n_mine) load_w1();
         // ---- the epilogue has rewritten the x tile in place: store it, then reuse the buffer ------------------------------------
         mbar_wait(epi_done, ph);
+        tm_trace(tr, it, 5);
         {
           int b, row0, col0;
-          region_coords((int)blockIdx.x + it * (int)gridDim.x, b, row0, col0);
+          region_coords(rg_begin + it, b, row0, col0);
           tma_store_4d(&tmOut, xt, col0, 0, row0, b);
           tma_store_commit();
         }
+        tm_trace(tr, it, 6);
         if (it + NXB < n_mine) {
           tma_store_wait_read();                                            // (NXB = 2: this also covers the other buffer's older store)
           load_x(it + NXB);
@@ -315,6 +424,7 @@ token_mixer_fused_kernel(TmArgs A, const __grid_constant__ CUtensorMap tmX, cons
     }
     __syncwarp();
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TM_REGS_COMPUTE));
     // ================================ compute warps ===============================================================================
     const int e = warp & 3, j = warp >> 2;                               // head (TMEM lane quarter), 64-point block
     const int d = lane;
@@ -325,16 +435,18 @@ token_mixer_fused_kernel(TmArgs A, const __grid_constant__ CUtensorMap tmX, cons
     // epilogue role: C = 128: channel 32e + lane, points 64j..+63;  C = 64: channel 32(e&1) + lane, points 64j + 32(e>>1)..+31
     const int oc = C == 128 ? 32 * e + lane : 32 * (e & 1) + lane;
     const float b2 = __ldg(A.b2 + oc), ls = A.ls ? __ldg(A.ls + oc) : 1.f;
-    const uint32_t scratch = smem_u32(sO) + (uint32_t)(j * 16384 + e * 4096);        // == this warp's chunk of the o operand
-    const uint32_t cdw = smem_u32(smem + S::off_cd) + (uint32_t)warp * 1024u;
-    const uint32_t wq_e = smem_u32(wq) + (uint32_t)e * 4096u;
+    const int dq = lane & 3, pg = lane >> 2;                             // pass-2 read mapping: channels 8dq..8dq+7, points 4pg..4pg+3
+    // 4 KB transposition scratch, inside the k-slab of the o operand that this head pair writes later (pass 4)
+    const uint32_t scratch = smem_u32(sO) + (uint32_t)((e >> 1) * 32768 + ((e & 1) * 4 + j) * 4096);
+    const uint32_t wb_base = smem_u32(smem + S::off_wb);
+    float* apriv = reinterpret_cast<float*>(smem + S::off_cd) + warp * (4 * 36);    // this warp's copy of a[m][d]
     float ssum = 0.f, ssq = 0.f;
     int cur_b = -1;
     float mu = 0.f, rstd = 1.f;
     constexpr float inv_q = 1.0f / 64.0f;
 
     for (int it = 0; it < n_mine; ++it) {
-      const int rg = (int)blockIdx.x + it * (int)gridDim.x;
+      const int rg = rg_begin + it;
       int b, row0, col0;
       region_coords(rg, b, row0, col0);
       const uint32_t ph = (uint32_t)it & 1u;
@@ -347,13 +459,15 @@ token_mixer_fused_kernel(TmArgs A, const __grid_constant__ CUtensorMap tmX, cons
           }
           ssum = 0.f; ssq = 0.f;
         }
-        gn_mean_rstd(A.gn_sums, b, (double)C * (double)A.H * (double)A.W, A.gn_eps, mu, rstd);
+        const float2 st = stat[b];
+        mu = st.x; rstd = st.y;
         cur_b = b;
       }
       const float ehf = fmaf(-rstd * mu, k1f, k0f), ehv = fmaf(-rstd * mu, k1v, k0v);   // feat = rstd*acc + ehf, value = rstd*acc + ehv
 
       mbar_wait(acc1_full, ph);
       tm_fence_after();
+      tm_trace(tr, it, 8);
 
       // ---- pass 1: quadrant sums of feat over this warp's 4 region rows (16 columns = one row; cols 0-7 left, 8-15 right) -------
       {
@@ -372,178 +486,230 @@ token_mixer_fused_kernel(TmArgs A, const __grid_constant__ CUtensorMap tmX, cons
         part1[((e * 4 + j) * 2 + 1) * 32 + d] = fmaf(rstd, sr, 32.f * ehf);
       }
       named_bar(1 + e, 128);
+      // normalised centres of THIS LANE's eight channels 8*dq .. 8*dq+7 (pass-2 mapping), kept in registers:
+      // cc[t][m], m = 2*(bottom half) + (right half); rows 0-7 = warps j 0,1
+      float cc[8][4];
       {
-        // centres m = 2*(bottom half) + (right half); rows 0-7 = warps j 0,1
-        float c[4];
-        const float* p = part1 + e * 4 * 2 * 32 + d;
-        c[0] = (p[0 * 64] + p[1 * 64]) * inv_q;
-        c[1] = (p[0 * 64 + 32] + p[1 * 64 + 32]) * inv_q;
-        c[2] = (p[2 * 64] + p[3 * 64]) * inv_q;
-        c[3] = (p[2 * 64 + 32] + p[3 * 64 + 32]) * inv_q;
+        const uint32_t p1 = smem_u32(part1) + (uint32_t)((e * 4 * 2 * 32 + 8 * dq) * 4);
+        float ssm[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {                                   // channels 8dq + 4hf .. + 3
+          float q[4][2][4];                                                // [j][side][channel]
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd) {
+              const uint4 v = lds128(p1 + (uint32_t)(((jj * 2 + sd) * 32 + 4 * hf) * 4));
+              q[jj][sd][0] = __uint_as_float(v.x); q[jj][sd][1] = __uint_as_float(v.y);
+              q[jj][sd][2] = __uint_as_float(v.z); q[jj][sd][3] = __uint_as_float(v.w);
+            }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            cc[4 * hf + t][0] = (q[0][0][t] + q[1][0][t]) * inv_q; cc[4 * hf + t][1] = (q[0][1][t] + q[1][1][t]) * inv_q;
+            cc[4 * hf + t][2] = (q[2][0][t] + q[3][0][t]) * inv_q; cc[4 * hf + t][3] = (q[2][1][t] + q[3][1][t]) * inv_q;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) ssm[m] = fmaf(cc[4 * hf + t][m], cc[4 * hf + t][m], ssm[m]);
+          }
+        }
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          const float ss = warp_sum(c[m] * c[m]);
-          c[m] *= 1.0f / fmaxf(sqrtf(ss), TM_EPS);
+          ssm[m] += __shfl_xor_sync(0xffffffffu, ssm[m], 1);
+          ssm[m] += __shfl_xor_sync(0xffffffffu, ssm[m], 2);
+          const float inv = fminf(rsqrtf(ssm[m]), 1.0f / TM_EPS);         // 1 / max(|c|, eps) to 2 ulp
+#pragma unroll
+          for (int t = 0; t < 8; ++t) cc[t][m] *= inv;
         }
-        sts128(cdw + (uint32_t)d * 32u, __float_as_uint(c[0]), __float_as_uint(c[0]), __float_as_uint(c[1]), __float_as_uint(c[1]));
-        sts128(cdw + (uint32_t)d * 32u + 16u, __float_as_uint(c[2]), __float_as_uint(c[2]), __float_as_uint(c[3]), __float_as_uint(c[3]));
+      }
+      // zero this warp's part of the aggregation GEMM's B operand (rows of head e, its 64 points): pass 2 then only writes the
+      // two non-zero entries of each point
+      {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int u = lane + 32 * i;                                     // 8 rows (4 hi + 4 lo) x 8 chunks of 16 B
+          const int r = (u >> 3) < 4 ? 4 * e + (u >> 3) : 16 + 4 * e + (u >> 3) - 4;
+          sts128(wb_base + (uint32_t)(j * TM_WB_SLAB + (r >> 3) * 1024 + (r & 7) * 128 + (u & 7) * 16), 0u, 0u, 0u, 0u);
+        }
       }
       __syncwarp();
+      tm_trace(tr, it, 9);
 
       // ---- pass 2: similarity / arg-max / gate, 32 points per chunk ----------------------------------------------------------------
+      // The chunk is transposed through the scratch: written lane = channel (TMEM order), read lane = (dq, pg): 4 channels x 8 points,
+      // centres from registers -> no broadcast loads; 40 partial sums are then transpose-reduced over the 8 dq lanes so that lane L
+      // ends up with the complete |f|^2 and 4 dot products of point L of the chunk.
       int cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
+      uint32_t gk[2];                                                      // (gate bits & ~3) | centre of this lane's point, per chunk
       {
-        const int p = lane & 15, h = lane >> 4;
+        const uint32_t swzw = (uint32_t)((((d >> 3) << 1) ^ (d & 7)) & 7);   // conflict-free for both access patterns
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {
           {
             uint32_t r[32];
             tm_ld32(T_FEAT + lane_off + (uint32_t)(64 * j + 32 * q), r);
-            // row d of the scratch: 32 points fp32 = 128 B, 16-byte chunks XOR-swizzled by (d & 7)
 #pragma unroll
             for (int c16 = 0; c16 < 8; ++c16)
-              sts128(scratch + (uint32_t)d * 128u + (uint32_t)(((c16 ^ (d & 7))) << 4),
+              sts128(scratch + (uint32_t)d * 128u + (((uint32_t)c16 ^ swzw) << 4),
                      __float_as_uint(fmaf(rstd, __uint_as_float(r[4 * c16]), ehf)), __float_as_uint(fmaf(rstd, __uint_as_float(r[4 * c16 + 1]), ehf)),
                      __float_as_uint(fmaf(rstd, __uint_as_float(r[4 * c16 + 2]), ehf)), __float_as_uint(fmaf(rstd, __uint_as_float(r[4 * c16 + 3]), ehf)));
           }
           __syncwarp();
-          uint64_t ss = 0ull, d0 = 0ull, d1 = 0ull, d2 = 0ull, d3 = 0ull;
-#pragma unroll 8
-          for (int i = 0; i < 16; ++i) {
-            const int dd = 16 * h + i;
-            const uint2 xr = lds64(scratch + (uint32_t)dd * 128u + (uint32_t)((((p >> 1) ^ (dd & 7)) << 4) + (p & 1) * 8));
-            const uint64_t x = ((uint64_t)xr.y << 32) | xr.x;
-            const uint4 c01 = lds128(cdw + (uint32_t)dd * 32u), c23 = lds128(cdw + (uint32_t)dd * 32u + 16u);
-            ss = fma2(x, x, ss);
-            d0 = fma2(((uint64_t)c01.y << 32) | c01.x, x, d0);
-            d1 = fma2(((uint64_t)c01.w << 32) | c01.z, x, d1);
-            d2 = fma2(((uint64_t)c23.y << 32) | c23.x, x, d2);
-            d3 = fma2(((uint64_t)c23.w << 32) | c23.z, x, d3);
-          }
-          float ssv[2], dv[4][2];
-          upk(ss, ssv[0], ssv[1]);
-          upk(d0, dv[0][0], dv[0][1]); upk(d1, dv[1][0], dv[1][1]); upk(d2, dv[2][0], dv[2][1]); upk(d3, dv[3][0], dv[3][1]);
+          uint64_t acc2[2][5];
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            ssv[t] += __shfl_xor_sync(0xffffffffu, ssv[t], 16);
+          for (int pr = 0; pr < 2; ++pr)
 #pragma unroll
-            for (int m = 0; m < 4; ++m) dv[m][t] += __shfl_xor_sync(0xffffffffu, dv[m][t], 16);
-          }
-          int kb[2];
-          float gv[2];
+            for (int v = 0; v < 5; ++v) acc2[pr][v] = 0ull;
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const float inv = fminf(rsqrtf(ssv[t]), 1.0f / TM_EPS);
-            float tb = alpha * dv[0][t], db = dv[0][t];
-            int k = 0;
-            if (alpha * dv[1][t] > tb) { tb = alpha * dv[1][t]; db = dv[1][t]; k = 1; }
-            if (alpha * dv[2][t] > tb) { tb = alpha * dv[2][t]; db = dv[2][t]; k = 2; }
-            if (alpha * dv[3][t] > tb) { tb = alpha * dv[3][t]; db = dv[3][t]; k = 3; }
-            kb[t] = k;
-            gv[t] = __fdividef(1.0f, 1.0f + __expf(-fmaf(alpha, db * inv, beta)));
-          }
-          // one-hot weights of the point pair: [pair][m][2]; half h stores centres 2h, 2h+1
-          const int pi = (64 * j + 32 * q) / 2 + p;
-          const int m0 = 2 * h;
-          sts128(wq_e + (uint32_t)pi * 32u + (uint32_t)h * 16u, __float_as_uint(kb[0] == m0 ? gv[0] : 0.f), __float_as_uint(kb[1] == m0 ? gv[1] : 0.f),
-                 __float_as_uint(kb[0] == m0 + 1 ? gv[0] : 0.f), __float_as_uint(kb[1] == m0 + 1 ? gv[1] : 0.f));
-          if (h == 0) {
-            if (A.idx_out || A.smax_out) {
-              const int n = 64 * j + 32 * q + 2 * p;
-              const int64_t io = ((int64_t)(b * TM_E + e) * A.H + row0 + (n >> 4)) * A.W + col0 + (n & 15);
-              if (A.idx_out) *reinterpret_cast<uint16_t*>(A.idx_out + io) = (uint16_t)(kb[0] | (kb[1] << 8));
-              if (A.smax_out) *reinterpret_cast<float2*>(A.smax_out + io) = make_float2(gv[0], gv[1]);
+          for (int t = 0; t < 8; ++t) {
+            const int dd = 8 * dq + t;
+            const uint32_t swzr = (uint32_t)(((2 * dq) ^ t) & 7);
+            const uint4 f = lds128(scratch + (uint32_t)dd * 128u + ((((uint32_t)pg) ^ swzr) << 4));     // points 4pg .. 4pg+3 of channel dd
+            const uint64_t x2[2] = {((uint64_t)f.y << 32) | f.x, ((uint64_t)f.w << 32) | f.z};
+            const uint64_t c0 = pk(cc[t][0], cc[t][0]), c1 = pk(cc[t][1], cc[t][1]), c2 = pk(cc[t][2], cc[t][2]), c3 = pk(cc[t][3], cc[t][3]);
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {
+              acc2[pr][0] = fma2(x2[pr], x2[pr], acc2[pr][0]);
+              acc2[pr][1] = fma2(c0, x2[pr], acc2[pr][1]);
+              acc2[pr][2] = fma2(c1, x2[pr], acc2[pr][2]);
+              acc2[pr][3] = fma2(c2, x2[pr], acc2[pr][3]);
+              acc2[pr][4] = fma2(c3, x2[pr], acc2[pr][4]);
             }
           }
-          const unsigned half = 0x0000ffffu;
-          cnt0 += __popc(__ballot_sync(0xffffffffu, kb[0] == 0) & half) + __popc(__ballot_sync(0xffffffffu, kb[1] == 0) & half);
-          cnt1 += __popc(__ballot_sync(0xffffffffu, kb[0] == 1) & half) + __popc(__ballot_sync(0xffffffffu, kb[1] == 1) & half);
-          cnt2 += __popc(__ballot_sync(0xffffffffu, kb[0] == 2) & half) + __popc(__ballot_sync(0xffffffffu, kb[1] == 2) & half);
-          cnt3 += __popc(__ballot_sync(0xffffffffu, kb[0] == 3) & half) + __popc(__ballot_sync(0xffffffffu, kb[1] == 3) & half);
+          // transpose-reduce over the 4 dq lanes: bit 1 halves the 4 points to 2, bit 0 to 1 -> lane L holds point L of the chunk
+          float a4[4][5];
+#pragma unroll
+          for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+            for (int v = 0; v < 5; ++v) upk(acc2[pr][v], a4[2 * pr][v], a4[2 * pr + 1][v]);
+          float a2[2][5], a1[5];
+          const bool b1_ = (dq & 2) != 0, b0_ = (dq & 1) != 0;
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int v = 0; v < 5; ++v) {
+              const float keep = b1_ ? a4[i + 2][v] : a4[i][v], send = b1_ ? a4[i][v] : a4[i + 2][v];
+              a2[i][v] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+#pragma unroll
+          for (int v = 0; v < 5; ++v) {
+            const float keep = b0_ ? a2[1][v] : a2[0][v], send = b0_ ? a2[0][v] : a2[1][v];
+            a1[v] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          }
+          // this lane's point: n = 64j + 32q + lane
+          const float inv = fminf(rsqrtf(a1[0]), 1.0f / TM_EPS);
+          float tb = alpha * a1[1], db = a1[1];
+          int k = 0;
+          if (alpha * a1[2] > tb) { tb = alpha * a1[2]; db = a1[2]; k = 1; }
+          if (alpha * a1[3] > tb) { tb = alpha * a1[3]; db = a1[3]; k = 2; }
+          if (alpha * a1[4] > tb) { tb = alpha * a1[4]; db = a1[4]; k = 3; }
+          const float gv = __fdividef(1.0f, 1.0f + __expf(-fmaf(alpha, db * inv, beta)));
+          // the centre index rides in the two lowest mantissa bits of the gate (2^-22 relative); passes 3 and 4 both use the masked gate
+          gk[q] = (__float_as_uint(gv) & ~3u) | (uint32_t)k;
+          const int n = 64 * j + 32 * q + lane;
+          {
+            // B operand of the aggregation GEMM, K-major SW128 [k-slab = n / 64][row][128 B]: rows 4e+m = bf16 hi part of the gate
+            // where m is this point's centre (0 elsewhere), rows 16+4e+m = the lo part (hi + lo carries the gate to 2^-17)
+            const float gm = __uint_as_float(gk[q] & ~3u);
+            const __nv_bfloat16 hb = __float2bfloat16_rn(gm);
+            const uint32_t hi16 = (uint32_t)__bfloat16_as_ushort(hb);
+            const uint32_t lo16 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gm - __bfloat162float(hb)));
+            const uint32_t colb = wb_base + (uint32_t)((n >> 6) * TM_WB_SLAB + (n & 7) * 2);
+            const uint32_t ch = (uint32_t)((n & 63) >> 3);
+            const int r1 = 4 * e + k, r2 = 16 + 4 * e + k;                 // the other rows of this point were zeroed above
+            sts16(colb + (uint32_t)((r1 >> 3) * 1024 + (r1 & 7) * 128) + ((ch ^ (uint32_t)(r1 & 7)) << 4), hi16);
+            sts16(colb + (uint32_t)((r2 >> 3) * 1024 + (r2 & 7) * 128) + ((ch ^ (uint32_t)(r2 & 7)) << 4), lo16);
+          }
+          if (A.idx_out || A.smax_out) {
+            const int64_t io = ((int64_t)(b * TM_E + e) * A.H + row0 + (n >> 4)) * A.W + col0 + (n & 15);
+            if (A.idx_out) A.idx_out[io] = (uint8_t)k;
+            if (A.smax_out) A.smax_out[io] = __uint_as_float(gk[q] & ~3u);
+          }
+          cnt0 += __popc(__ballot_sync(0xffffffffu, k == 0));
+          cnt1 += __popc(__ballot_sync(0xffffffffu, k == 1));
+          cnt2 += __popc(__ballot_sync(0xffffffffu, k == 2));
+          cnt3 += __popc(__ballot_sync(0xffffffffu, k == 3));
           __syncwarp();                                                    // the scratch is rewritten by the next chunk
         }
         if (lane == 0) *reinterpret_cast<int4*>(cntp + (e * 4 + j) * 4) = make_int4(cnt0, cnt1, cnt2, cnt3);
       }
-      named_bar(1 + e, 128);                                               // weights + counts of the head complete
+      // the scratch of the two heads of a k-slab lives in that slab of the o operand: both heads must have left pass 2 before
+      // either writes o (pass 4)
+      named_bar(5 + (e >> 1), 256);
+      tm_trace(tr, it, 10);
 
-      // ---- pass 3: aggregate value (TMEM, lane = channel) to the centres --------------------------------------------------------------
+      // ---- pass 3 on the tensor core: value -> bf16 pairs in the (dead) feat columns of TMEM = the A operand of the aggregation GEMM;
+      //      the one-hot gate rows written in pass 2 are its B operand.  (The CUDA-core forms of this pass were the hot spot of the
+      //      first two versions: 4 shared-memory cycles per point and warp for broadcast one-hot weights, or 19 instructions per point
+      //      for predicated accumulation from packed (gate | centre) words.) -----------------------------------------------------------
       {
-        uint64_t A2[4] = {0ull, 0ull, 0ull, 0ull};
-        uint64_t ql = 0ull, qr = 0ull;
-#pragma unroll 1
+        uint32_t pw[32];
+#pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
           uint32_t r[32];
           tm_ld32(T_VAL + lane_off + (uint32_t)(64 * j + 32 * h2), r);
-          const uint32_t wbase = wq_e + (uint32_t)((64 * j + 32 * h2) / 2) * 32u;
 #pragma unroll
-          for (int pp = 0; pp < 16; ++pp) {
-            const uint4 w01 = lds128(wbase + (uint32_t)pp * 32u), w23 = lds128(wbase + (uint32_t)pp * 32u + 16u);
-            // value is a bf16 tensor in the reference pipeline (stored, then read by the core): same rounding here
-            const uint64_t v2 = pk(bf16_round(fmaf(rstd, __uint_as_float(r[2 * pp]), ehv)), bf16_round(fmaf(rstd, __uint_as_float(r[2 * pp + 1]), ehv)));
-            A2[0] = fma2(((uint64_t)w01.y << 32) | w01.x, v2, A2[0]);
-            A2[1] = fma2(((uint64_t)w01.w << 32) | w01.z, v2, A2[1]);
-            A2[2] = fma2(((uint64_t)w23.y << 32) | w23.x, v2, A2[2]);
-            A2[3] = fma2(((uint64_t)w23.w << 32) | w23.z, v2, A2[3]);
-            if ((pp & 7) < 4) ql = add2(ql, v2); else qr = add2(qr, v2);
-          }
+          for (int i = 0; i < 16; ++i)
+            pw[16 * h2 + i] = bf16x2(fmaf(rstd, __uint_as_float(r[2 * i]), ehv), fmaf(rstd, __uint_as_float(r[2 * i + 1]), ehv));
         }
-        float* p3 = part3 + (e * 4 + j) * 4 * 32 + d;
-        p3[0] = hsum(A2[0]); p3[32] = hsum(A2[1]); p3[64] = hsum(A2[2]); p3[96] = hsum(A2[3]);
-        float* pq = partq + (e * 4 + j) * 2 * 32 + d;
-        pq[0] = hsum(ql); pq[32] = hsum(qr);
+        tm_st32(T_FEAT + lane_off + (uint32_t)(32 * j), pw);               // points 64j + 2c, 64j + 2c + 1 -> column 32j + c
       }
-      named_bar(1 + e, 128);
-
-      // ---- pass 4: centre aggregates, dispatch, bf16, MN-major SW128 operand of GEMM 2 --------------------------------------------------
+      fence_async_smem();                                                  // the gate rows (generic-proxy stores) before the MMA reads them
+      tm_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(va_ready);
+      tm_trace(tr, it, 11);
+      // ---- pass 4: centre aggregates (lane = channel) -> private table; dispatch with lane = POINT: o[n][:] = g_n * a[k_n][:],
+      //      bf16, written as the K-major SW128 B operand of GEMM 2 (row = point, 64 bytes = this head's 32 channels) -------------------
       {
-        float a[4];
+        mbar_wait(accA_full, ph);
+        tm_fence_after();
+        tm_trace(tr, it, 7);
         {
+          // D_A columns (from T_FEAT + 128): [4e, 4e+4) = sum of hi-gated value, [16 + 4e, ..) = lo part, [32, 36) = quadrant means
+          uint32_t dh[4], dl[4], dqm[4];
+          tm_ld4_issue(T_FEAT + lane_off + (uint32_t)(128 + 4 * e), dh);
+          tm_ld4_issue(T_FEAT + lane_off + (uint32_t)(128 + 16 + 4 * e), dl);
+          tm_ld4_issue(T_FEAT + lane_off + (uint32_t)(128 + 32), dqm);
+          tm_ld_wait12(dh, dl, dqm);
           int cn[4] = {0, 0, 0, 0};
-          float As[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const int4 c4 = *reinterpret_cast<const int4*>(cntp + (e * 4 + jj) * 4);
             cn[0] += c4.x; cn[1] += c4.y; cn[2] += c4.z; cn[3] += c4.w;
-            const float* p3 = part3 + (e * 4 + jj) * 4 * 32 + d;
-            As[0] += p3[0]; As[1] += p3[32]; As[2] += p3[64]; As[3] += p3[96];
           }
-          const float* pq = partq + e * 4 * 2 * 32 + d;
-          const float Q0 = pq[0 * 64] + pq[1 * 64], Q1 = pq[0 * 64 + 32] + pq[1 * 64 + 32];
-          const float Q2 = pq[2 * 64] + pq[3 * 64], Q3 = pq[2 * 64 + 32] + pq[3 * 64 + 32];
-          a[0] = fmaf(Q0, inv_q, As[0]) * __fdividef(1.0f, (float)(cn[0] + 1));
-          a[1] = fmaf(Q1, inv_q, As[1]) * __fdividef(1.0f, (float)(cn[1] + 1));
-          a[2] = fmaf(Q2, inv_q, As[2]) * __fdividef(1.0f, (float)(cn[2] + 1));
-          a[3] = fmaf(Q3, inv_q, As[3]) * __fdividef(1.0f, (float)(cn[3] + 1));
+          // rows of 36 floats: lanes that read different centres hit different banks
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+            apriv[m * 36 + d] = (__uint_as_float(dh[m]) + __uint_as_float(dl[m]) + __uint_as_float(dqm[m])) * __fdividef(1.0f, (float)(cn[m] + 1));
         }
-        const uint64_t a0 = pk(a[0], a[0]), a1 = pk(a[1], a[1]), a2 = pk(a[2], a[2]), a3 = pk(a[3], a[3]);
-        // this lane's k-row of the o operand: n-block j, row 32e + d -> (4e + d/8) * 1024 + (d % 8) * 128, chunks XOR (d & 7)
-        const uint32_t orow = smem_u32(sO) + (uint32_t)(j * 16384 + (4 * e + (d >> 3)) * 1024 + (d & 7) * 128);
+        __syncwarp();
 #pragma unroll 1
-        for (int h2 = 0; h2 < 2; ++h2) {
-          const uint32_t wbase = wq_e + (uint32_t)((64 * j + 32 * h2) / 2) * 32u;
+        for (int q = 0; q < 2; ++q) {
+          const float g = __uint_as_float(gk[q] & ~3u);
+          const uint32_t arow = smem_u32(apriv) + (gk[q] & 3u) * 144u;
+          const int n = 64 * j + 32 * q + lane;
           uint32_t ow[16];
 #pragma unroll
-          for (int pp = 0; pp < 16; ++pp) {
-            const uint4 w01 = lds128(wbase + (uint32_t)pp * 32u), w23 = lds128(wbase + (uint32_t)pp * 32u + 16u);
-            const uint64_t o2 = fma2(((uint64_t)w01.y << 32) | w01.x, a0,
-                                     fma2(((uint64_t)w01.w << 32) | w01.z, a1, fma2(((uint64_t)w23.y << 32) | w23.x, a2, mul2(((uint64_t)w23.w << 32) | w23.z, a3))));
-            float lo, hi;
-            upk(o2, lo, hi);
-            ow[pp] = bf16x2(lo, hi);
+          for (int c = 0; c < 8; ++c) {
+            const uint4 a4 = lds128(arow + (uint32_t)c * 16u);
+            ow[2 * c] = bf16x2(g * __uint_as_float(a4.x), g * __uint_as_float(a4.y));
+            ow[2 * c + 1] = bf16x2(g * __uint_as_float(a4.z), g * __uint_as_float(a4.w));
           }
+          const uint32_t orow = smem_u32(sO) + (uint32_t)((e >> 1) * 32768 + n * 128);
 #pragma unroll
           for (int t = 0; t < 4; ++t)
-            sts128(orow + (uint32_t)((((4 * h2 + t) ^ (d & 7))) << 4), ow[4 * t], ow[4 * t + 1], ow[4 * t + 2], ow[4 * t + 3]);
+            sts128(orow + ((((uint32_t)(4 * (e & 1) + t)) ^ (uint32_t)(n & 7)) << 4), ow[4 * t], ow[4 * t + 1], ow[4 * t + 2], ow[4 * t + 3]);
         }
       }
       fence_async_smem();
       tm_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_ready);
+      tm_trace(tr, it, 12);
 
       // ---- epilogue: + b2, * ls, + x (the tile itself), statistics, bf16 in place ------------------------------------------------------------
       mbar_wait(acc2_full, ph);
       tm_fence_after();
+      tm_trace(tr, it, 13);
       {
         const uint32_t xt = smem_u32(sX + (it % NXB) * S::XB);
         constexpr int ROWS = C == 128 ? 4 : 2;                            // region rows (16 points each) this warp finishes
@@ -574,6 +740,7 @@ token_mixer_fused_kernel(TmArgs A, const __grid_constant__ CUtensorMap tmX, cons
       tm_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(epi_done);
+      tm_trace(tr, it, 14);
     }
     if (A.out_sums && cur_b >= 0) {
       ssum = warp_sum(ssum); ssq = warp_sum(ssq);
@@ -604,6 +771,10 @@ int launch_tm(const TmArgs& A, const CUtensorMap& tx, const CUtensorMap& to, con
 }  // namespace vrcoc
 
 using namespace vrcoc;
+
+extern "C" int vrcoc_debug_set_tm_trace(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(g_tm_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : -2;
+}
 
 extern "C" int vrcoc_token_mixer_supported(int dtype, int C, int H, int W, int heads, int head_dim, int fold_w, int fold_h,
                                            int proposal_w, int proposal_h) {

@@ -66,6 +66,7 @@ SIGNATURES = {
     "vrcoc_debug_set_cm": (_I, [_I]),
     "vrcoc_mlp_fused_supported": (_I, [_I, _I, _I, _I]),
     "vrcoc_mlp_fused_fwd": (_I, [_P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "vrcoc_debug_set_tm_trace": (_I, [_P]),
     "vrcoc_token_mixer_supported": (_I, [_I] * 10),
     "vrcoc_token_mixer_fwd": (_I, [_P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P] + [_I] * 8 + [_P]),
     "vrcoc_im2col": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

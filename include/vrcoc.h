@@ -229,6 +229,8 @@ int vrcoc_mlp_fused_fwd(const void* x, const double* gn_sums, const float* gamma
  * tells; everything else runs the three-launch path. */
 int vrcoc_token_mixer_supported(int dtype, int C, int H, int W, int heads, int head_dim, int fold_w, int fold_h, int proposal_w,
                                 int proposal_h);
+/* Debug aid: non-NULL `buf` (u64 [grid][4 iterations][16]) makes the fused token-mixer kernel record %globaltimer phase stamps. */
+int vrcoc_debug_set_tm_trace(unsigned long long* buf);
 int vrcoc_token_mixer_fwd(const void* x, const double* gn_sums, float gn_eps, const void* w_fold, const float* k0, const float* k1,
                           const float* alpha, const float* beta, const void* w2, const float* b2, const float* layer_scale, void* out,
                           double* out_sample_sums, uint8_t* idx, float* sim_max, int B, int C, int H, int W, int heads, int head_dim,

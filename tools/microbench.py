@@ -28,6 +28,8 @@ CASES = {
     "s1_mlpf": ("mlpf", 64, 512, 128, {}),
     "s2_mlpf": ("mlpf", 128, 1024, 64, {}),
     "s3_mlpf": ("mlpf", 320, 1280, 32, {}),
+    "s1_tmf": ("tmf", 64, 0, 128, {}),
+    "s2_tmf": ("tmf", 128, 0, 64, {}),
     "s1_core": ("core", 128, 0, 128, dict(E=4, fold=8)),
     "s2_core": ("core", 128, 0, 64, dict(E=4, fold=4)),
     "s3_core": ("core", 256, 0, 32, dict(E=8, fold=2)),
@@ -49,6 +51,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--trace", action="store_true", help="tmf cases: print the per-CTA phase timeline (us) of one launch")
     args = ap.parse_args()
     dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     dev = "cuda"
@@ -95,6 +98,39 @@ def main():
             osum = ops.new_sample_sums(B, dev)
             fn = lambda: ops.mlp_fused_fwd(x, sums, gamma, beta, 1e-5, w1, b1, w2, b2, ls, osum)
             by, fl = B * P * 3 * C * es, 4.0 * B * P * C * O
+        elif kind == "tmf":
+            # fused token-mixer half (csrc/token_mixer_fused.cu): algorithmic bytes = x in + out out (SURVEY 8d, 2*C*P*s)
+            x = torch.randn(B, C, H, H, device=dev, generator=g).to(dt)
+            ED = 128
+            w1 = (torch.randn(ED, C, device=dev, generator=g) / C ** 0.5).to(dt)
+            wv = (torch.randn(ED, C, device=dev, generator=g) / C ** 0.5).to(dt)
+            w2 = (torch.randn(C, ED, device=dev, generator=g) / ED ** 0.5).to(dt)
+            zED, zC = torch.zeros(ED, device=dev), torch.zeros(C, device=dev)
+            w_fold, k0, k1 = ops.fold_gn_weights(w1, zED, wv, zED, torch.ones(C, device=dev), zC)
+            sums = ops.sample_sums_of(x)
+            osum = ops.new_sample_sums(B, dev)
+            a, b_ = torch.ones(1, device=dev), torch.zeros(1, device=dev)
+            fold = H // 16
+            fn = lambda: ops.token_mixer_fused_fwd(x, sums, 1e-5, w_fold, k0, k1, a, b_, w2, zC, torch.ones(C, device=dev), osum, 4, 32, fold, fold)
+            by, fl = B * P * 2 * C * es, B * P * (2.0 * C * ED * 4 + 13.0 * ED)
+            if args.trace:
+                from vrcoc._lib import lib
+                nb = min(148, B * fold * fold)
+                buf = torch.zeros(nb * 4 * 16, dtype=torch.int64, device=dev)
+                lib.vrcoc_debug_set_tm_trace(buf.data_ptr())
+                fn(); torch.cuda.synchronize()
+                lib.vrcoc_debug_set_tm_trace(None)
+                t = buf.cpu().reshape(nb, 4, 16).double()
+                names = {0: "x+W1 landed", 1: "GEMM1 issued", 2: "GEMM1 done", 8: "w0: GEMM1 seen", 9: "w0: pass1", 10: "w0: pass2", 11: "w0: V conv",
+                         7: "w0: agg seen", 12: "w0: pass4", 3: "o ready seen", 4: "GEMM2 done", 13: "w0: GEMM2 seen", 14: "w0: epilogue", 5: "epi seen",
+                         6: "store issued", 15: "entry"}
+                for cta in (0, nb // 2, nb - 1):
+                    t0 = t[cta, 0, 0]
+                    for it in range(4):
+                        if t[cta, it, 0] == 0:
+                            continue
+                        order = sorted((k for k in names if t[cta, it, k] > 0), key=lambda k: t[cta, it, k])
+                        print(f"  cta {cta} it {it}: " + "  ".join(f"{names[k]} {((t[cta, it, k] - t0) / 1e3).item():.2f}" for k in order))
         elif kind == "conv3":
             x = torch.randn(B, C, H, H, device=dev, generator=g).to(dt)
             w = (torch.randn(O, C * 9, device=dev, generator=g) / (C * 9) ** 0.5).to(dt)
