@@ -162,6 +162,29 @@ class VRCoC(nn.Module):
         return self.head(x.mean([-2, -1]))
 
 
+def replace_pos_buffers(model, img_h, img_w=None):
+    """Frames other than 512x512 (BASELINE.json configs[4]: 1024x1024): the reference bakes the positional grid into two fixed
+    [512, 512, 2] buffers (vr_coc.py:402-413) and its forward then fails at the cat of :582-583 for any other size.  This is the
+    buffer replacement of SURVEY 8c.5, applied to every module under `model` that owns a `fea_pos` buffer (the product's VRCoC or
+    the reference's own): same formula, new size.  The kernels themselves are size-agnostic (regions become 32x32 / 64x64)."""
+    img_w = img_h if img_w is None else img_w
+    n = 0
+    for m in model.modules():
+        if isinstance(getattr(m, "fea_pos", None), torch.Tensor) and "fea_pos" in m._buffers:
+            old = m._buffers["fea_pos"]
+            rw = torch.arange(0, img_w, step=1) / (img_w - 1.0)
+            rh = torch.arange(0, img_h, step=1) / (img_h - 1.0)
+            pos = (torch.stack(torch.meshgrid(rw, rh, indexing='ij'), dim=-1).float() - 0.5).to(device=old.device, dtype=old.dtype)
+            m._buffers["fea_pos"] = pos
+            if "fea_pos_r" in m._buffers:
+                m._buffers["fea_pos_r"] = pos.clone()
+            m.__dict__.pop("_vrcoc_cache", None)          # derived views of the old grid
+            n += 1
+    if n == 0:
+        raise ValueError("replace_pos_buffers: no module with a fea_pos buffer found")
+    return model
+
+
 def _build(layers, embed_dims, heads, head_dim, proposal, fold, cfg_name, **kwargs):
     model = VRCoC(layers, embed_dims=embed_dims, norm_layer=GroupNorm, mlp_ratios=[8, 8, 4, 4],
                   downsamples=[True, True, True, True], down_patch_size=3, down_pad=1,

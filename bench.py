@@ -29,7 +29,7 @@ for p in (ROOT, os.path.join(ROOT, "asy-vrnet_b200")):
 
 import torch  # noqa: E402
 
-METRIC = "frames/sec (512x512 img+radar), ASY-VRNet multi-task inference"
+METRIC = "frames/sec (512x512 img+radar), ASY-VRNet multi-task inference"     # --img 1024 renames it in the line
 UNIT = "frames/s"
 PER_GPU_BATCH = 8
 IMG = 512
@@ -219,10 +219,12 @@ class KernelAccounting:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def build_model(phi, dtype, device):
+def build_model(phi, dtype, device, img=512):
     import vrcoc
     torch.manual_seed(0)
     m = vrcoc.EfficientVRNet(num_classes=4, num_seg_classes=9, phi=phi).eval()
+    if img != 512:
+        vrcoc.replace_pos_buffers(m, img)          # the reference's positional grid is a fixed 512x512 buffer
     g = torch.Generator().manual_seed(1)
     with torch.no_grad():
         # the reference's training-time init (nets/yolo_training.py:482-500): conv weights N(0, 0.02), BN weight N(1, 0.02)
@@ -235,11 +237,24 @@ def build_model(phi, dtype, device):
     return m.to(device=device, dtype=dtype)
 
 
-def synth_batch(batch, seed, dtype):
+def synth_batch(batch, seed, dtype, img=IMG):
     g = torch.Generator().manual_seed(seed)
-    x = torch.randn(batch, 3, IMG, IMG, generator=g).to(dtype)
-    r = torch.rand(batch, 4, IMG, IMG, generator=g).to(dtype)
+    x = torch.randn(batch, 3, img, img, generator=g).to(dtype)
+    r = torch.rand(batch, 4, img, img, generator=g).to(dtype)
     return x, r
+
+
+def _fit_pos(ref_model, img):
+    """the reference model with its fea_pos buffers regenerated for `img` (same formula; oracle-side helper, no product import)"""
+    if img == 512:
+        return ref_model
+    for m in ref_model.modules():
+        if isinstance(getattr(m, "fea_pos", None), torch.Tensor) and "fea_pos" in m._buffers:
+            rw = torch.arange(0, img, step=1) / (img - 1.0)
+            pos = torch.stack(torch.meshgrid(rw, rw, indexing="ij"), dim=-1).float() - 0.5
+            m._buffers["fea_pos"] = pos
+            m._buffers["fea_pos_r"] = pos.clone()
+    return ref_model
 
 
 def load_reference():
@@ -281,10 +296,10 @@ def run_reference(args):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    x, r = synth_batch(1, 100, torch.float32)
+    x, r = synth_batch(1, 100, torch.float32, args.img)
     make = load_reference()
     if make is not None:
-        model = make(args.phi)
+        model = _fit_pos(make(args.phi), args.img)
         fwd, kind = (lambda a, b: model(a, b)), "reference"
         what = "the reference's own nets/efficient_vrnet.py:EfficientVRNet, unmodified (baseline/_ref)"
     else:
@@ -300,10 +315,10 @@ def run_reference(args):
     fps = args.steps / dt
     sample = f"1 frame/step (one frame of the {args.batch}-frame per-GPU batch), fp32, phi={args.phi}"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC.replace("512x512", f"{args.img}x{args.img}"), "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ASY-VRNet(phi={args.phi}) multi-task inference fwd, 512x512 RGB + 4x512x512 radar (CPU: {what})"},
+        "config": {"workload": f"ASY-VRNet(phi={args.phi}) multi-task inference fwd, {args.img}x{args.img} RGB + 4x{args.img}x{args.img} radar (CPU: {what})"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -314,10 +329,10 @@ def cpu_baseline(args, model):
     the host cores over a bounded sample."""
     torch.set_num_threads(os.cpu_count() or 1)
     sd = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
-    x, r = synth_batch(1, 100, torch.float32)
+    x, r = synth_batch(1, 100, torch.float32, args.img)
     make = load_reference()
     if make is not None:
-        ref = make(args.phi)
+        ref = _fit_pos(make(args.phi), args.img)
         ref.load_state_dict(sd, strict=True)
         fwd, kind = (lambda a, b: ref(a, b)), "reference"
     else:
@@ -337,10 +352,10 @@ def reference_eager_gpu(args, model, dev):
     make = load_reference()
     if make is None:
         return None
-    ref = make(args.phi)
+    ref = _fit_pos(make(args.phi), args.img)
     ref.load_state_dict({k: v.detach().float().cpu() for k, v in model.state_dict().items()}, strict=True)
     ref = ref.to(dev)
-    x, r = (t.to(dev) for t in synth_batch(args.batch, 100, torch.float32))
+    x, r = (t.to(dev) for t in synth_batch(args.batch, 100, torch.float32, args.img))
     out = {}
 
     def run(name, tf32, autocast):
@@ -422,12 +437,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.allow_tf32 = True
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    model = build_model(args.phi, dtype, dev)
+    model = build_model(args.phi, dtype, dev, args.img)
     B = args.batch
 
     # a ring of distinct device-resident batches so no step re-reads a warm input
     NBUF = 3
-    host = [tuple(t.pin_memory() for t in synth_batch(B, 100 + rank * 10 + i, dtype)) for i in range(NBUF)]
+    host = [tuple(t.pin_memory() for t in synth_batch(B, 100 + rank * 10 + i, dtype, args.img)) for i in range(NBUF)]
     devb = [(x.to(dev), r.to(dev)) for x, r in host]
     sx, sr = torch.empty_like(devb[0][0]), torch.empty_like(devb[0][1])
 
@@ -621,11 +636,11 @@ def run_ours(args):
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     d2h = sum(t.numel() * t.element_size() for t in host_out)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC.replace("512x512", f"{args.img}x{args.img}"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": f"ASY-VRNet(phi={args.phi}) multi-task inference fwd (3 det maps + seg class map), 512x512 RGB + "
-                               f"4x512x512 radar, random init, batch {B}/GPU (global {B * world}), batch-sharded, no collective",
+        "config": {"workload": f"ASY-VRNet(phi={args.phi}) multi-task inference fwd (3 det maps + seg class map), {args.img}x{args.img} RGB + "
+                               f"4x{args.img}x{args.img} radar, random init, batch {B}/GPU (global {B * world}), batch-sharded, no collective",
                    "cuda_graph": graph is not None,
                    "l2": f"inputs rotate over {NBUF} distinct batches; per-step activation traffic >> 126 MB L2"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
@@ -645,8 +660,9 @@ def run_ours(args):
                                  "hbm_frac": 100.7e6 * fps_gpu / 1e9 / pk["hbm_gbs"], "tc_frac": 66.6e9 * fps_gpu / 1e12 / pk["bf16_tflops"]}
     if rank == 0 and world == 1:
         from tools import block_sweep
-        with torch.no_grad():
-            line["roofline_block"] = block_sweep.live_rows(B, dtype, iters=10)      # per live row: all launches of one ClusterBlock fwd
+        if args.img == 512:
+            with torch.no_grad():
+                line["roofline_block"] = block_sweep.live_rows(B, dtype, iters=10)  # per live row: all launches of one ClusterBlock fwd
         if not args.no_ref_gpu:
             line["reference_eager_gpu"] = reference_eager_gpu(args, model, dev)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
