@@ -132,6 +132,7 @@ def _conv_launch(x, weight, bias32, stride, pad, extra, extra_bstride, act, e_sc
     return out
 
 
+@ops.amp_function
 class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, pad, extra, extra_bstride, act, e_scale, out_minmax, out_dtype):
@@ -248,13 +249,17 @@ class BaseConv(nn.Module):
         return self.act(self.conv(x))
 
 
-def _base_conv_forward(mod, x, out_minmax):
+def _base_conv_forward(mod, x, out_minmax, weight=None):
+    """`weight`: the (possibly autocast-cast) weight tensor the autograd Function received; defaults to the module's own"""
     conv, bn = mod.conv, mod.bn
+    weight = conv.weight if weight is None else weight
     act = _ACT_CODE[mod._act_name]
     stride, pad = conv.stride[0], conv.padding[0]
     bias32 = _f32(conv.bias)
+    if x.dtype != weight.dtype and x.is_floating_point():
+        x = x.to(weight.dtype)
     if bn.training or not bn.track_running_stats:
-        u = _conv_launch(x, conv.weight, bias32, stride, pad, None, None, ACT_NONE, None, None, None)
+        u = _conv_launch(x, weight, bias32, stride, pad, None, None, ACT_NONE, None, None, None)
         B, O, H, W = u.shape
         cs, _ = ops.channel_sums(u)
         sc, sh = _bn_affine(bn, cs, B * H * W)
@@ -264,7 +269,7 @@ def _base_conv_forward(mod, x, out_minmax):
     sc, sh = _bn_affine(bn)
     if bias32 is not None:
         sh = ops.cached(mod, "bias_fold", [conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var], lambda: sh + bias32 * sc)
-    return _conv_launch(x, conv.weight, sh, stride, pad, None, None, act, sc, out_minmax, None)
+    return _conv_launch(x, weight, sh, stride, pad, None, None, act, sc, out_minmax, None)
 
 
 class _NoGradCtx:
@@ -284,6 +289,7 @@ def _apply(fn, *args):
     return fn.forward(_NoGradCtx(), *args)
 
 
+@ops.amp_function
 class _BaseConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, bn_w, bn_b, mod, out_minmax):
@@ -291,7 +297,7 @@ class _BaseConvFn(torch.autograd.Function):
         need_bwd = any(ctx.needs_input_grad)
         rm = None if training or not need_bwd else mod.bn.running_mean.detach().clone()
         rv = None if training or not need_bwd else mod.bn.running_var.detach().clone()
-        out = _base_conv_forward(mod, x, out_minmax)
+        out = _base_conv_forward(mod, x, out_minmax, weight)
         if need_bwd:
             ctx.save_for_backward(x, weight, bias, bn_w, bn_b, rm, rv)
             ctx.meta = (mod.conv.stride[0], mod.conv.padding[0], mod._act_name, mod.bn.eps, training)
@@ -377,6 +383,7 @@ def _group_norm_maybe_empty(q):
     return gn
 
 
+@ops.amp_function
 class _ShuffleAttentionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, cw, cb, sw, sb, gw, gb, mod):
@@ -419,6 +426,7 @@ class eca_block(nn.Module):
         return _apply(_EcaFn, x, self.conv.weight)
 
 
+@ops.amp_function
 class _EcaFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w):
@@ -469,6 +477,7 @@ class ImageEnhanceByRadar(nn.Module):
                                      self.norm.weight, self.norm.bias, self)
 
 
+@ops.amp_function
 class _ImageEnhanceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image, radar, w, g1, b1, g2, b2, mod):
@@ -483,7 +492,7 @@ class _ImageEnhanceFn(torch.autograd.Function):
                           ((train1, rp.bn.running_mean), (train1, rp.bn.running_var), (train2, bn2.running_mean), (train2, bn2.running_var)))
         B, Ci, H, W = image.shape
         minmax = torch.zeros(2, device=image.device, dtype=torch.int32)
-        k = _base_conv_forward(rp, radar if radar.dtype == image.dtype else radar.to(image.dtype), minmax)
+        k = _base_conv_forward(rp, radar if radar.dtype == image.dtype else radar.to(image.dtype), minmax, w)
         out = torch.empty_like(image)
         if train2:
             cs = torch.empty(B, Ci, 2, device=image.device, dtype=torch.float32)
@@ -547,6 +556,7 @@ def _concat_order_weight(w2, chan_src):
     return wn.contiguous()
 
 
+@ops.amp_function
 class _RadarEnhanceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image, radar, w, g1, b1, g2, b2, eca_w, cw, cb, sw, sb, gw, gb, mod):

@@ -16,6 +16,7 @@ from .fusion import BaseConv, DWConv, ShuffleAttention, eca_block, shuffle_chann
 from .vr_coc import coc_medium, coc_small  # noqa: F401
 
 
+@ops.amp_function
 class _UpsampleFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, scale):

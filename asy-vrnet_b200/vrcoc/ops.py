@@ -21,6 +21,36 @@ def _dt(t):
         raise _lib.VrcocError(f"unsupported dtype {t.dtype}: the CoC path runs in float32 or bfloat16") from None
 
 
+# ------------------------------------------------------------------------------------------------------------
+# autocast
+# ------------------------------------------------------------------------------------------------------------
+def _amp_cast(a):
+    """activations ([B,C,H,W]) and projection / convolution weights (ndim >= 2) -> bf16; vectors (biases, norm affines, layer
+    scales, sim_alpha / sim_beta), fp64 statistics and non-floating arguments stay as they are (the kernels consume them in fp32)"""
+    if isinstance(a, torch.Tensor) and a.is_cuda and a.is_floating_point() and a.ndim >= 2 and a.dtype in (torch.float32, torch.float16):
+        return a.to(torch.bfloat16)
+    return a
+
+
+def amp_function(cls):
+    """Class decorator for the autograd Functions of the native path: under torch.autocast (reference utils/utils_fit.py:86-109
+    runs the model under autocast with fp16 by default, train.py:56) the kernels compute in bf16 — fp32 master weights and fp32 /
+    fp16 activations are cast on the way in, the forward body runs with autocast off, and autograd casts the returned gradients
+    back to the dtype of the original inputs.  The kernels have no fp16 storage type; fp16 autocast regions therefore get bf16
+    activations back (same exponent range as fp32, so no GradScaler is needed for them)."""
+    fwd = cls.forward
+
+    def forward(ctx, *args):
+        if torch.is_autocast_enabled("cuda"):
+            args = tuple(_amp_cast(a) for a in args)
+            with torch.autocast("cuda", enabled=False):
+                return fwd(ctx, *args)
+        return fwd(ctx, *args)
+
+    cls.forward = staticmethod(forward)
+    return cls
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -446,7 +476,7 @@ def cluster_core_bwd(feat, value, dout, idx, smax, alpha, beta, heads, fold_w, f
     return dfeat, dvalue, dab
 
 
-class ClusterCoreFn(torch.autograd.Function):
+class ClusterCoreFn(torch.autograd.Function):          # (no autocast cast: `feat` must stay fp32)
     """out = cluster_core(feat, value; alpha, beta)   (reference vr_coc.py:158-190)"""
 
     @staticmethod
@@ -485,6 +515,7 @@ def _w2d(w):
     return w.detach().reshape(w.shape[0], -1)
 
 
+@amp_function
 class GNProjFn(torch.autograd.Function):
     """y = act(W * GroupNorm1(x) + b), optionally split along the output channels into (y[:split] as fp32, rest).
     `sums=None` skips the GroupNorm prologue (stand-alone Cluster.forward).
@@ -579,6 +610,7 @@ class GNProjFn(torch.autograd.Function):
                 None if db is None else db.to(bdt), None, None)
 
 
+@amp_function
 class ProjResidualFn(torch.autograd.Function):
     """out = res + ls * (W h + b)  (+ per-sample {sum, sum^2} of out for the next GroupNorm as a side output).
 
@@ -626,6 +658,7 @@ class ProjResidualFn(torch.autograd.Function):
                 None if dls is None else dls.to(lsdt), dout)
 
 
+@amp_function
 class ProjFn(torch.autograd.Function):
     """y = act(W x + b) for a 1x1 projection (stand-alone Cluster / Mlp forward without the block fusion)."""
 

@@ -45,6 +45,8 @@ def parse():
                     help="infer: BASELINE configs[2] (the driver's line); train: configs[3] (training step, NCCL gradient all-reduce); "
                          "block-sweep: configs[1] (tools/block_sweep.py; extra flags after --)")
     ap.add_argument("--img", type=int, default=512, help="frame side (1024: BASELINE configs[4], fea_pos buffers replaced)")
+    ap.add_argument("--train-graph", action="store_true", help="train mode: network forward/backward as CUDA graphs (N=1)")
+    ap.add_argument("--no-train", action="store_true", help="skip the short training-step measurement appended to the inference line")
     ap.add_argument("--no-check", action="store_true", help="skip the pre-timing oracle spot check of the benched outputs")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the unmodified reference eager on the GPU")
     ap.add_argument("--phi", default="l")
@@ -425,6 +427,197 @@ def oracle_spot_check(args, model, static_in, batch, graph, graph_outs):
     return res
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: training step with the multitask loss, batch 16 / GPU, bf16, NCCL gradient all-reduce
+# ----------------------------------------------------------------------------------------------------------------
+class FusedEMA:
+    """nets/yolo_training.py:449-475 (ModelEMA) with the same decay ramp, as two multi-tensor launches per step instead of a
+    Python loop over ~900 state-dict entries."""
+
+    def __init__(self, model, decay=0.9999, tau=2000):
+        import copy
+        import math
+        self.ema = copy.deepcopy(model).eval()
+        for p in self.ema.parameters():
+            p.requires_grad_(False)
+        self.updates, self.decay = 0, (lambda x: decay * (1 - math.exp(-x / tau)))
+        self.dst = [v for v in self.ema.state_dict().values() if v.dtype.is_floating_point and v.numel()]
+        self.src = [v for v in model.state_dict().values() if v.dtype.is_floating_point and v.numel()]
+
+    def update(self):
+        self.updates += 1
+        d = self.decay(self.updates)
+        with torch.no_grad():
+            torch._foreach_mul_(self.dst, d)
+            torch._foreach_add_(self.dst, self.src, alpha=1 - d)
+
+
+def train_setup(args, dev, world, batch):
+    """model + optimizer + loss + synthetic batch exactly as train.py:297-473 / utils_fit.py:86-118 put them together:
+    weights_init, SGD(momentum 0.937, nesterov) over the three parameter groups, YOLOLoss(num_classes=4) + 5 * (Focal + Dice),
+    EMA; autocast in bf16 (the reference uses fp16 + GradScaler: bf16 needs no scaler)."""
+    import contextlib
+    import io
+    import vrcoc
+    from oracle import ref_shim
+    torch.manual_seed(0)
+    model = vrcoc.EfficientVRNet(num_classes=4, num_seg_classes=9, phi=args.phi)
+    loss_kind = "surrogate (sum of squares; baseline/_ref absent)"
+    yolo_loss = focal = dice = None
+    if ref_shim.available(ref_shim.VENDORED):
+        ref_shim.install(ref_shim.VENDORED)
+        from nets.deeplabv3_training import Dice_loss, Focal_Loss
+        from nets.yolo_training import YOLOLoss, weights_init
+        with contextlib.redirect_stdout(io.StringIO()):
+            weights_init(model)
+        yolo_loss, focal, dice = YOLOLoss(4, True), Focal_Loss, Dice_loss      # fp16=True: its SimOTA cost leaves autocast (yolo_training.py:240-247)
+        loss_kind = "reference YOLOLoss(4, fp16=True) + 5*(Focal_Loss + Dice_loss) (nets/yolo_training.py:60, nets/deeplabv3_training.py:22,41)"
+    model = model.to(dev).train()
+    for p in model.parameters():
+        if p.numel() == 0:
+            p.requires_grad_(False)          # the six zero-size tensors of radar_enhance_by_image1.image_attn: no gradient, no bucket
+    pg0, pg1, pg2 = [], [], []
+    for k, v in model.named_modules():       # train.py:460-467
+        if hasattr(v, "bias") and isinstance(v.bias, torch.nn.Parameter) and v.bias.numel():
+            pg2.append(v.bias)
+        if isinstance(v, torch.nn.BatchNorm2d) or "bn" in k:
+            pg0.append(v.weight)
+        elif hasattr(v, "weight") and isinstance(v.weight, torch.nn.Parameter) and v.weight.numel():
+            pg1.append(v.weight)
+    opt = torch.optim.SGD(pg0, 1e-3, momentum=0.937, nesterov=True)
+    opt.add_param_group({"params": pg1, "weight_decay": 5e-4})
+    opt.add_param_group({"params": pg2})
+    net = model
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        net = DDP(model, device_ids=[dev.index], bucket_cap_mb=25, gradient_as_bucket_view=True)    # train.py:367 (DDP over NCCL)
+    ema = FusedEMA(model)
+    g = torch.Generator().manual_seed(7 + int(os.environ.get("RANK", "0")))
+    B, S = batch, args.img
+    images = torch.randn(B, 3, S, S, generator=g).to(dev)
+    radars = torch.rand(B, 4, S, S, generator=g).to(dev)
+    targets = []
+    for _ in range(B):                         # 3 boxes / image, cx cy w h class in pixels (utils_fit.py:34 batch layout)
+        cxcy = torch.rand(3, 2, generator=g) * (S - 112) + 56
+        wh = torch.rand(3, 2, generator=g) * 80 + 16
+        cls = torch.randint(0, 4, (3, 1), generator=g).float()
+        targets.append(torch.cat([cxcy, wh, cls], 1).to(dev))
+    pngs = torch.randint(0, 9, (B, S, S), generator=g).to(dev)
+    seg_labels = torch.nn.functional.one_hot(pngs, 10).float()
+    weights = torch.ones(9, device=dev)
+
+    fwd_call = net
+    if getattr(args, "train_graph", False) and world == 1:
+        # forward and backward of the network as two CUDA graphs (torch.cuda.make_graphed_callables); the loss (SimOTA: data-dependent
+        # shapes, host syncs) stays eager between them
+        fwd_call = torch.cuda.make_graphed_callables(net, (images, radars), allow_unused_input=True)
+
+    def step(timing=None):
+        def mark(name, t0):
+            if timing is not None:
+                torch.cuda.synchronize()
+                timing[name] = timing.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+            return time.perf_counter()
+        t = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            det, seg = fwd_call(images, radars)
+            t = mark("forward_ms", t)
+            if yolo_loss is not None:
+                loss_seg = focal(seg, pngs, weights, num_classes=9) + dice(seg, seg_labels)
+                loss_det = yolo_loss([d.float() for d in det], targets)
+                loss = loss_det + 5 * loss_seg
+            else:
+                loss = sum(d.float().square().mean() for d in det) + seg.float().square().mean()
+        t = mark("loss_ms", t)
+        loss.backward()
+        t = mark("backward_ms", t)
+        opt.step()
+        ema.update()
+        mark("optimizer_ema_ms", t)
+        return loss
+
+    nparam = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    return step, net, model, loss_kind, nparam
+
+
+def measure_train(args, dev, world, dist, batch, steps, warmup):
+    step, net, model, loss_kind, nparam = train_setup(args, dev, world, batch)
+    loss = None
+    for _ in range(warmup):
+        loss = step()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        loss = step()
+    e.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = torch.tensor([s.elapsed_time(e)], device=dev)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = ms.item() / steps
+    out = {"value": batch * world / (ms_step / 1e3), "unit": "frames/s", "ms_per_step": ms_step, "batch_per_gpu": batch,
+           "global_batch": batch * world, "steps": steps, "warmup": warmup, "dtype": "bf16 autocast, fp32 master weights",
+           "loss": loss_kind, "final_loss": float(loss.detach().float().item()), "finite": bool(torch.isfinite(loss.detach()).item()),
+           "optimizer": "SGD(momentum 0.937, nesterov), 3 parameter groups (train.py:460-473), fused multi-tensor EMA",
+           "trainable_params": nparam, "grad_bytes_per_step": nparam * 4}
+    timing = {}
+    for _ in range(3):                       # phase split of a step (host-synchronised after every phase: sums to more than ms_per_step)
+        step(timing)
+    out["phases_ms_synced"] = {k: v / 3 for k, v in timing.items()}
+    if dist is not None:
+        # exposed all-reduce time: the same steps without gradient synchronisation (DDP no_sync), max over ranks
+        with net.no_sync():
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            dist.barrier()
+            s.record()
+            for _ in range(steps):
+                step()
+            e.record()
+            torch.cuda.synchronize()
+        ms2 = torch.tensor([s.elapsed_time(e)], device=dev)
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        out["ms_per_step_no_allreduce"] = ms2.item() / steps
+        out["allreduce_exposed_ms"] = ms_step - ms2.item() / steps
+        out["collective"] = f"DDP bucketed NCCL all-reduce of {nparam * 4 / 1e6:.0f} MB fp32 gradients per step, overlapped with backward"
+    del step, net, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_train(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    batch = args.batch if args.batch != PER_GPU_BATCH else 16
+    with ClockSampler(local) as clk:
+        res = measure_train(args, dev, world, dist, batch, args.steps if args.steps != 200 else 20, max(args.warmup, 3))
+    if rank == 0:
+        line = {"metric": f"training frames/sec ({args.img}x{args.img} img+radar), ASY-VRNet multitask step", "value": res["value"], "unit": "frames/s",
+                "n_gpus": world, "steps": res["steps"], "warmup": res["warmup"], "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"ASY-VRNet(phi={args.phi}) training step (fwd + multitask loss + bwd + SGD + EMA), batch {batch}/GPU, "
+                                       f"gradient all-reduce over NCCL" if world > 1 else f"ASY-VRNet(phi={args.phi}) training step, batch {batch}, 1 GPU"},
+                "clocks": clk.summary(), "train": res}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -665,6 +858,16 @@ def run_ours(args):
                 line["roofline_block"] = block_sweep.live_rows(B, dtype, iters=10)  # per live row: all launches of one ClusterBlock fwd
         if not args.no_ref_gpu:
             line["reference_eager_gpu"] = reference_eager_gpu(args, model, dev)
+    if not args.no_train and args.img == 512:
+        # BASELINE configs[3] beside the headline: a short training-step measurement at the same N (its gradient all-reduce is the
+        # one collective of this repository); the full run is `bench.py --mode train`
+        del graph, slots
+        torch.cuda.empty_cache()
+        try:
+            tr = measure_train(args, dev, world, dist, 16, 8, 3)
+        except Exception as ex:      # never lose the inference line to the secondary measurement
+            tr = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+        line["train_step"] = tr
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, model)
     if rank == 0:
@@ -678,6 +881,10 @@ def main():
     if args.mode == "block-sweep":
         from tools import block_sweep
         return block_sweep.main(args.rest)
+    if args.mode == "train" and args.impl == "ours":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --mode train needs a CUDA device")
+        return run_train(args)
     if args.impl == "reference":
         run_reference(args)
     else:
