@@ -1,0 +1,254 @@
+// Small backward kernels of the training path: everything that used to be O(B*C)- or O(O*K)-sized "coefficient algebra" done
+// with dozens of tiny library launches per autograd node (torch profiler, tools/prof_train.py: 11 K launches per training step,
+// host-bound) plus the adjoint passes of the k x k convolutions and the per-channel normalisations.
+//
+//   vrcoc_gn_bwd_coef       GroupNorm(1,C) backward coefficients from the per-(b,c) sums        (vr_coc.py:105-111, :265,270)
+//   vrcoc_proj_res_bwd_coef layer-scale / bias / weight gradients of  out = res + ls * (W h + b) (vr_coc.py:191,222,266-271)
+//   vrcoc_col2im            adjoint of vrcoc_im2col (tap-major): input gradient of a k x k convolution (vr_coc.py:99-102,313)
+//   vrcoc_chan_bwd_sums / vrcoc_chan_bwd_apply
+//                           per-channel affine (+ activation) backward = BatchNorm2d backward in train and eval mode
+//                           (normal_conv.py:45-49, vr_coc.py:315,341,356)
+#include "common.cuh"
+
+namespace vrcoc {
+namespace {
+
+__device__ __forceinline__ void block_sum2d(double& a, double& b, double* red) {
+  a = warp_sum(a); b = warp_sum(b);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { red[w] = a; red[32 + w] = b; }
+  __syncthreads();
+  double x = 0.0, y = 0.0;
+  for (int i = 0; i < nw; ++i) { x += red[i]; y += red[32 + i]; }
+  a = x; b = y;
+}
+
+// one CTA per sample: m1, m2 -> a[b][c], bb[b], cc[b]; sxh[b][c] kept for the channel reduction
+__global__ void __launch_bounds__(256) gn_bwd_coef_sample_kernel(const float* __restrict__ s, const double* __restrict__ gn_sums,
+                                                                 const float* __restrict__ gamma, float eps, int C, int HW,
+                                                                 float* __restrict__ a, float* __restrict__ bb, float* __restrict__ cc,
+                                                                 float* __restrict__ sxh) {
+  __shared__ double red[64];
+  const int b = blockIdx.x;
+  const double cnt = (double)C * (double)HW;
+  double t0 = 0.0, t1 = 0.0;
+  if (threadIdx.x < VRCOC_STAT_SLOTS) {
+    t0 = gn_sums[((int64_t)b * VRCOC_STAT_SLOTS + threadIdx.x) * 2];
+    t1 = gn_sums[((int64_t)b * VRCOC_STAT_SLOTS + threadIdx.x) * 2 + 1];
+  }
+  block_sum2d(t0, t1, red);
+  const double mean = t0 / cnt;
+  double var = t1 / cnt - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  double m1 = 0.0, m2 = 0.0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double s1 = s[((int64_t)b * C + c) * 2], s2 = s[((int64_t)b * C + c) * 2 + 1];
+    const double xh = (s2 - mean * s1) * rstd;                    // sum dz * xhat
+    sxh[(int64_t)b * C + c] = (float)xh;
+    const double g = gamma[c];
+    m1 += s1 * g; m2 += xh * g;
+    a[(int64_t)b * C + c] = (float)(rstd * g);
+  }
+  block_sum2d(m1, m2, red);
+  m1 /= cnt; m2 /= cnt;
+  if (threadIdx.x == 0) {
+    bb[b] = (float)(-(rstd * rstd * m2));
+    cc[b] = (float)(rstd * (mean * rstd * m2 - m1));
+  }
+}
+
+// dgamma[c] = sum_b sxh[b][c], dbeta[c] = sum_b s1[b][c]   (fixed order: deterministic)
+__global__ void gn_bwd_coef_chan_kernel(const float* __restrict__ s, const float* __restrict__ sxh, int B, int C,
+                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double g = 0.0, h = 0.0;
+  for (int b = 0; b < B; ++b) { g += sxh[(int64_t)b * C + c]; h += s[((int64_t)b * C + c) * 2]; }
+  dgamma[c] = (float)g; dbeta[c] = (float)h;
+}
+
+// one CTA per output row o of the projection
+template <typename TW>
+__global__ void __launch_bounds__(128) proj_res_bwd_coef_kernel(const float* __restrict__ G, const float* __restrict__ sdy, const TW* __restrict__ W,
+                                                                const float* __restrict__ bias, const float* __restrict__ ls, int O, int K,
+                                                                float* __restrict__ dW, float* __restrict__ db, float* __restrict__ dls,
+                                                                TW* __restrict__ wt) {
+  __shared__ float red[4];
+  const int o = blockIdx.x;
+  const float l = ls ? ls[o] : 1.f;
+  float acc = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float g = G[(int64_t)o * K + k], w = ldf<TW>(W + (int64_t)o * K + k);
+    dW[(int64_t)o * K + k] = l * g;
+    acc = fmaf(w, g, acc);
+    stf<TW>(wt + (int64_t)k * O + o, w * l);                        // (W * ls)^T: the dgrad weight
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float t = red[0] + red[1] + red[2] + red[3];
+    const float sy = sdy[o];
+    if (db) db[o] = l * sy;
+    if (dls) dls[o] = t + (bias ? bias[o] * sy : 0.f);
+  }
+}
+
+// dx[b][c][y][x] = sum over taps (ky,kx) and output positions (oy,ox) with oy*s - p + ky*d == y, ox*s - p + kx*d == x of
+// dcol[b][(ky*kw + kx)*C + c][oy][ox]   (gather form: one thread per input element, no atomics)
+template <typename T>
+__global__ void __launch_bounds__(256) col2im_kernel(const T* __restrict__ dcol, T* __restrict__ dx, int C, int H, int W, int kh, int kw,
+                                                     int stride, int pad, int dil, int Ho, int Wo, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % W), y = (int)((i / W) % H), c = (int)((i / ((int64_t)W * H)) % C);
+  const int64_t b = i / ((int64_t)W * H * C);
+  const int64_t plane = (int64_t)Ho * Wo;
+  const T* base = dcol + b * (int64_t)kh * kw * C * plane;
+  float acc = 0.f;
+  for (int ky = 0; ky < kh; ++ky) {
+    const int ty = y + pad - ky * dil;
+    if (ty < 0 || ty % stride) continue;
+    const int oy = ty / stride;
+    if (oy >= Ho) continue;
+    for (int kx = 0; kx < kw; ++kx) {
+      const int tx = x + pad - kx * dil;
+      if (tx < 0 || tx % stride) continue;
+      const int ox = tx / stride;
+      if (ox >= Wo) continue;
+      acc += ldf<T>(base + ((int64_t)(ky * kw + kx) * C + c) * plane + (int64_t)oy * Wo + ox);
+    }
+  }
+  stf<T>(dx + i, acc);
+}
+
+// act'(.) evaluated from the forward OUTPUT y of the activation (relu / lrelu: sign of y; none: 1); SiLU needs the
+// pre-activation z = u * zs[c] + zt[c] (the normalised convolution output), recomputed from u
+__device__ __forceinline__ float act_grad_from_out(float y, int act) {
+  if (act == VRCOC_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == VRCOC_ACT_LRELU) return y > 0.f ? 1.f : 0.1f;
+  return 1.f;
+}
+__device__ __forceinline__ float silu_grad(float z) {
+  const float sg = 1.0f / (1.0f + expf(-z));
+  return sg * (1.0f + z * (1.0f - sg));
+}
+
+// per (b, c): { sum_p g, sum_p g * u }  with g = dy * act'(y)
+template <typename T>
+__global__ void __launch_bounds__(256) chan_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const T* __restrict__ u, int act, int C, int HW,
+                                                            const float* __restrict__ zs, const float* __restrict__ zt, float* __restrict__ out) {
+  __shared__ float red[64];
+  const int64_t base = (int64_t)blockIdx.x * HW;
+  const int c = blockIdx.x % C;
+  const float z_s = zs ? zs[c] : 1.f, z_t = zt ? zt[c] : 0.f;
+  float s = 0.f, su = 0.f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    float g = ldf<T>(dy + base + i);
+    const float uu = ldf<T>(u + base + i);
+    if (act == VRCOC_ACT_SILU) g *= silu_grad(fmaf(uu, z_s, z_t));
+    else if (yact) g *= act_grad_from_out(ldf<T>(yact + base + i), act);
+    s += g; su = fmaf(g, uu, su);
+  }
+  s = warp_sum(s); su = warp_sum(su);
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = s; red[32 + (threadIdx.x >> 5)] = su; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[i]; b += red[32 + i]; }
+    out[2 * blockIdx.x] = a; out[2 * blockIdx.x + 1] = b;
+  }
+}
+
+// out = (dy * act'(y)) * ca[c] + u * cb[c] + cd[c]  (+ extra)
+template <typename T>
+__global__ void __launch_bounds__(256) chan_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const T* __restrict__ u, const T* __restrict__ extra,
+                                                             int act, const float* __restrict__ ca, const float* __restrict__ cb, const float* __restrict__ cd,
+                                                             const float* __restrict__ zs, const float* __restrict__ zt, int C, int HW, T* __restrict__ out) {
+  const int plane = blockIdx.y, c = plane % C;
+  const float a = ca[c], b = cb ? cb[c] : 0.f, d0 = cd ? cd[c] : 0.f;
+  const float z_s = zs ? zs[c] : 1.f, z_t = zt ? zt[c] : 0.f;
+  const int64_t base = (int64_t)plane * HW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    float g = ldf<T>(dy + base + i);
+    const float uu = u ? ldf<T>(u + base + i) : 0.f;
+    if (act == VRCOC_ACT_SILU) g *= silu_grad(fmaf(uu, z_s, z_t));
+    else if (yact) g *= act_grad_from_out(ldf<T>(yact + base + i), act);
+    float r = fmaf(g, a, d0);
+    if (cb) r = fmaf(uu, b, r);
+    if (extra) r += ldf<T>(extra + base + i);
+    stf<T>(out + base + i, r);
+  }
+}
+
+}  // namespace
+}  // namespace vrcoc
+
+using namespace vrcoc;
+
+extern "C" int vrcoc_gn_bwd_coef(const float* s, const double* gn_sums, const float* gamma, float eps, int B, int C, int HW, float* a,
+                                 float* bb, float* cc, float* dgamma, float* dbeta, float* workspace, void* stream) {
+  VRCOC_REQUIRE(s && gn_sums && gamma && a && bb && cc && dgamma && dbeta && workspace && B > 0 && C > 0 && HW > 0, "gn_bwd_coef: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  gn_bwd_coef_sample_kernel<<<B, 256, 0, st>>>(s, gn_sums, gamma, eps, C, HW, a, bb, cc, workspace);
+  gn_bwd_coef_chan_kernel<<<(C + 127) / 128, 128, 0, st>>>(s, workspace, B, C, dgamma, dbeta);
+  return check_launch("gn_bwd_coef");
+}
+
+extern "C" int vrcoc_proj_res_bwd_coef(const float* G, const float* sum_dy, const void* W, int w_dtype, const float* bias, const float* ls,
+                                       int O, int K, float* dW, float* db, float* dls, void* wt, void* stream) {
+  VRCOC_REQUIRE(G && sum_dy && W && dW && wt && O > 0 && K > 0, "proj_res_bwd_coef: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (w_dtype == VRCOC_BF16)
+    proj_res_bwd_coef_kernel<__nv_bfloat16><<<O, 128, 0, st>>>(G, sum_dy, (const __nv_bfloat16*)W, bias, ls, O, K, dW, db, dls, (__nv_bfloat16*)wt);
+  else
+    proj_res_bwd_coef_kernel<float><<<O, 128, 0, st>>>(G, sum_dy, (const float*)W, bias, ls, O, K, dW, db, dls, (float*)wt);
+  return check_launch("proj_res_bwd_coef");
+}
+
+extern "C" int vrcoc_col2im(const void* dcol, void* dx, int dtype, int B, int C, int H, int W, int kh, int kw, int stride, int pad, int dil,
+                            void* stream) {
+  VRCOC_REQUIRE(dcol && dx && B > 0 && C > 0 && H > 0 && W > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0, "col2im: bad argument");
+  if (dil <= 0) dil = 1;
+  const int Ho = (H + 2 * pad - dil * (kh - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dil * (kw - 1) - 1) / stride + 1;
+  VRCOC_REQUIRE(Ho > 0 && Wo > 0, "col2im: empty output");
+  const int64_t total = (int64_t)B * C * H * W;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)cdiv(total, 256);
+  if (dtype == VRCOC_BF16)
+    col2im_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)dcol, (__nv_bfloat16*)dx, C, H, W, kh, kw, stride, pad, dil, Ho, Wo, total);
+  else
+    col2im_kernel<float><<<blocks, 256, 0, st>>>((const float*)dcol, (float*)dx, C, H, W, kh, kw, stride, pad, dil, Ho, Wo, total);
+  return check_launch("col2im");
+}
+
+extern "C" int vrcoc_chan_bwd_sums(const void* dy, const void* y_act, const void* u, int dtype, int act, const float* z_scale,
+                                   const float* z_shift, int B, int C, int HW, float* out, void* stream) {
+  VRCOC_REQUIRE(dy && u && out && B > 0 && C > 0 && HW > 0, "chan_bwd_sums: bad argument");
+  VRCOC_REQUIRE(act != VRCOC_ACT_GELU, "chan_bwd_sums: GELU is handled by vrcoc_gelu_bwd");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VRCOC_BF16)
+    chan_bwd_sums_kernel<__nv_bfloat16><<<B * C, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y_act, (const __nv_bfloat16*)u, act, C, HW,
+                                                               z_scale, z_shift, out);
+  else
+    chan_bwd_sums_kernel<float><<<B * C, 256, 0, st>>>((const float*)dy, (const float*)y_act, (const float*)u, act, C, HW, z_scale, z_shift, out);
+  return check_launch("chan_bwd_sums");
+}
+
+extern "C" int vrcoc_chan_bwd_apply(const void* dy, const void* y_act, const void* u, const void* extra, void* out, int dtype, int act,
+                                    const float* ca, const float* cb, const float* cd, const float* z_scale, const float* z_shift, int B,
+                                    int C, int HW, void* stream) {
+  VRCOC_REQUIRE(dy && out && ca && B > 0 && C > 0 && HW > 0 && (!cb || u) && (act != VRCOC_ACT_SILU || u), "chan_bwd_apply: bad argument");
+  VRCOC_REQUIRE(act != VRCOC_ACT_GELU, "chan_bwd_apply: GELU is handled by vrcoc_gelu_bwd");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)(HW >= 16384 ? cdiv(HW, 4096) : 1), (unsigned)(B * C));
+  if (dtype == VRCOC_BF16)
+    chan_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y_act, (const __nv_bfloat16*)u,
+                                                                (const __nv_bfloat16*)extra, act, ca, cb, cd, z_scale, z_shift, C, HW, (__nv_bfloat16*)out);
+  else
+    chan_bwd_apply_kernel<float><<<grid, 256, 0, st>>>((const float*)dy, (const float*)y_act, (const float*)u, (const float*)extra, act, ca, cb, cd, z_scale,
+                                                       z_shift, C, HW, (float*)out);
+  return check_launch("chan_bwd_apply");
+}

@@ -72,6 +72,11 @@ SIGNATURES = {
     "vrcoc_im2col": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vrcoc_dwconv": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vrcoc_upsample_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "vrcoc_gn_bwd_coef": (_I, [_P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "vrcoc_proj_res_bwd_coef": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "vrcoc_col2im": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "vrcoc_chan_bwd_sums": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _P, _P]),
+    "vrcoc_chan_bwd_apply": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "vrcoc_gelu_bwd": (_I, [_P, _P, _P, _I, _L, _P]),
     "vrcoc_gn_bwd_sums": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     "vrcoc_gn_bwd_apply": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _P]),

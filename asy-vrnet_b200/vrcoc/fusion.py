@@ -132,6 +132,98 @@ def _conv_launch(x, weight, bias32, stride, pad, extra, extra_bstride, act, e_sc
     return out
 
 
+def _im2col(x, kh, kw, stride, pad, dil=1):
+    B, Cin, H, W = x.shape
+    Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+    col = torch.empty(B, kh * kw * Cin, Ho, Wo, device=x.device, dtype=x.dtype)
+    check(lib.vrcoc_im2col(_ptr(x), _ptr(col), _dt(x), B, Cin, H, W, kh, kw, stride, pad, dil, _stream()), "im2col")
+    return col
+
+
+def _conv_backward(x, weight, dy, stride, pad, extra=None, need_dx=True, need_dw=True, need_db=False):
+    """Native backward of y = conv2d(cat[x, extra], weight) (reference vr_coc.py:99-102, normal_conv.py:42-43) given dy = dL/dy:
+         dW = dy . im2col(x)^T     tap-major im2col + the 1x1 weight-gradient kernel (tensor cores for bf16), permuted back
+         dx = col2im(W^T . dy)     1x1 GEMM with the transposed tap-major weight + the adjoint of im2col
+    Returns (dx [B,C0,H,W] in x's dtype or None, dW [O,Cin,kh,kw] fp32 or None, db [O] fp32 or None)."""
+    x = x.contiguous()
+    dy = dy.contiguous()
+    B, C0, H, W = x.shape
+    O, Cin, kh, kw = weight.shape
+    if dy.dtype != x.dtype:
+        dy = dy.to(x.dtype)
+    xin = x
+    if extra is not None:
+        e = extra if extra.dim() == 4 else extra.unsqueeze(0).expand(B, -1, -1, -1)
+        xin = torch.cat([x, e.to(x.dtype)], dim=1)
+    one = kh == 1 and kw == 1 and stride == 1 and pad == 0
+    w2 = weight.detach().reshape(O, -1).contiguous() if one else ops.tap_major(weight)          # [O][K]
+    if w2.dtype != x.dtype:
+        w2 = w2.to(x.dtype)
+    dW = db = dx = None
+    if need_dw or need_db:
+        col = xin if one else _im2col(xin, kh, kw, stride, pad)
+        dWk, db = ops.conv1x1_wgrad(conv_desc(col, w2, dy), dy, want_db=need_db)
+        dW = dWk.view(O, Cin, 1, 1) if one else dWk.view(O, kh, kw, Cin).permute(0, 3, 1, 2)
+    if need_dx:
+        wt = w2.t().contiguous()                                                                 # [K][O]
+        dcol = torch.empty(B, wt.shape[0], dy.shape[2], dy.shape[3], device=x.device, dtype=x.dtype)
+        conv_fwd(conv_desc(dy, wt, dcol))
+        if one:
+            dxin = dcol
+        else:
+            dxin = torch.empty(B, Cin, H, W, device=x.device, dtype=x.dtype)
+            check(lib.vrcoc_col2im(_ptr(dcol), _ptr(dxin), _dt(dxin), B, Cin, H, W, kh, kw, stride, pad, 1, _stream()), "col2im")
+        dx = dxin if extra is None else dxin[:, :C0].contiguous()
+    return dx, dW, db
+
+
+def _bn_coefficients(S, mean, rstd, gamma, N, training):
+    """(ca, cb, cd, dgamma, dbeta) from S = [C,2] = {sum g, sum g*u} (fp64)"""
+    S1, S2 = S[:, 0], S[:, 1]
+    sgx = (S2 - mean * S1) * rstd                              # sum g * xhat
+    ca = gamma * rstd
+    if training:
+        cb = -gamma * rstd * rstd * sgx / N
+        cd = -gamma * rstd * S1 / N - cb * mean
+        return ca.float().contiguous(), cb.float().contiguous(), cd.float().contiguous(), sgx.float(), S1.float()
+    return ca.float().contiguous(), None, None, sgx.float(), S1.float()
+
+
+def _batch_stats(u):
+    """biased batch mean / variance per channel (fp64 [C]) from the native channel sums"""
+    B, C, H, W = u.shape
+    cs, _ = ops.channel_sums(u)
+    s = cs.double().sum(0)
+    n = float(B * H * W)
+    mean = s[:, 0] / n
+    return mean, (s[:, 1] / n - mean * mean).clamp_min(0)
+
+
+def _norm_act_backward(dy, y_act, u, act, bn_w, bn_b, mean, var, eps, training, extra=None):
+    """du, dgamma, dbeta for y = act(BN(u)); `extra` (optional) is added to du (a residual branch's gradient)."""
+    B, C, H, W = u.shape
+    HW, N = H * W, B * H * W
+    dy = dy.contiguous()
+    if dy.dtype != u.dtype:
+        dy = dy.to(u.dtype)
+    rstd = torch.rsqrt(var + eps)
+    gamma = bn_w.detach().double() if bn_w is not None else torch.ones_like(mean)
+    zs = zt = None
+    if act == ACT_SILU:
+        beta = bn_b.detach().double() if bn_b is not None else torch.zeros_like(mean)
+        zs = (gamma * rstd).float().contiguous()
+        zt = (beta - mean * gamma * rstd).float().contiguous()
+    ya = y_act if act in (ACT_RELU, ACT_LRELU) else None
+    sums = torch.empty(B, C, 2, device=u.device, dtype=torch.float32)
+    check(lib.vrcoc_chan_bwd_sums(_ptr(dy), _ptr(ya), _ptr(u), _dt(u), act, _ptr(zs), _ptr(zt), B, C, HW, _ptr(sums), _stream()), "chan_bwd_sums")
+    ca, cb, cd, dgamma, dbeta = _bn_coefficients(sums.double().sum(0), mean, rstd, gamma, N, training)
+    du = torch.empty_like(u)
+    check(lib.vrcoc_chan_bwd_apply(_ptr(dy), _ptr(ya), _ptr(u), _ptr(extra), _ptr(du), _dt(u), act, _ptr(ca), _ptr(cb), _ptr(cd), _ptr(zs),
+                                   _ptr(zt), B, C, HW, _stream()), "chan_bwd_apply")
+    return du, dgamma, dbeta
+
+
 @ops.amp_function
 class _ConvFn(torch.autograd.Function):
     @staticmethod
@@ -144,12 +236,14 @@ class _ConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        from . import _autograd_ref as R
         x, weight, bias, extra, e_scale = ctx.saved_tensors
         stride, pad, act = ctx.meta
-        return R.grads(lambda x_, w_, b_, e_: R.conv_act(x_, w_, b_, stride, pad, extra, act, e_),
-                       [x, weight, bias, e_scale], dy,
-                       tuple(ctx.needs_input_grad[i] for i in (0, 1, 2, 8)), slots=(0, 1, 2, 8), total=11)
+        if act != ACT_NONE or e_scale is not None:
+            raise VrcocError("conv2d_native: backward is implemented for the plain convolution (PointRecuder, vr_coc.py:99-102); "
+                             "conv + BatchNorm + activation trains through BaseConv")
+        dx, dW, db = _conv_backward(x, weight, dy, stride, pad, extra, need_dx=ctx.needs_input_grad[0], need_dw=ctx.needs_input_grad[1],
+                                    need_db=bias is not None and ctx.needs_input_grad[2])
+        return (dx, dW, db) + (None,) * 8
 
 
 _ACT_CODE = {"relu": ACT_RELU, "silu": ACT_SILU, "lrelu": ACT_LRELU}
@@ -299,17 +393,29 @@ class _BaseConvFn(torch.autograd.Function):
         rv = None if training or not need_bwd else mod.bn.running_var.detach().clone()
         out = _base_conv_forward(mod, x, out_minmax, weight)
         if need_bwd:
-            ctx.save_for_backward(x, weight, bias, bn_w, bn_b, rm, rv)
+            ctx.save_for_backward(x, weight, bias, bn_w, bn_b, rm, rv, out)
             ctx.meta = (mod.conv.stride[0], mod.conv.padding[0], mod._act_name, mod.bn.eps, training)
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        from . import _autograd_ref as R
-        x, weight, bias, bn_w, bn_b, rm, rv = ctx.saved_tensors
+        x, weight, bias, bn_w, bn_b, rm, rv, y = ctx.saved_tensors
         stride, pad, act, eps, training = ctx.meta
-        return R.grads(lambda x_, w_, b_, g_, h_: R.base_conv(x_, w_, b_, g_, h_, rm, rv, stride, pad, act, eps, training),
-                       [x, weight, bias, bn_w, bn_b], dy, ctx.needs_input_grad[:5], slots=(0, 1, 2, 3, 4), total=7)
+        dx, dW, db, dg, dbt = _base_conv_backward(x, weight, bias, bn_w, bn_b, rm, rv, y, stride, pad, act, eps, training, dy,
+                                                  need_dx=ctx.needs_input_grad[0])
+        return dx, dW, db, dg, dbt, None, None
+
+
+def _base_conv_backward(x, weight, bias, bn_w, bn_b, rm, rv, y, stride, pad, act, eps, training, dy, need_dx=True):
+    """Native backward of BaseConv (normal_conv.py:36-52): recompute the convolution output u (not saved: it was rewritten in
+    place by the BatchNorm + activation pass), BatchNorm + activation backward, convolution backward."""
+    if x.dtype != weight.dtype:
+        x = x.to(weight.dtype)
+    u = _conv_launch(x, weight, _f32(bias), stride, pad, None, None, ACT_NONE, None, None, None)
+    mean, var = _batch_stats(u) if training else (rm.double(), rv.double())
+    du, dgamma, dbeta = _norm_act_backward(dy, y, u, _ACT_CODE[act], bn_w, bn_b, mean, var, eps, training)
+    dx, dW, db = _conv_backward(x, weight, du, stride, pad, None, need_dx=need_dx, need_dw=True, need_db=bias is not None)
+    return dx, dW, db, dgamma, dbeta
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -505,7 +505,7 @@ class ClusterCoreFn(torch.autograd.Function):          # (no autocast cast: `fea
         else:
             dfeat = dvalue = None
         dfeat, dvalue, dab = cluster_core_bwd(feat, value, dout, idx, smax, a32, b32, *ctx.cfg, dfeat=dfeat, dvalue=dvalue)
-        return dfeat, dvalue, dab[0:1].to(ctx.ab_dtype), dab[1:2].to(ctx.ab_dtype), None, None, None, None, None
+        return dfeat, dvalue, dab[0:1], dab[1:2], None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -583,31 +583,21 @@ class GNProjFn(torch.autograd.Function):
         dz = torch.empty(B, Cc, H, W, device=x.device, dtype=x.dtype)
         conv_fwd(conv_desc(dy, wt, dz))
         if gn is None:
-            return (dz, None, None, None, None, dW.reshape(wshape).to(wdt), None if db is None else db.to(bdt), None, None)
-        # GroupNorm(1,C) backward
+            return (dz, None, None, None, None, dW.reshape(wshape), db, None, None)
+        # GroupNorm(1,C) backward: per-(b,c) sums -> coefficients (one small kernel pair) -> dx = dz*a + x*bb + cc
         s = torch.empty(B, Cc, 2, device=x.device, dtype=torch.float32)
         check(lib.vrcoc_gn_bwd_sums(_ptr(dz), _ptr(x), _dt(x), B, Cc, P, _ptr(s), _stream()), "gn_bwd_sums")
-        cnt = float(Cc * P)
-        tot = sums.sum(dim=1)                                                   # reduce the slots -> [B,2]
-        mean = (tot[:, 0] / cnt)
-        var = (tot[:, 1] / cnt - mean * mean).clamp_min(0)
-        rstd = torch.rsqrt(var + eps)
-        mean32, rstd32 = mean.float(), rstd.float()
-        s1, s2 = s[..., 0].double(), s[..., 1].double()                       # sum dz, sum dz*x   [B,C]
-        sxh = (s2 - mean[:, None] * s1) * rstd[:, None]                         # sum dz*xhat
-        dgamma = sxh.sum(0)
-        dbeta = s1.sum(0)
-        g64 = g32.double()
-        m1 = (s1 * g64).sum(1) / cnt                                            # mean(gamma*dz)
-        m2 = (sxh * g64).sum(1) / cnt                                           # mean(gamma*dz*xhat)
-        a = (rstd32[:, None] * g32[None, :]).contiguous()                       # [B,C]
-        bb = (-(rstd * rstd * m2)).float().contiguous()                         # [B]
-        cc = (rstd * (mean * rstd * m2 - m1)).float().contiguous()              # [B]
+        small = torch.empty(2 * B * Cc + 2 * B + 2 * Cc, device=x.device, dtype=torch.float32)
+        a, ws = small[:B * Cc], small[B * Cc:2 * B * Cc]
+        o = 2 * B * Cc
+        bb, cc, dgamma, dbeta = small[o:o + B], small[o + B:o + 2 * B], small[o + 2 * B:o + 2 * B + Cc], small[o + 2 * B + Cc:]
+        check(lib.vrcoc_gn_bwd_coef(_ptr(s), _ptr(sums), _ptr(g32), float(eps), B, Cc, P, _ptr(a), _ptr(bb), _ptr(cc), _ptr(dgamma),
+                                    _ptr(dbeta), _ptr(ws), _stream()), "gn_bwd_coef")
         dx = torch.empty_like(x)
         check(lib.vrcoc_gn_bwd_apply(_ptr(dz), _ptr(x), None, _ptr(dx), _dt(x), _ptr(a), _ptr(bb), _ptr(cc), B, Cc, P, _stream()),
               "gn_bwd_apply")
-        return (dx, None, dgamma.to(gdt), dbeta.to(gdt), None, dW.reshape(wshape).to(wdt),
-                None if db is None else db.to(bdt), None, None)
+        # gradients are returned in fp32: autograd casts them to the dtype of the corresponding input
+        return (dx, None, dgamma, dbeta, None, dW.reshape(wshape), db, None, None)
 
 
 @amp_function
@@ -642,20 +632,15 @@ class ProjResidualFn(torch.autograd.Function):
         B, K, H, W = h.shape
         # G[o,k] = sum dout[o,p] h[k,p];  s[o] = sum dout[o,p]
         G, s = conv1x1_wgrad(conv_desc(h, w2, dout), dout, want_db=True)
-        if ls32 is not None:
-            dW = ls32[:, None] * G
-            db = ls32 * s
-            dls = (w2.float() * G).sum(1)
-            if bias32 is not None:
-                dls = dls + bias32 * s
-            wt = (w2.float() * ls32[:, None]).t().contiguous().to(w2.dtype)
-        else:
-            dW, db, dls = G, s, None
-            wt = w2.t().contiguous()
+        O = w2.shape[0]
+        small = torch.empty(O * K + 2 * O, device=h.device, dtype=torch.float32)
+        dW, db, dls = small[:O * K].view(O, K), small[O * K:O * K + O], small[O * K + O:]
+        wt = torch.empty(K, O, device=h.device, dtype=w2.dtype)
+        check(lib.vrcoc_proj_res_bwd_coef(_ptr(G), _ptr(s), _ptr(w2), _dt(w2), _ptr(bias32), _ptr(ls32), O, K, _ptr(dW), _ptr(db), _ptr(dls),
+                                          _ptr(wt), _stream()), "proj_res_bwd_coef")
         dh = torch.empty_like(h)
         conv_fwd(conv_desc(dout, wt, dh))
-        return (dh, dW.reshape(wshape).to(wdt), None if bias32 is None else db.to(bdt),
-                None if dls is None else dls.to(lsdt), dout)
+        return (dh, dW.reshape(wshape), None if bias32 is None else db, None if ls32 is None else dls, dout)
 
 
 @amp_function
@@ -691,4 +676,4 @@ class ProjFn(torch.autograd.Function):
         dW, db = conv1x1_wgrad(conv_desc(x, w2, dy), dy, want_db=bias32 is not None)
         dx = torch.empty_like(x)
         conv_fwd(conv_desc(dy, w2.t().contiguous(), dx))
-        return dx, dW.reshape(wshape).to(wdt), None if db is None else db.to(bdt), None
+        return dx, dW.reshape(wshape), db, None

@@ -470,6 +470,12 @@ def train_setup(args, dev, world, batch):
         from nets.yolo_training import YOLOLoss, weights_init
         with contextlib.redirect_stdout(io.StringIO()):
             weights_init(model)
+        import nets.yolo_training as _yt
+        # the reference calls torch.cuda.empty_cache() once per image inside its SimOTA loop (yolo_training.py:169): 16 times per
+        # step it hands the caching allocator's whole pool back to the driver and every later allocation of the step pays
+        # cudaMalloc.  Numerically a no-op; replaced by one here (the loss code itself is the reference's, unmodified).
+        _yt.torch = type("_TorchNoEmptyCache", (), {"__getattr__": lambda self, k: getattr(torch, k),
+                                                    "cuda": type("_Cuda", (), {"__getattr__": lambda self, k: (lambda: None) if k == "empty_cache" else getattr(torch.cuda, k)})()})()
         yolo_loss, focal, dice = YOLOLoss(4, True), Focal_Loss, Dice_loss      # fp16=True: its SimOTA cost leaves autocast (yolo_training.py:240-247)
         loss_kind = "reference YOLOLoss(4, fp16=True) + 5*(Focal_Loss + Dice_loss) (nets/yolo_training.py:60, nets/deeplabv3_training.py:22,41)"
     model = model.to(dev).train()

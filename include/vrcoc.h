@@ -263,6 +263,34 @@ int vrcoc_gn_bwd_sums(const void* dz, const void* x, int dtype, int B, int C, in
 int vrcoc_gn_bwd_apply(const void* dz, const void* x, const void* extra /*nullable*/, void* out, int dtype, const float* a,
                        const float* bb, const float* cc, int B, int C, int HW, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Training path, small backward kernels (csrc/bwd.cu).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* GroupNorm(1,C) backward coefficients (vr_coc.py:105-111 inside :265,:270) from s = vrcoc_gn_bwd_sums output [B][C][2] and the
+ * forward statistics: a[b][c] = rstd_b*gamma_c, bb[b], cc[b] for vrcoc_gn_bwd_apply (dx = dz*a + x*bb + cc), dgamma[c], dbeta[c].
+ * workspace: float [B][C].  Deterministic (fixed reduction order). */
+int vrcoc_gn_bwd_coef(const float* s, const double* gn_sums, const float* gamma, float eps, int B, int C, int HW, float* a, float* bb,
+                      float* cc, float* dgamma, float* dbeta, float* workspace, void* stream);
+/* Gradients of out = res + ls * (W h + b) w.r.t. W, b, ls from G[o][k] = sum dout*h and sum_dy[o] = sum dout (vrcoc_conv1x1_wgrad):
+ * dW = ls*G, db = ls*sum_dy, dls = sum_k W*G + b*sum_dy, and wt[k][o] = W[o][k]*ls[o] (the dgrad weight, in W's dtype).
+ * bias / ls / db / dls nullable (vr_coc.py:191,222 with the layer scale of :266-271). */
+int vrcoc_proj_res_bwd_coef(const float* G, const float* sum_dy, const void* W, int w_dtype, const float* bias, const float* ls, int O,
+                            int K, float* dW, float* db, float* dls, void* wt, void* stream);
+/* Adjoint of vrcoc_im2col (same tap-major layout): dx[b][c][y][x] = sum of the dcol entries that were copies of x[b][c][y][x];
+ * with dcol = W^T . dy this is the input gradient of a k x k convolution (PointRecuder / BaseConv, vr_coc.py:99-102,313). */
+int vrcoc_col2im(const void* dcol, void* dx, int dtype, int B, int C, int H, int W, int kh, int kw, int stride, int pad, int dil,
+                 void* stream);
+/* Per-channel affine (+ activation) backward = BatchNorm2d backward (normal_conv.py:45-49; vr_coc.py:315,341,356):
+ *   g = dy * act'(.)   relu / lrelu: from y_act = forward output of the activation (NULL = no activation);
+ *                      silu: from z = u*z_scale[c] + z_shift[c], the recomputed pre-activation
+ *   sums : out[b][c] = { sum_p g, sum_p g*u }
+ *   apply: out = g*ca[c] + u*cb[c] + cd[c] (+ extra)          (cb / cd / extra / z_* nullable) */
+int vrcoc_chan_bwd_sums(const void* dy, const void* y_act, const void* u, int dtype, int act, const float* z_scale, const float* z_shift,
+                        int B, int C, int HW, float* out, void* stream);
+int vrcoc_chan_bwd_apply(const void* dy, const void* y_act, const void* u, const void* extra, void* out, int dtype, int act,
+                         const float* ca, const float* cb, const float* cd, const float* z_scale, const float* z_shift, int B, int C,
+                         int HW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
