@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(256) chan_bwd_sums_kernel(const T* __restrict_
     const float uu = ldf<T>(u + base + i);
     if (act == VRCOC_ACT_SILU) g *= silu_grad(fmaf(uu, z_s, z_t));
     else if (yact) g *= act_grad_from_out(ldf<T>(yact + base + i), act);
+    else if (zs) g *= act_grad_from_out(fmaf(uu, z_s, z_t), act);          // sign of the recomputed pre-activation
     s += g; su = fmaf(g, uu, su);
   }
   s = warp_sum(s); su = warp_sum(su);
@@ -176,8 +177,119 @@ __global__ void __launch_bounds__(256) chan_bwd_apply_kernel(const T* __restrict
     const float uu = u ? ldf<T>(u + base + i) : 0.f;
     if (act == VRCOC_ACT_SILU) g *= silu_grad(fmaf(uu, z_s, z_t));
     else if (yact) g *= act_grad_from_out(ldf<T>(yact + base + i), act);
+    else if (zs) g *= act_grad_from_out(fmaf(uu, z_s, z_t), act);
     float r = fmaf(g, a, d0);
     if (cb) r = fmaf(uu, b, r);
+    if (extra) r += ldf<T>(extra + base + i);
+    stf<T>(out + base + i, r);
+  }
+}
+
+__device__ __forceinline__ void decode_minmax(const uint32_t* mm, float& mn, float& mx) {
+  mx = __uint_as_float(mm[0]);
+  mn = __uint_as_float(~mm[1]);
+}
+
+// ImageEnhanceByRadar tail backward (vr_coc.py:314: y = (1 + (k - mn)/(mx - mn)) * image), given dyv = dL/dy:
+//   dimage = dyv * (1 + kn),  dk = dyv * image / (mx - mn)  (the direct path),
+//   part[plane] = { sum dkn, sum dkn * k, #(k == mn), #(k == mx) }  with dkn = dyv * image   (for the min / max paths)
+template <typename T>
+__global__ void __launch_bounds__(256) img_enh_bwd_kernel(const T* __restrict__ dyv, const T* __restrict__ image, const T* __restrict__ k,
+                                                          const uint32_t* __restrict__ minmax, int HW, T* __restrict__ dimage, T* __restrict__ dk,
+                                                          float* __restrict__ part) {
+  __shared__ float red[4][8];
+  float mn, mx;
+  decode_minmax(minmax, mn, mx);
+  const float r = 1.0f / (mx - mn);
+  const int64_t base = (int64_t)blockIdx.x * HW;
+  float s0 = 0.f, s1 = 0.f, c0 = 0.f, c1 = 0.f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float g = ldf<T>(dyv + base + i), im = ldf<T>(image + base + i), kk = ldf<T>(k + base + i);
+    const float kn = (kk - mn) * r, dkn = g * im;
+    stf<T>(dimage + base + i, g * (1.0f + kn));
+    stf<T>(dk + base + i, dkn * r);
+    s0 += dkn; s1 = fmaf(dkn, kk, s1);
+    c0 += (kk == mn) ? 1.f : 0.f; c1 += (kk == mx) ? 1.f : 0.f;
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1); c0 = warp_sum(c0); c1 = warp_sum(c1);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[0][w] = s0; red[1][w] = s1; red[2][w] = c0; red[3][w] = c1; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[threadIdx.x][i];
+    part[4 * blockIdx.x + threadIdx.x] = t;
+  }
+}
+
+// dk += (k == mn) * coef[0] + (k == mx) * coef[1]: the gradient that reaches k through the global min / max (evenly over ties)
+template <typename T>
+__global__ void __launch_bounds__(256) minmax_scatter_kernel(const T* __restrict__ k, T* __restrict__ dk, const uint32_t* __restrict__ minmax,
+                                                             const float* __restrict__ coef, int64_t n) {
+  float mn, mx;
+  decode_minmax(minmax, mn, mx);
+  const float a = coef[0], b = coef[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float kk = ldf<T>(k + i);
+    if (kk == mn || kk == mx) stf<T>(dk + i, ldf<T>(dk + i) + (kk == mn ? a : 0.f) + (kk == mx ? b : 0.f));
+  }
+}
+
+// ---- backward of the table-driven prologue  z = x * s * h(x) * e,  h(x) = sigmoid(ga*x + gc)  (ShuffleAttention gates + ECA scale of
+//      RadarEnhanceByImage, vr_coc.py:344-350; shuffle_attention.py:48-72; eca.py:16-22).  Source-channel order; dz is read at the logical
+//      channel kidx[c] of source channel c.  The statistics chain (channel means / variances -> gates -> ECA) is O(B*C) algebra on the
+//      six sums below; its results come back as the four coefficients of the apply pass. ------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) table_bwd_sums_kernel(const T* __restrict__ dz, const T* __restrict__ x, const int32_t* __restrict__ kidx,
+                                                             const float* __restrict__ gate, int C, int K, int HW, float* __restrict__ out) {
+  __shared__ float red[6][8];
+  const int b = blockIdx.x / C, c = blockIdx.x % C;
+  const int k = kidx ? kidx[c] : c;
+  const float ga = gate ? gate[2 * blockIdx.x] : 0.f, gc = gate ? gate[2 * blockIdx.x + 1] : 0.f;
+  const T* dzp = dz + ((int64_t)b * K + k) * HW;
+  const T* xp = x + (int64_t)blockIdx.x * HW;
+  float a1 = 0.f, a2 = 0.f, a3 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float g = ldf<T>(dzp + i), xv = ldf<T>(xp + i);
+    const float h = gate ? 1.0f / (1.0f + expf(-fmaf(ga, xv, gc))) : 1.0f;
+    const float xh = xv * h, xd = xv * h * (1.0f - h);
+    a1 = fmaf(g, xh, a1); a2 = fmaf(g * xv, xd, a2); a3 = fmaf(g, xd, a3);
+    j1 += xh; j2 = fmaf(xv, xd, j2); j3 += xd;
+  }
+  float v[6] = {a1, a2, a3, j1, j2, j3};
+  const int w = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    v[q] = warp_sum(v[q]);
+    if ((threadIdx.x & 31) == 0) red[q][w] = v[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[threadIdx.x][i];
+    out[6 * (int64_t)blockIdx.x + threadIdx.x] = t;
+  }
+}
+
+// dx = (dz*cd + cj) * (h + x*ga*h*(1-h)) + c1 + 2*x*c2 (+ extra),  coef[b][c] = {cd, cj, c1, c2}
+template <typename T>
+__global__ void __launch_bounds__(256) table_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ x, const T* __restrict__ extra,
+                                                              const int32_t* __restrict__ kidx, const float* __restrict__ gate,
+                                                              const float* __restrict__ coef, int C, int K, int HW, T* __restrict__ out) {
+  const int plane = blockIdx.y, b = plane / C, c = plane % C;
+  const int k = kidx ? kidx[c] : c;
+  const float ga = gate ? gate[2 * plane] : 0.f, gc = gate ? gate[2 * plane + 1] : 0.f;
+  const float cd = coef[4 * plane], cj = coef[4 * plane + 1], c1 = coef[4 * plane + 2], c2 = coef[4 * plane + 3];
+  const T* dzp = dz + ((int64_t)b * K + k) * HW;
+  const int64_t base = (int64_t)plane * HW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const float g = ldf<T>(dzp + i), xv = ldf<T>(x + base + i);
+    float t = 1.0f;
+    if (gate) {
+      const float h = 1.0f / (1.0f + expf(-fmaf(ga, xv, gc)));
+      t = h + xv * ga * h * (1.0f - h);
+    }
+    float r = fmaf(fmaf(g, cd, cj), t, fmaf(2.0f * xv, c2, c1));
     if (extra) r += ldf<T>(extra + base + i);
     stf<T>(out + base + i, r);
   }
@@ -187,6 +299,53 @@ __global__ void __launch_bounds__(256) chan_bwd_apply_kernel(const T* __restrict
 }  // namespace vrcoc
 
 using namespace vrcoc;
+
+extern "C" int vrcoc_table_bwd_sums(const void* dz, const void* x, int dtype, const int32_t* kidx, const float* gate, int B, int C, int K,
+                                    int HW, float* out, void* stream) {
+  VRCOC_REQUIRE(dz && x && out && B > 0 && C > 0 && K >= C && HW > 0, "table_bwd_sums: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VRCOC_BF16)
+    table_bwd_sums_kernel<__nv_bfloat16><<<B * C, 256, 0, st>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)x, kidx, gate, C, K, HW, out);
+  else
+    table_bwd_sums_kernel<float><<<B * C, 256, 0, st>>>((const float*)dz, (const float*)x, kidx, gate, C, K, HW, out);
+  return check_launch("table_bwd_sums");
+}
+
+extern "C" int vrcoc_table_bwd_apply(const void* dz, const void* x, const void* extra, void* out, int dtype, const int32_t* kidx,
+                                     const float* gate, const float* coef, int B, int C, int K, int HW, void* stream) {
+  VRCOC_REQUIRE(dz && x && out && coef && B > 0 && C > 0 && K >= C && HW > 0, "table_bwd_apply: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)(HW >= 16384 ? cdiv(HW, 4096) : 1), (unsigned)(B * C));
+  if (dtype == VRCOC_BF16)
+    table_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dz, (const __nv_bfloat16*)x, (const __nv_bfloat16*)extra, kidx, gate,
+                                                                 coef, C, K, HW, (__nv_bfloat16*)out);
+  else
+    table_bwd_apply_kernel<float><<<grid, 256, 0, st>>>((const float*)dz, (const float*)x, (const float*)extra, kidx, gate, coef, C, K, HW, (float*)out);
+  return check_launch("table_bwd_apply");
+}
+
+extern "C" int vrcoc_img_enh_bwd(const void* dyv, const void* image, const void* k, int dtype, const uint32_t* minmax, int B, int C, int HW,
+                                 void* dimage, void* dk, float* part, void* stream) {
+  VRCOC_REQUIRE(dyv && image && k && minmax && dimage && dk && part && B > 0 && C > 0 && HW > 0, "img_enh_bwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VRCOC_BF16)
+    img_enh_bwd_kernel<__nv_bfloat16><<<B * C, 256, 0, st>>>((const __nv_bfloat16*)dyv, (const __nv_bfloat16*)image, (const __nv_bfloat16*)k, minmax, HW,
+                                                             (__nv_bfloat16*)dimage, (__nv_bfloat16*)dk, part);
+  else
+    img_enh_bwd_kernel<float><<<B * C, 256, 0, st>>>((const float*)dyv, (const float*)image, (const float*)k, minmax, HW, (float*)dimage, (float*)dk, part);
+  return check_launch("img_enh_bwd");
+}
+
+extern "C" int vrcoc_minmax_scatter(const void* k, void* dk, int dtype, const uint32_t* minmax, const float* coef, int64_t n, void* stream) {
+  VRCOC_REQUIRE(k && dk && minmax && coef && n > 0, "minmax_scatter: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)(cdiv(n, 256) < 1184 ? cdiv(n, 256) : 1184);
+  if (dtype == VRCOC_BF16)
+    minmax_scatter_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)k, (__nv_bfloat16*)dk, minmax, coef, n);
+  else
+    minmax_scatter_kernel<float><<<blocks, 256, 0, st>>>((const float*)k, (float*)dk, minmax, coef, n);
+  return check_launch("minmax_scatter");
+}
 
 extern "C" int vrcoc_gn_bwd_coef(const float* s, const double* gn_sums, const float* gamma, float eps, int B, int C, int HW, float* a,
                                  float* bb, float* cc, float* dgamma, float* dbeta, float* workspace, void* stream) {

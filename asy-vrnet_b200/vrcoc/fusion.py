@@ -9,8 +9,10 @@ Forward (eval AND train mode) runs on the hand-written kernels:
   RadarEnhanceByImage  = [channel sums x2] -> [ShuffleAttention gate params + attended means] -> [ECA + prologue table]
                          -> [1x1 GEMM whose prologue applies attention/ECA/shuffle and whose epilogue applies
                              BN + ReLU + radar residual + BN]
-Backward of these modules (training) is obtained by re-running a differentiable restatement of the same maths with
-torch CUDA ops inside the autograd Function (`_autograd_ref`); a native backward is future work.
+Backward (training) is native as well: the big-tensor passes are kernels of csrc/bwd.cu (k x k convolution backward through
+im2col / col2im and the tensor-core weight gradient, BatchNorm + activation backward, the min/max-normalised gate of
+ImageEnhanceByRadar, the gated prologue of RadarEnhanceByImage); only O(B*C)-sized statistics algebra runs as torch ops on
+tiny tensors (`_prologue_backward`, `_bn_coefficients`).
 """
 import math
 
@@ -210,7 +212,8 @@ def _norm_act_backward(dy, y_act, u, act, bn_w, bn_b, mean, var, eps, training, 
     rstd = torch.rsqrt(var + eps)
     gamma = bn_w.detach().double() if bn_w is not None else torch.ones_like(mean)
     zs = zt = None
-    if act == ACT_SILU:
+    if act == ACT_SILU or (act in (ACT_RELU, ACT_LRELU) and y_act is None):
+        # the activation derivative from the recomputed pre-activation z = u * zs + zt
         beta = bn_b.detach().double() if bn_b is not None else torch.zeros_like(mean)
         zs = (gamma * rstd).float().contiguous()
         zt = (beta - mean * gamma * rstd).float().contiguous()
@@ -489,6 +492,113 @@ def _group_norm_maybe_empty(q):
     return gn
 
 
+def _prologue_backward(dzf, image, radar, chan_src, sa, eca_w, initial=False, extra_radar=None):
+    """Backward of the gated / scaled prologue  z'_k = x * s * sigmoid(ga*x + gc) * e_k  in front of RadarEnhanceByImage's projection
+    (vr_coc.py:344-350: ShuffleAttention on the image channels, cat + shuffle, eca_block) — and of ShuffleAttention / eca_block alone.
+
+    dzf  [B,K,H,W]  gradient w.r.t. z' in LOGICAL channel order;  image [B,Ci,H,W] / radar [B,Cr,H,W] (either may be None);
+    chan_src int32 [K]: logical k -> channel of the virtual concat [image | radar] (None = identity);
+    sa = (cw, cb, sw, sb, gw, gb, G) or None;  eca_w conv1d weight or None.
+
+    Two native passes over the maps per source (six sums per (b, channel); the elementwise apply) around the O(B*K) chain
+    statistics -> gates -> ECA, which is evaluated on [B,K]-sized tensors with autograd: the sums enter as first-order models so
+    that its gradients are exact.  Returns (dimage, dradar, sa_param_grads or None, deca_w or None)."""
+    B, K, H, W = dzf.shape
+    HW = H * W
+    dev = dzf.device
+    dzf = dzf.contiguous()
+    Ci = 0 if image is None else image.shape[1]
+    Cr = 0 if radar is None else radar.shape[1]
+    if chan_src is None:
+        inv = torch.arange(K, device=dev, dtype=torch.int32)
+        src = inv.long()
+    else:
+        src = chan_src.long()
+        inv = torch.empty(K, device=dev, dtype=torch.int32)
+        inv[src] = torch.arange(K, device=dev, dtype=torch.int32)
+    kidx_i, kidx_r = inv[:Ci].contiguous(), inv[Ci:].contiguous()
+    D = torch.float64
+
+    def leaf(t):
+        return t.detach().to(D).requires_grad_(True)
+
+    with torch.enable_grad():
+        params = None
+        Sx_i = Sxx_i = Sx_r = J1 = None
+        gate = None
+        if Ci:
+            cs_i, _ = ops.channel_sums(image)
+            Sx_i, Sxx_i = leaf(cs_i[..., 0]), leaf(cs_i[..., 1])
+            if sa is not None and not initial:
+                cw, cb, sw, sb, gw, gb, G = sa
+                q = Ci // (2 * G)
+                params = [leaf(t.reshape(-1)) for t in (cw, cb, sw, sb, gw, gb)]
+                c = torch.arange(Ci, device=dev)
+                j, half = c % q, (c // q) % 2
+                m = Sx_i / HW
+                rstd = torch.rsqrt(Sxx_i / HW - m * m + 1e-5)
+                pc = [t[j] for t in params]
+                s_i = torch.where(half == 0, torch.sigmoid(pc[0] * m + pc[1]), torch.ones_like(m))
+                ga = torch.where(half == 1, pc[2] * pc[4] * rstd, torch.zeros_like(m))
+                gc = torch.where(half == 1, pc[2] * (pc[5] - pc[4] * m * rstd) + pc[3], torch.full_like(m, 88.0))
+                gate = torch.stack([ga.detach(), gc.detach()], dim=-1).float().contiguous()
+            else:
+                s_i = torch.ones_like(Sx_i)
+                ga = gc = None
+            sums_i = torch.empty(B, Ci, 6, device=dev, dtype=torch.float32)
+            check(lib.vrcoc_table_bwd_sums(_ptr(dzf), _ptr(image), _dt(image), _ptr(kidx_i), _ptr(gate), B, Ci, K, HW, _ptr(sums_i), _stream()),
+                  "table_bwd_sums")
+            si = sums_i.to(D)
+            J1 = leaf(si[..., 3])
+            J1v = J1
+            if gate is not None:
+                J1v = J1 + si[..., 4] * (ga - ga.detach()) + si[..., 5] * (gc - gc.detach())
+            mean_att = s_i * J1v / HW
+        if Cr:
+            cs_r, _ = ops.channel_sums(radar)
+            Sx_r = leaf(cs_r[..., 0])
+            sums_r = torch.empty(B, Cr, 6, device=dev, dtype=torch.float32)
+            check(lib.vrcoc_table_bwd_sums(_ptr(dzf), _ptr(radar), _dt(radar), _ptr(kidx_r), None, B, Cr, K, HW, _ptr(sums_r), _stream()),
+                  "table_bwd_sums")
+            sr = sums_r.to(D)
+        M_src = torch.cat([t for t in ((mean_att if Ci else None), (Sx_r / HW if Cr else None)) if t is not None], dim=1)
+        ew = None
+        if eca_w is not None:
+            ew = leaf(eca_w.reshape(-1))
+            k = ew.numel()
+            a = F.conv1d(M_src[:, src].unsqueeze(1), ew.view(1, 1, k), padding=(k - 1) // 2).squeeze(1)
+            e_src = torch.sigmoid(a)[:, inv.long()]
+        else:
+            e_src = torch.ones_like(M_src)
+        e_i, e_r = e_src[:, :Ci], e_src[:, Ci:]
+        L = 0.0
+        if Ci:
+            es = e_i * s_i
+            L = L + (es * si[..., 0]).sum()
+            if gate is not None:
+                L = L + (es.detach() * si[..., 1] * ga).sum() + (es.detach() * si[..., 2] * gc).sum()
+        if Cr:
+            L = L + (e_r * sr[..., 0]).sum()
+        wrt = [t for t in (Sx_i, Sxx_i, J1, Sx_r, ew) if t is not None] + (params or [])
+        got = torch.autograd.grad(L, wrt, allow_unused=True)
+    g = {id(t): (v if v is not None else torch.zeros_like(t)) for t, v in zip(wrt, got)}
+    dimage = dradar = None
+    if Ci:
+        coef = torch.stack([es.detach(), g[id(J1)], g[id(Sx_i)], g[id(Sxx_i)]], dim=-1).float().contiguous()
+        dimage = torch.empty_like(image)
+        check(lib.vrcoc_table_bwd_apply(_ptr(dzf), _ptr(image), None, _ptr(dimage), _dt(image), _ptr(kidx_i), _ptr(gate), _ptr(coef), B, Ci, K, HW,
+                                        _stream()), "table_bwd_apply")
+    if Cr:
+        z = torch.zeros_like(e_r)
+        coef = torch.stack([e_r.detach(), z, g[id(Sx_r)], z], dim=-1).float().contiguous()
+        dradar = torch.empty_like(radar)
+        ex = None if extra_radar is None else extra_radar.contiguous()
+        check(lib.vrcoc_table_bwd_apply(_ptr(dzf), _ptr(radar), _ptr(ex), _ptr(dradar), _dt(radar), _ptr(kidx_r), None, _ptr(coef), B, Cr, K, HW,
+                                        _stream()), "table_bwd_apply")
+    sa_grads = None if params is None else [g[id(t)].float() for t in params]
+    return dimage, dradar, sa_grads, (None if ew is None else g[id(ew)].float())
+
+
 @ops.amp_function
 class _ShuffleAttentionFn(torch.autograd.Function):
     @staticmethod
@@ -505,14 +615,15 @@ class _ShuffleAttentionFn(torch.autograd.Function):
         if any(ctx.needs_input_grad):
             ctx.save_for_backward(x, cw, cb, sw, sb, gw, gb)
             ctx.G = mod.G
+            ctx.perm = perm
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        from . import _autograd_ref as R
-        saved = list(ctx.saved_tensors)
-        G = ctx.G
-        return R.grads(lambda *a: R.shuffle_attention(*a, G=G), saved, dy, ctx.needs_input_grad[:7], slots=tuple(range(7)), total=8)
+        x, cw, cb, sw, sb, gw, gb = ctx.saved_tensors
+        dx, _, pg, _ = _prologue_backward(dy.to(x.dtype), x, None, ctx.perm, (cw, cb, sw, sb, gw, gb, ctx.G), None)
+        shapes = [t.shape for t in (cw, cb, sw, sb, gw, gb)]
+        return (dx,) + tuple(p.reshape(sh) for p, sh in zip(pg, shapes)) + (None,)
 
 
 class eca_block(nn.Module):
@@ -558,8 +669,9 @@ class _EcaFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        from . import _autograd_ref as R
-        return R.grads(R.eca, list(ctx.saved_tensors), dy, ctx.needs_input_grad[:2], slots=(0, 1), total=2)
+        x, w = ctx.saved_tensors
+        _, dx, _, dw = _prologue_backward(dy.to(x.dtype), None, x, None, None, w)
+        return dx, dw.reshape(w.shape)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -612,17 +724,47 @@ class _ImageEnhanceFn(torch.autograd.Function):
             check(lib.vrcoc_img_enh_finish(_ptr(k), _dt(k), _ptr(image), _dt(image), _ptr(out), _dt(out), _ptr(minmax),
                                            _ptr(sc), _ptr(sh), B, Ci, H * W, None, _stream()), "img_enh_finish")
         if stats is not None:
-            ctx.save_for_backward(image, radar, w, g1, b1, g2, b2, *stats)
+            ctx.save_for_backward(image, radar, w, g1, b1, g2, b2, k, minmax, *stats)
             ctx.meta = (rp.bn.eps, bn2.eps, train1, train2)
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        from . import _autograd_ref as R
-        image, radar, w, g1, b1, g2, b2, rm1, rv1, rm2, rv2 = ctx.saved_tensors
+        """native: recompute y = (1 + kn) * image -> BatchNorm backward -> tail backward (+ the min / max paths) -> BaseConv backward"""
+        image, radar, w, g1, b1, g2, b2, k, minmax, rm1, rv1, rm2, rv2 = ctx.saved_tensors
         eps1, eps2, t1, t2 = ctx.meta
-        return R.grads(lambda *a: R.image_enhance(*a, rm1, rv1, rm2, rv2, eps1, eps2, t1, t2),
-                       [image, radar, w, g1, b1, g2, b2], dy, ctx.needs_input_grad[:7], slots=tuple(range(7)), total=8)
+        B, Ci, H, W = image.shape
+        HW = H * W
+        dev = image.device
+        yv = torch.empty_like(image)
+        cs = torch.empty(B, Ci, 2, device=dev, dtype=torch.float32)
+        check(lib.vrcoc_img_enh_finish(_ptr(k), _dt(k), _ptr(image), _dt(image), _ptr(yv), _dt(yv), _ptr(minmax), None, None, B, Ci, HW,
+                                       _ptr(cs), _stream()), "img_enh_finish")
+        if t2:
+            s = cs.double().sum(0)
+            n = float(B * HW)
+            mean2 = s[:, 0] / n
+            var2 = (s[:, 1] / n - mean2 * mean2).clamp_min(0)
+        else:
+            mean2, var2 = rm2.double(), rv2.double()
+        dyv, dg2, db2 = _norm_act_backward(dy, None, yv, ACT_NONE, g2, b2, mean2, var2, eps2, t2)
+        dimage = torch.empty_like(image)
+        dk = torch.empty_like(k)
+        part = torch.empty(B * Ci, 4, device=dev, dtype=torch.float32)
+        check(lib.vrcoc_img_enh_bwd(_ptr(dyv), _ptr(image), _ptr(k), _dt(k), _ptr(minmax), B, Ci, HW, _ptr(dimage), _ptr(dk), _ptr(part),
+                                    _stream()), "img_enh_bwd")
+        # d mn = r^2 * sum dkn*(k - mx),  d mx = -r^2 * sum dkn*(k - mn): O(1)-sized algebra on device scalars, then spread over the ties
+        p = part.double().sum(0)
+        mm = minmax.view(torch.int32)
+        mx = mm[0:1].view(torch.float32).double()
+        mn = (~mm[1:2]).view(torch.float32).double()
+        r2 = 1.0 / ((mx - mn) * (mx - mn))
+        coef = torch.cat([r2 * (p[1] - mx * p[0]) / p[2].clamp_min(1.0), -r2 * (p[1] - mn * p[0]) / p[3].clamp_min(1.0)]).float().contiguous()
+        check(lib.vrcoc_minmax_scatter(_ptr(k), _ptr(dk), _dt(k), _ptr(minmax), _ptr(coef), k.numel(), _stream()), "minmax_scatter")
+        rad = radar if radar.dtype == image.dtype else radar.to(image.dtype)
+        drad, dW, _, dg1, db1 = _base_conv_backward(rad, w, None, g1, b1, rm1, rv1, k, 1, 1, "relu", eps1, t1, dk,
+                                                   need_dx=ctx.needs_input_grad[1])
+        return dimage, drad, dW, dg1, db1, dg2, db2, None
 
 
 class RadarEnhanceByImage(nn.Module):
@@ -730,15 +872,52 @@ class _RadarEnhanceFn(torch.autograd.Function):
             conv_fwd(conv_desc(image, w2, out, src1=radar, chan_src=mod._chan_src, table=table, has_gate=gate,
                                e_scale=s1, e_shift=t1, act=ACT_RELU, res=radar, f_scale=s2, f_shift=t2))
         if stats is not None:
-            ctx.save_for_backward(image, radar, w, g1, b1, g2, b2, eca_w, cw, cb, sw, sb, gw, gb, *stats)
+            ctx.save_for_backward(image, radar, w, g1, b1, g2, b2, eca_w, cw, cb, sw, sb, gw, gb, table, *stats)
             ctx.meta = (ip.bn.eps, bn2.eps, train1, train2, mod.initial, sa.G)
+            ctx.chan_src = mod._chan_src
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        from . import _autograd_ref as R
-        t = ctx.saved_tensors
-        diff, (rm1, rv1, rm2, rv2) = list(t[:14]), t[14:]
+        """native: recompute u = W . prologue(image | radar) and t = ReLU(BN1(u)) + radar; BN2 backward; ReLU + BN1 backward; weight
+        gradient (prologue applied inside the kernel) and dgrad GEMM; prologue backward (gates, shuffle, ECA)."""
+        tsv = ctx.saved_tensors
+        image, radar, w, g1, b1, g2, b2, eca_w, cw, cb, sw, sb, gw, gb, table = tsv[:15]
+        rm1, rv1, rm2, rv2 = tsv[15:]
         eps1, eps2, t1, t2, initial, G = ctx.meta
-        return R.grads(lambda *a: R.radar_enhance(*a, rm1, rv1, rm2, rv2, eps1, eps2, t1, t2, initial, G),
-                       diff, dy, ctx.needs_input_grad[:14], slots=tuple(range(14)), total=15)
+        chan_src = ctx.chan_src
+        B, Ci, H, W = image.shape
+        Cr = radar.shape[1]
+        HW = H * W
+        dev = image.device
+        gate = not initial
+        w2 = w.detach().reshape(Cr, -1).contiguous()
+        if w2.dtype != radar.dtype:
+            w2 = w2.to(radar.dtype)
+        u = torch.empty_like(radar)
+        conv_fwd(conv_desc(image, w2, u, src1=radar, chan_src=chan_src, table=table, has_gate=gate))
+        mean1, var1 = _batch_stats(u) if t1 else (rm1.double(), rv1.double())
+        s1, sh1 = _fold_bn(mean1.float(), var1.float(), g1.detach().float(), b1.detach().float(), eps1)
+        t = torch.empty_like(radar)
+        cs_t = torch.empty(B, Cr, 2, device=dev, dtype=torch.float32)
+        check(lib.vrcoc_chan_affine(_ptr(u), _dt(u), _ptr(radar), _dt(radar), _ptr(t), _dt(t), _ptr(s1), _ptr(sh1), ACT_RELU, None, None,
+                                    B, Cr, HW, _ptr(cs_t), None, _stream()), "chan_affine")
+        if t2:
+            sm = cs_t.double().sum(0)
+            n = float(B * HW)
+            mean2 = sm[:, 0] / n
+            var2 = (sm[:, 1] / n - mean2 * mean2).clamp_min(0)
+        else:
+            mean2, var2 = rm2.double(), rv2.double()
+        dt, dg2, db2 = _norm_act_backward(dy, None, t, ACT_NONE, g2, b2, mean2, var2, eps2, t2)
+        du, dg1, db1 = _norm_act_backward(dt, None, u, ACT_RELU, g1, b1, mean1, var1, eps1, t1)
+        dWk, _ = ops.conv1x1_wgrad(conv_desc(image, w2, du, src1=radar, chan_src=chan_src, table=table, has_gate=gate), du, want_db=False)
+        dzf = torch.empty(B, Ci + Cr, H, W, device=dev, dtype=radar.dtype)
+        conv_fwd(conv_desc(du, w2.t().contiguous(), dzf))
+        sa = None if initial else (cw, cb, sw, sb, gw, gb, G)
+        dimage, dradar, pg, dew = _prologue_backward(dzf, image, radar, chan_src, sa, eca_w, initial=initial, extra_radar=dt)
+        if pg is None:
+            pg = [None] * 6
+        else:
+            pg = [p.reshape(tt.shape) for p, tt in zip(pg, (cw, cb, sw, sb, gw, gb))]
+        return (dimage, dradar, dWk.reshape(w.shape), dg1, db1, dg2, db2, dew.reshape(eca_w.shape), *pg, None)

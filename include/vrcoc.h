@@ -291,6 +291,26 @@ int vrcoc_chan_bwd_apply(const void* dy, const void* y_act, const void* u, const
                          const float* ca, const float* cb, const float* cd, const float* z_scale, const float* z_shift, int B, int C,
                          int HW, void* stream);
 
+/* ImageEnhanceByRadar tail backward (vr_coc.py:314-315, data_normal :59-67): given dyv = dL/d((1 + kn) * image),
+ *   dimage = dyv*(1 + kn),  dk = dyv*image/(mx - mn),  part[b*C + c] = { sum dkn, sum dkn*k, #(k == mn), #(k == mx) }, dkn = dyv*image;
+ * vrcoc_minmax_scatter then adds coef[0] at k == mn and coef[1] at k == mx (the gradient through the global min / max, spread
+ * evenly over ties like torch's min() / max() backward). */
+int vrcoc_img_enh_bwd(const void* dyv, const void* image, const void* k, int dtype, const uint32_t* minmax, int B, int C, int HW,
+                      void* dimage, void* dk, float* part, void* stream);
+int vrcoc_minmax_scatter(const void* k, void* dk, int dtype, const uint32_t* minmax, const float* coef /*device [2]*/, int64_t n,
+                         void* stream);
+
+/* Backward of the table-driven prologue z = x*s*h(x)*e, h = sigmoid(ga*x + gc) (the ShuffleAttention gates and the ECA scale in front
+ * of RadarEnhanceByImage's projection, vr_coc.py:344-350; also ShuffleAttention / eca_block on their own), source-channel order:
+ *   sums : out[b][c] = { sum dz*x*h, sum dz*x^2*h(1-h), sum dz*x*h(1-h), sum x*h, sum x^2*h(1-h), sum x*h(1-h) }
+ *   apply: dx = (dz*cd + cj)*(h + x*ga*h(1-h)) + c1 + 2*x*c2 (+ extra),   coef[b][c] = {cd, cj, c1, c2}
+ * dz is [B][K][HW] in LOGICAL channel order and is read at kidx[c] (NULL = identity); gate [B][C][2] = {ga, gc} (NULL = no gate).
+ * The O(B*C) chain from the sums to the coefficients (means / variances -> gates -> ECA conv1d) lives on the host side. */
+int vrcoc_table_bwd_sums(const void* dz, const void* x, int dtype, const int32_t* kidx, const float* gate, int B, int C, int K, int HW,
+                         float* out, void* stream);
+int vrcoc_table_bwd_apply(const void* dz, const void* x, const void* extra, void* out, int dtype, const int32_t* kidx, const float* gate,
+                          const float* coef, int B, int C, int K, int HW, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
