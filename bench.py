@@ -45,7 +45,7 @@ def parse():
                     help="infer: BASELINE configs[2] (the driver's line); train: configs[3] (training step, NCCL gradient all-reduce); "
                          "block-sweep: configs[1] (tools/block_sweep.py; extra flags after --)")
     ap.add_argument("--img", type=int, default=512, help="frame side (1024: BASELINE configs[4], fea_pos buffers replaced)")
-    ap.add_argument("--train-graph", action="store_true", help="train mode: network forward/backward as CUDA graphs (N=1)")
+    ap.add_argument("--no-train-graph", action="store_true", help="train mode: eager forward/backward instead of the two CUDA graphs")
     ap.add_argument("--no-train", action="store_true", help="skip the short training-step measurement appended to the inference line")
     ap.add_argument("--no-check", action="store_true", help="skip the pre-timing oracle spot check of the benched outputs")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the unmodified reference eager on the GPU")
@@ -493,10 +493,6 @@ def train_setup(args, dev, world, batch):
     opt = torch.optim.SGD(pg0, 1e-3, momentum=0.937, nesterov=True)
     opt.add_param_group({"params": pg1, "weight_decay": 5e-4})
     opt.add_param_group({"params": pg2})
-    net = model
-    if world > 1:
-        from torch.nn.parallel import DistributedDataParallel as DDP
-        net = DDP(model, device_ids=[dev.index], bucket_cap_mb=25, gradient_as_bucket_view=True)    # train.py:367 (DDP over NCCL)
     ema = FusedEMA(model)
     g = torch.Generator().manual_seed(7 + int(os.environ.get("RANK", "0")))
     B, S = batch, args.img
@@ -512,11 +508,24 @@ def train_setup(args, dev, world, batch):
     seg_labels = torch.nn.functional.one_hot(pngs, 10).float()
     weights = torch.ones(9, device=dev)
 
+    graphed = not getattr(args, "no_train_graph", False)
+    if graphed:
+        # forward and backward of the network as two CUDA graphs (torch.cuda.make_graphed_callables replaces model.forward): the eager
+        # step is host-bound (~9 K launches); the loss (SimOTA: data-dependent shapes, host syncs) stays eager between the two graphs
+        s_ = torch.cuda.Stream()
+        s_.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s_), torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
+            torch.cuda.make_graphed_callables(model, (images, radars), allow_unused_input=True)
+        torch.cuda.current_stream().wait_stream(s_)
+    net = model
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        s_ = torch.cuda.Stream()
+        s_.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s_):                       # (documented recipe for DDP around graphed callables)
+            net = DDP(model, device_ids=[dev.index], bucket_cap_mb=25, gradient_as_bucket_view=True)    # train.py:367 (DDP over NCCL)
+        torch.cuda.current_stream().wait_stream(s_)
     fwd_call = net
-    if getattr(args, "train_graph", False) and world == 1:
-        # forward and backward of the network as two CUDA graphs (torch.cuda.make_graphed_callables); the loss (SimOTA: data-dependent
-        # shapes, host syncs) stays eager between them
-        fwd_call = torch.cuda.make_graphed_callables(net, (images, radars), allow_unused_input=True)
 
     def step(timing=None):
         def mark(name, t0):
@@ -526,7 +535,7 @@ def train_setup(args, dev, world, batch):
             return time.perf_counter()
         t = time.perf_counter()
         opt.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+        with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=not graphed):
             det, seg = fwd_call(images, radars)
             t = mark("forward_ms", t)
             if yolo_loss is not None:
@@ -544,6 +553,7 @@ def train_setup(args, dev, world, batch):
         return loss
 
     nparam = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    step.graphed = graphed
     return step, net, model, loss_kind, nparam
 
 
@@ -570,6 +580,7 @@ def measure_train(args, dev, world, dist, batch, steps, warmup):
     ms_step = ms.item() / steps
     out = {"value": batch * world / (ms_step / 1e3), "unit": "frames/s", "ms_per_step": ms_step, "batch_per_gpu": batch,
            "global_batch": batch * world, "steps": steps, "warmup": warmup, "dtype": "bf16 autocast, fp32 master weights",
+           "cuda_graphs": "network forward and backward replayed as two CUDA graphs; loss, optimizer, EMA eager" if step.graphed else "eager",
            "loss": loss_kind, "final_loss": float(loss.detach().float().item()), "finite": bool(torch.isfinite(loss.detach()).item()),
            "optimizer": "SGD(momentum 0.937, nesterov), 3 parameter groups (train.py:460-473), fused multi-tensor EMA",
            "trainable_params": nparam, "grad_bytes_per_step": nparam * 4}

@@ -6,7 +6,7 @@ import torch
 import bench
 from torch.profiler import profile, ProfilerActivity
 
-args = types.SimpleNamespace(phi="l", img=512, train_graph=False)
+args = types.SimpleNamespace(phi="l", img=512, no_train_graph=True)
 dev = torch.device("cuda", 0)
 step, net, model, kind, nparam = bench.train_setup(args, dev, 1, int(os.environ.get("B", "16")))
 for _ in range(3):
