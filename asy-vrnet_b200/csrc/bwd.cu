@@ -235,6 +235,45 @@ __global__ void __launch_bounds__(256) minmax_scatter_kernel(const T* __restrict
   }
 }
 
+// Adjoint of the bilinear upsample with align_corners=True (CoCUpsample, coc_fpn_dual.py:19-22): gather form, one thread per INPUT
+// pixel; the output rows / columns that touch it are found with the forward kernel's own index arithmetic (stats.cu), so the
+// weights are bit-identical to the forward ones.
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_bilinear_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int H, int W, int Ho, int Wo,
+                                                                    float sy, float sx, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % W), y = (int)((i / W) % H);
+  const int64_t plane = i / ((int64_t)W * H);
+  // candidate output rows: fy = oy*sy in (y-1, y+1)
+  int oy0 = sy > 0.f ? (int)floorf((float)(y - 1) / sy) : 0, oy1 = sy > 0.f ? (int)ceilf((float)(y + 1) / sy) : Ho - 1;
+  int ox0 = sx > 0.f ? (int)floorf((float)(x - 1) / sx) : 0, ox1 = sx > 0.f ? (int)ceilf((float)(x + 1) / sx) : Wo - 1;
+  oy0 = max(oy0, 0); oy1 = min(oy1, Ho - 1); ox0 = max(ox0, 0); ox1 = min(ox1, Wo - 1);
+  const T* base = dy + plane * (int64_t)Ho * Wo;
+  float acc = 0.f;
+  for (int oy = oy0; oy <= oy1; ++oy) {
+    const float fy = oy * sy;
+    int y0 = (int)fy;
+    if (y0 > H - 1) y0 = H - 1;
+    const int y1 = min(y0 + 1, H - 1);
+    const float wy = fy - (float)y0;
+    const float cy = (y0 == y ? 1.f - wy : 0.f) + (y1 == y ? wy : 0.f);
+    if (cy == 0.f) continue;
+    float row = 0.f;
+    for (int ox = ox0; ox <= ox1; ++ox) {
+      const float fx = ox * sx;
+      int x0 = (int)fx;
+      if (x0 > W - 1) x0 = W - 1;
+      const int x1 = min(x0 + 1, W - 1);
+      const float wx = fx - (float)x0;
+      const float cx = (x0 == x ? 1.f - wx : 0.f) + (x1 == x ? wx : 0.f);
+      if (cx != 0.f) row = fmaf(cx, ldf<T>(base + (int64_t)oy * Wo + ox), row);
+    }
+    acc = fmaf(cy, row, acc);
+  }
+  stf<T>(dx + i, acc);
+}
+
 // ---- backward of the table-driven prologue  z = x * s * h(x) * e,  h(x) = sigmoid(ga*x + gc)  (ShuffleAttention gates + ECA scale of
 //      RadarEnhanceByImage, vr_coc.py:344-350; shuffle_attention.py:48-72; eca.py:16-22).  Source-channel order; dz is read at the logical
 //      channel kidx[c] of source channel c.  The statistics chain (channel means / variances -> gates -> ECA) is O(B*C) algebra on the
@@ -299,6 +338,19 @@ __global__ void __launch_bounds__(256) table_bwd_apply_kernel(const T* __restric
 }  // namespace vrcoc
 
 using namespace vrcoc;
+
+extern "C" int vrcoc_upsample_bilinear_bwd(const void* dy, void* dx, int dtype, int planes, int H, int W, int Ho, int Wo, void* stream) {
+  VRCOC_REQUIRE(dy && dx && planes > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0, "upsample_bilinear_bwd: bad argument");
+  const float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f, sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const int64_t total = (int64_t)planes * H * W;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)cdiv(total, 256);
+  if (dtype == VRCOC_BF16)
+    upsample_bilinear_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, H, W, Ho, Wo, sy, sx, total);
+  else
+    upsample_bilinear_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)dy, (float*)dx, H, W, Ho, Wo, sy, sx, total);
+  return check_launch("upsample_bilinear_bwd");
+}
 
 extern "C" int vrcoc_table_bwd_sums(const void* dz, const void* x, int dtype, const int32_t* kidx, const float* gate, int B, int C, int K,
                                     int HW, float* out, void* stream) {

@@ -69,8 +69,15 @@ class GroupNorm(nn.GroupNorm):
     def forward(self, x):
         if not x.is_cuda:
             raise VrcocError("vrcoc GroupNorm needs a CUDA tensor (no CPU fallback exists)")
+        if not torch.is_grad_enabled():
+            # one streaming pass: statistics, then the normalisation as the stand-alone prologue kernel (no contraction)
+            x = x.contiguous()
+            out = torch.empty_like(x)
+            d = ops.conv_desc(x, x, out, gn=(ops.sample_sums_of(x), ops._f32(self.weight), ops._f32(self.bias), self.eps))
+            ops.check(ops.lib.vrcoc_table_apply(d, ops._stream()), "table_apply")
+            return out
         C = x.shape[1]
-        eye = torch.eye(C, device=x.device, dtype=x.dtype)
+        eye = torch.eye(C, device=x.device, dtype=x.dtype)          # with autograd: the projection Function with an identity weight
         return ops.GNProjFn.apply(x, ops.sample_sums_of(x), self.weight, self.bias, self.eps, eye, None, ACT_NONE, 0)
 
 
@@ -236,16 +243,14 @@ class ClusterBlock(nn.Module):
             # both large stages: the hidden activation (8 x C channels) stays on chip
             x2 = ops.mlp_fused_fwd(x1, sums[0], f32(n2.weight), f32(n2.bias), n2.eps, mlp.fc1.weight.detach().reshape(hid, C),
                                    f32(mlp.fc1.bias), mlp.fc2.weight.detach().reshape(C, hid), f32(mlp.fc2.bias), ls2, sums[1])
-            x2._vrcoc_sums = ops.tag_like(sums[1], sums)
-            return x2
+            return ops.attach_sums(x2, ops.tag_like(sums[1], sums))
         h = torch.empty(B, hid, H, W, device=dev, dtype=dt)
         ops.conv_fwd(ops.conv_desc(x1, mlp.fc1.weight.detach().reshape(hid, C), h, gn=(sums[0], f32(n2.weight), f32(n2.bias), n2.eps),
                                    e_shift=f32(mlp.fc1.bias), act=ACT_GELU))
         x2 = torch.empty_like(x)
         ops.conv_fwd(ops.conv_desc(h, mlp.fc2.weight.detach().reshape(C, hid), x2, e_shift=f32(mlp.fc2.bias), post_scale=ls2, res=x1,
                                    out_sample_sums=sums[1]))
-        x2._vrcoc_sums = ops.tag_like(sums[1], sums)
-        return x2
+        return ops.attach_sums(x2, ops.tag_like(sums[1], sums))
 
     def forward(self, x):
         if not x.is_cuda:
@@ -265,8 +270,7 @@ class ClusterBlock(nn.Module):
         h = ops.GNProjFn.apply(x1, sums1, self.norm2.weight, self.norm2.bias, self.norm2.eps,
                                mlp.fc1.weight, mlp.fc1.bias, ACT_GELU, 0)
         x2, sums2 = ops.ProjResidualFn.apply(h, mlp.fc2.weight, mlp.fc2.bias, ls2, x1)
-        x2._vrcoc_sums = sums2        # rides along to the next block's norm1 (same python object through nn.Sequential)
-        return x2
+        return ops.attach_sums(x2, sums2)        # rides along to the next block's norm1 (same python object through nn.Sequential)
 
     def _forward_composed(self, x):
         """Non-default configurations (BatchNorm norm_layer, active DropPath/Dropout, other activations): same

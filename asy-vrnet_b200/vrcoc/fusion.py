@@ -63,6 +63,12 @@ def _bn_affine(bn, chan_sums=None, count=None):
     def wb():
         return (bn.weight.detach().float() if bn.affine else None, bn.bias.detach().float() if bn.affine else None)
     use_batch = bn.training or not bn.track_running_stats
+    if use_batch and isinstance(bn, nn.SyncBatchNorm) and torch.distributed.is_available() and torch.distributed.is_initialized() \
+            and torch.distributed.get_world_size() > 1:
+        # train.py:356-357 (sync_bn=True, off by default) converts BatchNorm2d to SyncBatchNorm: the native path computes
+        # per-replica statistics and must not silently pretend otherwise
+        raise VrcocError("SyncBatchNorm inside a native BaseConv / fusion module is not supported (per-replica batch statistics only): "
+                         "train with sync_bn=False (the reference default, train.py:51)")
     if use_batch:
         s = chan_sums.double().sum(0)                       # [C,2]
         n = float(count)

@@ -31,12 +31,14 @@ class _UpsampleFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        # adjoint of a fixed linear map: obtained from the differentiable library op on a dummy input
+        # adjoint of a fixed linear map, native (gather form, the forward kernel's own weights)
         H, W, scale = ctx.shape
-        with torch.enable_grad():
-            z = torch.zeros(dy.shape[0], dy.shape[1], H, W, device=dy.device, dtype=dy.dtype, requires_grad=True)
-            y = F.interpolate(z, scale_factor=scale, mode="bilinear", align_corners=True)
-        return torch.autograd.grad(y, z, dy)[0], None
+        dy = dy.contiguous()
+        B, C, Ho, Wo = dy.shape
+        dx = torch.empty(B, C, H, W, device=dy.device, dtype=dy.dtype)
+        check(lib.vrcoc_upsample_bilinear_bwd(dy.data_ptr(), dx.data_ptr(), ops._dt(dy), B * C, H, W, Ho, Wo, ops._stream()),
+              "upsample_bilinear_bwd")
+        return dx, None
 
 
 class BilinearUpsample(nn.Upsample):
@@ -174,12 +176,15 @@ class CoCFpnDual(nn.Module):
         self.p4_3_det = CoCUpsample(in_channels=in_channels[-2], out_channels=in_channels[-3])
         self.p3_out_det = Conv(in_channels=in_channels[-3] * 2, out_channels=in_channels[-3])
 
-    def forward(self, x, x_radar, det_level=None):
-        """det_level (optional, not in the reference signature): a callable (k, p_k) applied to each detection map as soon
-        as it exists — EfficientVRNet passes DecoupleHead.forward_level, so that the head of a coarse level runs next to the
-        neck of the finer ones and the whole detection half next to the segmentation half."""
+    # Optional hook (an ATTRIBUTE, so that forward keeps the reference signature (x, x_radar), coc_fpn_dual.py:184): a callable
+    # (k, p_k) applied to each detection map as soon as it exists.  EfficientVRNet sets it to DecoupleHead.forward_level for the
+    # duration of its own forward, so that the head of a coarse level runs next to the neck of the finer ones and the whole
+    # detection half next to the segmentation half; forward then returns the head outputs in place of (p3, p4, p5).
+    det_level_hook = None
+
+    def forward(self, x, x_radar):
         with ops.sums_arena(x.shape[0], x.device):
-            return self._forward(x, x_radar, det_level)
+            return self._forward(x, x_radar, self.det_level_hook)
 
     def _forward(self, x, x_radar, det_level):
         x_out, x_radar_out = self.backbone(x, x_radar)

@@ -15,5 +15,11 @@ class EfficientVRNet(nn.Module):
         self.head = DecoupleHead(num_classes, width, depthwise=True)
 
     def forward(self, x, x_radar):
-        det_outputs, seg_outputs = self.backbone.forward(x, x_radar, det_level=self.head.forward_level)
+        # reference: fpn_outs, seg = backbone.forward(x, x_radar); det = head.forward(fpn_outs).  Same calls, except that the head
+        # is handed to the neck as a per-level hook so that its levels overlap the rest of the neck (CoCFpnDual.det_level_hook).
+        self.backbone.det_level_hook = self.head.forward_level
+        try:
+            det_outputs, seg_outputs = self.backbone.forward(x, x_radar)
+        finally:
+            self.backbone.det_level_hook = None
         return det_outputs, seg_outputs

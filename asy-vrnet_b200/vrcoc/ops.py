@@ -179,7 +179,13 @@ def _f32(t):
     memo = t.__dict__.get("_vrcoc_f32") if hasattr(t, "__dict__") else None
     if memo is not None and memo[0] == sig:
         return memo[1]
-    v = t.detach().float().contiguous()
+    if memo is not None and memo[1].shape == t.shape and memo[1].device == t.device:
+        # refreshed IN PLACE: a captured CUDA graph that reads the old copy keeps reading valid, current memory
+        with torch.no_grad():
+            memo[1].copy_(t.detach())
+        v = memo[1]
+    else:
+        v = t.detach().float().contiguous()
     try:
         t._vrcoc_f32 = (sig, v)
     except Exception:
@@ -197,9 +203,31 @@ def cached(mod, key, sources, build):
     ent = store.get(key)
     if ent is None or ent[0] != sig:
         with torch.no_grad():
-            ent = (sig, build())
+            new = build()
+            if ent is not None and _refresh_in_place(ent[1], new):
+                ent = (sig, ent[1])          # same storage, new values: pointers baked into captured CUDA graphs stay valid
+            else:
+                ent = (sig, new)
         store[key] = ent
     return ent[1]
+
+
+def _refresh_in_place(old, new):
+    """copy `new` into the storage of `old` when both are tensors (or equal-length tuples of tensors) of the same shape / dtype /
+    device.  Graph-capture contract: buffers whose pointers were handed to kernels are never freed or replaced while
+    their module lives; derived parameter tensors are refreshed in place after load_state_dict / optimizer steps."""
+    if isinstance(old, torch.Tensor) and isinstance(new, torch.Tensor):
+        if old.shape == new.shape and old.dtype == new.dtype and old.device == new.device:
+            old.copy_(new)
+            return True
+        return False
+    if isinstance(old, (tuple, list)) and isinstance(new, (tuple, list)) and len(old) == len(new):
+        if all(isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor) and a.shape == b.shape and a.dtype == b.dtype and a.device == b.device
+               for a, b in zip(old, new)):
+            for a, b in zip(old, new):
+                a.copy_(b)
+            return True
+    return False
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -224,40 +252,49 @@ class sums_arena:
     device buffer that is zeroed once on entry (one fill kernel instead of ~40 per forward; they sit on the critical path of
     the launch chain).  Slices carry the arena generation; a statistics tensor that rode along on an activation from an
     earlier forward is recognised as stale by sample_sums_of and recomputed.  Nested uses share the outermost arena."""
-    _state = {}      # device index -> [buffer, next_free, generation, depth]
+    _state = {}      # (device index, B) -> [buffer, next_free, generation, depth]; one arena per batch size, never freed:
+                     # a CUDA graph captured at batch size B keeps zeroing / accumulating into ITS arena (graph-capture contract)
+    _open = {}       # device index -> key of the arena opened by the outermost context
     SLOTS = 128
 
     def __init__(self, B, device):
         self.key = None
         if device.type == "cuda" and not torch.is_grad_enabled():
-            self.key, self.B, self.device = (device.index if device.index is not None else torch.cuda.current_device()), B, device
+            self.dev_index = device.index if device.index is not None else torch.cuda.current_device()
+            self.key, self.B, self.device = (self.dev_index, B), B, device
 
     def __enter__(self):
         if self.key is None:
             return self
+        cur = sums_arena._open.get(self.dev_index)
+        if cur is not None and cur != self.key:
+            self.key = None              # a different batch size inside an open arena: leave it alone
+            return self
         st = sums_arena._state.get(self.key)
-        if st is None or st[0].shape[1] != self.B:
-            if st is not None and st[3] > 0:
-                self.key = None          # a different batch size inside an open arena: leave it alone
-                return self
+        if st is None:
             st = sums_arena._state[self.key] = [torch.empty(sums_arena.SLOTS, self.B, STAT_SLOTS, 2, device=self.device, dtype=torch.float64), 0, 0, 0]
         if st[3] == 0:
             st[0].zero_()
             st[1] = 0
             st[2] += 1
+            sums_arena._open[self.dev_index] = self.key
         st[3] += 1
         return self
 
     def __exit__(self, *exc):
         if self.key is not None:
-            sums_arena._state[self.key][3] -= 1
+            st = sums_arena._state[self.key]
+            st[3] -= 1
+            if st[3] == 0:
+                sums_arena._open.pop(self.dev_index, None)
         return False
 
     @staticmethod
     def take(B, device, n):
         if device.type != "cuda" or torch.is_grad_enabled():
             return None
-        st = sums_arena._state.get(device.index if device.index is not None else torch.cuda.current_device())
+        di = device.index if device.index is not None else torch.cuda.current_device()
+        st = sums_arena._state.get(sums_arena._open.get(di))
         k = 1 if n is None else n
         if st is None or st[3] == 0 or st[0].shape[1] != B or st[1] + k > sums_arena.SLOTS:
             return None
@@ -295,10 +332,19 @@ def new_sample_sums(B, device, n=None):
     return torch.zeros(shape, device=device, dtype=torch.float64)
 
 
+def attach_sums(x, ss):
+    """let the per-sample statistics of x ride along on the tensor, tagged with its version counter and storage pointer: an
+    in-place update of x between two blocks (y.mul_(s), nn.ReLU(inplace=True), ...) invalidates them"""
+    x._vrcoc_sums = ss
+    x._vrcoc_sums_tag = (x._version, x.data_ptr())
+    return x
+
+
 def sample_sums_of(x):
     """GroupNorm(1,C) statistics of x: reuse the producer's side output when it rode along on the tensor."""
     ss = getattr(x, "_vrcoc_sums", None)
-    if ss is not None and ss.shape[0] == x.shape[0] and not sums_arena.stale(ss):
+    tag = getattr(x, "_vrcoc_sums_tag", None)
+    if ss is not None and ss.shape[0] == x.shape[0] and not sums_arena.stale(ss) and (tag is None or tag == (x._version, x.data_ptr())):
         return ss
     return channel_sums(x, want_chan=False, want_sample=True)[1]
 
@@ -390,6 +436,10 @@ def tap_major(weight):
     if memo is not None and memo[0] == sig:
         return memo[1]
     v = weight.detach().permute(0, 2, 3, 1).reshape(weight.shape[0], -1).contiguous()
+    if memo is not None and memo[1].shape == v.shape and memo[1].dtype == v.dtype and memo[1].device == v.device:
+        with torch.no_grad():
+            memo[1].copy_(v)                  # in place: see _refresh_in_place
+        v = memo[1]
     try:
         weight._vrcoc_tapmajor = (sig, v)
     except Exception:

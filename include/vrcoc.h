@@ -300,6 +300,8 @@ int vrcoc_img_enh_bwd(const void* dyv, const void* image, const void* k, int dty
 int vrcoc_minmax_scatter(const void* k, void* dk, int dtype, const uint32_t* minmax, const float* coef /*device [2]*/, int64_t n,
                          void* stream);
 
+/* Adjoint of vrcoc_upsample_bilinear (align_corners=True): dx[planes][H][W] from dy[planes][Ho][Wo]. */
+int vrcoc_upsample_bilinear_bwd(const void* dy, void* dx, int dtype, int planes, int H, int W, int Ho, int Wo, void* stream);
 /* Backward of the table-driven prologue z = x*s*h(x)*e, h = sigmoid(ga*x + gc) (the ShuffleAttention gates and the ECA scale in front
  * of RadarEnhanceByImage's projection, vr_coc.py:344-350; also ShuffleAttention / eca_block on their own), source-channel order:
  *   sums : out[b][c] = { sum dz*x*h, sum dz*x^2*h(1-h), sum dz*x*h(1-h), sum x*h, sum x^2*h(1-h), sum x*h(1-h) }
