@@ -274,6 +274,29 @@ __global__ void __launch_bounds__(256) upsample_bilinear_bwd_kernel(const T* __r
   stf<T>(dx + i, acc);
 }
 
+// YOLOX box decode of the three detection maps (utils/utils_bbox.py:32-84) in one launch: out[b][n][c], n over levels then cells
+// (row-major), c over the 5 + num_classes channels:  xy = (xy + cell) * stride / input,  wh = exp(wh) * stride / input,  rest = sigmoid.
+struct DecodeArgs { const void* maps[3]; int H[3], W[3], off[3]; float sy[3], sx[3]; };
+template <typename T>
+__global__ void __launch_bounds__(256) decode_outputs_kernel(DecodeArgs a, int B, int CH, int N, float inv_h, float inv_w, float* __restrict__ out) {
+  const int64_t total = (int64_t)B * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N);
+    const int64_t b = i / N;
+    const int l = n >= a.off[2] ? 2 : (n >= a.off[1] ? 1 : 0);
+    const int cell = n - a.off[l];
+    const int gy = cell / a.W[l], gx = cell % a.W[l];
+    const int64_t plane = (int64_t)a.H[l] * a.W[l];
+    const T* src = reinterpret_cast<const T*>(a.maps[l]) + b * CH * plane + cell;
+    float* o = out + i * CH;
+    o[0] = (ldf<T>(src) + (float)gx) * a.sx[l] * inv_w;
+    o[1] = (ldf<T>(src + plane) + (float)gy) * a.sy[l] * inv_h;
+    o[2] = expf(ldf<T>(src + 2 * plane)) * a.sx[l] * inv_w;
+    o[3] = expf(ldf<T>(src + 3 * plane)) * a.sy[l] * inv_h;
+    for (int c = 4; c < CH; ++c) o[c] = 1.0f / (1.0f + expf(-ldf<T>(src + c * plane)));
+  }
+}
+
 // ---- backward of the table-driven prologue  z = x * s * h(x) * e,  h(x) = sigmoid(ga*x + gc)  (ShuffleAttention gates + ECA scale of
 //      RadarEnhanceByImage, vr_coc.py:344-350; shuffle_attention.py:48-72; eca.py:16-22).  Source-channel order; dz is read at the logical
 //      channel kidx[c] of source channel c.  The statistics chain (channel means / variances -> gates -> ECA) is O(B*C) algebra on the
@@ -338,6 +361,24 @@ __global__ void __launch_bounds__(256) table_bwd_apply_kernel(const T* __restric
 }  // namespace vrcoc
 
 using namespace vrcoc;
+
+extern "C" int vrcoc_decode_outputs(const void* p3, const void* p4, const void* p5, int dtype, int B, int channels, int h3, int w3, int h4,
+                                    int w4, int h5, int w5, int input_h, int input_w, float* out, void* stream) {
+  VRCOC_REQUIRE(p3 && p4 && p5 && out && B > 0 && channels >= 5 && h3 > 0 && w3 > 0 && h4 > 0 && w4 > 0 && h5 > 0 && w5 > 0 && input_h > 0 && input_w > 0,
+                "decode_outputs: bad argument");
+  DecodeArgs a;
+  a.maps[0] = p3; a.maps[1] = p4; a.maps[2] = p5;
+  a.H[0] = h3; a.W[0] = w3; a.H[1] = h4; a.W[1] = w4; a.H[2] = h5; a.W[2] = w5;
+  a.off[0] = 0; a.off[1] = h3 * w3; a.off[2] = h3 * w3 + h4 * w4;
+  // the reference uses ONE stride per level, input_shape[0] / h, for both axes (utils_bbox.py:63)
+  for (int l = 0; l < 3; ++l) { a.sy[l] = (float)input_h / (float)a.H[l]; a.sx[l] = a.sy[l]; }
+  const int N = h3 * w3 + h4 * w4 + h5 * w5;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)(cdiv((int64_t)B * N, 256) < 1184 ? cdiv((int64_t)B * N, 256) : 1184);
+  if (dtype == VRCOC_BF16) decode_outputs_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(a, B, channels, N, 1.0f / input_h, 1.0f / input_w, out);
+  else decode_outputs_kernel<float><<<blocks, 256, 0, st>>>(a, B, channels, N, 1.0f / input_h, 1.0f / input_w, out);
+  return check_launch("decode_outputs");
+}
 
 extern "C" int vrcoc_upsample_bilinear_bwd(const void* dy, void* dx, int dtype, int planes, int H, int W, int Ho, int Wo, void* stream) {
   VRCOC_REQUIRE(dy && dx && planes > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0, "upsample_bilinear_bwd: bad argument");

@@ -10,4 +10,5 @@ from .fusion import (BaseConv, DWConv, ImageEnhanceByRadar, RadarEnhanceByImage,
 from .head import DecoupleHead  # noqa: F401
 from .neck import ASPP, CoC_Conv, CoCFpnDual, CoCUpsample  # noqa: F401
 from .nets import EfficientVRNet  # noqa: F401
+from .session import InferenceSession, decode_outputs  # noqa: F401
 from .vr_coc import VRCoC, coc_medium, coc_small, coc_tiny, coc_tiny2, replace_pos_buffers  # noqa: F401

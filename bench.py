@@ -122,7 +122,7 @@ KERNELS_PER_CALL = {"vrcoc_channel_sums": 1, "vrcoc_conv_fwd": 1, "vrcoc_table_a
                     "vrcoc_cluster_core_bwd": 2, "vrcoc_sa_gate_sums": 1, "vrcoc_radar_enh_table": 1, "vrcoc_chan_affine": 1,
                     "vrcoc_img_enh_finish": 1, "vrcoc_gelu_bwd": 1, "vrcoc_gn_bwd_sums": 1, "vrcoc_gn_bwd_apply": 1,
                     "vrcoc_conv1x1_wgrad": 3, "vrcoc_im2col": 1, "vrcoc_upsample_bilinear": 1,
-                    "vrcoc_dwconv": 1, "vrcoc_mlp_fused_fwd": 1}
+                    "vrcoc_dwconv": 1, "vrcoc_mlp_fused_fwd": 1, "vrcoc_token_mixer_fwd": 1}
 
 
 def _esz(dt):
@@ -165,6 +165,12 @@ def _describe(name, args):
         B, C, hid, P = args[12:16]
         side = int(round(P ** 0.5))
         return (f"mlp_fused[{C}->{hid}->{C}]@{side}x{P // side}", B * P * 3 * C * 2 + 4 * C * hid, 4.0 * B * P * C * hid)
+    if name == "vrcoc_token_mixer_fwd":
+        # fused token-mixer half: algorithmic bytes = x in + out out (2*C*P*s) + the folded weights once
+        B, C, H, W, E, D = args[15:21]
+        P, ED = H * W, E * D
+        return (f"token_mixer_fused[{C}|{E}x{D}]@{H}x{W}", B * P * 2 * C * 2 + (2 * ED * 2 * C + C * ED) * 2,
+                B * P * (2.0 * C * ED * 4 + (2 * 4 + 5) * ED))
     if name == "vrcoc_dwconv":
         dt, B, C, H, W, k, stride, pad = args[4:12]
         Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
@@ -692,67 +698,27 @@ def run_ours(args):
             for d, s in zip(list(det_out) + [seg_out], list(o[0]) + [o[1]]):
                 d.copy_(s)
 
-    # End to end, as a serving loop runs it: two pipeline slots (input buffers + captured graph + output buffers each), the
-    # host->device copy of step i+1 and the device->host read of step i-1 on their own streams under the forward of step i.
-    # Every step still copies its inputs from pinned host memory and reads its results back inside the timed region.
-    slots = None
-    if graph is not None:
-        with torch.no_grad():
-            sx2, sr2 = torch.empty_like(sx), torch.empty_like(sr)
-            sx2.copy_(devb[0][0]); sr2.copy_(devb[0][1])
-            for _ in range(2):
-                out2 = forward(sx2, sr2)
-            torch.cuda.synchronize()
-            graph2 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph2):
-                out2 = forward(sx2, sr2)
-        host_out2 = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in list(out2[0]) + [out2[1]]]
-        slots = [dict(sx=sx, sr=sr, graph=graph, outs=list(det_out) + [seg_out], host=host_out),
-                 dict(sx=sx2, sr=sr2, graph=graph2, outs=list(out2[0]) + [out2[1]], host=host_out2)]
-        for S in slots:
-            S["in"], S["done"], S["out"] = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
-            S["done"].record(); S["out"].record()
-        h2d_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
-        torch.cuda.synchronize()
-
-    def step_e2e_pipelined(i):
-        S, main = slots[i & 1], torch.cuda.current_stream()
-        x, r = host[i % NBUF]
-        with torch.cuda.stream(h2d_stream):
-            h2d_stream.wait_event(S["done"])                                # the slot's previous forward has consumed its inputs
-            S["sx"].copy_(x, non_blocking=True); S["sr"].copy_(r, non_blocking=True)     # H2D from pinned memory
-            S["in"].record(h2d_stream)
-        main.wait_event(S["in"])
-        main.wait_event(S["out"])                                           # the slot's previous results have left the device
-        S["graph"].replay()
-        S["done"].record(main)
-        with torch.cuda.stream(d2h_stream):
-            d2h_stream.wait_event(S["done"])
-            for h, d in zip(S["host"], S["outs"]):
-                h.copy_(d, non_blocking=True)                               # D2H of the step's results
-            S["out"].record(d2h_stream)
-        slots[(i & 1) ^ 1]["out"].synchronize()                             # the host has the PREVIOUS step's results
-
-    def drain_e2e():
-        if slots is not None:
-            for S in slots:
-                torch.cuda.current_stream().wait_event(S["out"])
+    # End to end through the product's serving API (vrcoc.InferenceSession): two pipeline slots (input buffers + captured graph +
+    # pinned output buffers each), the host->device copy of step i+1 and the device->host read of step i-1 on their own streams
+    # under the forward of step i.  Every step copies its inputs from pinned host memory and reads its results (decoded boxes and
+    # the per-pixel class map) back inside the timed region; the host holds the results of step i-1 before it queues step i+1.
+    import vrcoc
+    sess = vrcoc.InferenceSession(model, batch=B, img=args.img, slots=2, decode=True, cuda_graph=not args.no_graph)
+    slots = sess.slots
+    pending = [0]
 
     def step_e2e(i):
-        if slots is not None:
-            return step_e2e_pipelined(i)
         x, r = host[i % NBUF]
-        sx.copy_(x, non_blocking=True); sr.copy_(r, non_blocking=True)     # H2D from pinned memory
-        if graph is not None:
-            graph.replay()
-        else:
-            with torch.no_grad():
-                o = forward(sx, sr)
-            for d, s in zip(list(det_out) + [seg_out], list(o[0]) + [o[1]]):
-                d.copy_(s)
-        for h, d in zip(host_out, list(det_out) + [seg_out]):
-            h.copy_(d, non_blocking=True)                                   # D2H of the step's results
-        torch.cuda.current_stream().synchronize()
+        sess.submit(x, r)
+        pending[0] += 1
+        if pending[0] > 1:
+            sess.collect()
+            pending[0] -= 1
+
+    def drain_e2e():
+        while pending[0] > 0:
+            sess.collect()                                                  # the last step's read-back ends inside the timed region
+            pending[0] -= 1
 
     def timed(step_fn, drain=None):
         for i in range(args.warmup):
@@ -844,7 +810,7 @@ def run_ours(args):
                   f"{f_ / (t / 1e3) / 1e12 if t else 0:7.1f} TF/s  share {t / total_ms:5.1%}", file=sys.stderr)
 
     h2d = sum(t.numel() * t.element_size() for t in host[0])
-    d2h = sum(t.numel() * t.element_size() for t in host_out)
+    d2h = sum(t.numel() * t.element_size() for t in slots[0]["host"])
     line = {
         "metric": METRIC.replace("512x512", f"{args.img}x{args.img}"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -854,8 +820,8 @@ def run_ours(args):
                    "cuda_graph": graph is not None,
                    "l2": f"inputs rotate over {NBUF} distinct batches; per-step activation traffic >> 126 MB L2"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                "loop": "2 pipeline slots: H2D of step i+1 and D2H of step i-1 on side streams under the forward of step i" if slots is not None
-                        else "serial: H2D, forward, D2H, host sync"},
+                "api": "vrcoc.InferenceSession(model, batch, slots=2, decode=True).submit / .collect",
+                "loop": "2 pipeline slots: H2D of step i+1 and D2H of step i-1 (decoded boxes + class map) on side streams under the forward of step i"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clk.summary(),
         "roofline": roof,
@@ -878,7 +844,7 @@ def run_ours(args):
     if not args.no_train and args.img == 512:
         # BASELINE configs[3] beside the headline: a short training-step measurement at the same N (its gradient all-reduce is the
         # one collective of this repository); the full run is `bench.py --mode train`
-        del graph, slots
+        del graph, slots, sess
         torch.cuda.empty_cache()
         try:
             tr = measure_train(args, dev, world, dist, 16, 8, 3)

@@ -300,6 +300,11 @@ int vrcoc_img_enh_bwd(const void* dyv, const void* image, const void* k, int dty
 int vrcoc_minmax_scatter(const void* k, void* dk, int dtype, const uint32_t* minmax, const float* coef /*device [2]*/, int64_t n,
                          void* stream);
 
+/* YOLOX decode of the three detection maps [B][channels][h][w] (channels = 4 box + 1 objectness + classes) into
+ * out [B][h3*w3 + h4*w4 + h5*w5][channels] fp32, normalised box centre / size + sigmoid scores: utils/utils_bbox.py:32-84
+ * (decode_outputs) in one launch, no intermediate cat / permute / grid tensors. */
+int vrcoc_decode_outputs(const void* p3, const void* p4, const void* p5, int dtype, int B, int channels, int h3, int w3, int h4, int w4,
+                         int h5, int w5, int input_h, int input_w, float* out, void* stream);
 /* Adjoint of vrcoc_upsample_bilinear (align_corners=True): dx[planes][H][W] from dy[planes][Ho][Wo]. */
 int vrcoc_upsample_bilinear_bwd(const void* dy, void* dx, int dtype, int planes, int H, int W, int Ho, int Wo, void* stream);
 /* Backward of the table-driven prologue z = x*s*h(x)*e, h = sigmoid(ga*x + gc) (the ShuffleAttention gates and the ECA scale in front

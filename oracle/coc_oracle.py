@@ -386,3 +386,25 @@ def efficient_vrnet_forward(x, x_radar, sd, phi="l", training=False, update=None
     cfg = coc_small_cfg(PHI_WIDTH[phi])
     fpn, seg = neck_forward(x, x_radar, sd, cfg, "backbone.", training, update)
     return head_forward(fpn, sd, "head.", training, update), seg
+
+
+def decode_outputs(outputs, input_shape):
+    """utils/utils_bbox.py:32-84 (decode_outputs) without the device plumbing: [B, 5+nc, h, w] x 3 -> [B, sum hw, 5+nc] with
+    xy = (xy + cell) * stride, wh = exp(wh) * stride, both normalised by the input size, sigmoid on objectness / classes.
+    The reference uses stride = input_shape[0] / h for both axes (:63)."""
+    hw = [o.shape[-2:] for o in outputs]
+    out = torch.cat([o.flatten(start_dim=2) for o in outputs], dim=2).permute(0, 2, 1).clone()
+    out[:, :, 4:] = torch.sigmoid(out[:, :, 4:])
+    grids, strides = [], []
+    for h, w in hw:
+        gy, gx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+        grids.append(torch.stack((gx, gy), 2).view(1, -1, 2))
+        strides.append(torch.full((1, h * w, 1), input_shape[0] / h))
+    grids = torch.cat(grids, dim=1).to(out.dtype)
+    strides = torch.cat(strides, dim=1).to(out.dtype)
+    out[..., :2] = (out[..., :2] + grids) * strides
+    out[..., 2:4] = torch.exp(out[..., 2:4]) * strides
+    out[..., [0, 2]] = out[..., [0, 2]] / input_shape[1]
+    out[..., [1, 3]] = out[..., [1, 3]] / input_shape[0]
+    return out
+

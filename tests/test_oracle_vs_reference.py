@@ -37,3 +37,15 @@ def test_product_modules_match_reference_state_dict():
     assert list(ours.state_dict().keys()) == list(ref.keys())
     assert all(ours.state_dict()[k].shape == v.shape for k, v in ref.items())
     ours.load_state_dict(ref, strict=True)
+
+
+def test_decode_outputs_matches_reference(monkeypatch):
+    """oracle.decode_outputs against the reference's utils/utils_bbox.py:32-84 (its `.cuda(local_rank)` calls neutralised)"""
+    ref_shim.install()
+    from utils.utils_bbox import decode_outputs as ref_decode
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    g = torch.Generator().manual_seed(3)
+    outs = [torch.randn(2, 9, s, s, generator=g) for s in (64, 32, 16)]
+    ref = ref_decode([o.clone() for o in outs], (512, 512), 0)
+    got = O.decode_outputs(outs, (512, 512))
+    assert _rel(got, ref) < 1e-6
