@@ -59,7 +59,7 @@ static CoreSmem core_layout(const CoreGeom& q, bool staged, bool bwd, int maxm) 
   s.dz = take(bwd ? q.N * 4 : 0);
   s.off = take(q.N * 4);
   s.k = take(q.N);
-  s.mask = take(q.N * 2);
+  s.mask = take(q.N * (maxm > 16 ? 8 : 2));        // bin-membership bit mask per point: 16 bits, 64 for the wide-proposal path
   s.chat = take(q.D * maxm * 4);
   s.cnorm = take(maxm * 4);
   s.vc = take(q.D * maxm * 4);
@@ -138,18 +138,23 @@ __device__ __forceinline__ int bin_lo(int i, int n, int p) { return (i * n) / p;
 __device__ __forceinline__ int bin_hi(int i, int n, int p) { return ((i + 1) * n + p - 1) / p; }
 
 // Shared prologue: per-point offsets and bin-membership masks, 1/|bin|.
-__device__ __forceinline__ void setup_points(const CoreGeom& q, int row0, int col0, int* off, uint16_t* mask,
+// bin-membership masks: one bit per centre (AdaptiveAvgPool2d bins overlap when the region is not divisible by the proposal)
+template <int MAXM> struct MaskOf { using type = uint16_t; };
+template <> struct MaskOf<64> { using type = uint64_t; };
+
+template <typename MT>
+__device__ __forceinline__ void setup_points(const CoreGeom& q, int row0, int col0, int* off, MT* mask,
                                              float* binv, int* cnt) {
   for (int n = threadIdx.x; n < q.N; n += blockDim.x) {
     int r = n / q.rh, c = n % q.rh;
     off[n] = (row0 + r) * q.W + col0 + c;
-    uint32_t mk = 0;
+    uint64_t mk = 0;
     for (int i = 0; i < q.pw; ++i) {
       if (r < bin_lo(i, q.rw, q.pw) || r >= bin_hi(i, q.rw, q.pw)) continue;
       for (int j = 0; j < q.ph; ++j)
-        if (c >= bin_lo(j, q.rh, q.ph) && c < bin_hi(j, q.rh, q.ph)) mk |= 1u << (i * q.ph + j);
+        if (c >= bin_lo(j, q.rh, q.ph) && c < bin_hi(j, q.rh, q.ph)) mk |= 1ull << (i * q.ph + j);
     }
-    mask[n] = (uint16_t)mk;
+    mask[n] = (MT)mk;
   }
   if (threadIdx.x < q.M) {
     int i = threadIdx.x / q.ph, j = threadIdx.x % q.ph;
@@ -161,7 +166,7 @@ __device__ __forceinline__ void setup_points(const CoreGeom& q, int row0, int co
 
 // channel-major masked sums:  dst[d][m] = scale_m * sum_{n in bin m} A(d,n)      (centre proposal)
 template <int MAXM, bool STAGED, typename T>
-__device__ __forceinline__ void bin_means(const TileAccess<T>& A, const CoreGeom& q, const uint16_t* mask,
+__device__ __forceinline__ void bin_means(const TileAccess<T>& A, const CoreGeom& q, const typename MaskOf<MAXM>::type* mask,
                                           const float* binv, float* dst /*[D][MAXM]*/) {
   const int sub = threadIdx.x % q.TPD;
   const int dpb = blockDim.x / q.TPD;             // channels per sweep
@@ -173,9 +178,9 @@ __device__ __forceinline__ void bin_means(const TileAccess<T>& A, const CoreGeom
     if (d < q.D) {
       for (int n = sub; n < q.N; n += q.TPD) {
         float x = A.template at<STAGED>(d, n);
-        uint32_t mk = mask[n];
+        const uint64_t mk = mask[n];
 #pragma unroll
-        for (int m = 0; m < MAXM; ++m) acc[m] += ((mk >> m) & 1u) ? x : 0.f;
+        for (int m = 0; m < MAXM; ++m) acc[m] += ((mk >> m) & 1ull) ? x : 0.f;
       }
     }
 #pragma unroll
@@ -244,7 +249,8 @@ core_fwd_kernel(const TF* __restrict__ feat, const TV* __restrict__ value, TO* _
   float* g = reinterpret_cast<float*>(smem + L.g);
   int* off = reinterpret_cast<int*>(smem + L.off);
   uint8_t* k = smem + L.k;
-  uint16_t* mask = reinterpret_cast<uint16_t*>(smem + L.mask);
+  using MT = typename MaskOf<MAXM>::type;
+  MT* mask = reinterpret_cast<MT*>(smem + L.mask);
   float* chat = reinterpret_cast<float*>(smem + L.chat);
   float* cnorm = reinterpret_cast<float*>(smem + L.cnorm);
   float* vc = reinterpret_cast<float*>(smem + L.vc);
@@ -342,7 +348,8 @@ core_bwd_kernel(const TF* __restrict__ feat, const TV* __restrict__ value, const
   float* dz = reinterpret_cast<float*>(smem + L.dz);
   int* off = reinterpret_cast<int*>(smem + L.off);
   uint8_t* k = smem + L.k;
-  uint16_t* mask = reinterpret_cast<uint16_t*>(smem + L.mask);
+  using MT = typename MaskOf<MAXM>::type;
+  MT* mask = reinterpret_cast<MT*>(smem + L.mask);
   float* chat = reinterpret_cast<float*>(smem + L.chat);
   float* cnorm = reinterpret_cast<float*>(smem + L.cnorm);
   float* vc = reinterpret_cast<float*>(smem + L.vc);
@@ -481,7 +488,7 @@ core_bwd_kernel(const TF* __restrict__ feat, const TV* __restrict__ value, const
   for (int n = threadIdx.x; n < q.N; n += blockDim.x) {
     int kk = k[n];
     float cA = dz[n], cB = inv[n], gn = g[n];
-    uint32_t mk = mask[n];
+    const uint64_t mk = mask[n];
     int o = off[n];
     for (int d = 0; d < q.D; ++d) {
       float x = AF.template at<STAGED>(d, n);
@@ -489,7 +496,7 @@ core_bwd_kernel(const TF* __restrict__ feat, const TV* __restrict__ value, const
       float dv = gn * dA[d * MAXM + kk];
 #pragma unroll
       for (int m = 0; m < MAXM; ++m) {
-        if ((mk >> m) & 1u) {
+        if ((mk >> m) & 1ull) {
           df += dch[d * MAXM + m];
           dv = fmaf(dA[d * MAXM + m], binv[m], dv);
         }
@@ -517,7 +524,7 @@ __global__ void core_reduce_partials(const float* __restrict__ partials, int n, 
 // ---- host side -------------------------------------------------------------------------------------------
 static int make_geom(CoreGeom& q, int B, int E, int D, int H, int W, int fold_w, int fold_h, int pw, int ph) {
   VRCOC_REQUIRE(B > 0 && E > 0 && D > 0 && H > 0 && W > 0, "cluster_core: non-positive dimension");
-  VRCOC_REQUIRE(pw > 0 && ph > 0 && pw * ph <= 16, "cluster_core: proposal %dx%d unsupported (M must be <= 16)", pw, ph);
+  VRCOC_REQUIRE(pw > 0 && ph > 0 && pw * ph <= 64, "cluster_core: proposal %dx%d unsupported (M must be <= 64)", pw, ph);
   VRCOC_REQUIRE(D <= 256, "cluster_core: head_dim %d > 256 unsupported", D);
   bool folded = fold_w > 1 && fold_h > 1;  // vr_coc.py:160
   q.B = B; q.E = E; q.D = D; q.H = H; q.W = W;
@@ -552,7 +559,7 @@ constexpr int SMEM_LIMIT = 200 * 1024;
 template <typename TF, typename TV, typename TO>
 static int launch_fwd(const void* feat, const void* value, void* out, uint8_t* idx, float* smax, const float* alpha,
                       const float* beta, const CoreGeom& q, cudaStream_t st) {
-  int maxm = q.M <= 4 ? 4 : 16;
+  int maxm = q.M <= 4 ? 4 : (q.M <= 16 ? 16 : 64);
   CoreSmem Ls = core_layout(q, true, false, maxm);
   bool staged = Ls.total <= SMEM_LIMIT;
   CoreSmem L = staged ? Ls : core_layout(q, false, false, maxm);
@@ -565,7 +572,8 @@ static int launch_fwd(const void* feat, const void* value, void* out, uint8_t* i
     kern<<<R, CORE_THREADS, L.total, st>>>((const TF*)feat, (const TV*)value, (TO*)out, idx, smax, alpha, beta, q, L); \
   } while (0)
   if (maxm == 4) { if (staged) LAUNCH(4, true); else LAUNCH(4, false); }
-  else           { if (staged) LAUNCH(16, true); else LAUNCH(16, false); }
+  else if (maxm == 16) { if (staged) LAUNCH(16, true); else LAUNCH(16, false); }
+  else { if (staged) LAUNCH(64, true); else LAUNCH(64, false); }        // wide proposals (coc_tiny2: 7x7 = 49 centres, vr_coc.py:734-756)
 #undef LAUNCH
   return check_launch("cluster_core_fwd");
 }
@@ -574,7 +582,7 @@ template <typename TF, typename TV, typename TG, typename TDF, typename TDV>
 static int launch_bwd(const void* feat, const void* value, const void* dout, const uint8_t* idx, const float* smax,
                       const float* alpha, void* dfeat, void* dvalue, float* dab, float* partials, const CoreGeom& q,
                       cudaStream_t st) {
-  int maxm = q.M <= 4 ? 4 : 16;
+  int maxm = q.M <= 4 ? 4 : (q.M <= 16 ? 16 : 64);
   CoreSmem Ls = core_layout(q, true, true, maxm);
   bool staged = Ls.total <= SMEM_LIMIT;
   CoreSmem L = staged ? Ls : core_layout(q, false, true, maxm);
@@ -588,7 +596,8 @@ static int launch_bwd(const void* feat, const void* value, const void* dout, con
                                            (TDF*)dfeat, (TDV*)dvalue, partials, q, L);                             \
   } while (0)
   if (maxm == 4) { if (staged) LAUNCH(4, true); else LAUNCH(4, false); }
-  else           { if (staged) LAUNCH(16, true); else LAUNCH(16, false); }
+  else if (maxm == 16) { if (staged) LAUNCH(16, true); else LAUNCH(16, false); }
+  else { if (staged) LAUNCH(64, true); else LAUNCH(64, false); }
 #undef LAUNCH
   int rc = check_launch("cluster_core_bwd");
   if (rc) return rc;

@@ -261,3 +261,40 @@ def test_whole_model_1024_vs_oracle(V):
     assert rel_err(seg, seg_ref) < 2e-3
     for a, b in zip(det, det_ref):
         assert rel_err(a, b) < 2e-3
+
+
+@pytest.mark.parametrize("pw,ph,H,fold", [(7, 7, 32, 1), (5, 6, 28, 2)])
+def test_cluster_wide_proposal_vs_oracle(V, pw, ph, H, fold):
+    """more than 16 centres per region (coc_tiny2: 7x7 proposals, vr_coc.py:734-756; overlapping adaptive-pool bins when the region
+    is not divisible): Cluster forward + backward in fp32 against the oracle's autograd"""
+    from oracle import coc_oracle as O
+    torch.manual_seed(0)
+    m = V.Cluster(dim=24, out_dim=24, proposal_w=pw, proposal_h=ph, fold_w=fold, fold_h=fold, heads=2, head_dim=8)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        m.sim_alpha.fill_(1.4); m.sim_beta.fill_(-0.1)
+    x = torch.randn(2, 24, H, H, generator=g)
+    gout = torch.randn(2, 24, H, H, generator=g)
+    sd = {k: v.double().requires_grad_(True) for k, v in m.state_dict().items()}
+    x64 = x.double().requires_grad_(True)
+    ref = O.cluster(x64, sd, "", 2, fold, fold, pw, ph)
+    ref.backward(gout.double())
+    m = m.cuda()
+    xg = x.cuda().requires_grad_(True)
+    y = m(xg)
+    y.backward(gout.cuda())
+    errs = {"out": rel_err(y, ref), "dx": rel_err(xg.grad, x64.grad), "dfc1": rel_err(m.fc1.weight.grad, sd["fc1.weight"].grad),
+            "dfc_v": rel_err(m.fc_v.weight.grad, sd["fc_v.weight"].grad)}
+    print(pw, ph, {k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) < 1e-4
+
+
+def test_coc_tiny2_fails_where_the_reference_fails(V):
+    """coc_tiny2 (vr_coc.py:734-756): its 7x7 = 49 centres are covered by the wide-proposal core above, but the factory cannot run
+    end to end in the reference either — its stage-3 width (196) is not divisible by ShuffleAttention's 2*G = 8, and the reference
+    raises 'The size of tensor a (24) must match the size of tensor b (25)' in shuffle_attention.py:57 (checked in the dev
+    container).  The product fails at the same module with an explicit message."""
+    m = V.coc_tiny2().cuda().eval()
+    with pytest.raises(RuntimeError, match="not divisible"):
+        with torch.no_grad():
+            m(torch.randn(1, 3, 512, 512, device="cuda"), torch.rand(1, 4, 512, 512, device="cuda"))
