@@ -200,6 +200,239 @@ struct TmArgs {
   int B, H, W, F1, F2, regions;
 };
 
+// Everything between the projection GEMM and the dispatch, shared by the two kernels below: pass 1 (centres), pass 2 (similarity,
+// arg-max, gate, one-hot rows of the aggregation GEMM), value -> bf16 TMEM operand, wait for the aggregation GEMM, centre aggregates
+// into the warp's private table.  Leaves gk[q] = (gate bits & ~3) | centre of this lane's point in chunk q.
+struct TmCore {
+  uint32_t T_FEAT, T_VAL, lane_off, scratch, wb_base, ph;
+  int e, j, lane, it, Wimg;
+  float* part1; int* cntp; float* apriv;
+  uint64_t* va_ready; uint64_t* accA_full;
+  float rstd, ehf, ehv, alpha, beta;
+  uint8_t* idx_out; float* smax_out; int64_t io_base;
+  unsigned long long* tr;
+};
+
+__device__ __forceinline__ void tm_core_passes(const TmCore& c, uint32_t (&gk)[2]) {
+  const uint32_t T_FEAT = c.T_FEAT, T_VAL = c.T_VAL, lane_off = c.lane_off, scratch = c.scratch, wb_base = c.wb_base;
+  const int e = c.e, j = c.j, lane = c.lane, d = c.lane;
+  const int dq = lane & 3, pg = lane >> 2;                             // pass-2 read mapping: channels 8dq..8dq+7, points 4pg..4pg+3
+  float* part1 = c.part1; int* cntp = c.cntp; float* apriv = c.apriv;
+  const float rstd = c.rstd, ehf = c.ehf, ehv = c.ehv, alpha = c.alpha, beta = c.beta;
+  constexpr float inv_q = 1.0f / 64.0f;
+      // ---- pass 1: quadrant sums of feat over this warp's 4 region rows (16 columns = one row; cols 0-7 left, 8-15 right) -------
+      {
+        float sl = 0.f, sr = 0.f;
+#pragma unroll 1
+        for (int h2 = 0; h2 < 2; ++h2) {
+          uint32_t r[32];
+          tm_ld32(T_FEAT + lane_off + (uint32_t)(64 * j + 32 * h2), r);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if ((i & 15) < 8) sl += __uint_as_float(r[i]); else sr += __uint_as_float(r[i]);
+          }
+        }
+        // sum of (rstd*acc + ehf) over 32 points per side
+        part1[((e * 4 + j) * 2 + 0) * 32 + d] = fmaf(rstd, sl, 32.f * ehf);
+        part1[((e * 4 + j) * 2 + 1) * 32 + d] = fmaf(rstd, sr, 32.f * ehf);
+      }
+      named_bar(1 + e, 128);
+      // normalised centres of THIS LANE's eight channels 8*dq .. 8*dq+7 (pass-2 mapping), kept in registers:
+      // cc[t][m], m = 2*(bottom half) + (right half); rows 0-7 = warps j 0,1
+      float cc[8][4];
+      {
+        const uint32_t p1 = smem_u32(part1) + (uint32_t)((e * 4 * 2 * 32 + 8 * dq) * 4);
+        float ssm[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {                                   // channels 8dq + 4hf .. + 3
+          float q[4][2][4];                                                // [j][side][channel]
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd) {
+              const uint4 v = lds128(p1 + (uint32_t)(((jj * 2 + sd) * 32 + 4 * hf) * 4));
+              q[jj][sd][0] = __uint_as_float(v.x); q[jj][sd][1] = __uint_as_float(v.y);
+              q[jj][sd][2] = __uint_as_float(v.z); q[jj][sd][3] = __uint_as_float(v.w);
+            }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            cc[4 * hf + t][0] = (q[0][0][t] + q[1][0][t]) * inv_q; cc[4 * hf + t][1] = (q[0][1][t] + q[1][1][t]) * inv_q;
+            cc[4 * hf + t][2] = (q[2][0][t] + q[3][0][t]) * inv_q; cc[4 * hf + t][3] = (q[2][1][t] + q[3][1][t]) * inv_q;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) ssm[m] = fmaf(cc[4 * hf + t][m], cc[4 * hf + t][m], ssm[m]);
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          ssm[m] += __shfl_xor_sync(0xffffffffu, ssm[m], 1);
+          ssm[m] += __shfl_xor_sync(0xffffffffu, ssm[m], 2);
+          const float inv = fminf(rsqrtf(ssm[m]), 1.0f / TM_EPS);         // 1 / max(|c|, eps) to 2 ulp
+#pragma unroll
+          for (int t = 0; t < 8; ++t) cc[t][m] *= inv;
+        }
+      }
+      // zero this warp's part of the aggregation GEMM's B operand (rows of head e, its 64 points): pass 2 then only writes the
+      // two non-zero entries of each point
+      {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int u = lane + 32 * i;                                     // 8 rows (4 hi + 4 lo) x 8 chunks of 16 B
+          const int r = (u >> 3) < 4 ? 4 * e + (u >> 3) : 16 + 4 * e + (u >> 3) - 4;
+          sts128(wb_base + (uint32_t)(j * TM_WB_SLAB + (r >> 3) * 1024 + (r & 7) * 128 + (u & 7) * 16), 0u, 0u, 0u, 0u);
+        }
+      }
+      __syncwarp();
+      tm_trace(c.tr, c.it, 9);
+
+      // ---- pass 2: similarity / arg-max / gate, 32 points per chunk ----------------------------------------------------------------
+      // The chunk is transposed through the scratch: written lane = channel (TMEM order), read lane = (dq, pg): 4 channels x 8 points,
+      // centres from registers -> no broadcast loads; 40 partial sums are then transpose-reduced over the 8 dq lanes so that lane L
+      // ends up with the complete |f|^2 and 4 dot products of point L of the chunk.
+      int cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
+      {
+        const uint32_t swzw = (uint32_t)((((d >> 3) << 1) ^ (d & 7)) & 7);   // conflict-free for both access patterns
+#pragma unroll 1
+        for (int q = 0; q < 2; ++q) {
+          {
+            uint32_t r[32];
+            tm_ld32(T_FEAT + lane_off + (uint32_t)(64 * j + 32 * q), r);
+#pragma unroll
+            for (int c16 = 0; c16 < 8; ++c16)
+              sts128(scratch + (uint32_t)d * 128u + (((uint32_t)c16 ^ swzw) << 4),
+                     __float_as_uint(fmaf(rstd, __uint_as_float(r[4 * c16]), ehf)), __float_as_uint(fmaf(rstd, __uint_as_float(r[4 * c16 + 1]), ehf)),
+                     __float_as_uint(fmaf(rstd, __uint_as_float(r[4 * c16 + 2]), ehf)), __float_as_uint(fmaf(rstd, __uint_as_float(r[4 * c16 + 3]), ehf)));
+          }
+          __syncwarp();
+          uint64_t acc2[2][5];
+#pragma unroll
+          for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+            for (int v = 0; v < 5; ++v) acc2[pr][v] = 0ull;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int dd = 8 * dq + t;
+            const uint32_t swzr = (uint32_t)(((2 * dq) ^ t) & 7);
+            const uint4 f = lds128(scratch + (uint32_t)dd * 128u + ((((uint32_t)pg) ^ swzr) << 4));     // points 4pg .. 4pg+3 of channel dd
+            const uint64_t x2[2] = {((uint64_t)f.y << 32) | f.x, ((uint64_t)f.w << 32) | f.z};
+            const uint64_t c0 = pk(cc[t][0], cc[t][0]), c1 = pk(cc[t][1], cc[t][1]), c2 = pk(cc[t][2], cc[t][2]), c3 = pk(cc[t][3], cc[t][3]);
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {
+              acc2[pr][0] = fma2(x2[pr], x2[pr], acc2[pr][0]);
+              acc2[pr][1] = fma2(c0, x2[pr], acc2[pr][1]);
+              acc2[pr][2] = fma2(c1, x2[pr], acc2[pr][2]);
+              acc2[pr][3] = fma2(c2, x2[pr], acc2[pr][3]);
+              acc2[pr][4] = fma2(c3, x2[pr], acc2[pr][4]);
+            }
+          }
+          // transpose-reduce over the 4 dq lanes: bit 1 halves the 4 points to 2, bit 0 to 1 -> lane L holds point L of the chunk
+          float a4[4][5];
+#pragma unroll
+          for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+            for (int v = 0; v < 5; ++v) upk(acc2[pr][v], a4[2 * pr][v], a4[2 * pr + 1][v]);
+          float a2[2][5], a1[5];
+          const bool b1_ = (dq & 2) != 0, b0_ = (dq & 1) != 0;
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int v = 0; v < 5; ++v) {
+              const float keep = b1_ ? a4[i + 2][v] : a4[i][v], send = b1_ ? a4[i][v] : a4[i + 2][v];
+              a2[i][v] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+#pragma unroll
+          for (int v = 0; v < 5; ++v) {
+            const float keep = b0_ ? a2[1][v] : a2[0][v], send = b0_ ? a2[0][v] : a2[1][v];
+            a1[v] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          }
+          // this lane's point: n = 64j + 32q + lane
+          const float inv = fminf(rsqrtf(a1[0]), 1.0f / TM_EPS);
+          float tb = alpha * a1[1], db = a1[1];
+          int k = 0;
+          if (alpha * a1[2] > tb) { tb = alpha * a1[2]; db = a1[2]; k = 1; }
+          if (alpha * a1[3] > tb) { tb = alpha * a1[3]; db = a1[3]; k = 2; }
+          if (alpha * a1[4] > tb) { tb = alpha * a1[4]; db = a1[4]; k = 3; }
+          const float gv = __fdividef(1.0f, 1.0f + __expf(-fmaf(alpha, db * inv, beta)));
+          // the centre index rides in the two lowest mantissa bits of the gate (2^-22 relative); passes 3 and 4 both use the masked gate
+          gk[q] = (__float_as_uint(gv) & ~3u) | (uint32_t)k;
+          const int n = 64 * j + 32 * q + lane;
+          {
+            // B operand of the aggregation GEMM, K-major SW128 [k-slab = n / 64][row][128 B]: rows 4e+m = bf16 hi part of the gate
+            // where m is this point's centre (0 elsewhere), rows 16+4e+m = the lo part (hi + lo carries the gate to 2^-17)
+            const float gm = __uint_as_float(gk[q] & ~3u);
+            const __nv_bfloat16 hb = __float2bfloat16_rn(gm);
+            const uint32_t hi16 = (uint32_t)__bfloat16_as_ushort(hb);
+            const uint32_t lo16 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gm - __bfloat162float(hb)));
+            const uint32_t colb = wb_base + (uint32_t)((n >> 6) * TM_WB_SLAB + (n & 7) * 2);
+            const uint32_t ch = (uint32_t)((n & 63) >> 3);
+            const int r1 = 4 * e + k, r2 = 16 + 4 * e + k;                 // the other rows of this point were zeroed above
+            sts16(colb + (uint32_t)((r1 >> 3) * 1024 + (r1 & 7) * 128) + ((ch ^ (uint32_t)(r1 & 7)) << 4), hi16);
+            sts16(colb + (uint32_t)((r2 >> 3) * 1024 + (r2 & 7) * 128) + ((ch ^ (uint32_t)(r2 & 7)) << 4), lo16);
+          }
+          if (c.idx_out || c.smax_out) {
+            const int64_t io = c.io_base + (int64_t)(n >> 4) * c.Wimg + (n & 15);
+            if (c.idx_out) c.idx_out[io] = (uint8_t)k;
+            if (c.smax_out) c.smax_out[io] = __uint_as_float(gk[q] & ~3u);
+          }
+          cnt0 += __popc(__ballot_sync(0xffffffffu, k == 0));
+          cnt1 += __popc(__ballot_sync(0xffffffffu, k == 1));
+          cnt2 += __popc(__ballot_sync(0xffffffffu, k == 2));
+          cnt3 += __popc(__ballot_sync(0xffffffffu, k == 3));
+          __syncwarp();                                                    // the scratch is rewritten by the next chunk
+        }
+        if (lane == 0) *reinterpret_cast<int4*>(cntp + (e * 4 + j) * 4) = make_int4(cnt0, cnt1, cnt2, cnt3);
+      }
+      // the scratch of the two heads of a k-slab lives in that slab of the o operand: both heads must have left pass 2 before
+      // either writes o (pass 4)
+      named_bar(5 + (e >> 1), 256);
+      tm_trace(c.tr, c.it, 10);
+
+      // ---- pass 3 on the tensor core: value -> bf16 pairs in the (dead) feat columns of TMEM = the A operand of the aggregation GEMM;
+      //      the one-hot gate rows written in pass 2 are its B operand.  (The CUDA-core forms of this pass were the hot spot of the
+      //      first two versions: 4 shared-memory cycles per point and warp for broadcast one-hot weights, or 19 instructions per point
+      //      for predicated accumulation from packed (gate | centre) words.) -----------------------------------------------------------
+      {
+        uint32_t pw[32];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          uint32_t r[32];
+          tm_ld32(T_VAL + lane_off + (uint32_t)(64 * j + 32 * h2), r);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            pw[16 * h2 + i] = bf16x2(fmaf(rstd, __uint_as_float(r[2 * i]), ehv), fmaf(rstd, __uint_as_float(r[2 * i + 1]), ehv));
+        }
+        tm_st32(T_FEAT + lane_off + (uint32_t)(32 * j), pw);               // points 64j + 2c, 64j + 2c + 1 -> column 32j + c
+      }
+      fence_async_smem();                                                  // the gate rows (generic-proxy stores) before the MMA reads them
+      tm_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(c.va_ready);
+      tm_trace(c.tr, c.it, 11);
+      // ---- centre aggregates (lane = channel) from the aggregation GEMM -> this warp's private table a[m][d] -----------------------------
+      {
+        mbar_wait(c.accA_full, c.ph);
+        tm_fence_after();
+        tm_trace(c.tr, c.it, 7);
+        {
+          // D_A columns (from T_FEAT + 128): [4e, 4e+4) = sum of hi-gated value, [16 + 4e, ..) = lo part, [32, 36) = quadrant means
+          uint32_t dh[4], dl[4], dqm[4];
+          tm_ld4_issue(T_FEAT + lane_off + (uint32_t)(128 + 4 * e), dh);
+          tm_ld4_issue(T_FEAT + lane_off + (uint32_t)(128 + 16 + 4 * e), dl);
+          tm_ld4_issue(T_FEAT + lane_off + (uint32_t)(128 + 32), dqm);
+          tm_ld_wait12(dh, dl, dqm);
+          int cn[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int4 c4 = *reinterpret_cast<const int4*>(cntp + (e * 4 + jj) * 4);
+            cn[0] += c4.x; cn[1] += c4.y; cn[2] += c4.z; cn[3] += c4.w;
+          }
+          // rows of 36 floats: lanes that read different centres hit different banks
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+            apriv[m * 36 + d] = (__uint_as_float(dh[m]) + __uint_as_float(dl[m]) + __uint_as_float(dqm[m])) * __fdividef(1.0f, (float)(cn[m] + 1));
+        }
+      }
+}
+
 template <int C> struct TmSmem {
   static constexpr int KC = C / 64;                                    // k-slabs of x
   static constexpr int NXB = C == 64 ? 2 : 1;                          // x tile buffers
@@ -469,218 +702,22 @@ token_mixer_fused_kernel(TmArgs A, const __grid_constant__ CUtensorMap tmX, cons
       tm_fence_after();
       tm_trace(tr, it, 8);
 
-      // ---- pass 1: quadrant sums of feat over this warp's 4 region rows (16 columns = one row; cols 0-7 left, 8-15 right) -------
+      // ---- passes 1-3 + centre aggregates (tm_core_passes) ----------------------------------------------------------------------------
+      uint32_t gk[2];
       {
-        float sl = 0.f, sr = 0.f;
-#pragma unroll 1
-        for (int h2 = 0; h2 < 2; ++h2) {
-          uint32_t r[32];
-          tm_ld32(T_FEAT + lane_off + (uint32_t)(64 * j + 32 * h2), r);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if ((i & 15) < 8) sl += __uint_as_float(r[i]); else sr += __uint_as_float(r[i]);
-          }
-        }
-        // sum of (rstd*acc + ehf) over 32 points per side
-        part1[((e * 4 + j) * 2 + 0) * 32 + d] = fmaf(rstd, sl, 32.f * ehf);
-        part1[((e * 4 + j) * 2 + 1) * 32 + d] = fmaf(rstd, sr, 32.f * ehf);
+        TmCore cc_;
+        cc_.T_FEAT = T_FEAT; cc_.T_VAL = T_VAL; cc_.lane_off = lane_off; cc_.scratch = scratch; cc_.wb_base = wb_base; cc_.ph = ph;
+        cc_.e = e; cc_.j = j; cc_.lane = lane; cc_.it = it; cc_.Wimg = A.W;
+        cc_.part1 = part1; cc_.cntp = cntp; cc_.apriv = apriv; cc_.va_ready = va_ready; cc_.accA_full = accA_full;
+        cc_.rstd = rstd; cc_.ehf = ehf; cc_.ehv = ehv; cc_.alpha = alpha; cc_.beta = beta;
+        cc_.idx_out = A.idx_out; cc_.smax_out = A.smax_out;
+        cc_.io_base = ((int64_t)(b * TM_E + e) * A.H + row0) * A.W + col0;
+        cc_.tr = tr;
+        tm_core_passes(cc_, gk);
       }
-      named_bar(1 + e, 128);
-      // normalised centres of THIS LANE's eight channels 8*dq .. 8*dq+7 (pass-2 mapping), kept in registers:
-      // cc[t][m], m = 2*(bottom half) + (right half); rows 0-7 = warps j 0,1
-      float cc[8][4];
+      // ---- pass 4: dispatch with lane = POINT: o[n][:] = g_n * a[k_n][:], bf16, written as the K-major SW128 B operand of GEMM 2
+      //      (row = point, 64 bytes = this head's 32 channels) ------------------------------------------------------------------------------
       {
-        const uint32_t p1 = smem_u32(part1) + (uint32_t)((e * 4 * 2 * 32 + 8 * dq) * 4);
-        float ssm[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {                                   // channels 8dq + 4hf .. + 3
-          float q[4][2][4];                                                // [j][side][channel]
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-            for (int sd = 0; sd < 2; ++sd) {
-              const uint4 v = lds128(p1 + (uint32_t)(((jj * 2 + sd) * 32 + 4 * hf) * 4));
-              q[jj][sd][0] = __uint_as_float(v.x); q[jj][sd][1] = __uint_as_float(v.y);
-              q[jj][sd][2] = __uint_as_float(v.z); q[jj][sd][3] = __uint_as_float(v.w);
-            }
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            cc[4 * hf + t][0] = (q[0][0][t] + q[1][0][t]) * inv_q; cc[4 * hf + t][1] = (q[0][1][t] + q[1][1][t]) * inv_q;
-            cc[4 * hf + t][2] = (q[2][0][t] + q[3][0][t]) * inv_q; cc[4 * hf + t][3] = (q[2][1][t] + q[3][1][t]) * inv_q;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) ssm[m] = fmaf(cc[4 * hf + t][m], cc[4 * hf + t][m], ssm[m]);
-          }
-        }
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          ssm[m] += __shfl_xor_sync(0xffffffffu, ssm[m], 1);
-          ssm[m] += __shfl_xor_sync(0xffffffffu, ssm[m], 2);
-          const float inv = fminf(rsqrtf(ssm[m]), 1.0f / TM_EPS);         // 1 / max(|c|, eps) to 2 ulp
-#pragma unroll
-          for (int t = 0; t < 8; ++t) cc[t][m] *= inv;
-        }
-      }
-      // zero this warp's part of the aggregation GEMM's B operand (rows of head e, its 64 points): pass 2 then only writes the
-      // two non-zero entries of each point
-      {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int u = lane + 32 * i;                                     // 8 rows (4 hi + 4 lo) x 8 chunks of 16 B
-          const int r = (u >> 3) < 4 ? 4 * e + (u >> 3) : 16 + 4 * e + (u >> 3) - 4;
-          sts128(wb_base + (uint32_t)(j * TM_WB_SLAB + (r >> 3) * 1024 + (r & 7) * 128 + (u & 7) * 16), 0u, 0u, 0u, 0u);
-        }
-      }
-      __syncwarp();
-      tm_trace(tr, it, 9);
-
-      // ---- pass 2: similarity / arg-max / gate, 32 points per chunk ----------------------------------------------------------------
-      // The chunk is transposed through the scratch: written lane = channel (TMEM order), read lane = (dq, pg): 4 channels x 8 points,
-      // centres from registers -> no broadcast loads; 40 partial sums are then transpose-reduced over the 8 dq lanes so that lane L
-      // ends up with the complete |f|^2 and 4 dot products of point L of the chunk.
-      int cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
-      uint32_t gk[2];                                                      // (gate bits & ~3) | centre of this lane's point, per chunk
-      {
-        const uint32_t swzw = (uint32_t)((((d >> 3) << 1) ^ (d & 7)) & 7);   // conflict-free for both access patterns
-#pragma unroll 1
-        for (int q = 0; q < 2; ++q) {
-          {
-            uint32_t r[32];
-            tm_ld32(T_FEAT + lane_off + (uint32_t)(64 * j + 32 * q), r);
-#pragma unroll
-            for (int c16 = 0; c16 < 8; ++c16)
-              sts128(scratch + (uint32_t)d * 128u + (((uint32_t)c16 ^ swzw) << 4),
-                     __float_as_uint(fmaf(rstd, __uint_as_float(r[4 * c16]), ehf)), __float_as_uint(fmaf(rstd, __uint_as_float(r[4 * c16 + 1]), ehf)),
-                     __float_as_uint(fmaf(rstd, __uint_as_float(r[4 * c16 + 2]), ehf)), __float_as_uint(fmaf(rstd, __uint_as_float(r[4 * c16 + 3]), ehf)));
-          }
-          __syncwarp();
-          uint64_t acc2[2][5];
-#pragma unroll
-          for (int pr = 0; pr < 2; ++pr)
-#pragma unroll
-            for (int v = 0; v < 5; ++v) acc2[pr][v] = 0ull;
-#pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const int dd = 8 * dq + t;
-            const uint32_t swzr = (uint32_t)(((2 * dq) ^ t) & 7);
-            const uint4 f = lds128(scratch + (uint32_t)dd * 128u + ((((uint32_t)pg) ^ swzr) << 4));     // points 4pg .. 4pg+3 of channel dd
-            const uint64_t x2[2] = {((uint64_t)f.y << 32) | f.x, ((uint64_t)f.w << 32) | f.z};
-            const uint64_t c0 = pk(cc[t][0], cc[t][0]), c1 = pk(cc[t][1], cc[t][1]), c2 = pk(cc[t][2], cc[t][2]), c3 = pk(cc[t][3], cc[t][3]);
-#pragma unroll
-            for (int pr = 0; pr < 2; ++pr) {
-              acc2[pr][0] = fma2(x2[pr], x2[pr], acc2[pr][0]);
-              acc2[pr][1] = fma2(c0, x2[pr], acc2[pr][1]);
-              acc2[pr][2] = fma2(c1, x2[pr], acc2[pr][2]);
-              acc2[pr][3] = fma2(c2, x2[pr], acc2[pr][3]);
-              acc2[pr][4] = fma2(c3, x2[pr], acc2[pr][4]);
-            }
-          }
-          // transpose-reduce over the 4 dq lanes: bit 1 halves the 4 points to 2, bit 0 to 1 -> lane L holds point L of the chunk
-          float a4[4][5];
-#pragma unroll
-          for (int pr = 0; pr < 2; ++pr)
-#pragma unroll
-            for (int v = 0; v < 5; ++v) upk(acc2[pr][v], a4[2 * pr][v], a4[2 * pr + 1][v]);
-          float a2[2][5], a1[5];
-          const bool b1_ = (dq & 2) != 0, b0_ = (dq & 1) != 0;
-#pragma unroll
-          for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int v = 0; v < 5; ++v) {
-              const float keep = b1_ ? a4[i + 2][v] : a4[i][v], send = b1_ ? a4[i][v] : a4[i + 2][v];
-              a2[i][v] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-#pragma unroll
-          for (int v = 0; v < 5; ++v) {
-            const float keep = b0_ ? a2[1][v] : a2[0][v], send = b0_ ? a2[0][v] : a2[1][v];
-            a1[v] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-          }
-          // this lane's point: n = 64j + 32q + lane
-          const float inv = fminf(rsqrtf(a1[0]), 1.0f / TM_EPS);
-          float tb = alpha * a1[1], db = a1[1];
-          int k = 0;
-          if (alpha * a1[2] > tb) { tb = alpha * a1[2]; db = a1[2]; k = 1; }
-          if (alpha * a1[3] > tb) { tb = alpha * a1[3]; db = a1[3]; k = 2; }
-          if (alpha * a1[4] > tb) { tb = alpha * a1[4]; db = a1[4]; k = 3; }
-          const float gv = __fdividef(1.0f, 1.0f + __expf(-fmaf(alpha, db * inv, beta)));
-          // the centre index rides in the two lowest mantissa bits of the gate (2^-22 relative); passes 3 and 4 both use the masked gate
-          gk[q] = (__float_as_uint(gv) & ~3u) | (uint32_t)k;
-          const int n = 64 * j + 32 * q + lane;
-          {
-            // B operand of the aggregation GEMM, K-major SW128 [k-slab = n / 64][row][128 B]: rows 4e+m = bf16 hi part of the gate
-            // where m is this point's centre (0 elsewhere), rows 16+4e+m = the lo part (hi + lo carries the gate to 2^-17)
-            const float gm = __uint_as_float(gk[q] & ~3u);
-            const __nv_bfloat16 hb = __float2bfloat16_rn(gm);
-            const uint32_t hi16 = (uint32_t)__bfloat16_as_ushort(hb);
-            const uint32_t lo16 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(gm - __bfloat162float(hb)));
-            const uint32_t colb = wb_base + (uint32_t)((n >> 6) * TM_WB_SLAB + (n & 7) * 2);
-            const uint32_t ch = (uint32_t)((n & 63) >> 3);
-            const int r1 = 4 * e + k, r2 = 16 + 4 * e + k;                 // the other rows of this point were zeroed above
-            sts16(colb + (uint32_t)((r1 >> 3) * 1024 + (r1 & 7) * 128) + ((ch ^ (uint32_t)(r1 & 7)) << 4), hi16);
-            sts16(colb + (uint32_t)((r2 >> 3) * 1024 + (r2 & 7) * 128) + ((ch ^ (uint32_t)(r2 & 7)) << 4), lo16);
-          }
-          if (A.idx_out || A.smax_out) {
-            const int64_t io = ((int64_t)(b * TM_E + e) * A.H + row0 + (n >> 4)) * A.W + col0 + (n & 15);
-            if (A.idx_out) A.idx_out[io] = (uint8_t)k;
-            if (A.smax_out) A.smax_out[io] = __uint_as_float(gk[q] & ~3u);
-          }
-          cnt0 += __popc(__ballot_sync(0xffffffffu, k == 0));
-          cnt1 += __popc(__ballot_sync(0xffffffffu, k == 1));
-          cnt2 += __popc(__ballot_sync(0xffffffffu, k == 2));
-          cnt3 += __popc(__ballot_sync(0xffffffffu, k == 3));
-          __syncwarp();                                                    // the scratch is rewritten by the next chunk
-        }
-        if (lane == 0) *reinterpret_cast<int4*>(cntp + (e * 4 + j) * 4) = make_int4(cnt0, cnt1, cnt2, cnt3);
-      }
-      // the scratch of the two heads of a k-slab lives in that slab of the o operand: both heads must have left pass 2 before
-      // either writes o (pass 4)
-      named_bar(5 + (e >> 1), 256);
-      tm_trace(tr, it, 10);
-
-      // ---- pass 3 on the tensor core: value -> bf16 pairs in the (dead) feat columns of TMEM = the A operand of the aggregation GEMM;
-      //      the one-hot gate rows written in pass 2 are its B operand.  (The CUDA-core forms of this pass were the hot spot of the
-      //      first two versions: 4 shared-memory cycles per point and warp for broadcast one-hot weights, or 19 instructions per point
-      //      for predicated accumulation from packed (gate | centre) words.) -----------------------------------------------------------
-      {
-        uint32_t pw[32];
-#pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          uint32_t r[32];
-          tm_ld32(T_VAL + lane_off + (uint32_t)(64 * j + 32 * h2), r);
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            pw[16 * h2 + i] = bf16x2(fmaf(rstd, __uint_as_float(r[2 * i]), ehv), fmaf(rstd, __uint_as_float(r[2 * i + 1]), ehv));
-        }
-        tm_st32(T_FEAT + lane_off + (uint32_t)(32 * j), pw);               // points 64j + 2c, 64j + 2c + 1 -> column 32j + c
-      }
-      fence_async_smem();                                                  // the gate rows (generic-proxy stores) before the MMA reads them
-      tm_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(va_ready);
-      tm_trace(tr, it, 11);
-      // ---- pass 4: centre aggregates (lane = channel) -> private table; dispatch with lane = POINT: o[n][:] = g_n * a[k_n][:],
-      //      bf16, written as the K-major SW128 B operand of GEMM 2 (row = point, 64 bytes = this head's 32 channels) -------------------
-      {
-        mbar_wait(accA_full, ph);
-        tm_fence_after();
-        tm_trace(tr, it, 7);
-        {
-          // D_A columns (from T_FEAT + 128): [4e, 4e+4) = sum of hi-gated value, [16 + 4e, ..) = lo part, [32, 36) = quadrant means
-          uint32_t dh[4], dl[4], dqm[4];
-          tm_ld4_issue(T_FEAT + lane_off + (uint32_t)(128 + 4 * e), dh);
-          tm_ld4_issue(T_FEAT + lane_off + (uint32_t)(128 + 16 + 4 * e), dl);
-          tm_ld4_issue(T_FEAT + lane_off + (uint32_t)(128 + 32), dqm);
-          tm_ld_wait12(dh, dl, dqm);
-          int cn[4] = {0, 0, 0, 0};
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int4 c4 = *reinterpret_cast<const int4*>(cntp + (e * 4 + jj) * 4);
-            cn[0] += c4.x; cn[1] += c4.y; cn[2] += c4.z; cn[3] += c4.w;
-          }
-          // rows of 36 floats: lanes that read different centres hit different banks
-#pragma unroll
-          for (int m = 0; m < 4; ++m)
-            apriv[m * 36 + d] = (__uint_as_float(dh[m]) + __uint_as_float(dl[m]) + __uint_as_float(dqm[m])) * __fdividef(1.0f, (float)(cn[m] + 1));
-        }
         __syncwarp();
 #pragma unroll 1
         for (int q = 0; q < 2; ++q) {
@@ -748,6 +785,270 @@ token_mixer_fused_kernel(TmArgs A, const __grid_constant__ CUtensorMap tmX, cons
         double* dst = A.out_sums + ((int64_t)cur_b * VRCOC_STAT_SLOTS + ((blockIdx.x * TM_CWARPS + warp) & (VRCOC_STAT_SLOTS - 1))) * 2;
         atomicAdd(dst, (double)ssum); atomicAdd(dst + 1, (double)ssq);
       }
+    }
+  }
+  tm_fence_before();
+  __syncthreads();
+  if (warp == TM_CWARPS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+// ================================================================================================================================
+// Projection + cluster core of the token mixer for the WIDE stages (stage 3: C = 320, 8 heads): one CTA per (16x16 region, group of
+// four heads).  fc2 contracts over all heads, so it stays a separate launch; what is fused is GN-folded fc1|fc_v -> core, i.e. the
+// fp32 `feat` / bf16 `value` round trip and one launch per block disappear, and a launch needs only regions x head-groups CTAs
+// (64 at batch 8) — the image and the radar stacks run side by side on the 148 SMs.
+//   x tile (C x 256 points, 160 KB) by TMA in two channel blocks (box dimensions are limited to 256); the fc1|fc_v weight slabs
+//   (hi | lo for feat, hi for value) stream through a 3-deep TMA ring; after the projection the x tile is dead and its shared
+//   memory holds the transposition scratch, the aggregation operand, the aggregate tables and the output tile, which leaves by
+//   one TMA store in NCHW order.
+template <int C> struct TkSmem {
+  static_assert(C == 320, "projection + core kernel: the channel blocks below are laid out for C = 320");
+  static constexpr int KC = C / 64;
+  static constexpr int CA = 128, CB = C - 128;                         // channel blocks of the x tile (whole 64-channel slabs each)
+  static constexpr int XB = C * TM_N * 2;
+  static constexpr int off_x = 0;                                      // block A [16 rows][128][32 B], block B [16][192][32 B]
+  static constexpr int off_xb = CA * TM_N * 2;
+  // after GEMM 1 (x dead):
+  static constexpr int off_scratch = 0;                                // 16 warps x 4 KB
+  static constexpr int off_wb = 65536;                                 // aggregation operand, 4 x 6 KB
+  static constexpr int off_ot = off_wb + 4 * TM_WB_SLAB;               // output tile [16 rows][128 channels][32 B]
+  static_assert(off_ot % 1024 == 0 && off_ot + 65536 <= XB, "reuse of the x tile does not fit");
+  static constexpr int off_ring = XB;                                  // 3 x 16 KB weight slabs
+  static constexpr int off_p1 = off_ring + 3 * 16384;
+  static constexpr int off_ap = off_p1 + 4096;                         // 16 warps x 4 x 36 floats: centre aggregates a[m][d]
+  static constexpr int off_stat = off_ap + 16 * 4 * 36 * 4;
+  static constexpr int off_cnt = off_stat + 2048;
+  static constexpr int off_bar = off_cnt + 256;
+  static constexpr int total = off_bar + 256 + 1024;
+};
+
+template <int C>
+__global__ void __launch_bounds__(TM_THREADS, 1)
+token_mixer_core_kernel(TmArgs A, int heads, const __grid_constant__ CUtensorMap tmXa, const __grid_constant__ CUtensorMap tmXb,
+                        const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmW1) {
+  using S = TkSmem<C>;
+  constexpr int KC = S::KC;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const uint32_t pad = (1024u - (smem_u32(smem_raw) & 1023u)) & 1023u;
+  unsigned char* smem = smem_raw + pad;
+  unsigned char* sX = smem + S::off_x;
+  unsigned char* ring = smem + S::off_ring;
+  float* part1 = reinterpret_cast<float*>(smem + S::off_p1);
+  float2* stat = reinterpret_cast<float2*>(smem + S::off_stat);
+  int* cntp = reinterpret_cast<int*>(smem + S::off_cnt);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::off_bar);
+  uint64_t* x_full = bars;
+  uint64_t* w_full = bars + 1;          // [3]
+  uint64_t* w_free = bars + 4;          // [3]
+  uint64_t* acc1_full = bars + 7;
+  uint64_t* va_ready = bars + 8;
+  uint64_t* accA_full = bars + 9;
+  uint64_t* epi_done = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned long long* const tr = (tid == 0 || tid == TM_CWARPS * 32) ? g_tm_trace : nullptr;
+  if (tid == 0) tm_trace(tr, 0, 15);
+  const int HG = heads / 4, ED = heads * TM_D;
+  const int regions_per_sample = A.F1 * A.F2;
+  const int units = A.regions * HG;
+  const int u_begin = (int)(((long long)blockIdx.x * units) / gridDim.x);
+  const int n_mine = (int)(((long long)(blockIdx.x + 1) * units) / gridDim.x) - u_begin;
+
+  if (warp == TM_CWARPS) {
+    if (lane == 0) {
+      mbar_init(x_full, 1);
+      for (int i = 0; i < 3; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_free[i], 1); }
+      mbar_init(acc1_full, 1); mbar_init(accA_full, 1);
+      mbar_init(va_ready, TM_CWARPS); mbar_init(epi_done, TM_CWARPS);
+      mbar_fence_init();
+      tma_prefetch_desc(&tmXa); tma_prefetch_desc(&tmXb); tma_prefetch_desc(&tmO); tma_prefetch_desc(&tmW1);
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (warp < TM_CWARPS) {
+    for (int b = warp; b < A.B; b += TM_CWARPS) {
+      float mu, rstd;
+      gn_mean_rstd(A.gn_sums, b, (double)C * (double)A.H * (double)A.W, A.gn_eps, mu, rstd);
+      if (lane == 0) stat[b] = make_float2(mu, rstd);
+    }
+  }
+  tm_fence_before();
+  __syncthreads();
+  tm_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t T_FEAT = tmem_base, T_VAL = tmem_base + 256u;
+
+  auto unit_coords = [&](int u, int& b, int& g, int& row0, int& col0) {
+    const int rg = u / HG;
+    g = u - rg * HG;
+    b = rg / regions_per_sample;
+    const int q = rg - b * regions_per_sample;
+    row0 = (q / A.F2) * TM_RS;
+    col0 = (q % A.F2) * TM_RS;
+  };
+
+  if (warp >= TM_CWARPS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TM_REGS_AUX));
+    if (warp > TM_CWARPS && lane == 0) {
+      // ---- weight ring producers: per unit 2*KC feat slabs (hi | lo) then KC value slabs.  One issuing thread sustains one TMA box
+      //      per ~0.33 us whatever its size (tools/tma_bw_probe.cu), so the three spare warps each own one slot of the 3-deep ring ----
+      const int slot = warp - TM_CWARPS - 1;
+      int cnt = 0;
+      for (int it = 0; it < n_mine; ++it) {
+        int b, g, row0, col0;
+        unit_coords(u_begin + it, b, g, row0, col0);
+        for (int s = 0; s < 3 * KC; ++s, ++cnt) {
+          if (cnt % 3 != slot) continue;
+          if (cnt >= 3) mbar_wait(&w_free[slot], (uint32_t)((cnt / 3) - 1) & 1u);
+          mbar_expect_tx(&w_full[slot], 16384u);
+          if (s < 2 * KC) tma_load_2d(ring + slot * 16384, &tmW1, s * 64, 128 * g, &w_full[slot]);
+          else tma_load_2d(ring + slot * 16384, &tmW1, (s - 2 * KC) * 64, ED + 128 * g, &w_full[slot]);
+        }
+      }
+    }
+    if (warp == TM_CWARPS && lane == 0 && n_mine > 0) {
+      // ---- x loads, MMA issue, output stores -------------------------------------------------------------------------------------
+      auto load_x = [&](int it) {
+        int b, g, row0, col0;
+        unit_coords(u_begin + it, b, g, row0, col0);
+        mbar_expect_tx(x_full, (uint32_t)S::XB);
+        tma_load_4d(sX, &tmXa, col0, 0, row0, b, x_full);
+        tma_load_4d(sX + S::off_xb, &tmXb, col0, S::CA, row0, b, x_full);
+      };
+      load_x(0);
+      int cnt = 0;
+      for (int it = 0; it < n_mine; ++it) {
+        const uint32_t ph = (uint32_t)it & 1u;
+        mbar_wait(x_full, ph);
+        tm_fence_after();
+        tm_trace(tr, it, 0);
+        for (int s = 0; s < 3 * KC; ++s, ++cnt) {
+          const int slot = cnt % 3;
+          mbar_wait(&w_full[slot], (uint32_t)(cnt / 3) & 1u);
+          tm_fence_after();
+          const bool is_feat = s < 2 * KC;
+          const int kx = is_feat ? s % KC : s - 2 * KC;                   // x slab: 0,1 in block A, 2.. in block B
+          const uint32_t x_addr = kx < 2 ? smem_u32(sX) + (uint32_t)(kx * 64 * 32) : smem_u32(sX + S::off_xb) + (uint32_t)((kx - 2) * 64 * 32);
+          const uint32_t x_lbo = kx < 2 ? (uint32_t)(S::CA * 32) : (uint32_t)(S::CB * 32);
+          const uint32_t w_addr = smem_u32(ring + slot * 16384);
+          const bool first = is_feat ? s == 0 : s == 2 * KC;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            tm_mma(is_feat ? T_FEAT : T_VAL, tm_desc_lo(w_addr + ks * 32, 16), TM_HI_SW128, tm_desc_lo(x_addr + ks * 16 * 32, x_lbo), TM_HI_SW32,
+                   (first && ks == 0) ? 0u : 1u);
+          tm_commit(&w_free[slot]);
+        }
+        tm_commit(acc1_full);
+        tm_trace(tr, it, 1);
+        // ---- aggregation GEMM (pass 3) ---------------------------------------------------------------------------------------------
+        mbar_wait(va_ready, ph);
+        tm_fence_after();
+        tm_trace(tr, it, 3);
+        {
+          const uint32_t wb_addr = smem_u32(sX + S::off_wb);
+#pragma unroll 4
+          for (int ks = 0; ks < 16; ++ks)
+            tm_mma_ts(T_FEAT + 128u, T_FEAT + (uint32_t)(8 * ks), tm_desc_lo(wb_addr + (ks >> 2) * TM_WB_SLAB + (ks & 3) * 32, 16), TM_HI_SW128,
+                      TM_IDESC_AGG, ks > 0 ? 1u : 0u);
+          tm_commit(accA_full);
+        }
+        // ---- the output tile is complete: store it, then the x region may be refilled ----------------------------------------------------
+        mbar_wait(epi_done, ph);
+        tm_trace(tr, it, 5);
+        {
+          int b, g, row0, col0;
+          unit_coords(u_begin + it, b, g, row0, col0);
+          tma_store_4d(&tmO, sX + S::off_ot, col0, 128 * g, row0, b);
+          tma_store_commit();
+        }
+        tm_trace(tr, it, 6);
+        if (it + 1 < n_mine) {
+          tma_store_wait_read();
+          load_x(it + 1);
+        }
+      }
+      tma_store_wait_all();
+    }
+    __syncwarp();
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TM_REGS_COMPUTE));
+    const int e = warp & 3, j = warp >> 2;
+    const int d = lane;
+    const uint32_t lane_off = (uint32_t)(32 * e) << 16;
+    const float alpha = __ldg(A.alpha), beta = __ldg(A.beta);
+    float* apriv = reinterpret_cast<float*>(smem + S::off_ap) + warp * (4 * 36);
+    const uint32_t ot = smem_u32(sX + S::off_ot);
+
+    for (int it = 0; it < n_mine; ++it) {
+      int b, g, row0, col0;
+      unit_coords(u_begin + it, b, g, row0, col0);
+      const uint32_t ph = (uint32_t)it & 1u;
+      const int ch = 128 * g + 32 * e + d;                               // this lane's feat / value channel
+      const float2 st = stat[b];
+      const float ehf = fmaf(-st.y * st.x, __ldg(A.k1 + ch), __ldg(A.k0 + ch));
+      const float ehv = fmaf(-st.y * st.x, __ldg(A.k1 + ED + ch), __ldg(A.k0 + ED + ch));
+      mbar_wait(acc1_full, ph);
+      tm_fence_after();
+      tm_trace(tr, it, 8);
+      // the x tile is dead: constant rows of the aggregation operand (quadrant means, zero padding), one 16-byte chunk per thread
+      {
+        const int slab = tid >> 7, r = 32 + ((tid >> 3) & 15), c = tid & 7;
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t v = 0;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int n = slab * 64 + c * 8 + 2 * i + hf;
+            const int qd = 2 * ((n >> 4) >= 8) + ((n & 15) >= 8);
+            if (r < 36 && qd == r - 32) v |= 0x3C80u << (16 * hf);
+          }
+          w[i] = v;
+        }
+        sts128(smem_u32(sX + S::off_wb) + (uint32_t)(slab * TM_WB_SLAB + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)), w[0], w[1], w[2], w[3]);
+      }
+      uint32_t gk[2];
+      {
+        TmCore cc_;
+        cc_.T_FEAT = T_FEAT; cc_.T_VAL = T_VAL; cc_.lane_off = lane_off;
+        cc_.scratch = smem_u32(sX + S::off_scratch) + (uint32_t)((e * 4 + j) * 4096);
+        cc_.wb_base = smem_u32(sX + S::off_wb); cc_.ph = ph;
+        cc_.e = e; cc_.j = j; cc_.lane = lane; cc_.it = it; cc_.Wimg = A.W;
+        cc_.part1 = part1; cc_.cntp = cntp; cc_.apriv = apriv; cc_.va_ready = va_ready; cc_.accA_full = accA_full;
+        cc_.rstd = st.y; cc_.ehf = ehf; cc_.ehv = ehv; cc_.alpha = alpha; cc_.beta = beta;
+        cc_.idx_out = A.idx_out; cc_.smax_out = A.smax_out;
+        cc_.io_base = ((int64_t)(b * heads + 4 * g + e) * A.H + row0) * A.W + col0;
+        cc_.tr = tr;
+        tm_core_passes(cc_, gk);
+      }
+      // ---- pass 4: lane = point, o[n][:] = g_n * a[k_n][:] into the NCHW-ordered output tile [row][channel][16 cols] (SWIZZLE_32B) --
+      __syncwarp();
+#pragma unroll 1
+      for (int q = 0; q < 2; ++q) {
+        const float gq = __uint_as_float(gk[q] & ~3u);
+        const uint32_t arow = smem_u32(apriv) + (gk[q] & 3u) * 144u;
+        const int n = 64 * j + 32 * q + lane;
+        const uint32_t pbase = ot + (uint32_t)((n >> 4) * 4096 + (n & 7) * 2);
+        const uint32_t hi8 = (uint32_t)((n >> 3) & 1);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const uint4 a4 = lds128(arow + (uint32_t)c4 * 16u);
+          const float v[4] = {gq * __uint_as_float(a4.x), gq * __uint_as_float(a4.y), gq * __uint_as_float(a4.z), gq * __uint_as_float(a4.w)};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int c = 32 * e + 4 * c4 + t;                             // channel inside the tile
+            sts16(pbase + (uint32_t)(c * 32) + ((hi8 ^ (uint32_t)((c >> 2) & 1)) << 4), (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[t])));
+          }
+        }
+      }
+      fence_async_smem();
+      tm_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(epi_done);
+      tm_trace(tr, it, 12);
     }
   }
   tm_fence_before();
@@ -823,3 +1124,55 @@ extern "C" int vrcoc_token_mixer_fwd(const void* x, const double* gn_sums, float
   if (C == 64) return launch_tm<64>(A, tx, to, tw1, tw2, (cudaStream_t)stream);
   return launch_tm<128>(A, tx, to, tw1, tw2, (cudaStream_t)stream);
 }
+
+extern "C" int vrcoc_token_mixer_core_supported(int dtype, int C, int H, int W, int heads, int head_dim, int fold_w, int fold_h,
+                                                int proposal_w, int proposal_h) {
+  const char* knob = getenv("VRCOC_TM_FUSED");
+  if (knob && knob[0] == '0') return 0;
+  const bool folded = fold_w > 1 && fold_h > 1;
+  const int f1 = folded ? fold_w : 1, f2 = folded ? fold_h : 1;
+  return dtype == VRCOC_BF16 && C == 320 && heads > 0 && heads % TM_E == 0 && head_dim == TM_D && proposal_w == 2 && proposal_h == 2 &&
+         H % f1 == 0 && W % f2 == 0 && H / f1 == TM_RS && W / f2 == TM_RS && tma_encode_fn() != nullptr;
+}
+
+extern "C" int vrcoc_token_mixer_core_fwd(const void* x, const double* gn_sums, float gn_eps, const void* w_fold, const float* k0,
+                                          const float* k1, const float* alpha, const float* beta, void* o, uint8_t* idx, float* sim_max,
+                                          int B, int C, int H, int W, int heads, int head_dim, int fold_w, int fold_h, void* stream) {
+  VRCOC_REQUIRE(x && gn_sums && w_fold && k0 && k1 && alpha && beta && o && B > 0 && B <= 256, "token_mixer_core: null pointer / bad batch");
+  VRCOC_REQUIRE(vrcoc_token_mixer_core_supported(VRCOC_BF16, C, H, W, heads, head_dim, fold_w, fold_h, 2, 2),
+                "token_mixer_core: unsupported geometry C=%d %dx%d heads=%d head_dim=%d fold=%dx%d", C, H, W, heads, head_dim, fold_w, fold_h);
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  VRCOC_REQUIRE(al(x) && al(o) && al(w_fold), "token_mixer_core: tensors must be 16-byte aligned");
+  VRCOC_REQUIRE(!idx || (reinterpret_cast<uintptr_t>(idx) & 1) == 0, "token_mixer_core: idx must be 2-byte aligned");
+  const int ED = heads * head_dim;
+  TmArgs A;
+  A.gn_sums = gn_sums; A.gn_eps = gn_eps; A.k0 = k0; A.k1 = k1; A.alpha = alpha; A.beta = beta; A.b2 = nullptr; A.ls = nullptr;
+  A.out_sums = nullptr; A.idx_out = idx; A.smax_out = sim_max;
+  A.B = B; A.H = H; A.W = W; A.F1 = H / TM_RS; A.F2 = W / TM_RS; A.regions = B * A.F1 * A.F2;
+  CUtensorMap txa, txb, to, tw1;
+  int rc;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)H * W * 2, (cuuint64_t)W * 2, (cuuint64_t)C * H * W * 2};
+    cuuint32_t boxa[4] = {(cuuint32_t)TM_RS, 128, (cuuint32_t)TM_RS, 1}, boxb[4] = {(cuuint32_t)TM_RS, (cuuint32_t)(C - 128), (cuuint32_t)TM_RS, 1};
+    if ((rc = tma_encode_sw(&txa, VRCOC_BF16, x, 4, dims, strides, boxa, 32))) return rc;
+    if ((rc = tma_encode_sw(&txb, VRCOC_BF16, x, 4, dims, strides, boxb, 32))) return rc;
+    cuuint64_t odims[4] = {(cuuint64_t)W, (cuuint64_t)ED, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t ostr[3] = {(cuuint64_t)H * W * 2, (cuuint64_t)W * 2, (cuuint64_t)ED * H * W * 2};
+    cuuint32_t obox[4] = {(cuuint32_t)TM_RS, 128, (cuuint32_t)TM_RS, 1};
+    if ((rc = tma_encode_sw(&to, VRCOC_BF16, o, 4, odims, ostr, obox, 32))) return rc;
+    cuuint64_t d1[2] = {(cuuint64_t)(2 * C), (cuuint64_t)(2 * ED)}, s1[1] = {(cuuint64_t)(2 * C) * 2};
+    cuuint32_t b1[2] = {64, 128};
+    if ((rc = tma_encode_sw(&tw1, VRCOC_BF16, w_fold, 2, d1, s1, b1, 128))) return rc;
+  }
+  using S = TkSmem<320>;
+  auto kern = token_mixer_core_kernel<320>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total);
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  const int units = A.regions * (heads / TM_E);
+  int grid = sm_count();
+  if (grid > units) grid = units;
+  kern<<<grid, TM_THREADS, S::total, (cudaStream_t)stream>>>(A, heads, txa, txb, to, tw1);
+  return check_launch("token_mixer_core");
+}
+

@@ -211,13 +211,17 @@ class ClusterBlock(nn.Module):
         if ops.gn_fold_ok(x, 2 * ED, ED) and tm.fc1.weight.dtype == dt:
             fold_w = ops.cached(self, "w_fold", [tm.fc1.weight, tm.fc1.bias, tm.fc_v.weight, tm.fc_v.bias, n1.weight, n1.bias],
                                 lambda: ops.fold_gn_weights(tm.fc1.weight, tm.fc1.bias, tm.fc_v.weight, tm.fc_v.bias, n1.weight, n1.bias))
-        x1 = None
+        x1 = o_fused = None
         if fold_w is not None and tm.fc2.weight.dtype == dt and ops.token_mixer_fused_ok(x, tm.heads, tm.head_dim, tm.fold_w, tm.fold_h, pw, ph):
             # stages 1 and 2: the whole token-mixer half in one persistent kernel (feat / value / core output stay on chip)
             sums = ops.new_sample_sums(B, dev, n=2)
             x1, _, _ = ops.token_mixer_fused_fwd(x, sums0, n1.eps, fold_w[0], fold_w[1], fold_w[2], f32(tm.sim_alpha), f32(tm.sim_beta),
                                                  tm.fc2.weight.detach().reshape(C, ED), f32(tm.fc2.bias), ls1, sums[0],
                                                  tm.heads, tm.head_dim, tm.fold_w, tm.fold_h)
+        elif fold_w is not None and ops.token_mixer_core_ok(x, tm.heads, tm.head_dim, tm.fold_w, tm.fold_h, pw, ph):
+            # stage 3: projection + cluster core in one launch (one CTA per region and group of four heads); fc2 follows below
+            o_fused, _, _ = ops.token_mixer_core_fwd(x, sums0, n1.eps, fold_w[0], fold_w[1], fold_w[2], f32(tm.sim_alpha), f32(tm.sim_beta),
+                                                     tm.heads, tm.head_dim, tm.fold_w, tm.fold_h)
         elif fold_w is not None:
             w_fold, k0, k1 = fold_w
             feat = torch.empty(B, ED, H, W, device=dev, dtype=torch.float32)
@@ -232,8 +236,11 @@ class ClusterBlock(nn.Module):
             value = torch.empty(B, ED, H, W, device=dev, dtype=dt)
             ops.conv_fwd(ops.conv_desc(x, w_in, feat, gn=(sums0, f32(n1.weight), f32(n1.bias), n1.eps), e_shift=b_in, out2=value))
         if x1 is None:
-            o, _, _ = ops.cluster_core_fwd(feat, value, f32(tm.sim_alpha), f32(tm.sim_beta), tm.heads, tm.fold_w, tm.fold_h, pw, ph,
-                                           out_dtype=dt)
+            if o_fused is not None:
+                o = o_fused
+            else:
+                o, _, _ = ops.cluster_core_fwd(feat, value, f32(tm.sim_alpha), f32(tm.sim_beta), tm.heads, tm.fold_w, tm.fold_h, pw, ph,
+                                               out_dtype=dt)
             sums = ops.new_sample_sums(B, dev, n=2)
             x1 = torch.empty_like(x)
             ops.conv_fwd(ops.conv_desc(o, tm.fc2.weight.detach().reshape(C, ED), x1, e_shift=f32(tm.fc2.bias), post_scale=ls1, res=x,

@@ -136,6 +136,24 @@ def token_mixer_fused_fwd(x, sums, eps, w_fold, k0, k1, alpha, beta, w2, b2, ls,
     return out, idx, smax
 
 
+def token_mixer_core_ok(x, heads, head_dim, fold_w, fold_h, pw, ph):
+    B, C, H, W = x.shape
+    return FUSED_TOKEN_MIXER and x.dtype == torch.bfloat16 and B <= 256 and \
+        bool(lib.vrcoc_token_mixer_core_supported(BF16, C, H, W, heads, head_dim, fold_w, fold_h, pw, ph))
+
+
+def token_mixer_core_fwd(x, sums, eps, w_fold, k0, k1, alpha, beta, heads, head_dim, fold_w, fold_h, save_aux=False):
+    """o = cluster_core(fc1(GN(x)), fc_v(GN(x))) in one launch for the wide stage (csrc/token_mixer_fused.cu, second kernel;
+    reference vr_coc.py:155-190).  Returns (o [B, heads*head_dim, H, W], idx, sim_max)."""
+    B, C, H, W = x.shape
+    o = torch.empty(B, heads * head_dim, H, W, device=x.device, dtype=x.dtype)
+    idx = torch.empty(B, heads, H, W, device=x.device, dtype=torch.uint8) if save_aux else None
+    smax = torch.empty(B, heads, H, W, device=x.device, dtype=torch.float32) if save_aux else None
+    check(lib.vrcoc_token_mixer_core_fwd(_ptr(x), _ptr(sums), float(eps), _ptr(w_fold), _ptr(k0), _ptr(k1), _ptr(alpha), _ptr(beta), _ptr(o),
+                                         _ptr(idx), _ptr(smax), B, C, H, W, heads, head_dim, fold_w, fold_h, _stream()), "token_mixer_core_fwd")
+    return o, idx, smax
+
+
 class Fork:
     """f() on side stream number `lane` (>= 1) of the current device, ordered after everything already queued on the
     current stream; join() orders the current stream after it and returns f's result.  Same liveness rule as run_pair: the

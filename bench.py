@@ -122,7 +122,7 @@ KERNELS_PER_CALL = {"vrcoc_channel_sums": 1, "vrcoc_conv_fwd": 1, "vrcoc_table_a
                     "vrcoc_cluster_core_bwd": 2, "vrcoc_sa_gate_sums": 1, "vrcoc_radar_enh_table": 1, "vrcoc_chan_affine": 1,
                     "vrcoc_img_enh_finish": 1, "vrcoc_gelu_bwd": 1, "vrcoc_gn_bwd_sums": 1, "vrcoc_gn_bwd_apply": 1,
                     "vrcoc_conv1x1_wgrad": 3, "vrcoc_im2col": 1, "vrcoc_upsample_bilinear": 1,
-                    "vrcoc_dwconv": 1, "vrcoc_mlp_fused_fwd": 1, "vrcoc_token_mixer_fwd": 1}
+                    "vrcoc_dwconv": 1, "vrcoc_mlp_fused_fwd": 1, "vrcoc_token_mixer_fwd": 1, "vrcoc_token_mixer_core_fwd": 1}
 
 
 def _esz(dt):
@@ -171,6 +171,10 @@ def _describe(name, args):
         P, ED = H * W, E * D
         return (f"token_mixer_fused[{C}|{E}x{D}]@{H}x{W}", B * P * 2 * C * 2 + (2 * ED * 2 * C + C * ED) * 2,
                 B * P * (2.0 * C * ED * 4 + (2 * 4 + 5) * ED))
+    if name == "vrcoc_token_mixer_core_fwd":
+        B, C, H, W, E, D = args[11:17]
+        P, ED = H * W, E * D
+        return (f"token_mixer_proj_core[{C}|{E}x{D}]@{H}x{W}", B * P * (C + ED) * 2 + 3 * ED * C * 2, B * P * (2.0 * C * ED * 3 + (2 * 4 + 5) * ED))
     if name == "vrcoc_dwconv":
         dt, B, C, H, W, k, stride, pad = args[4:12]
         Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1

@@ -229,6 +229,14 @@ int vrcoc_mlp_fused_fwd(const void* x, const double* gn_sums, const float* gamma
  * tells; everything else runs the three-launch path. */
 int vrcoc_token_mixer_supported(int dtype, int C, int H, int W, int heads, int head_dim, int fold_w, int fold_h, int proposal_w,
                                 int proposal_h);
+/* The same fusion without fc2 for the wide stage (C = 320, heads a multiple of 4, head_dim 32, 16x16 regions: stage 3 of the
+ * backbone): GN-folded fc1|fc_v -> cluster core in one launch, one CTA per (region, group of four heads); o [B][E*D][H][W] bf16 is
+ * the input of the separate fc2 projection (fc2 contracts over all heads). */
+int vrcoc_token_mixer_core_supported(int dtype, int C, int H, int W, int heads, int head_dim, int fold_w, int fold_h, int proposal_w,
+                                     int proposal_h);
+int vrcoc_token_mixer_core_fwd(const void* x, const double* gn_sums, float gn_eps, const void* w_fold, const float* k0, const float* k1,
+                               const float* alpha, const float* beta, void* o, uint8_t* idx, float* sim_max, int B, int C, int H, int W,
+                               int heads, int head_dim, int fold_w, int fold_h, void* stream);
 /* Debug aid: non-NULL `buf` (u64 [grid][4 iterations][16]) makes the fused token-mixer kernel record %globaltimer phase stamps. */
 int vrcoc_debug_set_tm_trace(unsigned long long* buf);
 int vrcoc_token_mixer_fwd(const void* x, const double* gn_sums, float gn_eps, const void* w_fold, const float* k0, const float* k1,

@@ -85,3 +85,31 @@ def test_fused_token_mixer_vs_oracle(V, B, C, H):
     print(f"fused token mixer vs oracle C={C}: out {e:.2e}, assignment mismatches outside a 1e-4 margin {mism:.2e}, safe {safe.float().mean():.4f}")
     assert mism == 0.0
     assert e < 2e-2
+
+
+@pytest.mark.parametrize("B,heads", [(1, 8), (2, 8), (8, 8), (5, 4), (40, 8)])
+def test_fused_projection_core_stage3_vs_two_launches(V, B, heads):
+    """the wide-stage kernel (C = 320: GN-folded fc1|fc_v + cluster core per (region, four heads)) against projection + core as two
+    launches on the same folded weights; B = 40 makes a CTA loop over several units"""
+    from vrcoc import ops
+    C, H, ED = 320, 32, heads * 32
+    g = torch.Generator().manual_seed(4)
+    w1 = (torch.randn(ED, C, generator=g) / C ** 0.5).to(torch.bfloat16).cuda()
+    wv = (torch.randn(ED, C, generator=g) / C ** 0.5).to(torch.bfloat16).cuda()
+    b1, bv = (torch.randn(ED, generator=g) * 0.1).cuda(), (torch.randn(ED, generator=g) * 0.1).cuda()
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).cuda(), (torch.randn(C, generator=g) * 0.1).cuda()
+    x = (torch.randn(B, C, H, H, generator=g) * 1.3 + 0.4).to(torch.bfloat16).cuda()
+    alpha, sbeta = torch.tensor([1.3]).cuda(), torch.tensor([-0.2]).cuda()
+    assert ops.token_mixer_core_ok(x, heads, 32, 2, 2, 2, 2)
+    sums = ops.channel_sums(x, want_chan=False, want_sample=True)[1]
+    w_fold, k0, k1 = ops.fold_gn_weights(w1, b1, wv, bv, gamma, beta)
+    o_f, idx_f, smax_f = ops.token_mixer_core_fwd(x, sums, 1e-5, w_fold, k0, k1, alpha, sbeta, heads, 32, 2, 2, save_aux=True)
+    feat = torch.empty(B, ED, H, H, device="cuda", dtype=torch.float32)
+    value = torch.empty(B, ED, H, H, device="cuda", dtype=torch.bfloat16)
+    ops.conv_fwd(ops.conv_desc(x, w_fold, feat, gn_fold=(sums, k1, 1e-5), e_shift=k0, out2=value))
+    o_u, idx_u, smax_u = ops.cluster_core_fwd(feat, value, alpha, sbeta, heads, 2, 2, 2, 2, out_dtype=torch.bfloat16, save_aux=True)
+    torch.cuda.synchronize()
+    flips = (idx_f != idx_u).float().mean().item()
+    e_s, e_o = rel_err(smax_f, smax_u), rel_err(o_f.float(), o_u.float())
+    print(f"stage-3 fused projection+core B={B} heads={heads}: flips {flips:.2e} sim_max {e_s:.2e} out {e_o:.2e}")
+    assert torch.isfinite(o_f.float()).all() and flips < 2e-4 and e_s < 1e-4 and e_o < 4e-3

@@ -30,6 +30,7 @@ CASES = {
     "s3_mlpf": ("mlpf", 320, 1280, 32, {}),
     "s1_tmf": ("tmf", 64, 0, 128, {}),
     "s2_tmf": ("tmf", 128, 0, 64, {}),
+    "s3_tmc": ("tmc", 320, 0, 32, {}),
     "s1_core": ("core", 128, 0, 128, dict(E=4, fold=8)),
     "s2_core": ("core", 128, 0, 64, dict(E=4, fold=4)),
     "s3_core": ("core", 256, 0, 32, dict(E=8, fold=2)),
@@ -113,24 +114,20 @@ def main():
             fold = H // 16
             fn = lambda: ops.token_mixer_fused_fwd(x, sums, 1e-5, w_fold, k0, k1, a, b_, w2, zC, torch.ones(C, device=dev), osum, 4, 32, fold, fold)
             by, fl = B * P * 2 * C * es, B * P * (2.0 * C * ED * 4 + 13.0 * ED)
-            if args.trace:
-                from vrcoc._lib import lib
-                nb = min(148, B * fold * fold)
-                buf = torch.zeros(nb * 4 * 16, dtype=torch.int64, device=dev)
-                lib.vrcoc_debug_set_tm_trace(buf.data_ptr())
-                fn(); torch.cuda.synchronize()
-                lib.vrcoc_debug_set_tm_trace(None)
-                t = buf.cpu().reshape(nb, 4, 16).double()
-                names = {0: "x+W1 landed", 1: "GEMM1 issued", 2: "GEMM1 done", 8: "w0: GEMM1 seen", 9: "w0: pass1", 10: "w0: pass2", 11: "w0: V conv",
-                         7: "w0: agg seen", 12: "w0: pass4", 3: "o ready seen", 4: "GEMM2 done", 13: "w0: GEMM2 seen", 14: "w0: epilogue", 5: "epi seen",
-                         6: "store issued", 15: "entry"}
-                for cta in (0, nb // 2, nb - 1):
-                    t0 = t[cta, 0, 0]
-                    for it in range(4):
-                        if t[cta, it, 0] == 0:
-                            continue
-                        order = sorted((k for k in names if t[cta, it, k] > 0), key=lambda k: t[cta, it, k])
-                        print(f"  cta {cta} it {it}: " + "  ".join(f"{names[k]} {((t[cta, it, k] - t0) / 1e3).item():.2f}" for k in order))
+            nb_units = B * fold * fold
+        elif kind == "tmc":
+            # stage-3 projection + core (csrc/token_mixer_fused.cu, second kernel): x in, o out
+            heads, ED = 8, 256
+            x = torch.randn(B, C, H, H, device=dev, generator=g).to(dt)
+            w1 = (torch.randn(ED, C, device=dev, generator=g) / C ** 0.5).to(dt)
+            wv = (torch.randn(ED, C, device=dev, generator=g) / C ** 0.5).to(dt)
+            zED = torch.zeros(ED, device=dev)
+            w_fold, k0, k1 = ops.fold_gn_weights(w1, zED, wv, zED, torch.ones(C, device=dev), torch.zeros(C, device=dev))
+            sums = ops.sample_sums_of(x)
+            a, b_ = torch.ones(1, device=dev), torch.zeros(1, device=dev)
+            fn = lambda: ops.token_mixer_core_fwd(x, sums, 1e-5, w_fold, k0, k1, a, b_, heads, 32, 2, 2)
+            nb_units = B * 4 * 2
+            by, fl = B * P * (C + ED) * es, B * P * (2.0 * C * ED * 3 + 13.0 * ED)
         elif kind == "conv3":
             x = torch.randn(B, C, H, H, device=dev, generator=g).to(dt)
             w = (torch.randn(O, C * 9, device=dev, generator=g) / (C * 9) ** 0.5).to(dt)
@@ -153,6 +150,24 @@ def main():
             else:
                 fn = lambda: ops.cluster_core_fwd(feat, value, a, b_, E, fold, fold, 2, 2)
             by, fl = B * P * C * (4 + 2 * es), 13.0 * B * P * C
+        if kind in ("tmf", "tmc") and args.trace:
+            from vrcoc._lib import lib
+            nb = min(148, nb_units)
+            buf = torch.zeros(nb * 4 * 16, dtype=torch.int64, device=dev)
+            lib.vrcoc_debug_set_tm_trace(buf.data_ptr())
+            fn(); torch.cuda.synchronize()
+            lib.vrcoc_debug_set_tm_trace(None)
+            t = buf.cpu().reshape(nb, 4, 16).double()
+            names = {0: "x+W1 landed", 1: "GEMM1 issued", 2: "GEMM1 done", 8: "w0: GEMM1 seen", 9: "w0: pass1", 10: "w0: pass2", 11: "w0: V conv",
+                     7: "w0: agg seen", 12: "w0: pass4", 3: "o ready seen", 4: "GEMM2 done", 13: "w0: GEMM2 seen", 14: "w0: epilogue", 5: "epi seen",
+                     6: "store issued", 15: "entry"}
+            for cta in (0, nb // 2, nb - 1):
+                t0 = t[cta, 0, 0]
+                for it in range(4):
+                    if t[cta, it, 0] == 0:
+                        continue
+                    order = sorted((k for k in names if t[cta, it, k] > 0), key=lambda k: t[cta, it, k])
+                    print(f"  cta {cta} it {it}: " + "  ".join(f"{names[k]} {((t[cta, it, k] - t0) / 1e3).item():.2f}" for k in order))
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
