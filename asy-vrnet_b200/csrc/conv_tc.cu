@@ -143,12 +143,15 @@ __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
   return r;
 }
 
-// branch-free exact-erf GELU with ONE special-function op:
-//   gelu(x) = max(x, 0) - a * 2^P(a),   a = min(|x|, 6.0811),   2^P(a) ~ 0.5 erfc(a / sqrt 2)
-// P is a degree-6 fit of -(log2(e) * -ln erfc(a/sqrt2)) - 1 on [0, 6.0811] (weighted for the error of a * 0.5 erfc; beyond the
-// clamp the true term is < 4e-9).  |gelu error| < 3e-7 over the whole line, evaluated in fp32 (tools/fit_gelu.py).  The MUFU
-// pipe (16 lanes / clk / SM) is what bounds a GELU epilogue on sm_100a: the earlier A&S 7.1.26 form needed a reciprocal as
-// well as the exponential and ran at half the rate.
+// branch-free erf GELU with ONE special-function op:
+//   gelu(x) = max(x, 0) - a * 2^P(a),   a = min(|x|, AMAX),   2^P(a) ~ 0.5 erfc(a / sqrt 2)
+// P is a fit of -(log2(e) * -ln erfc(a/sqrt2)) - 1 on [0, AMAX], weighted for the error of a * 0.5 erfc (tools/fit_gelu.py).
+// These kernels contract bf16 operands and (the hidden layer of the channel MLP) store bf16: P has DEGREE 3, |gelu error|
+// < 5.5e-5 over the whole line — two orders below the bf16 rounding of the operands and of the result — and three FMAs per
+// value cheaper than the degree-6 fit (3e-7) used before: ncu showed the hidden-layer epilogues bound by instruction issue
+// (profiles/r01_ncu_final_cm_mlpf_core.csv).  The MUFU pipe (16 lanes / clk / SM) is the other bound of a GELU epilogue on
+// sm_100a: the earlier A&S 7.1.26 form needed a reciprocal as well as the exponential and ran at half the rate.
+// The fp32 engine (conv_simt.cu) keeps erff.
 __device__ __forceinline__ float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -159,20 +162,14 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-#define VRCOC_GELU_AMAX 6.081118f
-#define VRCOC_GELU_C0 -9.999930859e-01f
-#define VRCOC_GELU_C1 -1.151201725e+00f
-#define VRCOC_GELU_C2 -4.587709606e-01f
-#define VRCOC_GELU_C3 -5.341212451e-02f
-#define VRCOC_GELU_C4 8.080728352e-03f
-#define VRCOC_GELU_C5 -7.692232612e-04f
-#define VRCOC_GELU_C6 3.309320891e-05f
+#define VRCOC_GELU_AMAX 5.091169f
+#define VRCOC_GELU_C0 -1.003531933e+00f
+#define VRCOC_GELU_C1 -1.129245043e+00f
+#define VRCOC_GELU_C2 -4.988209009e-01f
+#define VRCOC_GELU_C3 -2.488539740e-02f
 __device__ __forceinline__ float gelu_fast(float x) {
   const float a = fminf(fabsf(x), VRCOC_GELU_AMAX);
-  float p = fmaf(VRCOC_GELU_C6, a, VRCOC_GELU_C5);
-  p = fmaf(p, a, VRCOC_GELU_C4);
-  p = fmaf(p, a, VRCOC_GELU_C3);
-  p = fmaf(p, a, VRCOC_GELU_C2);
+  float p = fmaf(VRCOC_GELU_C3, a, VRCOC_GELU_C2);
   p = fmaf(p, a, VRCOC_GELU_C1);
   p = fmaf(p, a, VRCOC_GELU_C0);
   return fmaf(-a, ex2_approx(p), fmaxf(x, 0.f));

@@ -102,10 +102,7 @@ __device__ __forceinline__ uint64_t gelu2(uint64_t x) {
   upk2(x, x0, x1);
   const float a0 = fminf(fabsf(x0), VRCOC_GELU_AMAX), a1 = fminf(fabsf(x1), VRCOC_GELU_AMAX);
   const uint64_t a = pk2(a0, a1);
-  uint64_t p = fma2(pk2(VRCOC_GELU_C6, VRCOC_GELU_C6), a, pk2(VRCOC_GELU_C5, VRCOC_GELU_C5));
-  p = fma2(p, a, pk2(VRCOC_GELU_C4, VRCOC_GELU_C4));
-  p = fma2(p, a, pk2(VRCOC_GELU_C3, VRCOC_GELU_C3));
-  p = fma2(p, a, pk2(VRCOC_GELU_C2, VRCOC_GELU_C2));
+  uint64_t p = fma2(pk2(VRCOC_GELU_C3, VRCOC_GELU_C3), a, pk2(VRCOC_GELU_C2, VRCOC_GELU_C2));
   p = fma2(p, a, pk2(VRCOC_GELU_C1, VRCOC_GELU_C1));
   p = fma2(p, a, pk2(VRCOC_GELU_C0, VRCOC_GELU_C0));
   float p0, p1;

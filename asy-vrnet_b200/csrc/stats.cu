@@ -191,11 +191,43 @@ __global__ void __launch_bounds__(256)
 sa_gate_sums_kernel(const T* __restrict__ img, int Ci, int HW, int G, const float* __restrict__ cs,
                     const float* __restrict__ cw, const float* __restrict__ cb, const float* __restrict__ sw,
                     const float* __restrict__ sb, const float* __restrict__ gw, const float* __restrict__ gb,
-                    float* __restrict__ attn) {
+                    float* __restrict__ attn, const T* __restrict__ radar, int Cr, float* __restrict__ cs_radar, int n_img_planes) {
   __shared__ float red[64];
+  if ((int)blockIdx.x >= n_img_planes) {
+    // extra blocks (vrcoc_fusion_stats): plane sums of the radar map for the ECA means, in the same launch
+    const int rp = blockIdx.x - n_img_planes;
+    const T* p = radar + (int64_t)rp * HW;
+    float s = 0.f, s2 = 0.f;
+    for_chunk8<T>(p, 0, HW, [&](int, const float (&v)[8], int n) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < n) { s += v[j]; s2 = fmaf(v[j], v[j], s2); }
+    });
+    block_sum2(s, s2, red);
+    if (threadIdx.x == 0) { cs_radar[2 * rp] = s; cs_radar[2 * rp + 1] = s2; }
+    return;
+  }
   const int plane = blockIdx.x, c = plane % Ci;
   const float inv_hw = 1.0f / (float)HW;
-  const float mean = cs[2 * plane] * inv_hw;
+  float psum, psq;
+  if (cs) {
+    psum = cs[2 * plane];
+    psq = cs[2 * plane + 1];
+  } else {
+    // no precomputed sums: first pass over the block's own plane (it stays in L1/L2 for the gated pass below)
+    const T* p = img + (int64_t)plane * HW;
+    float s = 0.f, s2 = 0.f;
+    for_chunk8<T>(p, 0, HW, [&](int, const float (&v)[8], int n) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < n) { s += v[j]; s2 = fmaf(v[j], v[j], s2); }
+    });
+    block_sum2(s, s2, red);
+    psum = s;
+    psq = s2;
+    __syncthreads();                                                   // red is reused by the gated sum
+  }
+  const float mean = psum * inv_hw;
   float scale = 1.f, ga = 0.f, gc = 88.f, amean = mean;
   if (G > 0) {
     const int q = Ci / (2 * G);
@@ -204,7 +236,7 @@ sa_gate_sums_kernel(const T* __restrict__ img, int Ci, int HW, int G, const floa
       scale = sigmoidf_exact(fmaf(cw[j], mean, cb[j]));
       amean = mean * scale;
     } else {
-      float var = fmaxf(cs[2 * plane + 1] * inv_hw - mean * mean, 0.f);
+      float var = fmaxf(psq * inv_hw - mean * mean, 0.f);
       float rstd = rsqrtf(var + 1e-5f);
       ga = sw[j] * gw[j] * rstd;
       gc = fmaf(sw[j], gb[j] - gw[j] * mean * rstd, sb[j]);
@@ -354,6 +386,122 @@ upsample_bilinear_kernel(const T* __restrict__ x, T* __restrict__ out, int plane
     T* o = out + (plane * Ho + oy) * (int64_t)Wo + c8 * 8;
     if (c8 * 8 + 8 <= Wo && (reinterpret_cast<uintptr_t>(o) & 15) == 0) st8<T>(o, v);
     else for (int j = 0; j < 8 && c8 * 8 + j < Wo; ++j) stf<T>(o + j, v[j]);
+  }
+}
+
+// The same map as two separable passes per (plane, strip of R output rows): the source rows the strip touches are interpolated
+// HORIZONTALLY once into shared memory at the output width (fp32: exactly the `top` / `bot` terms above), then every output
+// is one vertical lerp of two shared-memory values (128-bit reads, 8 outputs per thread and store).  Identical arithmetic per
+// output (bit-identical results), ~5x fewer instructions: ncu showed the one-pass kernel bound by instruction issue
+// (70 % issue-active, 64 % SM busy, 0.7 % DRAM on the 128 -> 512 logits map: coordinate math + four 2-byte loads per output).
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample_rows_kernel(const T* __restrict__ x, T* __restrict__ out, int H, int W, int Ho, int Wo, float sy, float sx, int R, int ns_max) {
+  extern __shared__ float hrow[];                                    // [ns_max][Wo]
+  const int strips = (Ho + R - 1) / R;
+  const int plane = blockIdx.x / strips, strip = blockIdx.x - plane * strips;
+  const int oy0 = strip * R, oy1 = min(Ho, oy0 + R);
+  const int y_lo = min((int)(oy0 * sy), H - 1);
+  const int y_hi = min(min((int)((oy1 - 1) * sy), H - 1) + 1, H - 1);
+  const int ns = min(y_hi - y_lo + 1, ns_max);
+  const T* xp = x + (int64_t)plane * H * W;
+  for (int ox = threadIdx.x; ox < Wo; ox += blockDim.x) {
+    const float fx = ox * sx;
+    int x0 = (int)fx;
+    if (x0 > W - 1) x0 = W - 1;
+    const int x1 = min(x0 + 1, W - 1);
+    const float wx = fx - (float)x0;
+    for (int r = 0; r < ns; ++r) {
+      const T* row = xp + (int64_t)(y_lo + r) * W;
+      const float a = ldf<T>(row + x0), b = ldf<T>(row + x1);
+      hrow[r * Wo + ox] = fmaf(wx, b - a, a);
+    }
+  }
+  __syncthreads();
+  const int cols8 = Wo >> 3;
+  const int tasks = (oy1 - oy0) * cols8;
+  for (int t = threadIdx.x; t < tasks; t += blockDim.x) {
+    const int r = t / cols8, c8 = t - r * cols8, oy = oy0 + r;
+    const float fy = oy * sy;
+    int y0 = (int)fy;
+    if (y0 > H - 1) y0 = H - 1;
+    const int y1 = min(y0 + 1, H - 1);
+    const float wy = fy - (float)y0;
+    const float4* tp = reinterpret_cast<const float4*>(hrow + (y0 - y_lo) * Wo + c8 * 8);
+    const float4* bp = reinterpret_cast<const float4*>(hrow + (y1 - y_lo) * Wo + c8 * 8);
+    const float4 t0 = tp[0], t1 = tp[1], b0 = bp[0], b1 = bp[1];
+    float v[8];
+    v[0] = fmaf(wy, b0.x - t0.x, t0.x); v[1] = fmaf(wy, b0.y - t0.y, t0.y); v[2] = fmaf(wy, b0.z - t0.z, t0.z); v[3] = fmaf(wy, b0.w - t0.w, t0.w);
+    v[4] = fmaf(wy, b1.x - t1.x, t1.x); v[5] = fmaf(wy, b1.y - t1.y, t1.y); v[6] = fmaf(wy, b1.z - t1.z, t1.z); v[7] = fmaf(wy, b1.w - t1.w, t1.w);
+    st8<T>(out + ((int64_t)plane * Ho + oy) * Wo + c8 * 8, v);
+  }
+}
+
+// Serving tail of the segmentation half (deeplab.py:149-167: interpolate the logits to the frame size, arg-max over the classes):
+// out[b][oy][ox] = argmax_c round_T( bilinear(x[b][c])[oy][ox] ), lowest class index on ties — the class map a frame consumer
+// reads, without the [B][classes][Ho][Wo] logits ever reaching memory (38 MB written and read again per 8-frame batch, and the
+// two launches were the serial tail of the forward: 46 + 40 us).  Same two passes as upsample_rows_kernel with all classes of
+// the strip resident; the value compared is rounded to the logits' dtype so that the map is bit-identical to the unfused path.
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample_argmax_kernel(const T* __restrict__ x, uint8_t* __restrict__ out, int C, int H, int W, int Ho, int Wo, float sy, float sx, int R,
+                       int ns_max) {
+  extern __shared__ float hrow[];                                    // [C][ns_max][Wo]
+  const int strips = (Ho + R - 1) / R;
+  const int b = blockIdx.x / strips, strip = blockIdx.x - b * strips;
+  const int oy0 = strip * R, oy1 = min(Ho, oy0 + R);
+  const int y_lo = min((int)(oy0 * sy), H - 1);
+  const int y_hi = min(min((int)((oy1 - 1) * sy), H - 1) + 1, H - 1);
+  const int ns = min(y_hi - y_lo + 1, ns_max);
+  const T* xb = x + (int64_t)b * C * H * W;
+  for (int i = threadIdx.x; i < C * Wo; i += blockDim.x) {
+    const int c = i / Wo, ox = i - c * Wo;
+    const float fx = ox * sx;
+    int x0 = (int)fx;
+    if (x0 > W - 1) x0 = W - 1;
+    const int x1 = min(x0 + 1, W - 1);
+    const float wx = fx - (float)x0;
+    const T* xp = xb + (int64_t)c * H * W;
+    float* hp = hrow + (int64_t)c * ns_max * Wo + ox;
+    for (int r = 0; r < ns; ++r) {
+      const T* row = xp + (int64_t)(y_lo + r) * W;
+      const float a = ldf<T>(row + x0), bb = ldf<T>(row + x1);
+      hp[r * Wo] = fmaf(wx, bb - a, a);
+    }
+  }
+  __syncthreads();
+  const int cols8 = Wo >> 3;
+  const int tasks = (oy1 - oy0) * cols8;
+  for (int t = threadIdx.x; t < tasks; t += blockDim.x) {
+    const int r = t / cols8, c8 = t - r * cols8, oy = oy0 + r;
+    const float fy = oy * sy;
+    int y0 = (int)fy;
+    if (y0 > H - 1) y0 = H - 1;
+    const int y1 = min(y0 + 1, H - 1);
+    const float wy = fy - (float)y0;
+    float best[8];
+    uint32_t arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -__int_as_float(0x7f800000); arg[j] = 0u; }
+    for (int c = 0; c < C; ++c) {
+      const float* base = hrow + (int64_t)c * ns_max * Wo + c8 * 8;
+      const float4* tp = reinterpret_cast<const float4*>(base + (y0 - y_lo) * Wo);
+      const float4* bp = reinterpret_cast<const float4*>(base + (y1 - y_lo) * Wo);
+      const float4 t0 = tp[0], t1 = tp[1], b0 = bp[0], b1 = bp[1];
+      float v[8];
+      v[0] = fmaf(wy, b0.x - t0.x, t0.x); v[1] = fmaf(wy, b0.y - t0.y, t0.y); v[2] = fmaf(wy, b0.z - t0.z, t0.z); v[3] = fmaf(wy, b0.w - t0.w, t0.w);
+      v[4] = fmaf(wy, b1.x - t1.x, t1.x); v[5] = fmaf(wy, b1.y - t1.y, t1.y); v[6] = fmaf(wy, b1.z - t1.z, t1.z); v[7] = fmaf(wy, b1.w - t1.w, t1.w);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float q = v[j];
+        if (sizeof(T) == 2) q = __bfloat162float(__float2bfloat16_rn(q));
+        if (q > best[j]) { best[j] = q; arg[j] = (uint32_t)c; }
+      }
+    }
+    uint2 w;
+    w.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+    w.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+    *reinterpret_cast<uint2*>(out + ((int64_t)b * Ho + oy) * Wo + c8 * 8) = w;
   }
 }
 
@@ -609,22 +757,38 @@ extern "C" int vrcoc_img_enh_finish(const void* k, int k_dtype, const void* imag
   });
 }
 
-extern "C" int vrcoc_sa_gate_sums(const void* image, int dtype, int B, int Ci, int HW, int G, const float* chan_sums_img,
-                                  const float* cweight, const float* cbias, const float* sweight, const float* sbias,
-                                  const float* gn_weight, const float* gn_bias, float* attn, void* stream) {
-  VRCOC_REQUIRE(image && chan_sums_img && attn, "sa_gate_sums: null pointer");
-  VRCOC_REQUIRE(B > 0 && Ci > 0 && HW > 0, "sa_gate_sums: non-positive dimension");
+static int launch_sa_gate_sums(const void* image, const void* radar, int dtype, int B, int Ci, int Cr, int HW, int G,
+                               const float* chan_sums_img, const float* cweight, const float* cbias, const float* sweight,
+                               const float* sbias, const float* gn_weight, const float* gn_bias, float* attn, float* cs_radar,
+                               void* stream, const char* what) {
+  VRCOC_REQUIRE(image && attn, "%s: null pointer", what);
+  VRCOC_REQUIRE(B > 0 && Ci > 0 && HW > 0 && Cr >= 0, "%s: bad dimension", what);
+  VRCOC_REQUIRE(Cr == 0 || (radar && cs_radar), "%s: null radar pointer", what);
   if (G > 0) {
-    VRCOC_REQUIRE(Ci % (2 * G) == 0 && Ci >= 2 * G, "sa_gate_sums: channels %d not divisible by 2*G=%d", Ci, 2 * G);
-    VRCOC_REQUIRE(cweight && cbias && sweight && sbias && gn_weight && gn_bias, "sa_gate_sums: null attention parameter");
+    VRCOC_REQUIRE(Ci % (2 * G) == 0 && Ci >= 2 * G, "%s: channels %d not divisible by 2*G=%d", what, Ci, 2 * G);
+    VRCOC_REQUIRE(cweight && cbias && sweight && sbias && gn_weight && gn_bias, "%s: null attention parameter", what);
   }
   cudaStream_t st = (cudaStream_t)stream;
   return by_dtype(dtype, [&](auto* t) {
     using T = typename std::remove_pointer<decltype(t)>::type;
-    sa_gate_sums_kernel<T><<<B * Ci, 256, 0, st>>>((const T*)image, Ci, HW, G, chan_sums_img, cweight, cbias, sweight, sbias,
-                                                   gn_weight, gn_bias, attn);
-    return check_launch("sa_gate_sums");
+    sa_gate_sums_kernel<T><<<B * (Ci + Cr), 256, 0, st>>>((const T*)image, Ci, HW, G, chan_sums_img, cweight, cbias, sweight, sbias,
+                                                          gn_weight, gn_bias, attn, (const T*)radar, Cr, cs_radar, B * Ci);
+    return check_launch(what);
   });
+}
+
+extern "C" int vrcoc_sa_gate_sums(const void* image, int dtype, int B, int Ci, int HW, int G, const float* chan_sums_img,
+                                  const float* cweight, const float* cbias, const float* sweight, const float* sbias,
+                                  const float* gn_weight, const float* gn_bias, float* attn, void* stream) {
+  return launch_sa_gate_sums(image, nullptr, dtype, B, Ci, 0, HW, G, chan_sums_img, cweight, cbias, sweight, sbias, gn_weight, gn_bias,
+                             attn, nullptr, stream, "sa_gate_sums");
+}
+
+extern "C" int vrcoc_fusion_stats(const void* image, const void* radar, int dtype, int B, int Ci, int Cr, int HW, int G,
+                                  const float* cweight, const float* cbias, const float* sweight, const float* sbias,
+                                  const float* gn_weight, const float* gn_bias, float* attn, float* chan_sums_radar, void* stream) {
+  return launch_sa_gate_sums(image, radar, dtype, B, Ci, Cr, HW, G, nullptr, cweight, cbias, sweight, sbias, gn_weight, gn_bias, attn,
+                             chan_sums_radar, stream, "fusion_stats");
 }
 
 extern "C" int vrcoc_radar_enh_table(const float* attn, const float* chan_sums_radar, const int32_t* chan_src,
@@ -683,17 +847,71 @@ extern "C" int vrcoc_gn_bwd_apply(const void* dz, const void* x, const void* ext
   });
 }
 
+// strip height and resident source rows of the two-pass upsample kernels
+static void upsample_plan(int H, int Ho, int Wo, float sy, int& R, int& ns_max, int& threads, int r_pref = 16) {
+  R = Ho < r_pref ? Ho : r_pref;
+  ns_max = (int)((R - 1) * sy) + 3;
+  if (ns_max > H) ns_max = H;
+  const int tasks = R * (Wo >> 3);
+  threads = tasks >= 256 ? 256 : (tasks <= 64 ? 64 : ((tasks + 31) / 32) * 32);
+}
+
 extern "C" int vrcoc_upsample_bilinear(const void* x, void* out, int dtype, int planes, int H, int W, int Ho, int Wo, void* stream) {
   VRCOC_REQUIRE(x && out && planes > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0, "upsample_bilinear: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
   const float sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  int R, ns_max, threads;
+  upsample_plan(H, Ho, Wo, sy, R, ns_max, threads);
+  const size_t smem = (size_t)ns_max * Wo * sizeof(float);
+  const int64_t nblk = (int64_t)planes * ((Ho + R - 1) / R);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if ((Wo & 7) == 0 && Ho >= H && Wo >= W && smem <= 48 * 1024 && nblk < (1ll << 31) && aligned) {
+    return by_dtype(dtype, [&](auto* t) {
+      using T = typename std::remove_pointer<decltype(t)>::type;
+      upsample_rows_kernel<T><<<(unsigned)nblk, threads, smem, st>>>((const T*)x, (T*)out, H, W, Ho, Wo, sy, sx, R, ns_max);
+      return check_launch("upsample_bilinear");
+    });
+  }
   const int64_t total = (int64_t)planes * Ho * ((Wo + 7) / 8);
   int blocks = (int)(cdiv(total, 256) < 148 * 16 ? cdiv(total, 256) : 148 * 16);
   return by_dtype(dtype, [&](auto* t) {
     using T = typename std::remove_pointer<decltype(t)>::type;
     upsample_bilinear_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, (T*)out, planes, H, W, Ho, Wo, sy, sx);
     return check_launch("upsample_bilinear");
+  });
+}
+
+extern "C" int vrcoc_upsample_argmax_supported(int C, int H, int W, int Ho, int Wo) {
+  if (C <= 0 || C > 255 || H <= 0 || W <= 0 || Ho < H || Wo < W || (Wo & 7) != 0) return 0;
+  const float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+  for (int r_pref = 16; r_pref >= 4; r_pref >>= 1) {                  // shorter strips when the classes of a 16-row strip do not fit
+    int R, ns_max, threads;
+    upsample_plan(H, Ho, Wo, sy, R, ns_max, threads, r_pref);
+    if ((size_t)C * ns_max * Wo * sizeof(float) <= 200 * 1024) return r_pref;
+  }
+  return 0;
+}
+
+extern "C" int vrcoc_upsample_argmax(const void* x, uint8_t* out, int dtype, int B, int C, int H, int W, int Ho, int Wo, void* stream) {
+  VRCOC_REQUIRE(x && out && B > 0, "upsample_argmax: bad argument");
+  const int r_pref = vrcoc_upsample_argmax_supported(C, H, W, Ho, Wo);
+  VRCOC_REQUIRE(r_pref > 0, "upsample_argmax: unsupported shape (classes <= 255, Wo %% 8 == 0, classes x strip rows x Wo floats within "
+                "shared memory)");
+  VRCOC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 7) == 0, "upsample_argmax: out must be 8-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+  const float sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  int R, ns_max, threads;
+  upsample_plan(H, Ho, Wo, sy, R, ns_max, threads, r_pref);
+  const size_t smem = (size_t)C * ns_max * Wo * sizeof(float);
+  const unsigned nblk = (unsigned)(B * ((Ho + R - 1) / R));
+  return by_dtype(dtype, [&](auto* t) {
+    using T = typename std::remove_pointer<decltype(t)>::type;
+    auto kern = upsample_argmax_kernel<T>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<nblk, 256, smem, st>>>((const T*)x, out, C, H, W, Ho, Wo, sy, sx, R, ns_max);
+    return check_launch("upsample_argmax");
   });
 }
 

@@ -58,6 +58,7 @@ SIGNATURES = {
     "vrcoc_cluster_core_fwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P] + [_I] * 9 + [_L] * 3 + [_P]),
     "vrcoc_cluster_core_bwd": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P] + [_I] * 9 + [_L] * 5 + [_P]),
     "vrcoc_sa_gate_sums": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "vrcoc_fusion_stats": (_I, [_P, _P, _I, _I, _I, _I, _I, _I] + [_P] * 8 + [_P]),
     "vrcoc_radar_enh_table": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "vrcoc_radar_enh_table_concat_order": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "vrcoc_chan_affine": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, _P, _P, _P]),
@@ -74,6 +75,8 @@ SIGNATURES = {
     "vrcoc_im2col": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vrcoc_dwconv": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vrcoc_upsample_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "vrcoc_upsample_argmax_supported": (_I, [_I] * 5),
+    "vrcoc_upsample_argmax": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vrcoc_gn_bwd_coef": (_I, [_P, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "vrcoc_proj_res_bwd_coef": (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "vrcoc_col2im": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

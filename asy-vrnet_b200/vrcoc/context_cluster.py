@@ -53,7 +53,14 @@ class PointRecuder(nn.Module):
     def forward(self, x, extra=None, extra_bstride=None):
         """`extra` (optional, [C1,H,W] or [B,C1,H,W]) is concatenated after x along the channels inside the kernel
         (the cat([x, pos]) of reference vr_coc.py:582-586 without materialising it)."""
-        from .fusion import conv2d_native
+        from .fusion import _conv_launch, conv2d_native
+        if x.is_cuda and not torch.is_grad_enabled() and isinstance(self.norm, nn.Identity):
+            # gradient-free: the reducer feeds the first ClusterBlock of a stage, whose GroupNorm needs the per-sample sums of
+            # this output - they leave the convolution's epilogue with it instead of costing a pass (and a launch) of their own
+            sums = ops.new_sample_sums(x.shape[0], x.device)
+            y = _conv_launch(x, self.proj.weight, ops._f32(self.proj.bias), self.proj.stride[0], self.proj.padding[0], extra,
+                             extra_bstride, ACT_NONE, None, None, None, out_sample_sums=sums)
+            return ops.attach_sums(y, sums)
         y = conv2d_native(x, self.proj.weight, self.proj.bias, stride=self.proj.stride[0], pad=self.proj.padding[0],
                           extra=extra, extra_bstride=extra_bstride)
         return self.norm(y)

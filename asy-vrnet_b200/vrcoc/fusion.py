@@ -103,7 +103,7 @@ def conv2d_native(x, weight, bias=None, stride=1, pad=0, extra=None, extra_bstri
     return _apply(_ConvFn, x, weight, bias, stride, pad, extra, extra_bstride, act, e_scale, out_minmax, out_dtype)
 
 
-def _conv_launch(x, weight, bias32, stride, pad, extra, extra_bstride, act, e_scale, out_minmax, out_dtype, dil=1):
+def _conv_launch(x, weight, bias32, stride, pad, extra, extra_bstride, act, e_scale, out_minmax, out_dtype, dil=1, out_sample_sums=None):
     ops._need_cuda(x)
     x = x.contiguous()
     B, C0, H, W = x.shape
@@ -131,11 +131,12 @@ def _conv_launch(x, weight, bias32, stride, pad, extra, extra_bstride, act, e_sc
         # 16-byte aligned, so the +-1 column taps fault - measured with tools/tma_probe.cu)
         col = torch.empty(B, kh * kw * Cin, Ho, Wo, device=x.device, dtype=x.dtype)
         check(lib.vrcoc_im2col(_ptr(x), _ptr(col), _dt(x), B, Cin, H, W, kh, kw, stride, pad, dil, _stream()), "im2col")
-        d = conv_desc(col, w2, out, e_scale=e_scale, e_shift=bias32, act=act, out_minmax=out_minmax)
+        d = conv_desc(col, w2, out, e_scale=e_scale, e_shift=bias32, act=act, out_minmax=out_minmax, out_sample_sums=out_sample_sums)
         conv_fwd(d)
         return out
     d = conv_desc(x, w2, out, src1=extra, src1_bstride=extra_bstride, kh=kh, kw=kw, stride=stride, pad=pad,
-                  e_scale=e_scale, e_shift=bias32, act=act, out_minmax=out_minmax, dil=dil, k_order=1 if tapm else 0)
+                  e_scale=e_scale, e_shift=bias32, act=act, out_minmax=out_minmax, dil=dil, k_order=1 if tapm else 0,
+                  out_sample_sums=out_sample_sums)
     conv_fwd(d)
     return out
 
@@ -475,7 +476,7 @@ class ShuffleAttention(nn.Module):
     def gate_table(self, x):
         """attn [B,C,4] = {scale, gate_a, gate_c, mean of the attended channel} for every input channel"""
         B, Cc, H, W = x.shape
-        cs, _ = ops.channel_sums(x)
+        cs = ops.channel_sums(x)[0] if H * W > 65536 else None          # small planes: each block reduces its own plane first
         attn = torch.empty(B, Cc, 4, device=x.device, dtype=torch.float32)
         cw, cb, sw, sb, gw, gb = self.params32()
         check(lib.vrcoc_sa_gate_sums(_ptr(x), _dt(x), B, Cc, H * W, self.G, _ptr(cs), _ptr(cw), _ptr(cb), _ptr(sw), _ptr(sb),
@@ -655,7 +656,7 @@ class _EcaFn(torch.autograd.Function):
     def forward(ctx, x, w):
         x = x.contiguous()
         B, Cc, H, W = x.shape
-        cs, _ = ops.channel_sums(x)
+        cs = ops.channel_sums(x)[0] if H * W > 65536 else None
         k = w.shape[-1]
         # attn records with scale 1 / gate off / mean = channel mean, then the same ECA table kernel as the fused path
         attn = torch.empty(B, Cc, 4, device=x.device, dtype=torch.float32)
@@ -830,15 +831,18 @@ class _RadarEnhanceFn(torch.autograd.Function):
         HW = H * W
         dev = image.device
         # statistics + attention parameters + ECA -> conv prologue table
-        cs_img, _ = ops.channel_sums(image)
-        cs_rad, _ = ops.channel_sums(radar)
         attn = torch.empty(B, Ci, 4, device=dev, dtype=torch.float32)
-        if mod.initial:
-            check(lib.vrcoc_sa_gate_sums(_ptr(image), _dt(image), B, Ci, HW, 0, _ptr(cs_img), None, None, None, None, None, None,
-                                         _ptr(attn), _stream()), "sa_gate_sums")
+        pc = [None] * 6 if mod.initial else sa.params32()
+        G = 0 if mod.initial else sa.G
+        if HW <= 65536:
+            # plane sums of both maps and the attention gates in one launch (a block per plane reduces its own plane)
+            cs_rad = torch.empty(B, Cr, 2, device=dev, dtype=torch.float32)
+            check(lib.vrcoc_fusion_stats(_ptr(image), _ptr(radar), _dt(image), B, Ci, Cr, HW, G, *[_ptr(p) for p in pc], _ptr(attn),
+                                         _ptr(cs_rad), _stream()), "fusion_stats")
         else:
-            pc = sa.params32()
-            check(lib.vrcoc_sa_gate_sums(_ptr(image), _dt(image), B, Ci, HW, sa.G, _ptr(cs_img), *[_ptr(p) for p in pc],
+            cs_img, _ = ops.channel_sums(image)
+            cs_rad, _ = ops.channel_sums(radar)
+            check(lib.vrcoc_sa_gate_sums(_ptr(image), _dt(image), B, Ci, HW, G, _ptr(cs_img), *[_ptr(p) for p in pc],
                                          _ptr(attn), _stream()), "sa_gate_sums")
         table = torch.empty(B, Ci + Cr, 4, device=dev, dtype=torch.float32)
         ew = _f32(eca_w).reshape(-1)

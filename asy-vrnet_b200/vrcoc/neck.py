@@ -2,8 +2,8 @@
 shuffle_channels, CoCFpnDual), same constructor arguments, module tree and state-dict keys.
 
 Hot-path content here = the three CoC_Conv ClusterBlocks, the 1x1 BaseConvs and the
-ShuffleAttention gates, all on the native kernels.  ASPP's dilated 3x3 convs and the bilinear upsamples are the
-"next" rows of SURVEY §8f and are cuDNN / ATen library calls for now.
+ShuffleAttention gates, all on the native kernels; so are the "next" rows of SURVEY §8f in this file: ASPP's dilated 3x3 convs
+(im2col + tcgen05 GEMM), the bilinear upsamples (csrc/stats.cu) and, for serving, the fused upsample + arg-max class map.
 """
 import torch
 import torch.nn as nn
@@ -51,6 +51,24 @@ class BilinearUpsample(nn.Upsample):
                 return _UpsampleFn.forward(type("_Ctx", (), {})(), x, float(self.scale_factor))
             return _UpsampleFn.apply(x, float(self.scale_factor))
         return super().forward(x)
+
+
+def upsample_argmax(x, scale):
+    """class map [B, H*scale, W*scale] uint8 = argmax over dim 1 of the align_corners=True bilinear upsample of the logits x
+    [B, C, H, W] (rounded to x.dtype, lowest index on ties): bit-identical to BilinearUpsample followed by argmax(1), one launch,
+    the full-size logits never reach memory (csrc/stats.cu: upsample_argmax_kernel; reference deeplab.py:149-167)."""
+    x = x.contiguous()
+    B, C, H, W = x.shape
+    Ho, Wo = int(H * scale), int(W * scale)
+    out = torch.empty(B, Ho, Wo, device=x.device, dtype=torch.uint8)
+    check(lib.vrcoc_upsample_argmax(x.data_ptr(), out.data_ptr(), ops._dt(x), B, C, H, W, Ho, Wo, ops._stream()), "upsample_argmax")
+    return out
+
+
+def upsample_argmax_ok(x, scale):
+    B, C, H, W = x.shape
+    return x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and \
+        bool(lib.vrcoc_upsample_argmax_supported(C, H, W, int(H * scale), int(W * scale)))
 
 
 class CoCUpsample(nn.Module):
@@ -181,6 +199,11 @@ class CoCFpnDual(nn.Module):
     # duration of its own forward, so that the head of a coarse level runs next to the neck of the finer ones and the whole
     # detection half next to the segmentation half; forward then returns the head outputs in place of (p3, p4, p5).
     det_level_hook = None
+    # Serving switch (an attribute for the same reason; vrcoc.InferenceSession sets it): True makes a gradient-free forward return
+    # the per-pixel CLASS MAP [B,H,W] uint8 in place of the full-size segmentation logits — the x4 upsample and the arg-max the
+    # reference's deeplab.py:149-167 applies to them fused into one kernel (neck.upsample_argmax), bit-identical to
+    # forward(...)[1].argmax(1).
+    seg_class_map = False
 
     def forward(self, x, x_radar):
         with ops.sums_arena(x.shape[0], x.device):
@@ -196,6 +219,12 @@ class CoCFpnDual(nn.Module):
             t = self.sc_attn_seg4(cat_shuffle(s4, self.upsample5_4(t)))
             t = self.sc_attn_seg3(cat_shuffle(self.upsample4_3(t), s3))
             t = self.sc_attn_seg2(cat_shuffle(self.upsample3_2(t), s2))
+            conv, up = self.upsample2_0.upsample[0], self.upsample2_0.upsample[1]
+            if self.seg_class_map and not torch.is_grad_enabled() and getattr(up, "mode", "") == "bilinear" and up.align_corners:
+                t = conv(t)
+                if upsample_argmax_ok(t, float(up.scale_factor)):
+                    return upsample_argmax(t, float(up.scale_factor))
+                return up(t).argmax(dim=1).to(torch.uint8)
             return self.upsample2_0(t)
 
         def det_branch():          # radar features

@@ -70,8 +70,17 @@ class InferenceSession:
             torch.cuda.synchronize(self.device)
 
     def _forward(self, x, r):
-        det, seg = self.model(x, r)
-        cls = seg.argmax(dim=1).to(torch.uint8)
+        # the neck returns the class map itself (upsample + arg-max in one kernel) when it has the serving switch
+        neck = getattr(self.model, "backbone", None)
+        fused = neck is not None and hasattr(neck, "seg_class_map")
+        if fused:
+            neck.seg_class_map = True
+        try:
+            det, seg = self.model(x, r)
+        finally:
+            if fused:
+                neck.seg_class_map = False
+        cls = seg if seg.dtype == torch.uint8 else seg.argmax(dim=1).to(torch.uint8)
         if self.decode:
             return [decode_outputs(det, (self.img, self.img)), cls]
         return list(det) + [cls]

@@ -121,7 +121,7 @@ class ClockSampler:
 KERNELS_PER_CALL = {"vrcoc_channel_sums": 1, "vrcoc_conv_fwd": 1, "vrcoc_table_apply": 1, "vrcoc_cluster_core_fwd": 1,
                     "vrcoc_cluster_core_bwd": 2, "vrcoc_sa_gate_sums": 1, "vrcoc_radar_enh_table": 1, "vrcoc_chan_affine": 1,
                     "vrcoc_img_enh_finish": 1, "vrcoc_gelu_bwd": 1, "vrcoc_gn_bwd_sums": 1, "vrcoc_gn_bwd_apply": 1,
-                    "vrcoc_conv1x1_wgrad": 3, "vrcoc_im2col": 1, "vrcoc_upsample_bilinear": 1,
+                    "vrcoc_conv1x1_wgrad": 3, "vrcoc_im2col": 1, "vrcoc_upsample_bilinear": 1, "vrcoc_upsample_argmax": 1,
                     "vrcoc_dwconv": 1, "vrcoc_mlp_fused_fwd": 1, "vrcoc_token_mixer_fwd": 1, "vrcoc_token_mixer_core_fwd": 1}
 
 
@@ -182,6 +182,9 @@ def _describe(name, args):
     if name == "vrcoc_upsample_bilinear":
         dt, planes, H, W, Ho, Wo = args[2:8]
         return f"upsample[{H}x{W}->{Ho}x{Wo}]", planes * _esz(dt) * (H * W + Ho * Wo), 0.0
+    if name == "vrcoc_upsample_argmax":
+        dt, B, C, H, W, Ho, Wo = args[2:9]
+        return f"upsample_argmax[{C}x{H}x{W}->{Ho}x{Wo}]", B * (C * _esz(dt) * H * W + Ho * Wo), 0.0
     return name.replace("vrcoc_", ""), 0, 0.0
 
 
@@ -667,8 +670,13 @@ def run_ours(args):
     sx, sr = torch.empty_like(devb[0][0]), torch.empty_like(devb[0][1])
 
     def forward(x, r):
-        det, seg = model(x, r)
-        return det, seg.argmax(dim=1).to(torch.uint8)
+        # detection maps + per-pixel class map; the neck's serving switch fuses the x4 logits upsample with the arg-max
+        model.backbone.seg_class_map = True
+        try:
+            det, seg = model(x, r)
+        finally:
+            model.backbone.seg_class_map = False
+        return det, (seg if seg.dtype == torch.uint8 else seg.argmax(dim=1).to(torch.uint8))
 
     if args.ncu_pass:
         with torch.no_grad():

@@ -168,10 +168,18 @@ int vrcoc_cluster_core_bwd(const void* feat, int feat_dtype, const void* value, 
  * attention parameters and the spatial sums of the attended image; step 2 runs the ECA conv1d over the
  * interleaved channel means and emits the conv prologue table [B][Ci+Cr][4]. */
 int vrcoc_sa_gate_sums(const void* image, int dtype, int B, int Ci, int HW, int G /*0 = no ShuffleAttention*/,
-                       const float* chan_sums_img /*[B][Ci][2]*/,
+                       const float* chan_sums_img /*[B][Ci][2]; NULL: each block reduces its own plane first*/,
                        const float* cweight, const float* cbias, const float* sweight, const float* sbias,
                        const float* gn_weight, const float* gn_bias,
                        float* attn /*[B][Ci][4] = {scale, gate_a, gate_c, mean of attended channel}*/, void* stream);
+/* Steps 0 and 1 of RadarEnhanceByImage's statistics in ONE launch (was: channel_sums(image), channel_sums(radar), sa_gate_sums —
+ * three dependent launches of ~7 us each in front of every fusion stage): a block per image plane reduces its own plane (the
+ * sums vrcoc_sa_gate_sums takes as an argument; chan_sums_img = NULL there does the same) and then the gated sum, a block per
+ * radar plane writes chan_sums_radar [B][Cr][2].  Meant for planes a single block streams quickly (HW <= 65536). */
+int vrcoc_fusion_stats(const void* image, const void* radar, int dtype, int B, int Ci, int Cr, int HW, int G,
+                       const float* cweight, const float* cbias, const float* sweight, const float* sbias,
+                       const float* gn_weight, const float* gn_bias, float* attn /*[B][Ci][4]*/,
+                       float* chan_sums_radar /*[B][Cr][2]*/, void* stream);
 int vrcoc_radar_enh_table(const float* attn /*[B][Ci][4]*/, const float* chan_sums_radar /*[B][Cr][2]*/,
                           const int32_t* chan_src /*[Ci+Cr] logical -> concat channel; image channels already
                                                     include ShuffleAttention's own channel_shuffle*/,
@@ -261,6 +269,14 @@ int vrcoc_dwconv(const void* x, const void* weight, const float* bias, void* out
 /* Bilinear upsample with align_corners=True over `planes` = B*C maps (nn.Upsample inside CoCUpsample,
  * reference neck/coc_fpn_dual.py:19-22). */
 int vrcoc_upsample_bilinear(const void* x, void* out, int dtype, int planes, int H, int W, int Ho, int Wo, void* stream);
+/* Serving tail of the segmentation half (reference deeplab.py:149-167: F.interpolate(logits, frame size, bilinear,
+ * align_corners=True) then arg-max over the classes) as ONE launch: out[b][oy][ox] (uint8) = argmax_c of the upsampled logits
+ * x [B][C][H][W], each value rounded to `dtype` first and the lowest class index winning ties — bit-identical to
+ * vrcoc_upsample_bilinear followed by an arg-max, without the [B][C][Ho][Wo] logits reaching memory.
+ * vrcoc_upsample_argmax_supported returns non-zero (the strip height used) when a shape fits: all classes of a 16-, 8- or 4-row
+ * strip of source rows resident in shared memory. */
+int vrcoc_upsample_argmax_supported(int C, int H, int W, int Ho, int Wo);
+int vrcoc_upsample_argmax(const void* x, uint8_t* out, int dtype, int B, int C, int H, int W, int Ho, int Wo, void* stream);
 
 /* Backward elementwise passes of the projections (training path of ClusterBlock, vr_coc.py:264-271).
  *   gelu_bwd    : out = dy * gelu'(u)                                   (all three tensors share `dtype`)

@@ -392,6 +392,92 @@ def test_upsample_matches_interpolate(V):
     assert rel_err(xr.grad, xr2.grad) < 1e-5
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_point_reducer_emits_groupnorm_sums(V, dtype):
+    """gradient-free PointRecuder: the per-sample sums riding on the output (conv epilogue side channel) are the sums of that
+    output (up to its own storage rounding), for the patch embed with the position grid and for the 3x3 stride-2 reducers"""
+    from vrcoc import ops
+    g = torch.Generator().manual_seed(5)
+    for cin, cout, k, s, p, H, extra in ((3, 64, 4, 4, 0, 128, 2), (64, 128, 3, 2, 1, 64, 0), (320, 512, 3, 2, 1, 32, 0)):
+        m = V.PointRecuder(patch_size=k, stride=s, padding=p, in_chans=cin + extra, embed_dim=cout).cuda().to(dtype)
+        x = torch.randn(3, cin, H, H, generator=g).cuda().to(dtype)
+        pos = torch.randn(extra, H, H, generator=g).cuda().to(dtype) if extra else None
+        with torch.no_grad():
+            y = m(x, extra=pos)
+        ss = ops.sample_sums_of(y)
+        assert ss is y._vrcoc_sums
+        got = ss.sum(dim=1)                                               # [B, 2] over the slots
+        ref = torch.stack([y.double().sum(dim=(1, 2, 3)), y.double().square().sum(dim=(1, 2, 3))], dim=1)
+        tol = 2e-3 if dtype == torch.bfloat16 else 1e-5
+        n = y[0].numel()
+        assert ((got[:, 0] - ref[:, 0]).abs() / n <= tol * y.double().abs().mean()).all()
+        assert rel_err(got[:, 1], ref[:, 1]) < tol
+
+
+def test_upsample_rows_kernel_shapes(V):
+    """the two-pass (strip) kernel at the live shapes (16->32 ... 128->512, also 256->1024) against F.interpolate in fp32, and in
+    bf16 against the fp32 result rounded once (the kernel interpolates in fp32 and rounds the output only)"""
+    import torch.nn.functional as F
+    from vrcoc.neck import BilinearUpsample
+    g = torch.Generator().manual_seed(7)
+    for shape, scale in (((2, 5, 16, 16), 2), ((1, 3, 32, 32), 2), ((1, 2, 64, 64), 2), ((2, 9, 128, 128), 4), ((1, 2, 256, 256), 4), ((1, 3, 24, 40), 2)):
+        x = torch.randn(*shape, generator=g).cuda()
+        up = BilinearUpsample(scale_factor=scale, mode="bilinear", align_corners=True)
+        ref = F.interpolate(x.double(), scale_factor=scale, mode="bilinear", align_corners=True)
+        got = up(x)
+        assert got.shape == ref.shape and rel_err(got, ref) < 5e-6      # fp32 source coordinates (ox * (W-1)/(Wo-1)) vs the fp64 reference
+        xb = x.bfloat16()
+        gb = up(xb)
+        refb = F.interpolate(xb.double(), scale_factor=scale, mode="bilinear", align_corners=True)
+        assert (gb.double() - refb).abs().max().item() <= 2.0 ** -8 * refb.abs().max().item() + 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_upsample_argmax_is_upsample_then_argmax(V, dtype):
+    """serving tail: the fused class map == BilinearUpsample(x4) followed by argmax(1), exactly (ties to the lowest class);
+    bf16 logits make ties common, so the tie rule is exercised"""
+    from vrcoc.neck import BilinearUpsample, upsample_argmax, upsample_argmax_ok
+    g = torch.Generator().manual_seed(11)
+    for shape, scale in (((8, 9, 128, 128), 4), ((2, 9, 32, 48), 4), ((1, 21, 64, 64), 2), ((1, 9, 256, 256), 4)):
+        x = (torch.randn(*shape, generator=g) * 0.5).cuda().to(dtype)
+        x[:, 3] = x[:, 1]                                               # exact ties between two classes wherever they win
+        assert upsample_argmax_ok(x, scale)
+        got = upsample_argmax(x, scale)
+        up = BilinearUpsample(scale_factor=scale, mode="bilinear", align_corners=True)(x)
+        ref = up.argmax(dim=1)
+        # torch.argmax does not promise an index on ties: compare through the values, and the tie rule explicitly
+        picked = torch.gather(up, 1, got.long().unsqueeze(1)).squeeze(1)
+        assert got.dtype == torch.uint8 and got.shape == ref.shape
+        assert torch.equal(picked, up.max(dim=1).values)
+        first = (up == up.max(dim=1, keepdim=True).values).float().argmax(dim=1)
+        assert torch.equal(got.long(), first)
+        assert (got != 3).all()                                         # class 3 always ties with class 1 and must lose
+
+
+def test_neck_class_map_switch(V):
+    """CoCFpnDual.seg_class_map: the gradient-free forward returns the class map, equal to argmax of the logits it returns otherwise"""
+    m = _randomised_model(V, "nano").cuda().bfloat16()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 512, 512, generator=g).cuda().bfloat16()
+    r = torch.randn(2, 4, 512, 512, generator=g).cuda().bfloat16()
+    with torch.no_grad():
+        det0, seg = m(x, r)
+        m.backbone.seg_class_map = True
+        try:
+            det1, cls = m(x, r)
+        finally:
+            m.backbone.seg_class_map = False
+    assert cls.dtype == torch.uint8 and cls.shape == (2, 512, 512)
+    # two forwards are not bit-identical (the GroupNorm statistics are accumulated with atomics): the class picked by the second
+    # must hold the maximum of the first's logits up to that noise, and nearly every pixel must agree outright
+    mx = seg.float().max(dim=1).values
+    picked = torch.gather(seg.float(), 1, cls.long().unsqueeze(1)).squeeze(1)
+    assert (picked >= mx - 2.0 ** -6 * mx.abs().clamp_min(1e-3)).all()
+    assert (cls.long() == seg.argmax(dim=1)).float().mean().item() > 0.995
+    for a, b in zip(det0, det1):
+        assert rel_err(a.float(), b.float()) < 1e-2
+
+
 def _randomised_model(V, phi):
     torch.manual_seed(0)
     m = V.EfficientVRNet(4, 9, phi).eval()
