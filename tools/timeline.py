@@ -84,11 +84,9 @@ def main():
     nb = int((t1 - t0) // 100) + 1
     sl = [0.0] * nb
     for s, e, n in ks:
-        a = s
-        while a < e:
-            b_ = min(e, t0 + (int((a - t0) // 100) + 1) * 100)
-            sl[int((a - t0) // 100)] += b_ - a
-            a = b_
+        for k in range(max(0, int((s - t0) // 100)), min(nb - 1, int((e - t0) // 100)) + 1):      # integer slices: no float stepping
+            lo, hi = t0 + 100.0 * k, t0 + 100.0 * (k + 1)
+            sl[k] += max(0.0, min(e, hi) - max(s, lo))
     P("  " + " ".join(f"{v / 100:.1f}" for v in sl))
     if args.list:
         P("# ordered kernel list: start us, duration us, kernels in flight at start, name")
