@@ -1285,7 +1285,10 @@ extern "C" int vrcoc_mlp_fused_fwd(const void* x, const double* gn_sums, const f
   L.nk1 = C / TC_BK;
   L.nh = hidden / TQ_MT;
   L.mt2 = (C + TQ_MT - 1) / TQ_MT;
-  L.h_bufs = L.mt2 == 1 ? 1 : 2;
+  // one hidden buffer everywhere: at C > 128 the second one bought nothing (the second GEMM of chunk j is 0.8 us and overlaps the
+  // accumulator read of chunk j+1) while its 32 KB as two more ring stages do — with a 4-deep ring 64 KB of weights were in
+  // flight per SM against ~1 us of L2 latency and each chunk needs 176 KB: 3.6 us per chunk (trace), i.e. latency-bound
+  L.h_bufs = 1;
   L.tmem_cols = L.mt2 == 1 ? 256 : 512;
   // ring depth: C <= 128: as deep as two resident CTAs per SM allow (227 KB, 1 KB reserved per CTA); else one CTA per SM
   const int budget = L.mt2 == 1 ? (227 * 1024) / 2 - 1024 : 220 * 1024;
@@ -1322,7 +1325,7 @@ extern "C" int vrcoc_mlp_fused_fwd(const void* x, const double* gn_sums, const f
     mlp_fused_kernel<true><<<grid, MF_THREADS, L.total, (cudaStream_t)stream>>>(a1, a2, L, b1, tmX, tmW1, tmW2, tmO, tmR);
   } else {
     set_smem(mlp_fused_kernel<false>, L.total);
-    mlp_fused_kernel<false><<<grid, MF_THREADS, L.total, (cudaStream_t)stream>>>(a1, a2, L, b1, tmX, tmW1, tmW2, tmO, tmR);
+    mlp_fused_kernel<false><<<grid, MF_THREADS_WIDE, L.total, (cudaStream_t)stream>>>(a1, a2, L, b1, tmX, tmW1, tmW2, tmO, tmR);
   }
   return check_launch("mlp_fused");
 }

@@ -20,8 +20,10 @@
 
 namespace vrcoc {
 
-constexpr int MF_THREADS = 320;
-constexpr int MF_MAX_STAGES = 6;
+constexpr int MF_THREADS = 320;                 // C <= 128: warps 0-7 epilogue, 8 TMA producer, 9 MMA issuer
+constexpr int MF_THREADS_WIDE = 384;            // C > 128: + warps 10, 11 = two more weight producers (see the producer block)
+constexpr int MF_PRODUCERS_WIDE = 3;
+constexpr int MF_MAX_STAGES = 8;
 constexpr int MF_MAX_NK1 = 6;
 
 struct MlpLayout {
@@ -35,7 +37,7 @@ struct MlpLayout {
 };
 
 template <bool SINGLE>      // SINGLE: C <= 128 — one output tile, one hidden buffer (compile-time, the hot configuration)
-__global__ void __launch_bounds__(MF_THREADS, 2)
+__global__ void __launch_bounds__(SINGLE ? MF_THREADS : MF_THREADS_WIDE, SINGLE ? 2 : 1)
 mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict__ b1, const __grid_constant__ CUtensorMap tmapX,
                  const __grid_constant__ CUtensorMap tmapW1, const __grid_constant__ CUtensorMap tmapW2,
                  const __grid_constant__ CUtensorMap tmapO, const __grid_constant__ CUtensorMap tmapR) {
@@ -86,30 +88,42 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
-    // ---- TMA producer: X slabs, then the weight slabs in MMA order ------------------------------------------------------------
+  if (warp == 8 || warp >= 10) {
+    // ---- TMA producers: X slabs, then the weight slabs in MMA order ---------------------------------------------------------------
+    // The weight stream of a CTA is nk1 + (nh-1)(nk1 + 2 MT2) + 2 MT2 boxes of 16 KB (110 at C = 320) and ONE issuing thread
+    // sustains one box per ~0.33 us whatever its size (tools/tma_bw_probe.cu): at C > 128 that alone was 36 of the 57 us of a
+    // stage-3 launch.  There the sequence is dealt round-robin to three producer warps (step `it` belongs to producer it % 3);
+    // a step's ring slot and barrier phases follow from `it` alone, so the producers share no state.
+    const int NP = SINGLE ? 1 : MF_PRODUCERS_WIDE;
+    const int prod = warp == 8 ? 0 : warp - 9;                         // 0, 1, 2
     if (lane == 0) {
-      for (int kc = 0; kc < nk1; ++kc) {
-        mbar_expect_tx(&x_full[kc], (uint32_t)TQ_X_BYTES);
-        tma_load_3d(sX + kc * TQ_X_BYTES, &tmapX, p0, kc * TC_BK, b, &x_full[kc]);
-        tma_load_3d(sX + kc * TQ_X_BYTES + TC_A_LBO, &tmapX, p0 + 64, kc * TC_BK, b, &x_full[kc]);
+      if (prod == 0) {
+        for (int kc = 0; kc < nk1; ++kc) {
+          mbar_expect_tx(&x_full[kc], (uint32_t)TQ_X_BYTES);
+          tma_load_3d(sX + kc * TQ_X_BYTES, &tmapX, p0, kc * TC_BK, b, &x_full[kc]);
+          tma_load_3d(sX + kc * TQ_X_BYTES + TC_A_LBO, &tmapX, p0 + 64, kc * TC_BK, b, &x_full[kc]);
+        }
       }
-      int it = 0;
-      auto put = [&](const CUtensorMap* map, int x, int y) {
+      const int bs = nk1 + 2 * MT2;                                    // steps of one hidden chunk: W1 of the NEXT chunk, then its own W2
+      const int total = nk1 + (nh - 1) * bs + 2 * MT2;
+      for (int it = prod; it < total; it += NP) {
+        const CUtensorMap* map;
+        int x, y;
+        if (it < nk1) {
+          map = &tmapW1; x = it * TC_BK; y = 0;
+        } else {
+          const int u = it - nk1, j = u / bs, r = u - j * bs;
+          if (j < nh - 1 && r < nk1) {
+            map = &tmapW1; x = r * TC_BK; y = (j + 1) * TQ_MT;
+          } else {
+            const int q = j < nh - 1 ? r - nk1 : r;
+            map = &tmapW2; x = j * TQ_MT + (q & 1) * TC_BK; y = (q >> 1) * TQ_MT;
+          }
+        }
         const int s = it % ST;
         if (it >= ST) mbar_wait(&bar_free[s], (uint32_t)((it / ST) - 1) & 1);
         mbar_expect_tx(&bar_full[s], (uint32_t)TQ_W_BYTES);
         tma_load_2d(ring + s * TQ_W_BYTES, map, x, y, &bar_full[s]);
-        ++it;
-      };
-      for (int kc = 0; kc < nk1; ++kc) put(&tmapW1, kc * TC_BK, 0);
-      for (int j = 0; j < nh; ++j) {
-        if (j + 1 < nh)
-          for (int kc = 0; kc < nk1; ++kc) put(&tmapW1, kc * TC_BK, (j + 1) * TQ_MT);
-        for (int m = 0; m < MT2; ++m) {
-          put(&tmapW2, j * TQ_MT, m * TQ_MT);
-          put(&tmapW2, j * TQ_MT + TC_BK, m * TQ_MT);
-        }
       }
     }
     __syncwarp();

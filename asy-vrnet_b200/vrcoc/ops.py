@@ -6,6 +6,8 @@ statistics) is done with torch ops on tiny tensors.
 """
 import ctypes as C
 
+import os
+
 import torch
 
 from . import _lib
@@ -93,7 +95,7 @@ def run_pair(f_main, f_side):
     return a, b
 
 
-FUSED_MLP_MAX_C = 128
+FUSED_MLP_MAX_C = int(os.environ.get("VRCOC_FUSED_MLP_MAX_C", "384"))   # the kernel's limit; "128" = stages 1-2 only (A/B switch)
 FUSED_MLP = True             # set False to run the channel MLP as two GEMM launches (debug / A-B)
 
 
