@@ -16,6 +16,8 @@
 //                   fall in disjoint banks.
 // STAGED=false is the general fallback for regions that do not fit in shared memory: the same passes read
 // feat/value straight from global/L2 through a per-point offset table.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vrcoc {
@@ -332,12 +334,18 @@ core_fwd_kernel(const TF* __restrict__ feat, const TV* __restrict__ value, TO* _
 }
 
 // Backward.  Inputs: feat, value, dout, saved idx + sim_max.  Outputs: dfeat, dvalue, per-CTA (dalpha, dbeta).
-template <typename TF, typename TV, typename TG, typename TDF, typename TDV, int MAXM, bool STAGED>
+// FD > 0: the live geometry at compile time (16x16 regions, 2x2 proposals, head_dim FD): the same code with every loop bound,
+// divisor and stride a constant.  ncu on the run-time-geometry instance at stage 1 (profiles/r02_ncu_core_bwd.txt): 147.5 M warp
+// instructions per launch = 281 per (point, channel) element, the hot lines being the integer divisions / modulos by q.rh, q.TPD,
+// q.N in the inner loops; 254 us where the tensors it touches (235 MB) would take 39 us at the HBM rate.
+template <typename TF, typename TV, typename TG, typename TDF, typename TDV, int MAXM, bool STAGED, int FD = 0>
 __global__ void __launch_bounds__(CORE_THREADS)
 core_bwd_kernel(const TF* __restrict__ feat, const TV* __restrict__ value, const TG* __restrict__ dout,
                 const uint8_t* __restrict__ idx_in, const float* __restrict__ smax_in,
                 const float* __restrict__ alpha_p, TDF* __restrict__ dfeat, TDV* __restrict__ dvalue,
-                float* __restrict__ partials, CoreGeom q, CoreSmem L) {
+                float* __restrict__ partials, CoreGeom q_in, CoreSmem L) {
+  CoreGeom q = q_in;
+  if (FD > 0) { q.D = FD; q.rw = 16; q.rh = 16; q.pw = 2; q.ph = 2; q.N = 256; q.M = 4; q.NS = 264; q.TPD = 8; }
   extern __shared__ __align__(16) unsigned char smem[];
   float* sf = reinterpret_cast<float*>(smem + L.f);
   float* sv = reinterpret_cast<float*>(smem + L.v);
@@ -595,9 +603,21 @@ static int launch_bwd(const void* feat, const void* value, const void* dout, con
     kern<<<R, CORE_THREADS, L.total, st>>>((const TF*)feat, (const TV*)value, (const TG*)dout, idx, smax, alpha,   \
                                            (TDF*)dfeat, (TDV*)dvalue, partials, q, L);                             \
   } while (0)
-  if (maxm == 4) { if (staged) LAUNCH(4, true); else LAUNCH(4, false); }
+  const bool live16 = maxm == 4 && staged && q.rw == 16 && q.rh == 16 && q.pw == 2 && q.ph == 2 && q.NS == 264 && q.TPD == 8;
+#define LAUNCH_FIXED(FDV)                                                                                          \
+  do {                                                                                                             \
+    auto kern = core_bwd_kernel<TF, TV, TG, TDF, TDV, 4, true, FDV>;                                               \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);                              \
+    kern<<<R, CORE_THREADS, L.total, st>>>((const TF*)feat, (const TV*)value, (const TG*)dout, idx, smax, alpha,   \
+                                           (TDF*)dfeat, (TDV*)dvalue, partials, q, L);                             \
+  } while (0)
+  static const bool fixed_on = []() { const char* k = getenv("VRCOC_CORE_BWD_FIXED"); return !(k && k[0] == '0'); }();   // "0": A/B switch
+  if (live16 && fixed_on && q.D == 32) LAUNCH_FIXED(32);
+  else if (live16 && fixed_on && q.D == 24) LAUNCH_FIXED(24);
+  else if (maxm == 4) { if (staged) LAUNCH(4, true); else LAUNCH(4, false); }
   else if (maxm == 16) { if (staged) LAUNCH(16, true); else LAUNCH(16, false); }
   else { if (staged) LAUNCH(64, true); else LAUNCH(64, false); }
+#undef LAUNCH_FIXED
 #undef LAUNCH
   int rc = check_launch("cluster_core_bwd");
   if (rc) return rc;
