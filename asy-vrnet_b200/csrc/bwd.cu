@@ -136,6 +136,18 @@ __device__ __forceinline__ float silu_grad(float z) {
   return sg * (1.0f + z * (1.0f - sg));
 }
 
+// 128-bit path of the plane kernels below: every pointer (at its plane base) aligned to 8 elements and HW a multiple of 8.  The
+// scalar loops moved 2-byte words and ran at ~1 TB/s (torch profiler of a training step: chan_bwd_sums 2.6 ms, table_bwd_sums 1.3 ms).
+template <typename T>
+__device__ __forceinline__ bool vec8_ok(int HW, const T* a, const T* b = nullptr, const T* c = nullptr, const T* d = nullptr, const T* e = nullptr) {
+  uintptr_t m = reinterpret_cast<uintptr_t>(a);
+  if (b) m |= reinterpret_cast<uintptr_t>(b);
+  if (c) m |= reinterpret_cast<uintptr_t>(c);
+  if (d) m |= reinterpret_cast<uintptr_t>(d);
+  if (e) m |= reinterpret_cast<uintptr_t>(e);
+  return (HW & 7) == 0 && (m & (8 * sizeof(T) - 1)) == 0;
+}
+
 // per (b, c): { sum_p g, sum_p g * u }  with g = dy * act'(y)
 template <typename T>
 __global__ void __launch_bounds__(256) chan_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ yact, const T* __restrict__ u, int act, int C, int HW,
@@ -145,13 +157,24 @@ __global__ void __launch_bounds__(256) chan_bwd_sums_kernel(const T* __restrict_
   const int c = blockIdx.x % C;
   const float z_s = zs ? zs[c] : 1.f, z_t = zt ? zt[c] : 0.f;
   float s = 0.f, su = 0.f;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    float g = ldf<T>(dy + base + i);
-    const float uu = ldf<T>(u + base + i);
+  auto one = [&](float g, float uu, float ya) {
     if (act == VRCOC_ACT_SILU) g *= silu_grad(fmaf(uu, z_s, z_t));
-    else if (yact) g *= act_grad_from_out(ldf<T>(yact + base + i), act);
+    else if (yact) g *= act_grad_from_out(ya, act);
     else if (zs) g *= act_grad_from_out(fmaf(uu, z_s, z_t), act);          // sign of the recomputed pre-activation
     s += g; su = fmaf(g, uu, su);
+  };
+  if (vec8_ok<T>(HW, dy + base, u + base, yact ? yact + base : nullptr)) {
+    for (int i = threadIdx.x * 8; i < HW; i += blockDim.x * 8) {
+      float g[8], uu[8], ya[8];
+      ld8<T>(dy + base + i, g);
+      ld8<T>(u + base + i, uu);
+      if (yact) ld8<T>(yact + base + i, ya);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) one(g[e], uu[e], yact ? ya[e] : 0.f);
+    }
+  } else {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x)
+      one(ldf<T>(dy + base + i), ldf<T>(u + base + i), yact ? ldf<T>(yact + base + i) : 0.f);
   }
   s = warp_sum(s); su = warp_sum(su);
   if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = s; red[32 + (threadIdx.x >> 5)] = su; }
@@ -172,17 +195,30 @@ __global__ void __launch_bounds__(256) chan_bwd_apply_kernel(const T* __restrict
   const float a = ca[c], b = cb ? cb[c] : 0.f, d0 = cd ? cd[c] : 0.f;
   const float z_s = zs ? zs[c] : 1.f, z_t = zt ? zt[c] : 0.f;
   const int64_t base = (int64_t)plane * HW;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-    float g = ldf<T>(dy + base + i);
-    const float uu = u ? ldf<T>(u + base + i) : 0.f;
+  auto one = [&](float g, float uu, float ya, float ex) {
     if (act == VRCOC_ACT_SILU) g *= silu_grad(fmaf(uu, z_s, z_t));
-    else if (yact) g *= act_grad_from_out(ldf<T>(yact + base + i), act);
+    else if (yact) g *= act_grad_from_out(ya, act);
     else if (zs) g *= act_grad_from_out(fmaf(uu, z_s, z_t), act);
     float r = fmaf(g, a, d0);
     if (cb) r = fmaf(uu, b, r);
-    if (extra) r += ldf<T>(extra + base + i);
-    stf<T>(out + base + i, r);
+    return r + ex;
+  };
+  if (vec8_ok<T>(HW, dy + base, out + base, u ? u + base : nullptr, yact ? yact + base : nullptr, extra ? extra + base : nullptr)) {
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8; i < HW; i += gridDim.x * blockDim.x * 8) {
+      float g[8], uu[8], ya[8], ex[8], r[8];
+      ld8<T>(dy + base + i, g);
+      if (u) ld8<T>(u + base + i, uu);
+      if (yact) ld8<T>(yact + base + i, ya);
+      if (extra) ld8<T>(extra + base + i, ex);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = one(g[e], u ? uu[e] : 0.f, yact ? ya[e] : 0.f, extra ? ex[e] : 0.f);
+      st8<T>(out + base + i, r);
+    }
+    return;
   }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
+    stf<T>(out + base + i, one(ldf<T>(dy + base + i), u ? ldf<T>(u + base + i) : 0.f, yact ? ldf<T>(yact + base + i) : 0.f,
+                               extra ? ldf<T>(extra + base + i) : 0.f));
 }
 
 __device__ __forceinline__ void decode_minmax(const uint32_t* mm, float& mn, float& mx) {
@@ -203,13 +239,31 @@ __global__ void __launch_bounds__(256) img_enh_bwd_kernel(const T* __restrict__ 
   const float r = 1.0f / (mx - mn);
   const int64_t base = (int64_t)blockIdx.x * HW;
   float s0 = 0.f, s1 = 0.f, c0 = 0.f, c1 = 0.f;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    const float g = ldf<T>(dyv + base + i), im = ldf<T>(image + base + i), kk = ldf<T>(k + base + i);
+  auto one = [&](float g, float im, float kk, float& di, float& dkv) {
     const float kn = (kk - mn) * r, dkn = g * im;
-    stf<T>(dimage + base + i, g * (1.0f + kn));
-    stf<T>(dk + base + i, dkn * r);
+    di = g * (1.0f + kn);
+    dkv = dkn * r;
     s0 += dkn; s1 = fmaf(dkn, kk, s1);
     c0 += (kk == mn) ? 1.f : 0.f; c1 += (kk == mx) ? 1.f : 0.f;
+  };
+  if (vec8_ok<T>(HW, dyv + base, image + base, k + base, dimage + base, dk + base)) {
+    for (int i = threadIdx.x * 8; i < HW; i += blockDim.x * 8) {
+      float g[8], im[8], kk[8], di[8], dkv[8];
+      ld8<T>(dyv + base + i, g);
+      ld8<T>(image + base + i, im);
+      ld8<T>(k + base + i, kk);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) one(g[e], im[e], kk[e], di[e], dkv[e]);
+      st8<T>(dimage + base + i, di);
+      st8<T>(dk + base + i, dkv);
+    }
+  } else {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      float di, dkv;
+      one(ldf<T>(dyv + base + i), ldf<T>(image + base + i), ldf<T>(k + base + i), di, dkv);
+      stf<T>(dimage + base + i, di);
+      stf<T>(dk + base + i, dkv);
+    }
   }
   s0 = warp_sum(s0); s1 = warp_sum(s1); c0 = warp_sum(c0); c1 = warp_sum(c1);
   const int w = threadIdx.x >> 5;
@@ -311,12 +365,22 @@ __global__ void __launch_bounds__(256) table_bwd_sums_kernel(const T* __restrict
   const T* dzp = dz + ((int64_t)b * K + k) * HW;
   const T* xp = x + (int64_t)blockIdx.x * HW;
   float a1 = 0.f, a2 = 0.f, a3 = 0.f, j1 = 0.f, j2 = 0.f, j3 = 0.f;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    const float g = ldf<T>(dzp + i), xv = ldf<T>(xp + i);
+  auto one = [&](float g, float xv) {
     const float h = gate ? 1.0f / (1.0f + expf(-fmaf(ga, xv, gc))) : 1.0f;
     const float xh = xv * h, xd = xv * h * (1.0f - h);
     a1 = fmaf(g, xh, a1); a2 = fmaf(g * xv, xd, a2); a3 = fmaf(g, xd, a3);
     j1 += xh; j2 = fmaf(xv, xd, j2); j3 += xd;
+  };
+  if (vec8_ok<T>(HW, dzp, xp)) {
+    for (int i = threadIdx.x * 8; i < HW; i += blockDim.x * 8) {
+      float g[8], xv[8];
+      ld8<T>(dzp + i, g);
+      ld8<T>(xp + i, xv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) one(g[e], xv[e]);
+    }
+  } else {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) one(ldf<T>(dzp + i), ldf<T>(xp + i));
   }
   float v[6] = {a1, a2, a3, j1, j2, j3};
   const int w = threadIdx.x >> 5;
@@ -344,17 +408,28 @@ __global__ void __launch_bounds__(256) table_bwd_apply_kernel(const T* __restric
   const float cd = coef[4 * plane], cj = coef[4 * plane + 1], c1 = coef[4 * plane + 2], c2 = coef[4 * plane + 3];
   const T* dzp = dz + ((int64_t)b * K + k) * HW;
   const int64_t base = (int64_t)plane * HW;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
-    const float g = ldf<T>(dzp + i), xv = ldf<T>(x + base + i);
+  auto one = [&](float g, float xv, float ex) {
     float t = 1.0f;
     if (gate) {
       const float h = 1.0f / (1.0f + expf(-fmaf(ga, xv, gc)));
       t = h + xv * ga * h * (1.0f - h);
     }
-    float r = fmaf(fmaf(g, cd, cj), t, fmaf(2.0f * xv, c2, c1));
-    if (extra) r += ldf<T>(extra + base + i);
-    stf<T>(out + base + i, r);
+    return fmaf(fmaf(g, cd, cj), t, fmaf(2.0f * xv, c2, c1)) + ex;
+  };
+  if (vec8_ok<T>(HW, dzp, x + base, out + base, extra ? extra + base : nullptr)) {
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 8; i < HW; i += gridDim.x * blockDim.x * 8) {
+      float g[8], xv[8], ex[8], r[8];
+      ld8<T>(dzp + i, g);
+      ld8<T>(x + base + i, xv);
+      if (extra) ld8<T>(extra + base + i, ex);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = one(g[e], xv[e], extra ? ex[e] : 0.f);
+      st8<T>(out + base + i, r);
+    }
+    return;
   }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x)
+    stf<T>(out + base + i, one(ldf<T>(dzp + i), ldf<T>(x + base + i), extra ? ldf<T>(extra + base + i) : 0.f));
 }
 
 }  // namespace
