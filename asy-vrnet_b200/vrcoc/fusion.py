@@ -905,7 +905,17 @@ class _RadarEnhanceFn(torch.autograd.Function):
         if w2.dtype != radar.dtype:
             w2 = w2.to(radar.dtype)
         u = torch.empty_like(radar)
-        conv_fwd(conv_desc(image, w2, u, src1=radar, chan_src=chan_src, table=table, has_gate=gate))
+        z = None
+        if radar.dtype == torch.bfloat16 and image.dtype == torch.bfloat16 and HW % 8 == 0:
+            # bf16: materialise z = prologue([image | radar]) (shuffle, gates, ECA scale) once - the recomputed projection and, above all,
+            # the weight gradient then run on the tensor core as plain 1x1 problems (the two-source / gated form of the weight gradient
+            # only exists on the CUDA cores: 0.65 ms per fusion stage in the training profile, profiles/r02_prof_train.txt)
+            z = torch.empty(B, Ci + Cr, H, W, device=dev, dtype=radar.dtype)
+            check(lib.vrcoc_table_apply(conv_desc(image, image, z, src1=radar, chan_src=chan_src, table=table, has_gate=gate), _stream()),
+                  "table_apply")
+            conv_fwd(conv_desc(z, w2, u))
+        else:
+            conv_fwd(conv_desc(image, w2, u, src1=radar, chan_src=chan_src, table=table, has_gate=gate))
         mean1, var1 = _batch_stats(u) if t1 else (rm1.double(), rv1.double())
         s1, sh1 = _fold_bn(mean1.float(), var1.float(), g1.detach().float(), b1.detach().float(), eps1)
         t = torch.empty_like(radar)
@@ -921,7 +931,10 @@ class _RadarEnhanceFn(torch.autograd.Function):
             mean2, var2 = rm2.double(), rv2.double()
         dt, dg2, db2 = _norm_act_backward(dy, None, t, ACT_NONE, g2, b2, mean2, var2, eps2, t2)
         du, dg1, db1 = _norm_act_backward(dt, None, u, ACT_RELU, g1, b1, mean1, var1, eps1, t1)
-        dWk, _ = ops.conv1x1_wgrad(conv_desc(image, w2, du, src1=radar, chan_src=chan_src, table=table, has_gate=gate), du, want_db=False)
+        if z is not None:
+            dWk, _ = ops.conv1x1_wgrad(conv_desc(z, w2, du), du, want_db=False)
+        else:
+            dWk, _ = ops.conv1x1_wgrad(conv_desc(image, w2, du, src1=radar, chan_src=chan_src, table=table, has_gate=gate), du, want_db=False)
         dzf = torch.empty(B, Ci + Cr, H, W, device=dev, dtype=radar.dtype)
         conv_fwd(conv_desc(du, w2.t().contiguous(), dzf))
         sa = None if initial else (cw, cb, sw, sb, gw, gb, G)
