@@ -23,14 +23,20 @@ csv.writer(open("$O/${R}_launches.csv", "w", newline="")).writerows(out)
 print("launches:", len(out) - 1)
 PY
 rm -f $O/${R}_launches_raw.csv
-for c in s1_tmf s2_tmf s3_tmc s1_mlpf s2_mlpf s3_mlp1 s3_mlp2; do
+for c in s1_tmf s2_tmf s3_tmc s1_mlpf s2_mlpf s3_mlpf s3_mlp1 s3_mlp2; do
   ncu --set full --clock-control none -k regex:"token_mixer|mlp_fused|conv_tc" -s 3 -c 1 -o /tmp/ncu_$c python tools/microbench.py --case $c --iters 2 > /dev/null 2>&1
   python tools/ncu_summary.py /tmp/ncu_$c.ncu-rep --out /tmp/ncu_$c.csv
 done
 head -1 /tmp/ncu_s1_tmf.csv > $O/${R}_ncu_dominant.csv
-for c in s1_tmf s2_tmf s3_tmc s1_mlpf s2_mlpf s3_mlp1 s3_mlp2; do tail -n +2 /tmp/ncu_$c.csv | sed "s/^/$c: /" >> $O/${R}_ncu_dominant.csv; done
-python tools/microbench.py --case s1_tmf s2_tmf s3_tmc s1_mlpf s2_mlpf s3_mlp1 s3_mlp2 s3_fc1v s4_mlp1 s4_mlp2 s1_core s2_core s3_core > $O/${R}_microbench.txt 2>&1
+for c in s1_tmf s2_tmf s3_tmc s1_mlpf s2_mlpf s3_mlpf s3_mlp1 s3_mlp2; do tail -n +2 /tmp/ncu_$c.csv | sed "s/^/$c: /" >> $O/${R}_ncu_dominant.csv; done
+python tools/microbench.py --case s1_tmf s2_tmf s3_tmc s1_mlpf s2_mlpf s3_mlpf s3_mlp1 s3_mlp2 s3_fc1v s4_mlp1 s4_mlp2 s1_core s2_core s3_core > $O/${R}_microbench.txt 2>&1
 python tools/block_sweep.py --batch 8 --dtype bf16 --quick --out $O/${R}_block_sweep_bf16_b8.txt > /dev/null 2>&1
-compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py tests/test_gpu_token_mixer.py -m gpu -q -x \
-    -k "upsample or point_reducer or head_level or class_map or fused_token_mixer or stage3 or fusion or radar_enh or shuffle" > $O/${R}_sanitizer_memcheck.log 2>&1
+compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py tests/test_gpu_token_mixer.py tests/test_gpu_engine.py -m gpu -q -x \
+    -k "upsample or point_reducer or head_level or class_map or fused_token_mixer or stage3 or fusion or radar_enh or shuffle or col2im or golden or mlp" > $O/${R}_sanitizer_memcheck.log 2>&1
 tail -5 $O/${R}_sanitizer_memcheck.log
+compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "upsample or point_reducer or class_map or col2im" > $O/${R}_sanitizer_racecheck.log 2>&1
+tail -3 $O/${R}_sanitizer_racecheck.log
+python tools/block_sweep.py --batch 8 --dtype bf16 --out $O/${R}_block_sweep_bf16_b8_full.txt > /dev/null 2>&1
+for b in 1 16 64; do python tools/block_sweep.py --batch $b --dtype bf16 --quick --out $O/${R}_block_sweep_bf16_b$b.txt > /dev/null 2>&1; done
+python tools/timeline.py --list --out $O/${R}_timeline.txt > /dev/null 2>&1
+python tools/prof_train.py > $O/${R}_prof_train.txt 2>&1
