@@ -7,6 +7,7 @@ from .context_cluster import (Cluster, ClusterBlock, DropPath, GroupNorm, Mlp, P
                               pairwise_cos_sim)
 from .fusion import (BaseConv, DWConv, ImageEnhanceByRadar, RadarEnhanceByImage, ShuffleAttention, SiLU,  # noqa: F401
                      data_normal, eca_block, get_activation, shuffle_channels)
+from . import losses  # noqa: F401
 from .head import DecoupleHead  # noqa: F401
 from .neck import ASPP, CoC_Conv, CoCFpnDual, CoCUpsample  # noqa: F401
 from .nets import EfficientVRNet  # noqa: F401

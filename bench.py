@@ -46,6 +46,7 @@ def parse():
                          "block-sweep: configs[1] (tools/block_sweep.py; extra flags after --)")
     ap.add_argument("--img", type=int, default=512, help="frame side (1024: BASELINE configs[4], fea_pos buffers replaced)")
     ap.add_argument("--no-train-graph", action="store_true", help="train mode: eager forward/backward instead of the two CUDA graphs")
+    ap.add_argument("--ref-loss", action="store_true", help="train mode: the reference's own per-image YOLOLoss instead of vrcoc.losses.YOLOLoss")
     ap.add_argument("--no-train", action="store_true", help="skip the short training-step measurement appended to the inference line")
     ap.add_argument("--no-check", action="store_true", help="skip the pre-timing oracle spot check of the benched outputs")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the unmodified reference eager on the GPU")
@@ -491,6 +492,13 @@ def train_setup(args, dev, world, batch):
                                                     "cuda": type("_Cuda", (), {"__getattr__": lambda self, k: (lambda: None) if k == "empty_cache" else getattr(torch.cuda, k)})()})()
         yolo_loss, focal, dice = YOLOLoss(4, True), Focal_Loss, Dice_loss      # fp16=True: its SimOTA cost leaves autocast (yolo_training.py:240-247)
         loss_kind = "reference YOLOLoss(4, fp16=True) + 5*(Focal_Loss + Dice_loss) (nets/yolo_training.py:60, nets/deeplabv3_training.py:22,41)"
+        if not getattr(args, "ref_loss", False):
+            # the product's detection loss: the reference's YOLOLoss arithmetic (decode, SimOTA dynamic-k assignment, IoU / objectness /
+            # class terms) over the whole batch with static shapes and no host sync; tests/test_losses.py pins value and gradients
+            # against the reference class.  --ref-loss runs the reference's own per-image loop instead.
+            yolo_loss = vrcoc.losses.YOLOLoss(4, True)
+            loss_kind = ("vrcoc.losses.YOLOLoss(4, fp16=True) [batched sync-free SimOTA, = reference nets/yolo_training.py:60 to 1e-5] "
+                         "+ 5*(reference Focal_Loss + Dice_loss, nets/deeplabv3_training.py:22,41)")
     model = model.to(dev).train()
     for p in model.parameters():
         if p.numel() == 0:
