@@ -476,10 +476,97 @@ __global__ void __launch_bounds__(256) table_bwd_apply_kernel(const T* __restric
     stf<T>(out + base + i, one(ldf<T>(dzp + i), ldf<T>(x + base + i), extra ? ldf<T>(extra + base + i) : 0.f));
 }
 
+// ---- BatchNorm2d bookkeeping of the training path as two tiny kernels (normal_conv.py:45-49, vr_coc.py:315,341,356).  The host
+//      side did this algebra with torch ops on [C]-sized tensors: ~22 launches per BatchNorm forward (batch statistics, running-stat
+//      update, folded scale / shift) and ~30 per backward, ~65 BatchNorms per step = ~3000 of the 6800 launches of a training step.
+// batch statistics from the per-(b, c) sums -> mean / biased variance (fp64), running-stat update of nn.BatchNorm2d (unbiased
+// variance, momentum), folded affine BN(x) = x * scale + shift
+__global__ void __launch_bounds__(128) bn_stats_kernel(const float* __restrict__ cs, int B, int C, double count, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps, float momentum, float* __restrict__ rmean,
+                                                       float* __restrict__ rvar, long long* __restrict__ nbt, float* __restrict__ scale,
+                                                       float* __restrict__ shift, double* __restrict__ mean_out, double* __restrict__ var_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  double s = 0.0, s2 = 0.0;
+  for (int b = 0; b < B; ++b) {
+    s += (double)cs[((int64_t)b * C + c) * 2];
+    s2 += (double)cs[((int64_t)b * C + c) * 2 + 1];
+  }
+  const double mean = s / count;
+  double var = s2 / count - mean * mean;
+  var = var > 0.0 ? var : 0.0;
+  if (rmean && momentum >= 0.f) {
+    rmean[c] = rmean[c] * (1.0f - momentum) + momentum * (float)mean;
+    const double unb = var * (count / (count > 1.0 ? count - 1.0 : 1.0));
+    rvar[c] = rvar[c] * (1.0f - momentum) + momentum * (float)unb;
+  }
+  if (mean_out) { mean_out[c] = mean; var_out[c] = var; }
+  if (scale) {
+    float sc = 1.0f / sqrtf((float)var + eps);
+    if (gamma) sc *= gamma[c];
+    scale[c] = sc;
+    shift[c] = -(float)mean * sc + (beta ? beta[c] : 0.f);
+  }
+}
+
+// backward coefficients of y = act(BN(u)) from S[b][c] = {sum g, sum g*u}: du = g*ca + u*cb + cd; dgamma, dbeta.  With sums == NULL
+// only the recomputation affine of the pre-activation, z = u * zs + zt, is produced (needed BEFORE the sums pass).
+__global__ void __launch_bounds__(128) bn_bwd_coef_kernel(const float* __restrict__ sums, int B, int C, const double* __restrict__ mean,
+                                                          const double* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float eps, double N, int training, float* __restrict__ zs, float* __restrict__ zt,
+                                                          float* __restrict__ ca, float* __restrict__ cb, float* __restrict__ cd,
+                                                          float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = mean[c], rstd = 1.0 / sqrt(var[c] + (double)eps), g = gamma ? (double)gamma[c] : 1.0;
+  if (zs) {
+    zs[c] = (float)(g * rstd);
+    zt[c] = (float)((beta ? (double)beta[c] : 0.0) - m * g * rstd);
+  }
+  if (!sums) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = 0; b < B; ++b) {
+    s1 += (double)sums[((int64_t)b * C + c) * 2];
+    s2 += (double)sums[((int64_t)b * C + c) * 2 + 1];
+  }
+  const double sgx = (s2 - m * s1) * rstd;
+  ca[c] = (float)(g * rstd);
+  if (training) {
+    const double b_ = -g * rstd * rstd * sgx / N;
+    cb[c] = (float)b_;
+    cd[c] = (float)(-g * rstd * s1 / N - b_ * m);
+  }
+  dgamma[c] = (float)sgx;
+  dbeta[c] = (float)s1;
+}
+
 }  // namespace
 }  // namespace vrcoc
 
 using namespace vrcoc;
+
+extern "C" int vrcoc_bn_stats(const float* chan_sums, int B, int C, double count, const float* gamma, const float* beta, float eps, float momentum,
+                              float* running_mean, float* running_var, long long* num_batches_tracked, float* scale, float* shift,
+                              double* mean_out, double* var_out, void* stream) {
+  VRCOC_REQUIRE(chan_sums && B > 0 && C > 0 && count > 0, "bn_stats: bad argument");
+  VRCOC_REQUIRE((scale == nullptr) == (shift == nullptr) && (mean_out == nullptr) == (var_out == nullptr) &&
+                (running_mean == nullptr) == (running_var == nullptr), "bn_stats: outputs come in pairs");
+  bn_stats_kernel<<<(unsigned)cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(chan_sums, B, C, count, gamma, beta, eps, momentum, running_mean,
+                                                                            running_var, num_batches_tracked, scale, shift, mean_out, var_out);
+  return check_launch("bn_stats");
+}
+
+extern "C" int vrcoc_bn_bwd_coef(const float* sums, int B, int C, const double* mean, const double* var, const float* gamma, const float* beta,
+                                 float eps, double N, int training, float* zs, float* zt, float* ca, float* cb, float* cd, float* dgamma,
+                                 float* dbeta, void* stream) {
+  VRCOC_REQUIRE(mean && var && C > 0 && N > 0, "bn_bwd_coef: bad argument");
+  VRCOC_REQUIRE((zs == nullptr) == (zt == nullptr), "bn_bwd_coef: zs / zt come as a pair");
+  VRCOC_REQUIRE(!sums || (B > 0 && ca && dgamma && dbeta && (!training || (cb && cd))), "bn_bwd_coef: null coefficient output");
+  bn_bwd_coef_kernel<<<(unsigned)cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, B, C, mean, var, gamma, beta, eps, N, training, zs, zt, ca, cb,
+                                                                               cd, dgamma, dbeta);
+  return check_launch("bn_bwd_coef");
+}
 
 extern "C" int vrcoc_decode_outputs(const void* p3, const void* p4, const void* p5, int dtype, int B, int channels, int h3, int w3, int h4,
                                     int w4, int h5, int w5, int input_h, int input_w, float* out, void* stream) {

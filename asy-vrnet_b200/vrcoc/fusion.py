@@ -69,6 +69,20 @@ def _bn_affine(bn, chan_sums=None, count=None):
         # per-replica statistics and must not silently pretend otherwise
         raise VrcocError("SyncBatchNorm inside a native BaseConv / fusion module is not supported (per-replica batch statistics only): "
                          "train with sync_bn=False (the reference default, train.py:51)")
+    if use_batch and chan_sums.is_cuda and chan_sums.dtype == torch.float32 and chan_sums.is_contiguous() and \
+            (not bn.track_running_stats or (bn.running_mean.dtype == torch.float32 and bn.momentum is not None)):
+        # one launch (csrc/bwd.cu: bn_stats_kernel) for what follows below as ~22 library launches on [C]-sized tensors
+        B_, C_ = chan_sums.shape[0], chan_sums.shape[1]
+        g32, b32 = wb()
+        sc = torch.empty(C_, device=chan_sums.device, dtype=torch.float32)
+        sh = torch.empty_like(sc)
+        upd = bn.training and bn.track_running_stats
+        with torch.no_grad():
+            check(lib.vrcoc_bn_stats(_ptr(chan_sums), B_, C_, float(count), _ptr(g32), _ptr(b32), float(bn.eps),
+                                     float(bn.momentum) if upd else -1.0, _ptr(bn.running_mean) if upd else None,
+                                     _ptr(bn.running_var) if upd else None, _ptr(bn.num_batches_tracked) if upd else None,
+                                     _ptr(sc), _ptr(sh), None, None, _stream()), "bn_stats")
+        return sc, sh
     if use_batch:
         s = chan_sums.double().sum(0)                       # [C,2]
         n = float(count)
@@ -199,12 +213,32 @@ def _bn_coefficients(S, mean, rstd, gamma, N, training):
     return ca.float().contiguous(), None, None, sgx.float(), S1.float()
 
 
+def _stats_from_sums(cs, n):
+    """biased batch mean / variance per channel (fp64 [C]) from per-(b, c) sums [B, C, 2]"""
+    B, C = cs.shape[0], cs.shape[1]
+    if cs.is_cuda and cs.dtype == torch.float32 and cs.is_contiguous():
+        mean = torch.empty(C, device=cs.device, dtype=torch.float64)
+        var = torch.empty_like(mean)
+        check(lib.vrcoc_bn_stats(_ptr(cs), B, C, float(n), None, None, 0.0, -1.0, None, None, None, None, None, _ptr(mean), _ptr(var), _stream()),
+              "bn_stats")
+        return mean, var
+    s = cs.double().sum(0)
+    mean = s[:, 0] / n
+    return mean, (s[:, 1] / n - mean * mean).clamp_min(0)
+
+
 def _batch_stats(u):
     """biased batch mean / variance per channel (fp64 [C]) from the native channel sums"""
     B, C, H, W = u.shape
     cs, _ = ops.channel_sums(u)
-    s = cs.double().sum(0)
     n = float(B * H * W)
+    if cs.is_cuda and cs.dtype == torch.float32 and cs.is_contiguous():
+        mean = torch.empty(C, device=u.device, dtype=torch.float64)
+        var = torch.empty_like(mean)
+        check(lib.vrcoc_bn_stats(_ptr(cs), B, C, n, None, None, 0.0, -1.0, None, None, None, None, None, _ptr(mean), _ptr(var), _stream()),
+              "bn_stats")
+        return mean, var
+    s = cs.double().sum(0)
     mean = s[:, 0] / n
     return mean, (s[:, 1] / n - mean * mean).clamp_min(0)
 
@@ -216,10 +250,35 @@ def _norm_act_backward(dy, y_act, u, act, bn_w, bn_b, mean, var, eps, training, 
     dy = dy.contiguous()
     if dy.dtype != u.dtype:
         dy = dy.to(u.dtype)
+    need_z = act == ACT_SILU or (act in (ACT_RELU, ACT_LRELU) and y_act is None)
+    if u.is_cuda and mean.dtype == torch.float64 and var.dtype == torch.float64 and mean.is_contiguous() and var.is_contiguous():
+        # two launches of bn_bwd_coef_kernel around the sums pass instead of ~30 library launches on [C]-sized tensors
+        dev = u.device
+        g32 = bn_w.detach().float().contiguous() if bn_w is not None else None
+        b32 = bn_b.detach().float().contiguous() if bn_b is not None else None
+        zs = zt = None
+        if need_z:
+            zs = torch.empty(C, device=dev, dtype=torch.float32)
+            zt = torch.empty_like(zs)
+            check(lib.vrcoc_bn_bwd_coef(None, B, C, _ptr(mean), _ptr(var), _ptr(g32), _ptr(b32), float(eps), float(N), int(training), _ptr(zs),
+                                        _ptr(zt), None, None, None, None, None, _stream()), "bn_bwd_coef")
+        ya = y_act if act in (ACT_RELU, ACT_LRELU) else None
+        sums = torch.empty(B, C, 2, device=dev, dtype=torch.float32)
+        check(lib.vrcoc_chan_bwd_sums(_ptr(dy), _ptr(ya), _ptr(u), _dt(u), act, _ptr(zs), _ptr(zt), B, C, HW, _ptr(sums), _stream()), "chan_bwd_sums")
+        ca = torch.empty(C, device=dev, dtype=torch.float32)
+        cb = torch.empty_like(ca) if training else None
+        cd = torch.empty_like(ca) if training else None
+        dgamma, dbeta = torch.empty_like(ca), torch.empty_like(ca)
+        check(lib.vrcoc_bn_bwd_coef(_ptr(sums), B, C, _ptr(mean), _ptr(var), _ptr(g32), _ptr(b32), float(eps), float(N), int(training), None, None,
+                                    _ptr(ca), _ptr(cb), _ptr(cd), _ptr(dgamma), _ptr(dbeta), _stream()), "bn_bwd_coef")
+        du = torch.empty_like(u)
+        check(lib.vrcoc_chan_bwd_apply(_ptr(dy), _ptr(ya), _ptr(u), _ptr(extra), _ptr(du), _dt(u), act, _ptr(ca), _ptr(cb), _ptr(cd), _ptr(zs),
+                                       _ptr(zt), B, C, HW, _stream()), "chan_bwd_apply")
+        return du, dgamma, dbeta
     rstd = torch.rsqrt(var + eps)
     gamma = bn_w.detach().double() if bn_w is not None else torch.ones_like(mean)
     zs = zt = None
-    if act == ACT_SILU or (act in (ACT_RELU, ACT_LRELU) and y_act is None):
+    if need_z:
         # the activation derivative from the recomputed pre-activation z = u * zs + zt
         beta = bn_b.detach().double() if bn_b is not None else torch.zeros_like(mean)
         zs = (gamma * rstd).float().contiguous()
@@ -748,10 +807,7 @@ class _ImageEnhanceFn(torch.autograd.Function):
         check(lib.vrcoc_img_enh_finish(_ptr(k), _dt(k), _ptr(image), _dt(image), _ptr(yv), _dt(yv), _ptr(minmax), None, None, B, Ci, HW,
                                        _ptr(cs), _stream()), "img_enh_finish")
         if t2:
-            s = cs.double().sum(0)
-            n = float(B * HW)
-            mean2 = s[:, 0] / n
-            var2 = (s[:, 1] / n - mean2 * mean2).clamp_min(0)
+            mean2, var2 = _stats_from_sums(cs, float(B * HW))
         else:
             mean2, var2 = rm2.double(), rv2.double()
         dyv, dg2, db2 = _norm_act_backward(dy, None, yv, ACT_NONE, g2, b2, mean2, var2, eps2, t2)
@@ -923,10 +979,7 @@ class _RadarEnhanceFn(torch.autograd.Function):
         check(lib.vrcoc_chan_affine(_ptr(u), _dt(u), _ptr(radar), _dt(radar), _ptr(t), _dt(t), _ptr(s1), _ptr(sh1), ACT_RELU, None, None,
                                     B, Cr, HW, _ptr(cs_t), None, _stream()), "chan_affine")
         if t2:
-            sm = cs_t.double().sum(0)
-            n = float(B * HW)
-            mean2 = sm[:, 0] / n
-            var2 = (sm[:, 1] / n - mean2 * mean2).clamp_min(0)
+            mean2, var2 = _stats_from_sums(cs_t, float(B * HW))
         else:
             mean2, var2 = rm2.double(), rv2.double()
         dt, dg2, db2 = _norm_act_backward(dy, None, t, ACT_NONE, g2, b2, mean2, var2, eps2, t2)

@@ -324,6 +324,18 @@ int vrcoc_img_enh_bwd(const void* dyv, const void* image, const void* k, int dty
 int vrcoc_minmax_scatter(const void* k, void* dk, int dtype, const uint32_t* minmax, const float* coef /*device [2]*/, int64_t n,
                          void* stream);
 
+/* BatchNorm2d bookkeeping of the training path (normal_conv.py:45-49; vr_coc.py:315,341,356), one launch each instead of 20-30
+ * [C]-sized library launches.
+ *   bn_stats   : per-(b,c) sums {sum x, sum x^2} [B][C][2] -> batch mean / biased variance (fp64, optional), the running-stat update
+ *                of nn.BatchNorm2d (momentum >= 0 and non-NULL running_*: unbiased variance; num_batches_tracked += 1 when given) and
+ *                the folded affine BN(x) = x*scale + shift (optional; gamma / beta may be NULL).
+ *   bn_bwd_coef: backward of y = act(BN(u)): z = u*zs + zt recomputes the pre-activation (optional outputs); with sums [B][C][2] =
+ *                {sum g, sum g*u}: du = g*ca + u*cb + cd (cb, cd only in training mode), dgamma, dbeta. */
+int vrcoc_bn_stats(const float* chan_sums, int B, int C, double count, const float* gamma, const float* beta, float eps, float momentum,
+                   float* running_mean, float* running_var, long long* num_batches_tracked, float* scale, float* shift, double* mean_out,
+                   double* var_out, void* stream);
+int vrcoc_bn_bwd_coef(const float* sums, int B, int C, const double* mean, const double* var, const float* gamma, const float* beta, float eps,
+                      double N, int training, float* zs, float* zt, float* ca, float* cb, float* cd, float* dgamma, float* dbeta, void* stream);
 /* YOLOX decode of the three detection maps [B][channels][h][w] (channels = 4 box + 1 objectness + classes) into
  * out [B][h3*w3 + h4*w4 + h5*w5][channels] fp32, normalised box centre / size + sigmoid scores: utils/utils_bbox.py:32-84
  * (decode_outputs) in one launch, no intermediate cat / permute / grid tensors. */
