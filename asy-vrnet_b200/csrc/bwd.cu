@@ -168,6 +168,52 @@ __global__ void __launch_bounds__(256) col2im3_s1_bf16_kernel(const __nv_bfloat1
   st8<__nv_bfloat16>(dx + ((b * C + c) * (int64_t)H + y) * W + x0, acc);
 }
 
+// 3x3 / stride 2 / pad 1 / bf16 (the point reducers between the stages, vr_coc.py:83-102): input column x takes tap kx = 1 from output
+// column x/2 when x is even, taps kx = 0 and kx = 2 from output columns (x+1)/2 and (x-1)/2 when it is odd, and the same for the rows;
+// one thread = 8 consecutive input columns of one row = four output columns per tap plane (one aligned 8-byte load each, plus one
+// halo element for kx = 0), instead of a 9-tap scalar gather with a division and a modulo per tap and element.
+__global__ void __launch_bounds__(256) col2im3_s2_bf16_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx, int C, int H, int W,
+                                                              int Ho, int Wo, int64_t total8) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total8) return;
+  const int w8 = W >> 3;
+  const int x0 = (int)(t % w8) * 8, y = (int)((t / w8) % H), c = (int)((t / ((int64_t)w8 * H)) % C);
+  const int64_t b = t / ((int64_t)w8 * H * C);
+  const int64_t plane = (int64_t)Ho * Wo;
+  const __nv_bfloat16* base = dcol + b * 9 * (int64_t)C * plane;
+  const int ox0 = x0 >> 1;                                            // multiple of 4: the 8-byte loads below are aligned
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  auto load4 = [&](const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+    const float2 bb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    v[0] = a.x; v[1] = a.y; v[2] = bb.x; v[3] = bb.y;
+  };
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int ty = y + 1 - ky;
+    if (ty < 0 || (ty & 1)) continue;
+    const int oy = ty >> 1;
+    if (oy >= Ho) continue;
+    const __nv_bfloat16* r0 = base + ((int64_t)(ky * 3 + 0) * C + c) * plane + (int64_t)oy * Wo;
+    const __nv_bfloat16* r1 = r0 + (int64_t)C * plane;
+    const __nv_bfloat16* r2 = r1 + (int64_t)C * plane;
+    float v[4];
+    load4(r1 + ox0, v);                                               // kx = 1: even columns x0 + 2i <- output column ox0 + i
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[2 * i] += v[i];
+    load4(r2 + ox0, v);                                               // kx = 2: odd columns x0 + 2i + 1 <- output column ox0 + i
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[2 * i + 1] += v[i];
+    load4(r0 + ox0, v);                                               // kx = 0: odd columns x0 + 2i + 1 <- output column ox0 + i + 1
+    const float edge = ox0 + 4 < Wo ? __bfloat162float(r0[ox0 + 4]) : 0.f;
+    acc[1] += v[1]; acc[3] += v[2]; acc[5] += v[3]; acc[7] += edge;
+  }
+  st8<__nv_bfloat16>(dx + ((b * C + c) * (int64_t)H + y) * W + x0, acc);
+}
+
 // act'(.) evaluated from the forward OUTPUT y of the activation (relu / lrelu: sign of y; none: 1); SiLU needs the
 // pre-activation z = u * zs[c] + zt[c] (the normalised convolution output), recomputed from u
 __device__ __forceinline__ float act_grad_from_out(float y, int act) {
@@ -680,6 +726,12 @@ extern "C" int vrcoc_col2im(const void* dcol, void* dx, int dtype, int B, int C,
     const int64_t total8 = total >> 3;
     col2im3_s1_bf16_kernel<<<(unsigned)cdiv(total8, 256), 256, 0, st>>>((const __nv_bfloat16*)dcol, (__nv_bfloat16*)dx, C, H, W, total8);
     return check_launch("col2im3");
+  }
+  if (dtype == VRCOC_BF16 && kh == 3 && kw == 3 && stride == 2 && pad == 1 && dil == 1 && (W & 7) == 0 && (H & 1) == 0 && Wo * 2 == W && Ho * 2 == H &&
+      ((reinterpret_cast<uintptr_t>(dcol) & 7) | (reinterpret_cast<uintptr_t>(dx) & 15)) == 0) {
+    const int64_t total8 = total >> 3;
+    col2im3_s2_bf16_kernel<<<(unsigned)cdiv(total8, 256), 256, 0, st>>>((const __nv_bfloat16*)dcol, (__nv_bfloat16*)dx, C, H, W, Ho, Wo, total8);
+    return check_launch("col2im3s2");
   }
   if (dtype == VRCOC_BF16)
     col2im_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)dcol, (__nv_bfloat16*)dx, C, H, W, kh, kw, stride, pad, dil, Ho, Wo, total);

@@ -445,6 +445,22 @@ def test_col2im_3x3_stride1_bf16_is_fold(V, shape):
     assert (dx.float() - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item()          # one bf16 rounding of a 9-term fp32 sum
 
 
+@pytest.mark.parametrize("shape", [(2, 16, 32, 32), (1, 8, 16, 24), (2, 5, 8, 8)])
+def test_col2im_3x3_stride2_bf16_is_fold(V, shape):
+    """the 64-bit-load col2im path of the point reducers (3x3, stride 2, pad 1, bf16) = F.fold of the same columns"""
+    import torch.nn.functional as F
+    from vrcoc import ops
+    B, C, H, W = shape
+    Ho, Wo = H // 2, W // 2
+    g = torch.Generator().manual_seed(17)
+    dcol = torch.randn(B, 9 * C, Ho, Wo, generator=g).cuda().bfloat16()
+    dx = torch.empty(B, C, H, W, device="cuda", dtype=torch.bfloat16)
+    ops.check(ops.lib.vrcoc_col2im(dcol.data_ptr(), dx.data_ptr(), 1, B, C, H, W, 3, 3, 2, 1, 1, ops._stream()), "col2im")
+    cols = dcol.float().view(B, 9, C, Ho * Wo).permute(0, 2, 1, 3).reshape(B, C * 9, Ho * Wo)
+    ref = F.fold(cols, output_size=(H, W), kernel_size=3, padding=1, stride=2)
+    assert (dx.float() - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item()
+
+
 def test_upsample_rows_kernel_shapes(V):
     """the two-pass (strip) kernel at the live shapes (16->32 ... 128->512, also 256->1024) against F.interpolate in fp32, and in
     bf16 against the fp32 result rounded once (the kernel interpolates in fp32 and rounds the output only)"""
