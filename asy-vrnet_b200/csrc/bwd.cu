@@ -214,6 +214,29 @@ __global__ void __launch_bounds__(256) col2im3_s2_bf16_kernel(const __nv_bfloat1
   st8<__nv_bfloat16>(dx + ((b * C + c) * (int64_t)H + y) * W + x0, acc);
 }
 
+// k x k / stride k / pad 0 / bf16, k = 4 (the patch embedding, vr_coc.py:582-586): a permutation — input pixel (y, x) is tap (y % 4, x % 4) of
+// output pixel (y / 4, x / 4); one thread = 8 consecutive input columns = two output columns of each of the four kx planes of its row's ky.
+__global__ void __launch_bounds__(256) col2im4_s4_bf16_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx, int C, int H, int W,
+                                                              int Ho, int Wo, int64_t total8) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total8) return;
+  const int w8 = W >> 3;
+  const int x0 = (int)(t % w8) * 8, y = (int)((t / w8) % H), c = (int)((t / ((int64_t)w8 * H)) % C);
+  const int64_t b = t / ((int64_t)w8 * H * C);
+  const int64_t plane = (int64_t)Ho * Wo;
+  const int ky = y & 3, oy = y >> 2, ox0 = x0 >> 2;                   // ox0 even: the 4-byte loads are aligned
+  const __nv_bfloat16* base = dcol + (b * 16 * (int64_t)C + (int64_t)(ky * 4) * C + c) * plane + (int64_t)oy * Wo + ox0;
+  float acc[8];
+#pragma unroll
+  for (int kx = 0; kx < 4; ++kx) {
+    const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)kx * C * plane));
+    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw));
+    acc[kx] = v.x;
+    acc[4 + kx] = v.y;
+  }
+  st8<__nv_bfloat16>(dx + ((b * C + c) * (int64_t)H + y) * W + x0, acc);
+}
+
 // act'(.) evaluated from the forward OUTPUT y of the activation (relu / lrelu: sign of y; none: 1); SiLU needs the
 // pre-activation z = u * zs[c] + zt[c] (the normalised convolution output), recomputed from u
 __device__ __forceinline__ float act_grad_from_out(float y, int act) {
@@ -726,6 +749,12 @@ extern "C" int vrcoc_col2im(const void* dcol, void* dx, int dtype, int B, int C,
     const int64_t total8 = total >> 3;
     col2im3_s1_bf16_kernel<<<(unsigned)cdiv(total8, 256), 256, 0, st>>>((const __nv_bfloat16*)dcol, (__nv_bfloat16*)dx, C, H, W, total8);
     return check_launch("col2im3");
+  }
+  if (dtype == VRCOC_BF16 && kh == 4 && kw == 4 && stride == 4 && pad == 0 && dil == 1 && (W & 7) == 0 && (H & 3) == 0 && Wo * 4 == W && Ho * 4 == H &&
+      ((reinterpret_cast<uintptr_t>(dcol) & 3) | (reinterpret_cast<uintptr_t>(dx) & 15)) == 0) {
+    const int64_t total8 = total >> 3;
+    col2im4_s4_bf16_kernel<<<(unsigned)cdiv(total8, 256), 256, 0, st>>>((const __nv_bfloat16*)dcol, (__nv_bfloat16*)dx, C, H, W, Ho, Wo, total8);
+    return check_launch("col2im4s4");
   }
   if (dtype == VRCOC_BF16 && kh == 3 && kw == 3 && stride == 2 && pad == 1 && dil == 1 && (W & 7) == 0 && (H & 1) == 0 && Wo * 2 == W && Ho * 2 == H &&
       ((reinterpret_cast<uintptr_t>(dcol) & 7) | (reinterpret_cast<uintptr_t>(dx) & 15)) == 0) {

@@ -461,6 +461,22 @@ def test_col2im_3x3_stride2_bf16_is_fold(V, shape):
     assert (dx.float() - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("shape", [(2, 5, 32, 32), (1, 3, 16, 24)])
+def test_col2im_4x4_stride4_bf16_is_fold(V, shape):
+    """the patch-embedding col2im path (4x4, stride 4, pad 0, bf16: a permutation) = F.fold of the same columns, exactly"""
+    import torch.nn.functional as F
+    from vrcoc import ops
+    B, C, H, W = shape
+    Ho, Wo = H // 4, W // 4
+    g = torch.Generator().manual_seed(19)
+    dcol = torch.randn(B, 16 * C, Ho, Wo, generator=g).cuda().bfloat16()
+    dx = torch.empty(B, C, H, W, device="cuda", dtype=torch.bfloat16)
+    ops.check(ops.lib.vrcoc_col2im(dcol.data_ptr(), dx.data_ptr(), 1, B, C, H, W, 4, 4, 4, 0, 1, ops._stream()), "col2im")
+    cols = dcol.float().view(B, 16, C, Ho * Wo).permute(0, 2, 1, 3).reshape(B, C * 16, Ho * Wo)
+    ref = F.fold(cols, output_size=(H, W), kernel_size=4, padding=0, stride=4)
+    assert torch.equal(dx.float(), ref)
+
+
 def test_upsample_rows_kernel_shapes(V):
     """the two-pass (strip) kernel at the live shapes (16->32 ... 128->512, also 256->1024) against F.interpolate in fp32, and in
     bf16 against the fp32 result rounded once (the kernel interpolates in fp32 and rounds the output only)"""
