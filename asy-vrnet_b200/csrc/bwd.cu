@@ -545,6 +545,58 @@ __global__ void __launch_bounds__(256) table_bwd_apply_kernel(const T* __restric
     stf<T>(out + base + i, one(ldf<T>(dzp + i), ldf<T>(x + base + i), extra ? ldf<T>(extra + base + i) : 0.f));
 }
 
+// ---- depthwise 3x3 / stride 1 / pad 1 weight gradient (the head's DWConv towers, normal_conv.py:23-33, decouplehead.py:24-37):
+//      dW[c][ky][kx] = sum_{b,y,x} dy[b][c][y][x] * x[b][c][y+ky-1][x+kx-1],  db[c] = sum dy.  One block per channel, a thread = 8
+//      columns of one row per step (dy vector, three x vectors + halos), fixed-order block reduction (deterministic).
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv3_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, int B, int C, int H, int W,
+                                                            float* __restrict__ dW, float* __restrict__ db) {
+  __shared__ float red[10][8];
+  const int c = blockIdx.x;
+  const int w8 = W >> 3;
+  const int per = H * w8;                                             // 8-column row segments per (b, c) plane
+  float acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+  for (int t = threadIdx.x; t < B * per; t += blockDim.x) {
+    const int b = t / per, r = t - b * per, y = r / w8, x0 = (r - y * w8) * 8;
+    const int64_t pl = ((int64_t)b * C + c) * H * W;
+    float g[8];
+    ld8<T>(dy + pl + (int64_t)y * W + x0, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[9] += g[j];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = y + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+      const T* row = x + pl + (int64_t)iy * W;
+      float v[10], mid[8];
+      ld8<T>(row + x0, mid);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j + 1] = mid[j];
+      v[0] = x0 > 0 ? ldf<T>(row + x0 - 1) : 0.f;
+      v[9] = x0 + 8 < W ? ldf<T>(row + x0 + 8) : 0.f;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[ky * 3 + kx] = fmaf(g[j], v[j + kx], acc[ky * 3 + kx]);
+    }
+  }
+  const int w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const float v = warp_sum(acc[i]);
+    if ((threadIdx.x & 31) == 0) red[i][w] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    float t = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[threadIdx.x][k];
+    if (threadIdx.x < 9) dW[c * 9 + threadIdx.x] = t;
+    else if (db) db[c] = t;
+  }
+}
+
 // ---- BatchNorm2d bookkeeping of the training path as two tiny kernels (normal_conv.py:45-49, vr_coc.py:315,341,356).  The host
 //      side did this algebra with torch ops on [C]-sized tensors: ~22 launches per BatchNorm forward (batch statistics, running-stat
 //      update, folded scale / shift) and ~30 per backward, ~65 BatchNorms per step = ~3000 of the 6800 launches of a training step.
@@ -614,6 +666,18 @@ __global__ void __launch_bounds__(128) bn_bwd_coef_kernel(const float* __restric
 }  // namespace vrcoc
 
 using namespace vrcoc;
+
+extern "C" int vrcoc_dwconv3_wgrad(const void* x, const void* dy, int dtype, int B, int C, int H, int W, float* dW, float* db, void* stream) {
+  VRCOC_REQUIRE(x && dy && dW && B > 0 && C > 0 && H > 0 && W > 0, "dwconv3_wgrad: bad argument");
+  VRCOC_REQUIRE((W & 7) == 0, "dwconv3_wgrad: the map width (%d) must be a multiple of 8", W);
+  const int es = dtype == VRCOC_F32 ? 4 : 2;
+  VRCOC_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & (8 * es - 1)) == 0, "dwconv3_wgrad: tensors must be aligned to 8 elements");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VRCOC_BF16) dwconv3_wgrad_kernel<__nv_bfloat16><<<C, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, B, C, H, W, dW, db);
+  else if (dtype == VRCOC_F32) dwconv3_wgrad_kernel<float><<<C, 256, 0, st>>>((const float*)x, (const float*)dy, B, C, H, W, dW, db);
+  else return fail(VRCOC_EINVAL, "dwconv3_wgrad: unsupported dtype %d", dtype);
+  return check_launch("dwconv3_wgrad");
+}
 
 extern "C" int vrcoc_bn_stats(const float* chan_sums, int B, int C, double count, const float* gamma, const float* beta, float eps, float momentum,
                               float* running_mean, float* running_var, long long* num_batches_tracked, float* scale, float* shift,

@@ -84,6 +84,7 @@ SIGNATURES = {
     "vrcoc_chan_bwd_apply": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "vrcoc_img_enh_bwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
     "vrcoc_minmax_scatter": (_I, [_P, _P, _I, _P, _P, _L, _P]),
+    "vrcoc_dwconv3_wgrad": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "vrcoc_bn_stats": (_I, [_P, _I, _I, C.c_double, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vrcoc_bn_bwd_coef": (_I, [_P, _I, _I, _P, _P, _P, _P, _F, C.c_double, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vrcoc_decode_outputs": (_I, [_P, _P, _P, _I] + [_I] * 10 + [_P, _P]),

@@ -347,9 +347,44 @@ def get_activation(name="silu", inplace=True):
     raise AttributeError("Unsupported act type: {}".format(name))
 
 
+@ops.amp_function
+class _DWConv3Fn(torch.autograd.Function):
+    """depthwise 3x3 / stride 1 / pad 1 with autograd on the native kernels: forward and input gradient = vrcoc_dwconv (the latter
+    on dy with the flipped kernel), weight / bias gradient = vrcoc_dwconv3_wgrad"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x = x.contiguous()
+        B, C, H, W = x.shape
+        w = weight.detach().to(x.dtype).reshape(C, 9).contiguous()
+        y = torch.empty_like(x)
+        check(lib.vrcoc_dwconv(_ptr(x), _ptr(w), _ptr(_f32(bias)), _ptr(y), _dt(x), B, C, H, W, 3, 1, 1, _stream()), "dwconv")
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        ctx.wshape = weight.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        B, C, H, W = x.shape
+        dy = dy.contiguous()
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            check(lib.vrcoc_dwconv(_ptr(dy), _ptr(w.flip(1).contiguous()), None, _ptr(dx), _dt(x), B, C, H, W, 3, 1, 1, _stream()), "dwconv")
+        dW = torch.empty(C, 9, device=x.device, dtype=torch.float32)
+        db = torch.empty(C, device=x.device, dtype=torch.float32) if ctx.has_bias else None
+        check(lib.vrcoc_dwconv3_wgrad(_ptr(x), _ptr(dy), _dt(x), B, C, H, W, _ptr(dW), _ptr(db), _stream()), "dwconv3_wgrad")
+        return dx, dW.reshape(ctx.wshape), db
+
+
 class DWConv(nn.Module):
     """reference normal_conv.py:23-33: depthwise k x k + pointwise 1x1.  Only used by the detection head (outside the
-    CoC/fusion hot path): the depthwise part is a cuDNN library call, the pointwise part is native."""
+    CoC/fusion hot path).  With autograd the 3x3 / stride-1 depthwise part runs on the native kernels (`_DWConv3Fn`); the
+    pointwise part is the nn.Conv2d module (BaseConv's gradient-free path folds it with BatchNorm into one native GEMM)."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, bias=True):
         super().__init__()
@@ -358,6 +393,10 @@ class DWConv(nn.Module):
         self.pconv = nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=1, groups=1, bias=bias)
 
     def forward(self, x):
+        d = self.dconv
+        if (x.is_cuda and d.kernel_size == (3, 3) and d.stride == (1, 1) and d.padding == (1, 1) and d.dilation == (1, 1)
+                and d.groups == x.shape[1] and x.shape[-1] % 8 == 0 and (x.dtype in (torch.float32, torch.bfloat16) or torch.is_autocast_enabled("cuda"))):
+            return self.pconv(_DWConv3Fn.apply(x, d.weight, d.bias))
         return self.pconv(self.dconv(x))
 
 

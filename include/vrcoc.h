@@ -324,6 +324,9 @@ int vrcoc_img_enh_bwd(const void* dyv, const void* image, const void* k, int dty
 int vrcoc_minmax_scatter(const void* k, void* dk, int dtype, const uint32_t* minmax, const float* coef /*device [2]*/, int64_t n,
                          void* stream);
 
+/* Weight (and bias) gradient of the depthwise 3x3 / stride 1 / pad 1 convolution of the head's DWConv towers (normal_conv.py:23-33):
+ * dW [C][3][3] fp32, db [C] fp32 (may be NULL); W % 8 == 0.  The input gradient is vrcoc_dwconv on dy with the flipped kernel. */
+int vrcoc_dwconv3_wgrad(const void* x, const void* dy, int dtype, int B, int C, int H, int W, float* dW, float* db, void* stream);
 /* BatchNorm2d bookkeeping of the training path (normal_conv.py:45-49; vr_coc.py:315,341,356), one launch each instead of 20-30
  * [C]-sized library launches.
  *   bn_stats   : per-(b,c) sums {sum x, sum x^2} [B][C][2] -> batch mean / biased variance (fp64, optional), the running-stat update

@@ -477,6 +477,26 @@ def test_col2im_4x4_stride4_bf16_is_fold(V, shape):
     assert torch.equal(dx.float(), ref)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+def test_dwconv_training_path_vs_conv2d(V, dtype, tol):
+    """DWConv with autograd: the native depthwise forward / input gradient / weight gradient against F.conv2d(groups=C) autograd"""
+    import torch.nn.functional as F
+    torch.manual_seed(3)
+    m = V.DWConv(16, 24, kernel_size=3, stride=1, padding=1, bias=True).cuda().to(dtype)
+    x = torch.randn(3, 16, 16, 24, device="cuda").to(dtype).requires_grad_(True)
+    g = torch.randn(3, 24, 16, 24, device="cuda").to(dtype)
+    y = m(x)
+    y.backward(g)
+    xr = x.detach().double().requires_grad_(True)
+    wd, bd = m.dconv.weight.detach().double().requires_grad_(True), m.dconv.bias.detach().double().requires_grad_(True)
+    yr = F.conv2d(F.conv2d(xr, wd, bd, padding=1, groups=16), m.pconv.weight.detach().double(), m.pconv.bias.detach().double())
+    yr.backward(g.double())
+    assert rel_err(y.float(), yr) < tol
+    assert rel_err(x.grad.float(), xr.grad) < tol
+    assert rel_err(m.dconv.weight.grad.float(), wd.grad) < tol
+    assert rel_err(m.dconv.bias.grad.float(), bd.grad) < tol
+
+
 def test_upsample_rows_kernel_shapes(V):
     """the two-pass (strip) kernel at the live shapes (16->32 ... 128->512, also 256->1024) against F.interpolate in fp32, and in
     bf16 against the fp32 result rounded once (the kernel interpolates in fp32 and rounds the output only)"""
