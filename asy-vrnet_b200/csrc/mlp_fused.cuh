@@ -18,6 +18,17 @@
 //                         of chunk j runs under the GELU of chunk j+1, one CTA per SM.
 #pragma once
 
+#ifndef VRCOC_MF_TRACE
+#define VRCOC_MF_TRACE 0   // 1: the MMA thread and epilogue warp 0 record their barrier wait cycles (tools/trace_mlpf.py --waits)
+#endif
+#if VRCOC_MF_TRACE
+#define MF_T0() t_ = clock64()
+#define MF_T1(acc) acc += clock64() - t_
+#else
+#define MF_T0()
+#define MF_T1(acc)
+#endif
+
 namespace vrcoc {
 
 constexpr int MF_THREADS = 320;                 // C <= 128: warps 0-7 epilogue, 8 TMA producer, 9 MMA issuer
@@ -88,25 +99,119 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8 || warp >= 10) {
-    // ---- TMA producers: X slabs, then the weight slabs in MMA order ---------------------------------------------------------------
-    // The weight stream of a CTA is nk1 + (nh-1)(nk1 + 2 MT2) + 2 MT2 boxes of 16 KB (110 at C = 320) and ONE issuing thread
-    // sustains one box per ~0.33 us whatever its size (tools/tma_bw_probe.cu): at C > 128 that alone was 36 of the 57 us of a
-    // stage-3 launch.  There the sequence is dealt round-robin to three producer warps (step `it` belongs to producer it % 3);
-    // a step's ring slot and barrier phases follow from `it` alone, so the producers share no state.
-    const int NP = SINGLE ? 1 : MF_PRODUCERS_WIDE;
-    const int prod = warp == 8 ? 0 : warp - 9;                         // 0, 1, 2
+  if (!SINGLE && (warp == 8 || warp == 10)) {
+    // ---- C > 128: TWO weight rings, one per GEMM, each with its own producer and its own MMA-issuing warp ----------------------
+    // The barrier-wait trace of the single-issuer form (tools/trace_mlpf.py on a VRCOC_MF_TRACE build, stage 3: C = 320) showed
+    // the MMA thread waiting for weights 4 us, for the epilogue 4 us and ISSUING for 27 of the 39 us of its loop: 0.24 us per
+    // 16 KB slab (4 MMAs + barrier wait + commit, ~65 dependent SASS instructions on a scheduler it shares with two GELU warps)
+    // against 0.13 us of tensor-pipe time.  The two GEMMs of a chunk write different accumulators, so they are issued by two
+    // warps on different schedulers: warp 9 = first GEMM (W1 ring, stages [0, SA)), warp 11 = second GEMM (W2 ring, stages
+    // [SA, ST)); warp 8 feeds ring A (and X), warp 10 ring B.
+    const int SA = ST / 2, SB = ST - SA;
     if (lane == 0) {
-      if (prod == 0) {
+      if (warp == 8) {
         for (int kc = 0; kc < nk1; ++kc) {
           mbar_expect_tx(&x_full[kc], (uint32_t)TQ_X_BYTES);
           tma_load_3d(sX + kc * TQ_X_BYTES, &tmapX, p0, kc * TC_BK, b, &x_full[kc]);
           tma_load_3d(sX + kc * TQ_X_BYTES + TC_A_LBO, &tmapX, p0 + 64, kc * TC_BK, b, &x_full[kc]);
         }
+        int sl = 0;
+        uint32_t ph = 1;                                               // parity of the slot's previous phase: passes on a fresh barrier
+        for (int j = 0; j < nh; ++j)
+          for (int kc = 0; kc < nk1; ++kc) {
+            mbar_wait(&bar_free[sl], ph);
+            mbar_expect_tx(&bar_full[sl], (uint32_t)TQ_W_BYTES);
+            tma_load_2d(ring + sl * TQ_W_BYTES, &tmapW1, kc * TC_BK, j * TQ_MT, &bar_full[sl]);
+            if (++sl == SA) { sl = 0; ph ^= 1u; }
+          }
+      } else {
+        int sl = 0;
+        uint32_t ph = 1;
+        for (int j = 0; j < nh; ++j)
+          for (int q = 0; q < 2 * MT2; ++q) {
+            mbar_wait(&bar_free[SA + sl], ph);
+            mbar_expect_tx(&bar_full[SA + sl], (uint32_t)TQ_W_BYTES);
+            tma_load_2d(ring + (SA + sl) * TQ_W_BYTES, &tmapW2, j * TQ_MT + (q & 1) * TC_BK, (q >> 1) * TQ_MT, &bar_full[SA + sl]);
+            if (++sl == SB) { sl = 0; ph ^= 1u; }
+          }
+      }
+    }
+    __syncwarp();
+  } else if (!SINGLE && (warp == 9 || warp == 11)) {
+    // ---- C > 128: MMA issuers (warp 9: hidden = W1 . X per chunk; warp 11: out += W2 . H per chunk) --------------------------------
+    const int SA = ST / 2, SB = ST - SA;
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_cm(TQ_NP);
+      const uint32_t acc1 = tmem_base, acc2 = tmem_base + TQ_NP;
+      int sl = 0;
+      uint32_t ph = 0;
+#if VRCOC_MF_TRACE
+      long long tw_ = 0, ta_ = 0, th_ = 0, t_; const long long tl0_ = clock64();
+      unsigned long long* q_ = g_tc_trace ? g_tc_trace + 4096 * 8 + (blockIdx.z * (size_t)gridDim.x + blockIdx.x) * 8 : nullptr;
+#endif
+      if (warp == 9) {
+        for (int j = 0; j < nh; ++j) {
+          if (j > 0) {
+            MF_T0();
+            mbar_wait(acc1_empty, (uint32_t)(j - 1) & 1);              // the epilogue warps have read hidden chunk j-1 out of TMEM
+            MF_T1(ta_);
+            tc_fence_after();
+          }
+          for (int kc = 0; kc < nk1; ++kc) {
+            if (j == 0) mbar_wait(&x_ready[kc], 0);
+            MF_T0();
+            mbar_wait(&bar_full[sl], ph);
+            MF_T1(tw_);
+            tc_fence_after();
+            tc_issue_slab<32 / 16, 2048 / 16>(acc1, tc_desc_lo(smem_u32(ring + sl * TQ_W_BYTES), 16),
+                                              tc_desc_lo(smem_u32(sX + kc * TQ_X_BYTES), TC_A_LBO), idesc, kc == 0 ? 0u : 1u, 4);
+            tc_commit(&bar_free[sl]);
+            if (++sl == SA) { sl = 0; ph ^= 1u; }
+          }
+          tc_commit(acc1_full);
+        }
+#if VRCOC_MF_TRACE
+        if (q_) { q_[0] = tw_; q_[1] = ta_; q_[3] = clock64() - tl0_; }
+#endif
+      } else {
+        for (int j = 0; j < nh; ++j) {
+          const int hb = j % HB;
+          MF_T0();
+          mbar_wait(&h_full[hb], (uint32_t)(j / HB) & 1);              // hidden chunk j is in shared memory (bf16 operand layout)
+          MF_T1(th_);
+          tc_fence_after();
+          const uint32_t hbuf = smem_u32(sH + hb * 2 * TQ_X_BYTES);
+          for (int q = 0; q < 2 * MT2; ++q) {
+            MF_T0();
+            mbar_wait(&bar_full[SA + sl], ph);
+            MF_T1(tw_);
+            tc_fence_after();
+            tc_issue_slab<32 / 16, 2048 / 16>(acc2 + (uint32_t)((q >> 1) * TQ_NP), tc_desc_lo(smem_u32(ring + (SA + sl) * TQ_W_BYTES), 16),
+                                              tc_desc_lo(hbuf + (uint32_t)((q & 1) * TQ_X_BYTES), TC_A_LBO), idesc,
+                                              (j == 0 && (q & 1) == 0) ? 0u : 1u, 4);
+            tc_commit(&bar_free[SA + sl]);
+            if (++sl == SB) { sl = 0; ph ^= 1u; }
+          }
+          tc_commit(&h_empty[hb]);
+          if (j == nh - 1) tc_commit(acc2_full);
+        }
+#if VRCOC_MF_TRACE
+        if (q_) { q_[2] = th_; q_[7] = tw_; }
+#endif
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
+    // ---- C <= 128: TMA producer: X slabs, then the weight slabs in MMA order --------------------------------------------------------
+    if (lane == 0) {
+      for (int kc = 0; kc < nk1; ++kc) {
+        mbar_expect_tx(&x_full[kc], (uint32_t)TQ_X_BYTES);
+        tma_load_3d(sX + kc * TQ_X_BYTES, &tmapX, p0, kc * TC_BK, b, &x_full[kc]);
+        tma_load_3d(sX + kc * TQ_X_BYTES + TC_A_LBO, &tmapX, p0 + 64, kc * TC_BK, b, &x_full[kc]);
       }
       const int bs = nk1 + 2 * MT2;                                    // steps of one hidden chunk: W1 of the NEXT chunk, then its own W2
       const int total = nk1 + (nh - 1) * bs + 2 * MT2;
-      for (int it = prod; it < total; it += NP) {
+      for (int it = 0; it < total; ++it) {
         const CUtensorMap* map;
         int x, y;
         if (it < nk1) {
@@ -134,8 +239,13 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
       const uint32_t acc1 = tmem_base, acc2 = tmem_base + TQ_NP;
       int s = 0;                                                       // ring slot and phase, advanced without divisions
       uint32_t ph = 0;
+#if VRCOC_MF_TRACE
+      long long tw_ = 0, ta_ = 0, th_ = 0, t_; const long long tl0_ = clock64();
+#endif
       auto slab = [&](uint32_t tacc, uint32_t x_addr, bool first) {
+        MF_T0();
         mbar_wait(&bar_full[s], ph);
+        MF_T1(tw_);
         tc_fence_after();
         const uint32_t w_addr = smem_u32(ring + s * TQ_W_BYTES);
         tc_issue_slab<32 / 16, 2048 / 16>(tacc, tc_desc_lo(w_addr, 16), tc_desc_lo(x_addr, TC_A_LBO), idesc, first ? 0u : 1u, 4);
@@ -152,12 +262,16 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
       gemm1(0);
       for (int j = 0; j < nh; ++j) {
         if (j + 1 < nh) {
+          MF_T0();
           mbar_wait(acc1_empty, (uint32_t)j & 1);                      // the epilogue warps have read hidden chunk j out of TMEM
+          MF_T1(ta_);
           tc_fence_after();
           gemm1(j + 1);
         }
         const int hb = j % HB;
+        MF_T0();
         mbar_wait(&h_full[hb], (uint32_t)(j / HB) & 1);                // hidden chunk j is in shared memory (bf16 operand layout)
+        MF_T1(th_);
         tc_fence_after();
         unsigned char* hbuf = sH + hb * 2 * TQ_X_BYTES;
         for (int m = 0; m < MT2; ++m) {
@@ -167,6 +281,12 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
         tc_commit(&h_empty[hb]);
         if (j == nh - 1) tc_commit(acc2_full);
       }
+#if VRCOC_MF_TRACE
+      if (g_tc_trace) {
+        unsigned long long* q = g_tc_trace + 4096 * 8 + (blockIdx.z * (size_t)gridDim.x + blockIdx.x) * 8;
+        q[0] = tw_; q[1] = ta_; q[2] = th_; q[3] = clock64() - tl0_;
+      }
+#endif
     }
     __syncwarp();
   } else {
@@ -201,12 +321,21 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
     const int sw = lane & 7;
     unsigned char* out_region = sX + (lq >> 1) * TQ_X_BYTES + ch * TC_A_LBO + (lq & 1) * 4096;   // [32 channels][64 points] of X
     const uint32_t tbase = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * (TQ_NP / 2));
+#if VRCOC_MF_TRACE
+    long long ea_ = 0, eh_ = 0, et_; const long long el0_ = clock64();
+#endif
     for (int j = 0; j < nh; ++j) {
       const float bias = __ldg(b1 + j * TQ_MT + lq * 32 + lane);
       const int hb = j % HB;
       const uint32_t hbase = hbase0 + (uint32_t)(hb * 2 * TQ_X_BYTES);
       const uint64_t one2 = pk2(1.f, 1.f), bias2 = pk2(bias, bias);
+#if VRCOC_MF_TRACE
+      et_ = clock64();
+#endif
       mbar_wait(acc1_full, (uint32_t)j & 1);
+#if VRCOC_MF_TRACE
+      ea_ += clock64() - et_;
+#endif
       tc_fence_after();
       if (tid == 0 && j == 0) trace(3);
       if (MT2 == 1 && j == nh - 1 && lq * 32 < a2.O && lane == 0) {
@@ -238,7 +367,13 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
           float lo[8], hi[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) { lo[i] = y[i]; hi[i] = y[8 + i]; }
+#if VRCOC_MF_TRACE
+          et_ = clock64();
+#endif
           if (c == 0 && j >= HB) mbar_wait(&h_empty[hb], (uint32_t)(j / HB - 1) & 1);   // the second GEMM of chunk j-HB has read it
+#if VRCOC_MF_TRACE
+          eh_ += clock64() - et_;
+#endif
           sts128(hbase + (uint32_t)(((2 * c) ^ sw) << 4), pack8_bf16(lo));
           sts128(hbase + (uint32_t)(((2 * c + 1) ^ sw) << 4), pack8_bf16(hi));
         }
@@ -247,6 +382,12 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&h_full[hb])) : "memory");
     }
+#if VRCOC_MF_TRACE
+    if (g_tc_trace && tid == 0) {
+      unsigned long long* q = g_tc_trace + 4096 * 8 + (blockIdx.z * (size_t)gridDim.x + blockIdx.x) * 8;
+      q[4] = ea_; q[5] = eh_; q[6] = clock64() - el0_;
+    }
+#endif
     // ---- output: + b2, layer scale, residual, statistics, TMA store (staged in the warp's part of the X slab) ----------------------
     if (MT2 == 1)
       cm_epilogue<VRCOC_ACT_NONE, false, 2>(a2, tmem_base + TQ_NP, acc2_full, acc2_empty, &res_bar[warp], out_region, 0, &tmapO, &tmapO,

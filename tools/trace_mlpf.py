@@ -25,7 +25,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev); flush.zero_()
 fn()
 torch.cuda.synchronize()
 lib.vrcoc_debug_set_trace(None)
-t = tr.view(-1, 8).cpu()
+t = tr.view(-1, 8)[:4096].cpu()
 t = t[t[:, 0] > 0]
 t0 = t[:, 0].min()
 rel = (t[:, :6] - t0).double() / 1e3
@@ -36,3 +36,14 @@ for i in range(5):
     print(f"  {names[i]:>9s} -> {names[i + 1]:<9s} mean {d_[:, i].mean():7.2f} us   p90 {d_[:, i].quantile(0.9):7.2f}   max {d_[:, i].max():7.2f}")
 print(f"  final epilogue, warp 0: waiting for acc2 {t[:, 6].double().mean() / 1e3:.2f} us, draining {t[:, 7].double().mean() / 1e3:.2f} us")
 print(f"  CTA lifetime mean {(rel[:, 5] - rel[:, 0]).mean():.2f} us; start times: p50 {rel[:, 0].median():.1f} us, max {rel[:, 0].max():.1f} us")
+# VRCOC_MF_TRACE=1 build (VRCOC_LIB=.../libvrcoc_trace.so): barrier wait cycles of the MMA thread and of epilogue warp 0
+w = tr.view(-1, 8)[4096:4096 + 4096].cpu().double()
+w = w[w[:, 3] > 0]
+if len(w):
+    mhz = 1965.0
+    m = w.mean(0) / mhz
+    nh = O // 128
+    print(f"  MMA thread ({len(w)} CTAs, us per CTA): weights {m[0]:.2f}  acc1_empty {m[1]:.2f}  h_full {m[2]:.2f}  loop {m[3]:.2f}"
+          f"  -> issuing/other {m[3] - m[0] - m[1] - m[2]:.2f};  per chunk {m[3] / nh:.2f} us")
+    print(f"  epilogue warp 0: waiting acc1_full {m[4]:.2f}  h_empty {m[5]:.2f}  hidden loop {m[6]:.2f}  -> GELU work {m[6] - m[4] - m[5]:.2f}"
+          f" ({(m[6] - m[4] - m[5]) / nh:.2f} per chunk)")
