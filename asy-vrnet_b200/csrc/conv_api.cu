@@ -13,8 +13,17 @@ static int fill_args(const vrcoc_conv_desc* d, ConvArgs& a) {
                 "conv: non-positive dimension");
   VRCOC_REQUIRE(d->kh > 0 && d->kw > 0 && d->stride > 0 && d->pad >= 0, "conv: bad kernel geometry");
   const int dil = d->dil > 0 ? d->dil : 1;
-  VRCOC_REQUIRE(d->H_out == (d->H_in + 2 * d->pad - dil * (d->kh - 1) - 1) / d->stride + 1 &&
-                    d->W_out == (d->W_in + 2 * d->pad - dil * (d->kw - 1) - 1) / d->stride + 1,
+  const bool rowtap = d->k_order == 2;
+  if (rowtap) {
+    // vertical taps only (the horizontal ones are materialised in src0): padding applies to the rows, the map size is kept
+    VRCOC_REQUIRE(d->kw == 1 && (d->kh & 1) == 1 && d->stride == 1 && d->pad == dil * (d->kh - 1) / 2 && d->H_out == d->H_in &&
+                      d->W_out == d->W_in && d->C1 == 0 && !d->chan_src && !d->gn_sums && !d->table && !d->has_gate && !d->gn_fold_k1 &&
+                      d->src0_dtype == VRCOC_BF16 && d->weight_dtype == VRCOC_BF16 && (d->C0 % 64) == 0 && ((dil * d->W_in) % 8) == 0,
+                  "conv: row-tap mode (k_order 2) needs kw = 1, stride 1, pad = dil * (kh - 1) / 2, one bf16 source with C0 %% 64 == 0, "
+                  "dil * W %% 8 == 0 and no prologue");
+  }
+  VRCOC_REQUIRE(rowtap || (d->H_out == (d->H_in + 2 * d->pad - dil * (d->kh - 1) - 1) / d->stride + 1 &&
+                    d->W_out == (d->W_in + 2 * d->pad - dil * (d->kw - 1) - 1) / d->stride + 1),
                 "conv: output size %dx%d inconsistent with input %dx%d k=%dx%d s=%d p=%d", d->H_out, d->W_out, d->H_in, d->W_in,
                 d->kh, d->kw, d->stride, d->pad);
   VRCOC_REQUIRE(d->src0 && d->weight && d->out, "conv: null src0/weight/out");
@@ -51,6 +60,15 @@ static int fill_args(const vrcoc_conv_desc* d, ConvArgs& a) {
   bool src_al = aligned16(d->src0) && (d->src0_bstride * esize(d->src0_dtype)) % 16 == 0 &&
                 (d->C1 == 0 || (aligned16(d->src1) && (d->src1_bstride * esize(d->src1_dtype)) % 16 == 0));
   a.fast1x1 = one && a.P_in % 8 == 0 && src_al;
+  a.rt_taps = a.rt_C = a.rt_dil = a.rt_W = 0;
+  if (rowtap) {
+    // from here on a 1x1 projection over kh * C0 virtual channels; only the TMA kernels understand the virtual source
+    VRCOC_REQUIRE(src_al && a.P_in % 8 == 0, "conv: row-tap mode needs a 16-byte aligned source and H * W %% 8 == 0");
+    a.rt_taps = d->kh; a.rt_C = d->C0; a.rt_dil = dil; a.rt_W = d->W_in;
+    a.C0 = a.Cin = a.K = d->C0 * d->kh;
+    a.kh = a.kw = 1; a.pad = 0; a.dil = 1; a.k_order = 0;
+    a.fast1x1 = 1;
+  }
   a.vec_out = a.P_out % 8 == 0 && aligned16(d->out) && (d->O_split == d->O || aligned16(d->out2)) && (!d->res || aligned16(d->res));
   return VRCOC_OK;
 }
@@ -237,6 +255,10 @@ extern "C" int vrcoc_conv_fwd(const vrcoc_conv_desc* d, void* stream) {
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (a.gn_fold_k1) return launch_conv_tc(a, st);        // only the channel-major tcgen05 kernel implements the fold
+  if (a.rt_taps) {                                       // row-tap mode: shifted TMA boxes, tcgen05 kernels only
+    VRCOC_REQUIRE(conv_tc_supported(a), "conv: row-tap mode: the problem is not supported by the tcgen05 engine");
+    return launch_conv_tc(a, st);
+  }
   if (d->engine == 2) {
     VRCOC_REQUIRE(conv_tc_supported(a), "conv: tcgen05 engine forced but the problem is not supported by it");
     return launch_conv_tc(a, st);

@@ -24,6 +24,10 @@ struct ConvArgs {
   double* out_sample_sums; uint32_t* out_minmax;
   int fast1x1;  // 1x1, stride 1, no pad, P % 8 == 0, 16-byte aligned sources: vectorised slab loads
   int vec_out;  // P_out % 8 == 0 and aligned outputs: vectorised stores
+  // row-tap mode (vrcoc.h, k_order 2): src0 is the horizontal-tap expansion [B][rt_C][H][W] of a k x k convolution's input
+  // (vrcoc_im2col_rows); the GEMM runs as a 1x1 projection over K = rt_taps * rt_C virtual channels whose slab (tap ky, c0) is the
+  // TMA box of src0 shifted by (ky - rt_taps/2) * rt_dil rows (zero fill outside the map).  0 taps = off.
+  int rt_taps, rt_C, rt_dil, rt_W;
 };
 
 // GroupNorm(1, C) statistics of sample b from the slot-wise partial sums: every warp reduces the 32 slots with shuffles

@@ -453,6 +453,27 @@ __device__ __forceinline__ void trace(int slot) {
   if (tr) tr[((blockIdx.z * gridDim.y + blockIdx.y) * (size_t)gridDim.x + blockIdx.x) * 8 + slot] = gtime();
 }
 
+// One 64-point x 64-channel activation box (MN-major SW128 block).  Row-tap mode (ConvArgs::rt_taps): virtual channel k0 = (tap,
+// c0); the box is the one of the horizontal-tap expansion [P | rt_C | B] moved by whole rows in the flattened point index - a
+// multiple of 8 elements, so the 16-byte rule on the innermost box start holds - and the map's own bounds [0, P) zero-fill the
+// rows above / below the image.  (A 4-D [W | H | C | B] box does not work for W < 64: under SWIZZLE_128B every inner row of the
+// box takes a full 128-byte row of shared memory, tools/tma_box_probe.cu.)
+__device__ __forceinline__ void tma_load_xbox(const ConvArgs& a, void* dst, const CUtensorMap* map, int p, int k0, int b, uint64_t* bar) {
+  if (a.rt_taps) {
+    const int tap = k0 / a.rt_C, c0 = k0 - tap * a.rt_C;
+    tma_load_3d(dst, map, p + (tap - (a.rt_taps >> 1)) * a.rt_dil * a.rt_W, c0, b, bar);
+  } else {
+    tma_load_3d(dst, map, p, k0, b, bar);
+  }
+}
+// host side: the activation map of the TMA kernels, [P | C | B] (row-tap mode: C = the channels of the expansion, not the virtual K)
+static int encode_xmap(CUtensorMap* tm, const ConvArgs& a) {
+  cuuint64_t dims[3] = {(cuuint64_t)a.P_in, (cuuint64_t)(a.rt_taps ? a.rt_C : a.C0), (cuuint64_t)a.B};
+  cuuint64_t strides[2] = {(cuuint64_t)a.P_in * 2, (cuuint64_t)a.src0_bstride * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)TC_BK, 1};
+  return tma_encode(tm, VRCOC_BF16, a.src0, 3, dims, strides, box, true);
+}
+
 // ---- kernel 1: both operands by TMA, warp-specialised -----------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_tma_kernel(ConvArgs a, TcLayout L, const __grid_constant__ CUtensorMap tmapA,
                                                                  const __grid_constant__ CUtensorMap tmapB,
@@ -482,8 +503,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_tma_kernel(ConvArgs a, 
       if (kc >= NS) mbar_wait(&S.bar_free[s], (uint32_t)((kc / NS) - 1) & 1);
       mbar_expect_tx(&S.bar_full[s], (uint32_t)(TC_A_BYTES + L.b_bytes));
       unsigned char* As = S.sA + s * TC_A_BYTES;
-      tma_load_3d(As, &tmapA, p0, kc * TC_BK, b, &S.bar_full[s]);
-      tma_load_3d(As + TC_A_LBO, &tmapA, p0 + 64, kc * TC_BK, b, &S.bar_full[s]);
+      tma_load_xbox(a, As, &tmapA, p0, kc * TC_BK, b, &S.bar_full[s]);
+      tma_load_xbox(a, As + TC_A_LBO, &tmapA, p0 + 64, kc * TC_BK, b, &S.bar_full[s]);
       tma_load_2d(S.sB + s * L.b_bytes, &tmapB, kc * TC_BK, n0, &S.bar_full[s]);
     }
   } else if (tid == 32) {
@@ -1166,10 +1187,8 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
       if (rc) return rc;
     }
     if (cm.xmode != 2) {
-      cuuint64_t dims[3] = {(cuuint64_t)a.P_in, (cuuint64_t)a.C0, (cuuint64_t)a.B};
-      cuuint64_t strides[2] = {(cuuint64_t)a.P_in * 2, (cuuint64_t)a.src0_bstride * 2};
       cuuint32_t box[3] = {64, (cuuint32_t)TC_BK, 1};
-      int rc = encode(&tmX, a.src0, 3, dims, strides, box);
+      int rc = encode_xmap(&tmX, a);
       if (rc) return rc;
       if (a.C1 > 0) {                                                  // second source, in the second-output slot (cm_plan)
         cuuint64_t dims1[3] = {(cuuint64_t)a.P_in, (cuuint64_t)a.C1, (cuuint64_t)a.B};
@@ -1196,15 +1215,13 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   dim3 grid((unsigned)cdiv(a.P_out, TC_BM), (unsigned)cdiv(a.O, L.n_tile), (unsigned)a.B);
   if (tma_a_eligible(a)) {
     // activations [B][C][P] bf16; box = 64 points (128 B) x 64 channels, lands as one MN-major SW128 block
-    cuuint64_t dims[3] = {(cuuint64_t)a.P_in, (cuuint64_t)a.C0, (cuuint64_t)a.B};
-    cuuint64_t strides[2] = {(cuuint64_t)a.P_in * 2, (cuuint64_t)a.src0_bstride * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)TC_BK, 1};
-    int rc = encode(&tmA, a.src0, 3, dims, strides, box);
+    int rc = encode_xmap(&tmA, a);
     if (rc) return rc;
     set_smem(conv_tc_tma_kernel, L.total);
     conv_tc_tma_kernel<<<grid, TC_THREADS, L.total, st>>>(a, L, tmA, tmB, tmR, tmO);
     return check_launch("conv_tc_tma");
   }
+  VRCOC_REQUIRE(!a.rt_taps, "conv(tcgen05): row-tap mode reached a kernel without shifted TMA boxes (K %% 8, aligned bf16 weight needed)");
   if (persist_eligible(a, L)) {
     TpLayout T = tp_layout(a);
     dim3 pgrid((unsigned)cdiv(a.P_out, TC_BM), (unsigned)cdiv(a.O, T.n_range), (unsigned)a.B);

@@ -384,8 +384,8 @@ __global__ void __launch_bounds__(TQ_THREADS, 2) conv_tc_cm_kernel(ConvArgs a, T
     if (need_x) {
       const int kx = (fold && kc >= nkx) ? kc - nkx : kc;               // the lo half of the fold contracts the same x slabs again
       unsigned char* dst = sX + (XMODE == 0 ? s : kc) * TQ_X_BYTES;
-      tma_load_3d(dst, &tmapX, p0, kx * TC_BK, b, &bar_full[s]);
-      tma_load_3d(dst + TC_A_LBO, &tmapX, p0 + 64, kx * TC_BK, b, &bar_full[s]);
+      tma_load_xbox(a, dst, &tmapX, p0, kx * TC_BK, b, &bar_full[s]);
+      tma_load_xbox(a, dst + TC_A_LBO, &tmapX, p0 + 64, kx * TC_BK, b, &bar_full[s]);
     }
   };
   const int early_steps = total_steps < ST ? total_steps : ST;       // need no free-slot wait

@@ -664,6 +664,47 @@ im2col3_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restri
   }
 }
 
+// Horizontal taps only (row-tap mode of the convolution engine, vrcoc.h k_order 2): cols[b][kx*C + c][y][x] = x[b][c][y][x + (kx-1)*dil].
+// The vertical taps are TMA boxes of THIS tensor shifted by rows, so a 3x3 convolution writes 3x its input instead of 9x.
+// dil == 1, bf16, W % 8 == 0: one thread = 8 columns, funnel shifts as above; otherwise a scalar kernel (small dilated maps).
+__global__ void __launch_bounds__(256)
+im2col_rows3_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ cols, uint32_t total, int C, int H, int W) {
+  const uint32_t cols8 = (uint32_t)W >> 3;
+  const int64_t P = (int64_t)H * W;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t c8 = t % cols8, r = t / cols8;
+    const uint32_t y = r % (uint32_t)H, plane = r / (uint32_t)H;       // plane = b * C + c
+    const uint32_t b = plane / (uint32_t)C, c = plane - b * (uint32_t)C;
+    const int x0 = (int)c8 * 8;
+    const __nv_bfloat16* row = x + (int64_t)plane * P + (int64_t)y * W;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(row + x0));
+    const uint32_t left = x0 > 0 ? (uint32_t)__bfloat16_as_ushort(row[x0 - 1]) : 0u;
+    const uint32_t right = x0 + 8 < W ? (uint32_t)__bfloat16_as_ushort(row[x0 + 8]) : 0u;
+    __nv_bfloat16* op = cols + ((int64_t)b * 3 * C + c) * P + (int64_t)y * W + x0;
+    *reinterpret_cast<uint4*>(op) =
+        make_uint4((v.x << 16) | left, __funnelshift_l(v.x, v.y, 16), __funnelshift_l(v.y, v.z, 16), __funnelshift_l(v.z, v.w, 16));
+    *reinterpret_cast<uint4*>(op + (int64_t)C * P) = v;
+    *reinterpret_cast<uint4*>(op + 2 * (int64_t)C * P) =
+        make_uint4(__funnelshift_r(v.x, v.y, 16), __funnelshift_r(v.y, v.z, 16), __funnelshift_r(v.z, v.w, 16), (v.w >> 16) | (right << 16));
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_rows_kernel(const T* __restrict__ x, T* __restrict__ cols, int64_t total, int C, int H, int W, int kw, int dil) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int xx = (int)(t % W);
+    const int64_t r = t / W;
+    const int y = (int)(r % H);
+    const int64_t q = r / H;                                            // (b * kw + kx) * C + c
+    const int c = (int)(q % C);
+    const int64_t bk = q / C;
+    const int kx = (int)(bk % kw);
+    const int64_t b = bk / kw;
+    const int ix = xx + (kx - kw / 2) * dil;
+    cols[t] = (ix >= 0 && ix < W) ? x[((b * C + c) * H + y) * (int64_t)W + ix] : T(0.f);
+  }
+}
+
 // ---- depthwise k x k convolution (DWConv.dconv of the decoupled head, reference normal_conv.py:26-27) -------------------
 // one thread = 8 consecutive output columns of one (plane, row); weights of the plane in registers; bandwidth-bound.
 template <typename T, int K>
@@ -1017,6 +1058,25 @@ extern "C" int vrcoc_im2col(const void* x, void* col, int dtype, int B, int C, i
     using T = typename std::remove_pointer<decltype(t)>::type;
     im2col_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, (T*)col, B, C, H, W, Ho, Wo, kh, kw, stride, pad, dil);
     return check_launch("im2col");
+  });
+}
+
+extern "C" int vrcoc_im2col_rows(const void* x, void* cols, int dtype, int B, int C, int H, int W, int kw, int dil, void* stream) {
+  VRCOC_REQUIRE(x && cols && B > 0 && C > 0 && H > 0 && W > 0 && kw > 0 && (kw & 1) == 1 && dil > 0, "im2col_rows: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t fast_total = (int64_t)B * C * H * (W / 8);
+  if (dtype == VRCOC_BF16 && kw == 3 && dil == 1 && (W % 8) == 0 && fast_total < (1ll << 31) &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(cols)) & 15) == 0) {
+    im2col_rows3_bf16_kernel<<<(unsigned)cdiv(fast_total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)cols,
+                                                                           (uint32_t)fast_total, C, H, W);
+    return check_launch("im2col_rows3");
+  }
+  const int64_t total = (int64_t)B * kw * C * H * W;
+  const int blocks = (int)(cdiv(total, 256) < 148 * 32 ? cdiv(total, 256) : 148 * 32);
+  return by_dtype(dtype, [&](auto* t) {
+    using T = typename std::remove_pointer<decltype(t)>::type;
+    im2col_rows_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, (T*)cols, total, C, H, W, kw, dil);
+    return check_launch("im2col_rows");
   });
 }
 

@@ -111,6 +111,9 @@ def _fold_bn(mean, var, w, b, eps):
     return scale.contiguous(), shift.contiguous()
 
 
+ROW_TAPS = True             # 3x3 stride-1 convolutions: horizontal-tap copies + row-shifted TMA boxes (False: full im2col; A/B switch)
+
+
 def conv2d_native(x, weight, bias=None, stride=1, pad=0, extra=None, extra_bstride=None, act=ACT_NONE,
                   e_scale=None, out_minmax=None, out_dtype=None):
     """Dense (groups=1) k x k convolution on the implicit-GEMM engine.  Differentiable through `_ConvFn`."""
@@ -134,10 +137,33 @@ def _conv_launch(x, weight, bias32, stride, pad, extra, extra_bstride, act, e_sc
     Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
     Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
     out = torch.empty(B, O, Ho, Wo, device=x.device, dtype=out_dtype or x.dtype)
+    if (kh == kw and kh > 1 and kh % 2 == 1 and stride == 1 and pad == dil * (kh // 2) and dil >= H and dil >= W and extra is None
+            and weight.dtype == torch.bfloat16):
+        # dilation >= the map: every off-centre tap reads zero padding only, the convolution IS the 1x1 projection by its centre tap
+        # (ASPP rate 18 on the 16x16 map at 512x512 input: 1/9 of the GEMM and no im2col)
+        d = conv_desc(x, ops.center_tap(weight), out, e_scale=e_scale, e_shift=bias32, act=act, out_minmax=out_minmax,
+                      out_sample_sums=out_sample_sums)
+        conv_fwd(d)
+        return out
     # k x k convs on the tensor-core path use the tap-major K order (cheap gathers); few-channel convs (the 512x512 ingest)
     # run on the streaming kernel, which takes the PyTorch order
     tapm = kh * kw > 1 and weight.dtype == torch.bfloat16 and not (O <= 8 and Cin * kh * kw <= 64)
     w2 = ops.tap_major(weight) if tapm else weight.detach().reshape(O, -1).contiguous()
+    if (ROW_TAPS and tapm and extra is None and x.dtype == torch.bfloat16 and kh == 3 and kw == 3 and stride == 1 and pad == dil
+            and dil == 1 and Cin % 64 == 0 and W % 64 == 0 and (H * W) % 8 == 0):
+        # row-tap mode (include/vrcoc.h, k_order 2): only the horizontal taps are materialised (3x the input instead of the 9x of
+        # the full im2col below); the vertical taps are TMA boxes of that tensor moved by whole rows in the flattened point index.
+        # (Moving a box by ONE element faults in NCHW - the innermost box start must be 16-byte aligned, tools/tma_probe.cu - which
+        # is why the horizontal taps are copies.)  Only where a row is a whole number of 128-byte lines (dil * W % 64 == 0): boxes
+        # that start mid-line cost two L2 requests per row, and on the 16x16 / 32x32 maps that ate the saving (measured: GEMM 34 ->
+        # 46 us at 16x16, 39 -> 43 us at 32x32 against 12 / 8 us less im2col); dense taps only (the dilated ASPP branches live on the
+        # 16x16 map, where most shifted boxes are zero fill and the full im2col + GEMM was faster: 53 vs 70 us at rate 12).
+        cols = torch.empty(B, 3 * Cin, H, W, device=x.device, dtype=x.dtype)
+        check(lib.vrcoc_im2col_rows(_ptr(x), _ptr(cols), _dt(x), B, Cin, H, W, 3, dil, _stream()), "im2col_rows")
+        d = conv_desc(cols, w2, out, kh=3, kw=1, stride=1, pad=dil, dil=dil, k_order=2, e_scale=e_scale, e_shift=bias32, act=act,
+                      out_minmax=out_minmax, out_sample_sums=out_sample_sums)
+        conv_fwd(d)
+        return out
     if tapm and extra is None and Cin >= 32 and x.dtype == torch.bfloat16 and (Ho * Wo) % 8 == 0:
         # many channels: materialise the tap-major im2col matrix once and run the TMA-only 1x1 kernel on it, instead of
         # re-gathering the same rows in every N-tile CTA (9x the input: a few MB on the 16x16..64x64 maps where this is used).

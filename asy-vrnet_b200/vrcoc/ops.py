@@ -467,6 +467,26 @@ def tap_major(weight):
     return v
 
 
+def center_tap(weight):
+    """[O, C, k, k] -> [O, C]: the centre tap as a contiguous 1x1 weight, memoised on the weight tensor like `tap_major`.  A dilated
+    k x k convolution whose dilation is >= the map size reads only zero padding through every other tap (ASPP's rate-18 branch on
+    the 16x16 map, reference neck/coc_fpn_dual.py:55-67)."""
+    sig = (weight.data_ptr(), weight._version)
+    memo = weight.__dict__.get("_vrcoc_centertap") if hasattr(weight, "__dict__") else None
+    if memo is not None and memo[0] == sig:
+        return memo[1]
+    v = weight.detach()[:, :, weight.shape[2] // 2, weight.shape[3] // 2].contiguous()
+    if memo is not None and memo[1].shape == v.shape and memo[1].dtype == v.dtype and memo[1].device == v.device:
+        with torch.no_grad():
+            memo[1].copy_(v)                  # in place: see _refresh_in_place
+        v = memo[1]
+    try:
+        weight._vrcoc_centertap = (sig, v)
+    except Exception:
+        pass
+    return v
+
+
 def conv_fwd(desc):
     check(lib.vrcoc_conv_fwd(C.byref(desc), _stream()), "conv_fwd")
 

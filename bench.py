@@ -122,7 +122,7 @@ class ClockSampler:
 KERNELS_PER_CALL = {"vrcoc_channel_sums": 1, "vrcoc_conv_fwd": 1, "vrcoc_table_apply": 1, "vrcoc_cluster_core_fwd": 1,
                     "vrcoc_cluster_core_bwd": 2, "vrcoc_sa_gate_sums": 1, "vrcoc_radar_enh_table": 1, "vrcoc_chan_affine": 1,
                     "vrcoc_img_enh_finish": 1, "vrcoc_gelu_bwd": 1, "vrcoc_gn_bwd_sums": 1, "vrcoc_gn_bwd_apply": 1,
-                    "vrcoc_conv1x1_wgrad": 3, "vrcoc_im2col": 1, "vrcoc_upsample_bilinear": 1, "vrcoc_upsample_argmax": 1,
+                    "vrcoc_conv1x1_wgrad": 3, "vrcoc_im2col": 1, "vrcoc_im2col_rows": 1, "vrcoc_upsample_bilinear": 1, "vrcoc_upsample_argmax": 1,
                     "vrcoc_dwconv": 1, "vrcoc_mlp_fused_fwd": 1, "vrcoc_token_mixer_fwd": 1, "vrcoc_token_mixer_core_fwd": 1}
 
 
@@ -156,6 +156,9 @@ def _describe(name, args):
         dt, B, C, H, W, kh, kw, stride, pad, dil = args[2:12]
         Ho, Wo = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1, (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
         return f"im2col{kh}x{kw}[{C}]@{Ho}x{Wo}", B * C * _esz(dt) * (H * W + kh * kw * Ho * Wo), 0.0
+    if name == "vrcoc_im2col_rows":
+        dt, B, C, H, W, kw, dil = args[2:9]
+        return f"im2col_rows{kw}[{C}]@{H}x{W}", B * C * _esz(dt) * H * W * (1 + kw), 0.0
     if name == "vrcoc_channel_sums":
         dt, B, C, P = args[1:5]
         return f"channel_sums[{C}]@{P}pt", B * C * P * _esz(dt), 2.0 * B * C * P

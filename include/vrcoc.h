@@ -109,7 +109,12 @@ typedef struct vrcoc_conv_desc {
   int32_t engine;
   int32_t dil;     /* dilation (0 or 1 = dense); ASPP branches use 6/12/18 (neck/coc_fpn_dual.py:55-67) */
   int32_t k_order; /* 0: weight[o][c][ky][kx] (PyTorch); 1: weight[o][ky][kx][c] (tap-major: the im2col rows of one k slab
-                      are consecutive channels of one tap -> cheap gathers on the tcgen05 path) */
+                      are consecutive channels of one tap -> cheap gathers on the tcgen05 path);
+                      2: ROW-TAP mode (bf16 tcgen05 TMA kernels only): src0 = vrcoc_im2col_rows(x) = [B][C0 = kw_orig*C][H][W],
+                      kh = vertical taps, kw = 1, stride 1, pad = dil*(kh-1)/2 (rows only: H_out = H_in, W_out = W_in),
+                      weight[o][ky][C0] (= the tap-major weight of the k x k convolution); C0 % 64 == 0, dil*W % 8 == 0,
+                      H*W % 8 == 0, no prologue / second source.  The k slab (ky, c0) is the 64-point x 64-channel TMA box of
+                      src0 moved by (ky - kh/2)*dil*W points (whole rows), zero-filled above / below the map. */
   /* GroupNorm(1,C0) FOLDED into a 1x1 projection (bf16 tcgen05 path; Cluster.fc1|fc_v after norm1, vr_coc.py:156-157,265):
    *   W.GN(x) + b  =  rstd_b * ((W diag(gamma)) . x)  -  rstd_b * mean_b * k1[o]  +  k0[o]
    * so the tensor core consumes the RAW activations and the per-sample statistics enter in the epilogue only.  When
@@ -260,6 +265,10 @@ int vrcoc_debug_set_cm(int on);
  * TMA-only tcgen05 kernel for k x k convolutions with many channels on small maps (vr_coc.py:99-102,313; coc_fpn_dual.py:55-67). */
 int vrcoc_im2col(const void* x, void* col, int dtype, int B, int C, int H, int W, int kh, int kw, int stride, int pad, int dil,
                  void* stream);
+/* Horizontal taps only: cols[b][kx*C + c][y][x] = x[b][c][y][x + (kx - kw/2)*dil] (zero outside), kw odd.  Source of the
+ * convolution engine's row-tap mode (vrcoc_conv_desc.k_order = 2): the vertical taps are TMA boxes of `cols` shifted by rows, so a
+ * 3x3 convolution materialises 3x its input instead of the 9x of vrcoc_im2col (vr_coc.py:99-102,313; coc_fpn_dual.py:55-67). */
+int vrcoc_im2col_rows(const void* x, void* cols, int dtype, int B, int C, int H, int W, int kw, int dil, void* stream);
 
 /* Depthwise k x k convolution (k = 3 or 5; weight [C][k][k] in the activation dtype, optional fp32 bias): DWConv.dconv of the
  * decoupled head (backbone/conv_utils/normal_conv.py:26-27, head/decouplehead.py:24-37). */

@@ -102,7 +102,9 @@ def test_tcgen05_full_epilogue_and_prologue(env):
                                    # the 3x3 im2col fast path (stride 1 / 2) + GEMM at the live map sizes, 5x5 and odd maps on the generic one
                                    (1, 64, 64, 128, 128, 3, 1, 1, 1), (2, 128, 128, 64, 64, 3, 1, 1, 1), (2, 320, 320, 32, 32, 3, 1, 1, 1),
                                    (2, 512, 512, 16, 16, 3, 1, 1, 1), (1, 64, 192, 32, 32, 3, 1, 2, 2), (1, 64, 96, 64, 64, 5, 1, 2, 1),
-                                   (1, 128, 64, 8, 16, 3, 1, 1, 1), (2, 64, 128, 64, 64, 3, 2, 1, 1), (1, 320, 512, 32, 32, 3, 2, 1, 1)])
+                                   (1, 128, 64, 8, 16, 3, 1, 1, 1), (2, 64, 128, 64, 64, 3, 2, 1, 1), (1, 320, 512, 32, 32, 3, 2, 1, 1),
+                                   # dilation >= the map: the centre-tap 1x1 shortcut (ASPP rate 18 at 16x16) and the case just below it
+                                   (2, 512, 512, 16, 16, 3, 1, 18, 18), (2, 128, 96, 16, 16, 3, 1, 16, 16), (1, 128, 96, 16, 16, 3, 1, 15, 15)])
 def test_tap_major_dilation_and_small_kernel(env, shape):
     """fusion._conv_launch picks: tap-major K order on the tensor-core path for k x k convs, dilation (ASPP), and the
     few-channel streaming kernel for the ingest convs; all against torch conv2d on the same bf16 operands"""
@@ -116,6 +118,63 @@ def test_tap_major_dilation_and_small_kernel(env, shape):
     got = fusion._conv_launch(x, w, bias, stride, pad, None, None, 0, None, None, torch.float32, dil=dil)
     assert got.shape == ref.shape
     assert rel_err(got, ref) < 1e-5
+
+
+@pytest.mark.parametrize("case", [(2, 64, 16, 128, 1, torch.bfloat16), (1, 128, 32, 32, 1, torch.bfloat16), (2, 64, 16, 16, 6, torch.bfloat16),
+                                  (1, 64, 8, 16, 12, torch.bfloat16), (1, 3, 5, 12, 2, torch.float32)],
+                         ids=lambda c: "x".join(map(str, c[:5])))
+def test_im2col_rows(env, case):
+    """vrcoc_im2col_rows: cols[b][kx*C + c][y][x] = x[b][c][y][x + (kx-1)*dil], zero outside (fast bf16 kernel and the generic one)"""
+    from vrcoc._lib import check, lib
+    B, C, H, W, dil, dtype = case
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, C, H, W, generator=g).to(dtype).cuda()
+    cols = torch.full((B, 3 * C, H, W), float("nan"), device="cuda", dtype=dtype)
+    check(lib.vrcoc_im2col_rows(x.data_ptr(), cols.data_ptr(), 0 if dtype == torch.float32 else 1, B, C, H, W, 3, dil,
+                                torch.cuda.current_stream().cuda_stream), "im2col_rows")
+    xp = F.pad(x, (dil, dil, 0, 0))
+    ref = torch.cat([xp[..., kx * dil: kx * dil + W] for kx in range(3)], dim=1)
+    assert torch.equal(cols, ref)
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 64, 128, 128, 1), (2, 128, 128, 64, 64, 1), (2, 320, 320, 32, 32, 1), (2, 512, 512, 16, 16, 1),
+                                   (2, 512, 512, 16, 16, 6), (1, 512, 512, 16, 16, 12), (1, 512, 512, 16, 16, 18), (2, 64, 96, 16, 16, 1),
+                                   (1, 128, 64, 8, 16, 1), (3, 64, 320, 32, 64, 1), (1, 64, 128, 24, 64, 1)],
+                         ids=lambda c: "x".join(map(str, c)))
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32], ids=["bf16out", "f32out"])
+def test_row_tap_conv3x3_matches_full_im2col_and_torch(env, shape, out_dtype):
+    """3x3 stride-1 convolutions in row-tap mode (vrcoc.h k_order 2: horizontal-tap copies + TMA boxes shifted by rows, both TMA
+    kernels, every live map width incl. dilated ASPP branches) against the full-im2col path and torch conv2d
+    (reference vr_coc.py:99-102,313; coc_fpn_dual.py:55-67)"""
+    from vrcoc import fusion
+    B, C, O, H, W, dil = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, C, H, W, generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn(O, C, 3, 3, generator=g) / (C * 9) ** 0.5).to(torch.bfloat16).cuda()
+    bias = torch.randn(O, generator=g).cuda()
+    scale = (torch.rand(O, generator=g) + 0.5).cuda()
+    ref = F.relu(F.conv2d(x.float(), w.float(), None, padding=dil, dilation=dil) * scale.view(1, -1, 1, 1) + bias.view(1, -1, 1, 1))
+    from vrcoc._lib import ACT_RELU, check, lib
+    ops = env
+    # the row-tap launch itself (fusion._conv_launch dispatches it only where a row is a whole number of 128-byte lines)
+    cols = torch.empty(B, 3 * C, H, W, device="cuda", dtype=torch.bfloat16)
+    check(lib.vrcoc_im2col_rows(x.data_ptr(), cols.data_ptr(), 1, B, C, H, W, 3, dil, torch.cuda.current_stream().cuda_stream), "im2col_rows")
+    got = torch.full((B, O, H, W), float("nan"), device="cuda", dtype=out_dtype)
+    ops.conv_fwd(ops.conv_desc(cols, ops.tap_major(w), got, kh=3, kw=1, stride=1, pad=dil, dil=dil, k_order=2, e_scale=scale, e_shift=bias,
+                               act=ACT_RELU))
+    fusion.ROW_TAPS = False
+    try:
+        full = fusion._conv_launch(x, w, bias, 1, dil, None, None, ACT_RELU, scale, None, out_dtype, dil=dil)
+    finally:
+        fusion.ROW_TAPS = True
+    if dil == 1 and W % 64 == 0:
+        via_dispatch = fusion._conv_launch(x, w, bias, 1, dil, None, None, ACT_RELU, scale, None, out_dtype, dil=dil)
+        assert torch.equal(via_dispatch, got)
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape and torch.isfinite(got.float()).all()
+    tol = 1e-5 if out_dtype == torch.float32 else 4e-3
+    assert rel_err(got.float(), ref) < tol
+    assert rel_err(got.float(), full.float()) < (2e-6 if out_dtype == torch.float32 else 2e-3)
 
 
 def test_auto_engine_picks_tcgen05_for_bf16_weights(env):
