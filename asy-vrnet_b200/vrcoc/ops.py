@@ -276,12 +276,14 @@ class sums_arena:
                      # a CUDA graph captured at batch size B keeps zeroing / accumulating into ITS arena (graph-capture contract)
     _open = {}       # device index -> key of the arena opened by the outermost context
     SLOTS = 128
+    lane = 0         # forwards that may run CONCURRENTLY on one device (the pipeline slots of InferenceSession: one captured
+                     # graph each, replayed on their own streams) must not share an arena: each is captured under its own lane
 
     def __init__(self, B, device):
         self.key = None
         if device.type == "cuda" and not torch.is_grad_enabled():
             self.dev_index = device.index if device.index is not None else torch.cuda.current_device()
-            self.key, self.B, self.device = (self.dev_index, B), B, device
+            self.key, self.B, self.device = (self.dev_index, B, sums_arena.lane), B, device
 
     def __enter__(self):
         if self.key is None:
