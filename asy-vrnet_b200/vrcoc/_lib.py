@@ -74,6 +74,8 @@ SIGNATURES = {
     "vrcoc_token_mixer_core_fwd": (_I, [_P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P] + [_I] * 8 + [_P]),
     "vrcoc_im2col": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vrcoc_im2col_rows": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "vrcoc_patch_embed_supported": (_I, [_I] * 7),
+    "vrcoc_patch_embed": (_I, [_P, _P, _L, _P, _P, _P, _P] + [_I] * 8 + [_P]),
     "vrcoc_dwconv": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "vrcoc_upsample_bilinear": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "vrcoc_upsample_argmax_supported": (_I, [_I] * 5),

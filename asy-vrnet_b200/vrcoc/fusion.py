@@ -111,6 +111,7 @@ def _fold_bn(mean, var, w, b, eps):
     return scale.contiguous(), shift.contiguous()
 
 
+PATCH_EMBED_KERNEL = True   # 4x4 / stride-4 patch embedding on its own gather + mma.sync kernel (False: the general engine; A/B switch)
 ROW_TAPS = True             # 3x3 stride-1 convolutions: horizontal-tap copies + row-shifted TMA boxes (False: full im2col; A/B switch)
 
 
@@ -137,6 +138,15 @@ def _conv_launch(x, weight, bias32, stride, pad, extra, extra_bstride, act, e_sc
     Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
     Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
     out = torch.empty(B, O, Ho, Wo, device=x.device, dtype=out_dtype or x.dtype)
+    if (PATCH_EMBED_KERNEL and kh == kw == stride == 4 and pad == 0 and dil == 1 and act == ACT_NONE and e_scale is None and out_minmax is None
+            and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and bias32 is not None
+            and (extra is None or extra.dtype == torch.bfloat16)
+            and lib.vrcoc_patch_embed_supported(_dt(x), C0, C1, H, W, O, 4)):
+        # the 4x4 / stride-4 patch embedding of a handful of channels: HBM-bound gather with a small contraction (csrc/patch_embed.cu)
+        ebs = 0 if (extra is None or extra.dim() == 3) else (extra_bstride if extra_bstride is not None else C1 * H * W)
+        check(lib.vrcoc_patch_embed(_ptr(x), _ptr(extra), ebs, _ptr(weight.detach().contiguous()), _ptr(bias32), _ptr(out),
+                                    _ptr(out_sample_sums), _dt(x), B, C0, C1, H, W, O, 4, _stream()), "patch_embed")
+        return out
     if (kh == kw and kh > 1 and kh % 2 == 1 and stride == 1 and pad == dil * (kh // 2) and dil >= H and dil >= W and extra is None
             and weight.dtype == torch.bfloat16):
         # dilation >= the map: every off-centre tap reads zero padding only, the convolution IS the 1x1 projection by its centre tap

@@ -122,7 +122,7 @@ class ClockSampler:
 KERNELS_PER_CALL = {"vrcoc_channel_sums": 1, "vrcoc_conv_fwd": 1, "vrcoc_table_apply": 1, "vrcoc_cluster_core_fwd": 1,
                     "vrcoc_cluster_core_bwd": 2, "vrcoc_sa_gate_sums": 1, "vrcoc_radar_enh_table": 1, "vrcoc_chan_affine": 1,
                     "vrcoc_img_enh_finish": 1, "vrcoc_gelu_bwd": 1, "vrcoc_gn_bwd_sums": 1, "vrcoc_gn_bwd_apply": 1,
-                    "vrcoc_conv1x1_wgrad": 3, "vrcoc_im2col": 1, "vrcoc_im2col_rows": 1, "vrcoc_upsample_bilinear": 1, "vrcoc_upsample_argmax": 1,
+                    "vrcoc_conv1x1_wgrad": 3, "vrcoc_im2col": 1, "vrcoc_im2col_rows": 1, "vrcoc_patch_embed": 1, "vrcoc_upsample_bilinear": 1, "vrcoc_upsample_argmax": 1,
                     "vrcoc_dwconv": 1, "vrcoc_mlp_fused_fwd": 1, "vrcoc_token_mixer_fwd": 1, "vrcoc_token_mixer_core_fwd": 1}
 
 
@@ -156,6 +156,10 @@ def _describe(name, args):
         dt, B, C, H, W, kh, kw, stride, pad, dil = args[2:12]
         Ho, Wo = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1, (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
         return f"im2col{kh}x{kw}[{C}]@{Ho}x{Wo}", B * C * _esz(dt) * (H * W + kh * kw * Ho * Wo), 0.0
+    if name == "vrcoc_patch_embed":
+        B, C0, C1, H, W, O = args[8:14]
+        return (f"patch_embed4[{C0 + C1}->{O}]@{H // 4}x{W // 4}", 2 * (B * C0 * H * W + C1 * H * W + B * O * (H // 4) * (W // 4)),
+                2.0 * B * O * (C0 + C1) * 16 * (H // 4) * (W // 4))
     if name == "vrcoc_im2col_rows":
         dt, B, C, H, W, kw, dil = args[2:9]
         return f"im2col_rows{kw}[{C}]@{H}x{W}", B * C * _esz(dt) * H * W * (1 + kw), 0.0

@@ -270,6 +270,16 @@ int vrcoc_im2col(const void* x, void* col, int dtype, int B, int C, int H, int W
  * 3x3 convolution materialises 3x its input instead of the 9x of vrcoc_im2col (vr_coc.py:99-102,313; coc_fpn_dual.py:55-67). */
 int vrcoc_im2col_rows(const void* x, void* cols, int dtype, int B, int C, int H, int W, int kw, int dil, void* stream);
 
+/* Patch embedding (vr_coc.py:83-102 PointRecuder with patch = stride = 4, pad 0, called from :575-587 on cat([x, pos])): a 4x4 / stride-4
+ * convolution of C0 (+ C1 from `extra`, [C1][H][W] with extra_bstride 0 = the batch-broadcast position grid, or [B][C1][H][W]) channels
+ * into O = 64 channels, bias added; weight [O][C0+C1][4][4] bf16 (PyTorch layout), out [B][O][H/4][W/4] bf16.  out_sample_sums
+ * (nullable, [B][VRCOC_STAT_SLOTS][2], accumulated) receives the per-sample sum / sum of squares of the output, as the convolution
+ * engine's epilogue does.  HBM-bound gather + a K = 16*(C0+C1) contraction on mma.sync (csrc/patch_embed.cu).
+ * _supported: bf16, patch 4, O = 64, C0 + C1 <= 8, W % 64 == 0, (H/4)*(W/4) % 128 == 0. */
+int vrcoc_patch_embed_supported(int dtype, int C0, int C1, int H, int W, int O, int patch);
+int vrcoc_patch_embed(const void* x, const void* extra, int64_t extra_bstride, const void* weight, const float* bias, void* out,
+                      double* out_sample_sums, int dtype, int B, int C0, int C1, int H, int W, int O, int patch, void* stream);
+
 /* Depthwise k x k convolution (k = 3 or 5; weight [C][k][k] in the activation dtype, optional fp32 bias): DWConv.dconv of the
  * decoupled head (backbone/conv_utils/normal_conv.py:26-27, head/decouplehead.py:24-37). */
 int vrcoc_dwconv(const void* x, const void* weight, const float* bias, void* out, int dtype, int B, int C, int H, int W, int k,

@@ -177,6 +177,43 @@ def test_row_tap_conv3x3_matches_full_im2col_and_torch(env, shape, out_dtype):
     assert rel_err(got.float(), full.float()) < (2e-6 if out_dtype == torch.float32 else 2e-3)
 
 
+@pytest.mark.parametrize("case", [(2, 3, 2, 512, 512, True), (2, 4, 2, 512, 512, True), (1, 4, 2, 128, 256, False), (3, 6, 0, 64, 128, False),
+                                  (1, 3, 2, 1024, 1024, True)], ids=lambda c: "x".join(map(str, c)))
+def test_patch_embed_kernel(env, case):
+    """vrcoc_patch_embed (csrc/patch_embed.cu): the 4x4 / stride-4 patch embedding of cat([x, pos]) (reference vr_coc.py:83-102 from
+    :575-587) against torch conv2d on the same bf16 operands and against the general engine, incl. the GroupNorm statistics that
+    leave with the output and the batch-broadcast position source"""
+    from vrcoc import fusion
+    ops = env
+    B, C0, C1, H, W, bcast = case
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(B, C0, H, W, generator=g).to(torch.bfloat16).cuda()
+    extra = None
+    if C1:
+        extra = (torch.rand(C1, H, W, generator=g) if bcast else torch.rand(B, C1, H, W, generator=g)).to(torch.bfloat16).cuda()
+    w = (torch.randn(64, C0 + C1, 4, 4, generator=g) / ((C0 + C1) * 16) ** 0.5).to(torch.bfloat16).cuda()
+    bias = torch.randn(64, generator=g).cuda()
+    full = x.float() if extra is None else torch.cat([x.float(), (extra.float().expand(B, -1, -1, -1) if bcast else extra.float())], 1)
+    ref = F.conv2d(full, w.float(), bias, stride=4)
+    assert fusion.PATCH_EMBED_KERNEL and ops.lib.vrcoc_patch_embed_supported(1, C0, C1, H, W, 64, 4)
+    s_new = ops.new_sample_sums(B, "cuda")
+    got = fusion._conv_launch(x, w, bias, 4, 0, extra, None, 0, None, None, None, out_sample_sums=s_new)
+    fusion.PATCH_EMBED_KERNEL = False
+    try:
+        s_old = ops.new_sample_sums(B, "cuda")
+        old = fusion._conv_launch(x, w, bias, 4, 0, extra, None, 0, None, None, None, out_sample_sums=s_old)
+    finally:
+        fusion.PATCH_EMBED_KERNEL = True
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape and got.dtype == torch.bfloat16
+    assert rel_err(got.float(), ref) < 4e-3                       # bf16 output rounding
+    assert rel_err(got.float(), old.float()) < 2e-3
+    ss = s_new.sum(1).cpu()                                       # [B, 2]: sum, sum of squares of the fp32 values
+    assert torch.allclose(ss[:, 0], ref.double().sum((1, 2, 3)).cpu(), rtol=1e-3, atol=1e-2 * ref[0].numel() ** 0.5)
+    assert torch.allclose(ss[:, 1], (ref.double() ** 2).sum((1, 2, 3)).cpu(), rtol=1e-3)
+    assert rel_err(s_new.sum(1), s_old.sum(1)) < 1e-4
+
+
 def test_auto_engine_picks_tcgen05_for_bf16_weights(env):
     """fp32 weights -> exact CUDA-core path; bf16 weights -> tensor cores.  Seen through the numerics: with fp32
     activations and bf16 weights the tcgen05 path rounds the activation operand to bf16, the CUDA-core path does not."""
