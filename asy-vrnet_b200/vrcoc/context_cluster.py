@@ -139,6 +139,9 @@ class Cluster(nn.Module):
         return ops.ProjFn.apply(out, self.fc2.weight, self.fc2.bias, ACT_NONE)
 
 
+SPLIT_WIDE_GN = True        # C > 576: GroupNorm as its own streaming pass in front of mlp.fc1 (False: transform-on-load GEMM; A/B switch)
+
+
 class Mlp(nn.Module):
     """reference vr_coc.py:195-223 (1x1-conv MLP, exact-erf GELU)."""
 
@@ -259,8 +262,17 @@ class ClusterBlock(nn.Module):
                                    f32(mlp.fc1.bias), mlp.fc2.weight.detach().reshape(C, hid), f32(mlp.fc2.bias), ls2, sums[1])
             return ops.attach_sums(x2, ops.tag_like(sums[1], sums))
         h = torch.empty(B, hid, H, W, device=dev, dtype=dt)
-        ops.conv_fwd(ops.conv_desc(x1, mlp.fc1.weight.detach().reshape(hid, C), h, gn=(sums[0], f32(n2.weight), f32(n2.bias), n2.eps),
-                                   e_shift=f32(mlp.fc1.bias), act=ACT_GELU))
+        if SPLIT_WIDE_GN and dt == torch.bfloat16 and C > 576 and C % 64 == 0 and mlp.fc1.weight.dtype == dt:
+            # more than nine k-slabs (neck N4, C = 640): the in-place-prologue GEMM cannot keep X resident and the transform-on-load
+            # kernel redoes the normalisation in every one of the 20 output-tile CTAs of a point tile (91 us).  One streaming pass
+            # writes GN(x) (the same bf16 operand), then the projection runs on the TMA-only kernel.
+            xn = torch.empty_like(x1)
+            ops.check(ops.lib.vrcoc_table_apply(ops.conv_desc(x1, x1, xn, gn=(sums[0], f32(n2.weight), f32(n2.bias), n2.eps)), ops._stream()),
+                      "table_apply")
+            ops.conv_fwd(ops.conv_desc(xn, mlp.fc1.weight.detach().reshape(hid, C), h, e_shift=f32(mlp.fc1.bias), act=ACT_GELU))
+        else:
+            ops.conv_fwd(ops.conv_desc(x1, mlp.fc1.weight.detach().reshape(hid, C), h, gn=(sums[0], f32(n2.weight), f32(n2.bias), n2.eps),
+                                       e_shift=f32(mlp.fc1.bias), act=ACT_GELU))
         x2 = torch.empty_like(x)
         ops.conv_fwd(ops.conv_desc(h, mlp.fc2.weight.detach().reshape(C, hid), x2, e_shift=f32(mlp.fc2.bias), post_scale=ls2, res=x1,
                                    out_sample_sums=sums[1]))
