@@ -111,6 +111,7 @@ def _fold_bn(mean, var, w, b, eps):
     return scale.contiguous(), shift.contiguous()
 
 
+SPLIT_WIDE_PROLOGUE = True  # RadarEnhanceByImage with > 576 input channels: prologue as its own pass + TMA-only GEMM (A/B switch)
 PATCH_EMBED_KERNEL = True   # 4x4 / stride-4 patch embedding on its own gather + mma.sync kernel (False: the general engine; A/B switch)
 ROW_TAPS = True             # 3x3 stride-1 convolutions: horizontal-tap copies + row-shifted TMA boxes (False: full im2col; A/B switch)
 
@@ -991,6 +992,14 @@ class _RadarEnhanceFn(torch.autograd.Function):
             w_nat = ops.cached(mod, "w_concat_order", [w], lambda: _concat_order_weight(w2, mod._chan_src))
             s1, t1 = _bn_affine(ip.bn)
             s2, t2 = _bn_affine(bn2)
+            if SPLIT_WIDE_PROLOGUE and Ci + Cr > 576:
+                # more than nine k-slabs (stages 3 and 4): the in-place-prologue GEMM cannot keep [image | radar] resident and the
+                # transform-on-load kernel re-applies attention / gate per output-tile CTA (50 us at stage 4).  One streaming pass
+                # writes the transformed operand (same bf16 values), the projection then takes both operands by TMA.
+                z = torch.empty(B, Ci + Cr, *image.shape[-2:], device=dev, dtype=image.dtype)
+                check(lib.vrcoc_table_apply(conv_desc(image, image, z, src1=radar, table=table, has_gate=gate), _stream()), "table_apply")
+                conv_fwd(conv_desc(z, w_nat, out, e_scale=s1, e_shift=t1, act=ACT_RELU, res=radar, f_scale=s2, f_shift=t2))
+                return out
             conv_fwd(conv_desc(image, w_nat, out, src1=radar, table=table, has_gate=gate,
                                e_scale=s1, e_shift=t1, act=ACT_RELU, res=radar, f_scale=s2, f_shift=t2))
             return out

@@ -202,11 +202,12 @@ def test_fusion_golden(V, name):
         _check_grads(mod, fx, xs, ["image", "radar"], y, FP32_TOL)
 
 
-@pytest.mark.parametrize("Ci,Cr,H,W,B", [(64, 64, 32, 32, 2), (128, 128, 16, 24, 3), (320, 320, 8, 8, 2), (64, 128, 16, 16, 1)])
+@pytest.mark.parametrize("Ci,Cr,H,W,B", [(64, 64, 32, 32, 2), (128, 128, 16, 24, 3), (320, 320, 8, 8, 2), (64, 128, 16, 16, 1), (512, 512, 16, 16, 2),
+                                         (320, 320, 32, 32, 2)])
 def test_radar_enhance_concat_order_path_vs_oracle(V, Ci, Cr, H, W, B):
     """gradient-free bf16 RadarEnhanceByImage with the image/radar boundary on a 64-channel slab: the shuffle is moved to the
     weight columns and the projection reads [image | radar] in memory order (channel-major tcgen05 kernel, both sources by
-    TMA; 640 input channels: the transform-on-load kernel on the same formulation) - against the fp64 oracle on the same
+    TMA; 640 / 1024 input channels: the prologue as a streaming pass + the TMA-only GEMM) - against the fp64 oracle on the same
     bf16-rounded weights and inputs"""
     from oracle import coc_oracle as O
     torch.manual_seed(5)
