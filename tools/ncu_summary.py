@@ -13,6 +13,10 @@ METRICS = [
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_pct"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pct"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy_pct"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem_lsu_pct"),
+    ("l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed", "smem_bank_rd_pct"),
+    ("l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed", "smem_bank_wr_pct"),
+    ("lts__t_sector_hit_rate.pct", "l2_hit_pct"),
     ("launch__registers_per_thread", "regs"), ("launch__occupancy_limit_shared_mem", "occ_lim_smem"),
     ("launch__waves_per_multiprocessor", "waves"), ("smsp__inst_executed.sum", "warp_insts"),
     ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "st_long_sb"),

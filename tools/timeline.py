@@ -58,6 +58,9 @@ def main():
         if e > cur_end:
             cur_end, prev = e, n
     P(f"# idle gaps: {len(gaps)}, total {sum(g[0] for g in gaps):.1f} us; the 12 longest:")
+    P("# (the ~190 us hole after the first ~10 kernels is the tail of the graph LAUNCH of this isolated replay - the head of the graph runs "
+      "while the rest is still being submitted; tools/gap_probe.py replays the same kernels captured alone without it, and back-to-back "
+      "replays hide it behind the previous step)")
     for g in sorted(gaps, reverse=True)[:12]:
         P(f"    {g[0]:6.1f} us at t={g[3]:7.1f}  after {g[1]}  before {g[2]}")
     # exclusive time per kernel name: the time a kernel runs with NOTHING else in flight (it alone stretches the step)
