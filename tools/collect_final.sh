@@ -6,7 +6,7 @@ R=${1:-r02}
 O=gpurun_out
 mkdir -p $O
 timeout 600 python bench.py --profile-kernels > $O/${R}_bench_n1.json 2> $O/${R}_bench_n1_kernels.txt
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/${R}_launches_raw.csv \
+timeout 200 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/${R}_launches_raw.csv \
     python bench.py --ncu-pass --steps 1 --warmup 1 > /dev/null 2>&1
 python - <<PY
 import csv
