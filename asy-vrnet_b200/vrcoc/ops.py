@@ -279,6 +279,14 @@ class sums_arena:
     lane = 0         # forwards that may run CONCURRENTLY on one device (the pipeline slots of InferenceSession: one captured
                      # graph each, replayed on their own streams) must not share an arena: each is captured under its own lane
 
+    _lanes = 0
+
+    @staticmethod
+    def new_lane():
+        """a lane id no other forward uses (lane 0 = everything that runs on the caller's stream)"""
+        sums_arena._lanes += 1
+        return sums_arena._lanes
+
     def __init__(self, B, device):
         self.key = None
         if device.type == "cuda" and not torch.is_grad_enabled():

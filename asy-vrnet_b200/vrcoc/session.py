@@ -66,7 +66,7 @@ class InferenceSession:
                 S = {"x": torch.zeros(batch, 3, img, img, device=self.device, dtype=self.dtype),
                      "r": torch.zeros(batch, 4, img, img, device=self.device, dtype=self.dtype), "graph": None,
                      # concurrent slots: own statistics arena (ops.sums_arena.lane), replayed on the session's compute streams
-                     "lane": i if self.concurrent else 0}
+                     "lane": ops.sums_arena.new_lane() if self.concurrent else 0}
                 lane, ops.sums_arena.lane = ops.sums_arena.lane, S["lane"]
                 try:
                     for _ in range(2):                               # warm-up: memoised parameter views, lazy module state
