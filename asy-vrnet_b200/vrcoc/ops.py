@@ -68,7 +68,7 @@ def _stream():
 
 
 _SIDE_STREAMS = {}
-PAIR_STREAMS = True          # set False to serialise the two modality branches (debug / A-B)
+PAIR_STREAMS = os.environ.get("VRCOC_PAIR_STREAMS", "1") != "0"   # False / env 0: serialise the two modality branches (debug / A-B)
 
 
 def run_pair(f_main, f_side):

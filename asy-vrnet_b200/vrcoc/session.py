@@ -12,6 +12,8 @@ grows, frames per second go up.
 
 `decode_outputs` is the reference's utils/utils_bbox.py:32-84 as one kernel (`vrcoc_decode_outputs`).
 """
+import os
+
 import torch
 
 from . import ops
@@ -57,7 +59,7 @@ class InferenceSession:
         self.slots, self._next, self._pending = [], 0, []
         # concurrent: number of compute streams the slots' forwards rotate over (True = 2, measured best at batch 8: a third forward
         # in flight only thrashes L2; more SLOTS than streams still help the host side of the pipeline, which then runs further ahead)
-        nstreams = 0 if (not concurrent or slots < 2) else min(slots, 2 if concurrent is True else int(concurrent))
+        nstreams = 0 if (not concurrent or slots < 2) else min(slots, int(os.environ.get("VRCOC_SESSION_STREAMS", "2")) if concurrent is True else int(concurrent))
         self.concurrent = nstreams > 1
         self._cstreams = [torch.cuda.Stream(self.device) for _ in range(nstreams)] if self.concurrent else []
         self._nsub = 0
