@@ -129,3 +129,50 @@ def test_world_size_2_sharding_gloo(tmp_path):
                        timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_center_tap_identity_and_memo():
+    """the shortcut fusion._conv_launch takes when dilation >= map size (ASPP rate 18 on the 16x16 map, reference
+    neck/coc_fpn_dual.py:55-67): every off-centre tap of the dilated k x k convolution reads only zero padding, so it IS the 1x1
+    projection by its centre tap; and ops.center_tap memoises that slice on the weight (refreshed in place after an update)"""
+    import torch.nn.functional as F
+    from vrcoc import ops
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 6, 16, 16, generator=g, dtype=torch.float64)
+    w = torch.nn.Parameter(torch.randn(5, 6, 3, 3, generator=g, dtype=torch.float64))
+    for dil in (16, 18, 40):
+        full = F.conv2d(x, w, padding=dil, dilation=dil)
+        assert torch.equal(full, F.conv2d(x, w[:, :, 1:2, 1:2]))
+    assert not torch.allclose(F.conv2d(x, w, padding=15, dilation=15), F.conv2d(x, w[:, :, 1:2, 1:2]))     # one row / column short
+    c = ops.center_tap(w)
+    assert c.shape == (5, 6) and c.is_contiguous() and torch.equal(c, w.detach()[:, :, 1, 1])
+    assert ops.center_tap(w) is c                                   # memo hit
+    with torch.no_grad():
+        w.mul_(2.0)                                                  # bumps the version counter
+    c2 = ops.center_tap(w)
+    assert c2 is c and torch.equal(c2, w.detach()[:, :, 1, 1])      # same storage (graph-capture contract), new values
+
+
+def test_row_tap_decomposition_matches_conv():
+    """the algebra behind the convolution engine's row-tap mode (include/vrcoc.h, k_order 2): a 3x3 / pad d / dilation d convolution
+    = a 3x1 convolution (vertical taps, rows zero-padded) over the horizontal-tap expansion cols[b, kx*C + c, y, x] = x[b, c, y,
+    x + (kx-1)*d] with the tap-major weight [O][ky][kx*C + c] - the layout vrcoc_im2col_rows writes and ops.tap_major produces"""
+    import torch.nn.functional as F
+    from vrcoc import ops
+    g = torch.Generator().manual_seed(8)
+    B, C, O, H, W = 2, 4, 3, 6, 8
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(O, C, 3, 3, generator=g, dtype=torch.float64)
+    for d in (1, 2):
+        xp = F.pad(x, (d, d, 0, 0))
+        cols = torch.cat([xp[..., kx * d: kx * d + W] for kx in range(3)], 1)                  # [B, 3C, H, W]
+        wt = ops.tap_major(w).view(O, 3, 3 * C)                                                 # [O][ky][kx*C + c]
+        got = F.conv2d(cols, wt.permute(0, 2, 1).reshape(O, 3 * C, 3, 1), padding=(d, 0), dilation=(d, 1))
+        assert torch.allclose(got, F.conv2d(x, w, padding=d, dilation=d), atol=1e-12)
+
+
+def test_arena_lanes_are_unique():
+    """every concurrent pipeline slot of InferenceSession captures its forward under its own statistics-arena lane"""
+    from vrcoc import ops
+    a, b = ops.sums_arena.new_lane(), ops.sums_arena.new_lane()
+    assert a != b and a > 0 and b > 0 and ops.sums_arena.lane == 0
