@@ -24,9 +24,15 @@
 #if VRCOC_MF_TRACE
 #define MF_T0() t_ = clock64()
 #define MF_T1(acc) acc += clock64() - t_
+// per-chunk time stamps (C > 128 variant): slot k of chunk j at g_tc_trace[4096*16 + cta*128 + j*8 + k] (clock64, same SM for all roles)
+#define MF_STAMP(j, k)                                                                                                     \
+  do {                                                                                                                     \
+    if (g_tc_trace && (j) < 16) g_tc_trace[4096 * 16 + (blockIdx.z * (size_t)gridDim.x + blockIdx.x) * 128 + (j) * 8 + (k)] = clock64(); \
+  } while (0)
 #else
 #define MF_T0()
 #define MF_T1(acc)
+#define MF_STAMP(j, k)
 #endif
 
 namespace vrcoc {
@@ -157,6 +163,7 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
             MF_T1(ta_);
             tc_fence_after();
           }
+          MF_STAMP(j, 0);
           for (int kc = 0; kc < nk1; ++kc) {
             if (j == 0) mbar_wait(&x_ready[kc], 0);
             MF_T0();
@@ -169,6 +176,7 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
             if (++sl == SA) { sl = 0; ph ^= 1u; }
           }
           tc_commit(acc1_full);
+          MF_STAMP(j, 1);
         }
 #if VRCOC_MF_TRACE
         if (q_) { q_[0] = tw_; q_[1] = ta_; q_[3] = clock64() - tl0_; }
@@ -179,6 +187,7 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
           MF_T0();
           mbar_wait(&h_full[hb], (uint32_t)(j / HB) & 1);              // hidden chunk j is in shared memory (bf16 operand layout)
           MF_T1(th_);
+          MF_STAMP(j, 2);
           tc_fence_after();
           const uint32_t hbuf = smem_u32(sH + hb * 2 * TQ_X_BYTES);
           for (int q = 0; q < 2 * MT2; ++q) {
@@ -193,6 +202,7 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
             if (++sl == SB) { sl = 0; ph ^= 1u; }
           }
           tc_commit(&h_empty[hb]);
+          MF_STAMP(j, 3);
           if (j == nh - 1) tc_commit(acc2_full);
         }
 #if VRCOC_MF_TRACE
@@ -335,6 +345,7 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
       mbar_wait(acc1_full, (uint32_t)j & 1);
 #if VRCOC_MF_TRACE
       ea_ += clock64() - et_;
+      if (tid == 0 && !SINGLE) MF_STAMP(j, 4);
 #endif
       tc_fence_after();
       if (tid == 0 && j == 0) trace(3);
@@ -344,18 +355,9 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
         mbar_expect_tx(&res_bar[warp], 4096u);
         tma_load_3d(out_region, &tmapR, p0 + ch * (TQ_NP / 2), lq * 32, b, &res_bar[warp]);
       }
-      // two 32-column reads; after the second one acc1 is free, so the next chunk's first GEMM runs under the second half of
-      // the GELU work.  sH is first written after the first 16 values are computed: by then the previous chunk's second GEMM
-      // (which reads it) has normally completed.
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t r[32];
-        tmem_ld32(tbase + (uint32_t)(32 * hh), r);
-        if (hh == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc1_empty)) : "memory");
-        }
+      // 32 columns (two 16-point operand rows of this lane's hidden channel) at a time: bias, GELU, bf16, operand layout.  sH is first
+      // written after the first 16 values are computed: by then the previous chunk's second GEMM (which reads it) has normally completed.
+      auto half = [&](const uint32_t (&r)[32], int hh) {
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
           const int c = 2 * hh + sub;
@@ -377,10 +379,39 @@ mlp_fused_kernel(ConvArgs a1, ConvArgs a2, MlpLayout L, const float* __restrict_
           sts128(hbase + (uint32_t)(((2 * c) ^ sw) << 4), pack8_bf16(lo));
           sts128(hbase + (uint32_t)(((2 * c + 1) ^ sw) << 4), pack8_bf16(hi));
         }
+      };
+      auto release_acc1 = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(acc1_empty)) : "memory");
+      };
+      if (SINGLE) {
+        // two 32-column reads; after the second one acc1 is free, so the next chunk's first GEMM runs under the second half of the GELU
+        // work (two CTAs per SM: 32 more registers per thread are not available)
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t r[32];
+          tmem_ld32(tbase + (uint32_t)(32 * hh), r);
+          if (hh == 1) release_acc1();
+          half(r, hh);
+        }
+      } else {
+        // one CTA per SM: both reads first, so acc1 is released BEFORE any GELU work - the per-chunk time stamps (tools/trace_mlpf.py)
+        // showed the first-GEMM issuer starting 1.0 us after the accumulator was seen (half of the GELU pass) and its MMAs then
+        // sharing the pipe with the second GEMM of the same chunk
+        uint32_t ra[32], rb[32];
+        tmem_ld32(tbase, ra);
+        tmem_ld32(tbase + 32u, rb);
+        release_acc1();
+        half(ra, 0);
+        half(rb, 1);
       }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&h_full[hb])) : "memory");
+#if VRCOC_MF_TRACE
+      if (tid == 0 && !SINGLE) MF_STAMP(j, 5);
+#endif
     }
 #if VRCOC_MF_TRACE
     if (g_tc_trace && tid == 0) {

@@ -47,3 +47,13 @@ if len(w):
           f"  -> issuing/other {m[3] - m[0] - m[1] - m[2]:.2f};  per chunk {m[3] / nh:.2f} us")
     print(f"  epilogue warp 0: waiting acc1_full {m[4]:.2f}  h_empty {m[5]:.2f}  hidden loop {m[6]:.2f}  -> GELU work {m[6] - m[4] - m[5]:.2f}"
           f" ({(m[6] - m[4] - m[5]) / nh:.2f} per chunk)")
+# per-chunk stamps of the C > 128 variant (VRCOC_MF_TRACE build): A = first-GEMM issuer, B = second-GEMM issuer, E = epilogue warp 0
+st = tr.view(-1)[4096 * 16:4096 * 16 + 4096 * 128].view(-1, 16, 8).cpu().double()
+st = st[st[:, 0, 4] > 0]
+if len(st):
+    t00 = st[:, 0, 4].view(-1, 1, 1)                      # chunk 0's accumulator seen by the epilogue
+    rel = ((st - t00) / 1965.0).mean(0)
+    print("  per-chunk timeline (us after the epilogue first sees acc1; mean over CTAs):")
+    print("   chunk | A: issue start  A: issued | B: H seen  B: issued | E: acc1 seen  E: GELU done")
+    for j in range(O // 128):
+        print(f"   {j:5d} | {rel[j, 0]:14.2f} {rel[j, 1]:10.2f} | {rel[j, 2]:9.2f} {rel[j, 3]:10.2f} | {rel[j, 4]:12.2f} {rel[j, 5]:13.2f}")
