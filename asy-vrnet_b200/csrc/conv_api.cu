@@ -276,7 +276,7 @@ extern "C" int vrcoc_table_apply(const vrcoc_conv_desc* d, void* stream) {
   ConvArgs a;
   int rc = fill_args(&dd, a);
   if (rc) return rc;
-  VRCOC_REQUIRE(a.O == a.Cin && a.kh == 1 && a.kw == 1 && a.stride == 1 && a.pad == 0 && a.O_split == a.O,
+  VRCOC_REQUIRE(a.O == a.Cin && a.kh == 1 && a.kw == 1 && a.stride == 1 && a.pad == 0 && a.O_split == a.O && !a.rt_taps,
                 "table_apply: needs O == C0+C1 and a 1x1 geometry");
   dim3 grid((unsigned)a.Cin, (unsigned)a.B);
   table_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
@@ -285,7 +285,7 @@ extern "C" int vrcoc_table_apply(const vrcoc_conv_desc* d, void* stream) {
 
 extern "C" int64_t vrcoc_conv1x1_wgrad_workspace(const vrcoc_conv_desc* d) {
   ConvArgs a;
-  if (fill_args(d, a)) return -1;
+  if (fill_args(d, a) || a.rt_taps) return -1;
   int sps, ups;
   int splits = wgrad_splits(a, sps, ups);
   const int64_t simt = (int64_t)splits * ((int64_t)a.O * a.Cin + a.O);
@@ -300,7 +300,7 @@ extern "C" int vrcoc_conv1x1_wgrad(const vrcoc_conv_desc* d, const void* dy, int
   int rc = fill_args(d, a);
   if (rc) return rc;
   VRCOC_REQUIRE(dy && dW && workspace, "wgrad: null pointer");
-  VRCOC_REQUIRE(a.kh == 1 && a.kw == 1 && a.stride == 1 && a.pad == 0, "wgrad: only 1x1 projections are supported");
+  VRCOC_REQUIRE(a.kh == 1 && a.kw == 1 && a.stride == 1 && a.pad == 0 && !a.rt_taps, "wgrad: only 1x1 projections are supported");
   int sps, ups;
   int splits = wgrad_splits(a, sps, ups);
   int64_t need = (int64_t)splits * ((int64_t)a.O * a.Cin + a.O);

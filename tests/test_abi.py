@@ -60,6 +60,41 @@ def test_validation_errors_do_not_need_a_gpu():
     assert rc == -1 and b"inconsistent" in lib.vrcoc_last_error()
 
 
+def test_new_entry_points_validate_without_a_gpu():
+    """vrcoc_patch_embed(_supported), vrcoc_im2col_rows and the row-tap mode of vrcoc_conv_desc (k_order 2): the argument checks
+    run before any CUDA call"""
+    from vrcoc import _lib
+    lib = _lib.lib
+    BF16, F32 = _lib.BF16, _lib.F32
+    assert lib.vrcoc_patch_embed_supported(BF16, 3, 2, 512, 512, 64, 4) == 1
+    assert lib.vrcoc_patch_embed_supported(BF16, 4, 2, 1024, 1024, 64, 4) == 1
+    assert lib.vrcoc_patch_embed_supported(F32, 3, 2, 512, 512, 64, 4) == 0          # bf16 only
+    assert lib.vrcoc_patch_embed_supported(BF16, 3, 2, 512, 512, 32, 4) == 0         # 64 output channels only
+    assert lib.vrcoc_patch_embed_supported(BF16, 7, 2, 512, 512, 64, 4) == 0         # at most 8 input channels
+    assert lib.vrcoc_patch_embed_supported(BF16, 3, 2, 512, 480, 64, 4) == 0         # W % 64
+    assert lib.vrcoc_patch_embed_supported(BF16, 3, 2, 512, 512, 64, 16) == 0        # patch 4 only
+    rc = lib.vrcoc_patch_embed(None, None, 0, None, None, None, None, BF16, 1, 3, 2, 512, 512, 64, 4, None)
+    assert rc == -1 and b"patch_embed" in lib.vrcoc_last_error()
+    rc = lib.vrcoc_im2col_rows(None, None, BF16, 1, 64, 16, 16, 3, 1, None)
+    assert rc == -1 and b"im2col_rows" in lib.vrcoc_last_error()
+    # row-tap descriptor with a horizontal kernel extent: rejected with the contract in the message
+    buf = ctypes.create_string_buffer(64)
+    d = _lib.ConvDesc()
+    d.B, d.H_in, d.W_in, d.H_out, d.W_out, d.C0, d.O = 1, 64, 64, 64, 64, 192, 64
+    d.kh, d.kw, d.stride, d.pad, d.dil, d.k_order = 3, 3, 1, 1, 1, 2
+    d.src0 = d.weight = d.out = ctypes.addressof(buf)
+    d.src0_dtype = d.weight_dtype = d.out_dtype = BF16
+    d.O_split = 64
+    rc = lib.vrcoc_conv_fwd(ctypes.byref(d), None)
+    assert rc == -1 and b"row-tap" in lib.vrcoc_last_error()
+    d.kw, d.C0 = 1, 100                                                               # C0 % 64
+    rc = lib.vrcoc_conv_fwd(ctypes.byref(d), None)
+    assert rc == -1 and b"row-tap" in lib.vrcoc_last_error()
+    # a row-tap descriptor is not a 1x1 projection for the weight-gradient entry points
+    d.C0 = 192
+    assert lib.vrcoc_conv1x1_wgrad_workspace(ctypes.byref(d)) == -1
+
+
 def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     import subprocess
     import sys
