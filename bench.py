@@ -5,14 +5,19 @@
 
 ours      : EfficientVRNet(4, 9, phi) built from the vrcoc modules (hand-written sm_100a kernels behind the reference's
             nn.Module API), eval mode, bf16, batch 8 per GPU (BASELINE.json configs[2]: batch 64 sharded over 8 GPUs), the
-            whole forward captured in a CUDA graph.  One step = one forward over one batch of synthetic frames.
-            `value`  = frames/s with the batch already resident in HBM (device-timed, max over ranks);
-            `e2e`    = frames/s through the public call with pinned-host inputs: H2D copy of the batch, forward, D2H of
-                       the detection maps and of the per-pixel segmentation class map, all inside the timed region;
-            `roofline` = the kernel with the largest share of the step, timed live with CUDA events;
-            `cpu_baseline` = the CPU port of the reference (oracle/) timed on this box's host cores (rank 0, N=1).
-reference : the reference's CPU implementation of the same path (the oracle port: the reference is pure Python and
-            cannot travel to the GPU box), all host threads, one frame per step.
+            whole forward captured in one CUDA graph per pipeline slot.  One step = one forward over one batch of synthetic frames.
+            `value`  = frames/s with the batch already resident in HBM (device-timed, max over ranks), two batches in flight
+                       (vrcoc.InferenceSession: one graph + statistics arena per slot, two compute streams; every batch is
+                       computed on its own);
+            `serial` = the same with ONE graph replayed one batch at a time (= the per-batch latency);
+            `e2e`    = frames/s through the public serving call with pinned-host inputs: H2D copy of the batch, forward, box
+                       decode, D2H of the decoded boxes and of the per-pixel class map, all inside the timed region;
+            `roofline` = the launch class with the largest share of the step, timed live with CUDA events per launch;
+            `cpu_baseline` = the unmodified reference (baseline/_ref, vendored by __graft_entry__.build()) timed on this box's
+                       host cores (rank 0, N=1); `reference_eager_gpu` = the same reference run eagerly on the GPU;
+            `train_step` = a short BASELINE configs[3] measurement (the full one: --mode train).
+reference : the unmodified reference's CPU forward of the same path (baseline/_ref; no product import in that arm), all host
+            threads, one frame per step.
 """
 import argparse
 import json
